@@ -1,0 +1,287 @@
+// fft_bodies.cuh -- the per-CTA bodies of the four FFT sweeps, written against an
+// "Exec" policy so that the very same code runs as a CUDA thread block
+// (kernels_fft.cu: DeviceExec) and as a sequential loop over emulated threads
+// (tests/hostemu: HostExec).  A body is a sequence of phases; every phase is executed
+// by all threads of the CTA and is followed by a block barrier.
+//
+//   row_fwd_body : delta (ft - base) + real FFT of one row  [replaces get_delta_for_models
+//                  shard/merge/base.py:121-137 + the row half of fft_transform
+//                  shard/tensor/functions.py:55-58; sum of squares for normalize_tensor :85]
+//   col_body     : one in-place sweep of the complex column FFT (forward or inverse)
+//   row_inv_body : inverse real FFT of one row + epilogue (x 1/N, NaN->0, Inf flag,
+//                  x target_norm, + base, NaN->0, Inf flag, bf16 RNE)
+//                  [replaces ifft_transform functions.py:70-73, :208-217 and
+//                  shard/merge/fast_fourier.py:243,269-276]
+#pragma once
+#include "fft_core.cuh"
+#include "plan.h"
+
+namespace smfft {
+
+// ------------------------------------------------------------------ smem accessors
+struct RowSmem {               // one contiguous sequence, optional 1-in-16 padding
+  cf* buf; int padmask;        // padmask = ~0 (padded) or 0
+  SM_HD int phys(int i) const { return i + ((i >> 4) & padmask); }
+  SM_HD void load(int i, float& re, float& im) const { cf v = buf[phys(i)]; re = v.x; im = v.y; }
+  SM_HD void store(int i, float re, float im) const { cf v; v.x = re; v.y = im; buf[phys(i)] = v; }
+};
+struct ColSmem {               // [idx][32 columns], lane fastest: conflict free by construction
+  cf* buf; int lane;
+  SM_HD void load(int i, float& re, float& im) const { cf v = buf[i * SM_COL_TILE + lane]; re = v.x; im = v.y; }
+  SM_HD void store(int i, float re, float im) const { cf v; v.x = re; v.y = im; buf[i * SM_COL_TILE + lane] = v; }
+};
+
+// ------------------------------------------------------------------ row forward
+struct RowFwdArgs {
+  int mode;                    // 0: bf16 base + bf16 finetune -> delta ; 1: fp32 input
+  const uint16_t* base; const uint16_t* ft;
+  const float* x32; float m1, m2;        // fp32 input is used as (x*m1)*m2
+  float* re; float* im;        // output planes [R][P]
+};
+
+struct RowDeltaSrc {           // stage-1 source: element idx is the packed pair (x[2idx], x[2idx+1])
+  int mode; const uint32_t* b32; const uint32_t* f32; const cf* x32; float m1, m2; double* acc;
+  SM_HD void load(int i, float& re, float& im) const {
+    float d0, d1;
+    if (mode == 0) {
+      uint32_t bb = b32[i], ff = f32[i];
+      d0 = bf16_bits_to_f32(ff & 0xffffu) - bf16_bits_to_f32(bb & 0xffffu);
+      d1 = bf16_bits_to_f32(ff >> 16) - bf16_bits_to_f32(bb >> 16);
+    } else {
+      cf v = x32[i];
+      d0 = v.x; d1 = v.y;
+    }
+    *acc += double(d0) * double(d0) + double(d1) * double(d1);
+    if (mode != 0) { d0 = (d0 * m1) * m2; d1 = (d1 * m1) * m2; }
+    re = d0; im = d1;
+  }
+};
+
+template <class Exec>
+SM_HD void row_fwd_body(Exec& ex, const SmPlan& pl, int row, const RowFwdArgs& a, const cf* twC,
+                        cf* smem, double* acc) {
+  const int Ch = pl.Ch, T = ex.nthreads();
+  const int bufstride = pl.row_pad ? (Ch + (Ch >> 4) + 1) : Ch;
+  const int padmask = pl.row_pad ? ~0 : 0;
+  RowDeltaSrc gsrc;
+  gsrc.mode = a.mode;
+  gsrc.b32 = a.mode == 0 ? reinterpret_cast<const uint32_t*>(a.base + (size_t)row * pl.C) : nullptr;
+  gsrc.f32 = a.mode == 0 ? reinterpret_cast<const uint32_t*>(a.ft + (size_t)row * pl.C) : nullptr;
+  gsrc.x32 = a.mode != 0 ? reinterpret_cast<const cf*>(a.x32 + (size_t)row * pl.C) : nullptr;
+  gsrc.m1 = a.m1; gsrc.m2 = a.m2; gsrc.acc = acc;
+  int s = 1, cur = 0;
+  for (int st = 0; st < pl.n_row; ++st) {
+    const int r = pl.row_rad[st], nb = Ch / r;
+    const bool last = (st == pl.n_row - 1);
+    RowSmem sin{smem + (size_t)(cur ^ 1) * bufstride, padmask};   // written by the previous stage
+    RowSmem sout{smem + (size_t)cur * bufstride, padmask};
+    ex.phase([&](int tid) {
+      for (int b = tid; b < nb; b += T) {
+        if (st == 0) {
+          if (last) stockham_bfly_rt<true>(r, b, Ch, s, 2, twC, gsrc, sout);
+          else      stockham_bfly_rt<false>(r, b, Ch, s, 2, twC, gsrc, sout);
+        } else {
+          if (last) stockham_bfly_rt<true>(r, b, Ch, s, 2, twC, sin, sout);
+          else      stockham_bfly_rt<false>(r, b, Ch, s, 2, twC, sin, sout);
+        }
+      }
+    });
+    s *= r; cur ^= 1;
+  }
+  // untangle the packed transform into the Hermitian half spectrum X[0..Ch]
+  RowSmem z{smem + (size_t)(cur ^ 1) * bufstride, padmask};
+  float* ore = a.re + (size_t)row * pl.P;
+  float* oim = a.im + (size_t)row * pl.P;
+  ex.phase([&](int tid) {
+    for (int k = tid; k <= Ch; k += T) {
+      const int k0 = (k == Ch) ? 0 : k;
+      const int k1 = (k == 0 || k == Ch) ? 0 : Ch - k;
+      float ar, ai, br, bi;
+      z.load(k0, ar, ai);
+      z.load(k1, br, bi);
+      const float er = 0.5f * (ar + br), ei = 0.5f * (ai - bi);
+      const float pr = 0.5f * (ai + bi), qi = -0.5f * (ar - br);
+      const cf w = twC[k];
+      ore[k] = er + (pr * w.x - qi * w.y);
+      oim[k] = ei + (pr * w.y + qi * w.x);
+    }
+  });
+}
+
+// ------------------------------------------------------------------ row inverse
+struct RowInvArgs {
+  const float* re; const float* im;      // spectrum planes [R][P] (after the inverse column sweeps)
+  const float* cull_thr;                 // nullable; only used when R == 1 (no column sweep)
+  int out_mode;                          // 0: bf16 = bf16(base + x*scale) ; 1: fp32 = x*scale
+  const uint16_t* base; uint16_t* out_bf16; float* out_f32;
+  float inv_n;                           // 1/(R*C)
+  const float* scale_ptr; float scale_host;
+  unsigned int* flags;                   // [0] nan after ifft [1] inf after ifft [2] nan final [3] inf final
+};
+
+struct RowTangleSrc {          // stage-1 source of the inverse: Z'[k] from X[k], X[Ch-k], already re/im swapped
+  const float* re; const float* im; const cf* twC; int Ch; float thr;
+  SM_HD float cull(float v) const { return (v < thr && -v < thr) ? 0.f : v; }   // |v| < thr, NaN kept
+  SM_HD void load(int k, float& ore, float& oim) const {
+    float xr = cull(re[k]), xi = im[k];
+    float mr = cull(re[Ch - k]), mi = im[Ch - k];
+    if (k == 0) { xi = 0.f; mi = 0.f; }    // .real semantics: bins 0 and Ch are real
+    const float Ar = xr + mr, Ai = xi - mi;
+    const float Br = xr - mr, Bi = xi + mi;
+    const cf w = twC[k];                  // (cos, -sin); conj(w) = (cos, +sin)
+    const float br = Br * w.x + Bi * w.y; // B * conj(w), conj(w) = (w.x, -w.y)
+    const float bi = Bi * w.x - Br * w.y;
+    // Z' = A + i*B' ; hand it to the forward engine swapped
+    const float zr = Ar - bi, zi = Ai + br;
+    ore = zi; oim = zr;
+  }
+};
+
+struct RowEpilogueDst {        // last-stage sink of the inverse: element j is (x[2j], x[2j+1]) swapped
+  int out_mode; const uint32_t* base32; uint32_t* out32; cf* outf; float inv_n, scale;
+  unsigned int* cnt;           // per-thread local counters [4]
+  SM_HD float fin(float v, int which) const {
+    uint32_t u = f32_bits(v) & 0x7fffffffu;
+    if (u > 0x7f800000u) { cnt[which] += 1; return 0.f; }
+    if (u == 0x7f800000u) cnt[which + 1] += 1;
+    return v;
+  }
+  SM_HD void store(int j, float a, float b) const {
+    float x0 = fin(b * inv_n, 0), x1 = fin(a * inv_n, 0);
+    x0 *= scale; x1 *= scale;
+    if (out_mode == 0) {
+      uint32_t bb = base32[j];
+      x0 = fin(bf16_bits_to_f32(bb & 0xffffu) + x0, 2);
+      x1 = fin(bf16_bits_to_f32(bb >> 16) + x1, 2);
+      out32[j] = f32_to_bf16_rne(x0) | (f32_to_bf16_rne(x1) << 16);
+    } else {
+      cf v; v.x = x0; v.y = x1; outf[j] = v;
+    }
+  }
+};
+
+template <class Exec>
+SM_HD void row_inv_body(Exec& ex, const SmPlan& pl, int row, const RowInvArgs& a, const cf* twC,
+                        cf* smem, unsigned int* cnt) {
+  const int Ch = pl.Ch, T = ex.nthreads();
+  const int bufstride = pl.row_pad ? (Ch + (Ch >> 4) + 1) : Ch;
+  const int padmask = pl.row_pad ? ~0 : 0;
+  RowTangleSrc gsrc;
+  gsrc.re = a.re + (size_t)row * pl.P; gsrc.im = a.im + (size_t)row * pl.P;
+  gsrc.twC = twC; gsrc.Ch = Ch;
+  gsrc.thr = (a.cull_thr != nullptr) ? *a.cull_thr : 0.f;
+  RowEpilogueDst gdst;
+  gdst.out_mode = a.out_mode;
+  gdst.base32 = a.out_mode == 0 ? reinterpret_cast<const uint32_t*>(a.base + (size_t)row * pl.C) : nullptr;
+  gdst.out32 = a.out_mode == 0 ? reinterpret_cast<uint32_t*>(a.out_bf16 + (size_t)row * pl.C) : nullptr;
+  gdst.outf = a.out_mode != 0 ? reinterpret_cast<cf*>(a.out_f32 + (size_t)row * pl.C) : nullptr;
+  gdst.inv_n = a.inv_n;
+  gdst.scale = a.scale_ptr ? *a.scale_ptr : a.scale_host;
+  gdst.cnt = cnt;
+  int s = 1, cur = 0;
+  for (int st = 0; st < pl.n_row; ++st) {
+    const int r = pl.row_rad[st], nb = Ch / r;
+    const bool first = (st == 0), last = (st == pl.n_row - 1);
+    RowSmem sin{smem + (size_t)(cur ^ 1) * bufstride, padmask};
+    RowSmem sout{smem + (size_t)cur * bufstride, padmask};
+    ex.phase([&](int tid) {
+      for (int b = tid; b < nb; b += T) {
+        if (first && last)  stockham_bfly_rt<true>(r, b, Ch, s, 2, twC, gsrc, gdst);
+        else if (first)     stockham_bfly_rt<false>(r, b, Ch, s, 2, twC, gsrc, sout);
+        else if (last)      stockham_bfly_rt<true>(r, b, Ch, s, 2, twC, sin, gdst);
+        else                stockham_bfly_rt<false>(r, b, Ch, s, 2, twC, sin, sout);
+      }
+    });
+    s *= r; cur ^= 1;
+  }
+}
+
+// ------------------------------------------------------------------ column sweep
+struct ColArgs {
+  float* re; float* im;        // planes [R][P], transformed in place
+  int L; int n_rad; int rad[SM_MAX_STAGES];
+  int inst_mul, elem_mul;      // stored row of element i of instance g: g*inst_mul + i*elem_mul
+  int tw_mul;                  // W_L^e = twR[e * tw_mul], tw_mul = R / L
+  int big_tw;                  // multiply output k of instance g by W_R^(g*k)
+  int swap;                    // inverse sweep: swap re/im on load and on store
+  const float* cull_thr;       // nullable: |re| < thr -> 0 on load (first inverse sweep)
+  const float* scale_ptr; float scale_host; int use_scale;   // outputs *= scale (last forward sweep)
+  int write_im;                // 0: do not store the imaginary plane
+};
+
+struct ColGlobalSrc {
+  const float* re; const float* im; size_t row0; size_t estride; bool valid; int swap; float thr;
+  SM_HD void load(int i, float& ore, float& oim) const {
+    float xr = 0.f, xi = 0.f;
+    if (valid) {
+      const size_t off = row0 + (size_t)i * estride;
+      xr = re[off]; xi = im[off];
+      if (xr < thr && -xr < thr) xr = 0.f;
+    }
+    if (swap) { ore = xi; oim = xr; } else { ore = xr; oim = xi; }
+  }
+};
+struct ColGlobalDst {
+  float* re; float* im; size_t row0; size_t estride; bool valid; int swap;
+  const cf* twR; int big_step;   // big_step = instance index (0 when no inter-sweep twiddle)
+  float scale; int write_im;
+  SM_HD void store(int k, float xr, float xi) const {
+    if (big_step != 0) { const cf w = twR[(size_t)big_step * k]; cmul(xr, xi, w.x, w.y); }
+    xr *= scale; xi *= scale;
+    if (!valid) return;
+    const size_t off = row0 + (size_t)k * estride;
+    if (swap) { re[off] = xi; if (write_im) im[off] = xr; }
+    else      { re[off] = xr; if (write_im) im[off] = xi; }
+  }
+};
+
+// One CTA = one FFT instance x 32 adjacent columns.  tid -> (warp = butterfly slot, lane = column).
+template <class Exec>
+SM_HD void col_body(Exec& ex, const SmPlan& pl, int tile, int inst, const ColArgs& a, const cf* twR, cf* smem) {
+  const int T = ex.nthreads(), nwarps = T / 32;
+  const int L = a.L;
+  const int col0 = tile * SM_COL_TILE;
+  int s = 1, cur = 0;
+  for (int st = 0; st < a.n_rad; ++st) {
+    const int r = a.rad[st], nb = L / r;
+    const bool first = (st == 0), last = (st == a.n_rad - 1);
+    ex.phase([&](int tid) {
+      const int lane = tid & 31, wid = tid >> 5;
+      const int c = col0 + lane;
+      const bool valid = (c <= pl.Ch);
+      const size_t row0 = (size_t)inst * a.inst_mul * pl.P + c;
+      const size_t estride = (size_t)a.elem_mul * pl.P;
+      ColGlobalSrc gsrc{a.re, a.im, row0, estride, valid, a.swap, a.cull_thr ? *a.cull_thr : 0.f};
+      ColGlobalDst gdst{a.re, a.im, row0, estride, valid, a.swap, twR, a.big_tw ? inst : 0,
+                        a.use_scale ? (a.scale_ptr ? *a.scale_ptr : a.scale_host) : 1.0f, a.write_im};
+      ColSmem sin{smem + (size_t)(cur ^ 1) * L * SM_COL_TILE, lane};
+      ColSmem sout{smem + (size_t)cur * L * SM_COL_TILE, lane};
+      for (int b = wid; b < nb; b += nwarps) {
+        if (first && last)  stockham_bfly_rt<true>(r, b, L, s, a.tw_mul, twR, gsrc, gdst);
+        else if (first)     stockham_bfly_rt<false>(r, b, L, s, a.tw_mul, twR, gsrc, sout);
+        else if (last)      stockham_bfly_rt<true>(r, b, L, s, a.tw_mul, twR, sin, gdst);
+        else                stockham_bfly_rt<false>(r, b, L, s, a.tw_mul, twR, sin, sout);
+      }
+    });
+    s *= r; cur ^= 1;
+  }
+}
+
+// fill ColArgs for forward (dir=0) / inverse (dir=1) sweep `which` (0: A = strided, 1: B = contiguous)
+static inline void sm_col_args(const SmPlan& pl, int which, int inverse, ColArgs* a, int* n_inst) {
+  if (pl.col_passes == 1) {
+    a->L = pl.R; a->n_rad = pl.nA; for (int i = 0; i < pl.nA; ++i) a->rad[i] = pl.radA[i];
+    a->inst_mul = 0; a->elem_mul = 1; a->tw_mul = 1; a->big_tw = 0; *n_inst = 1;
+  } else if (which == 0) {
+    a->L = pl.Ra; a->n_rad = pl.nA; for (int i = 0; i < pl.nA; ++i) a->rad[i] = pl.radA[i];
+    a->inst_mul = 1; a->elem_mul = pl.Rb; a->tw_mul = pl.Rb; *n_inst = pl.Rb;
+    a->big_tw = inverse ? 0 : 1;
+  } else {
+    a->L = pl.Rb; a->n_rad = pl.nB; for (int i = 0; i < pl.nB; ++i) a->rad[i] = pl.radB[i];
+    a->inst_mul = pl.Rb; a->elem_mul = 1; a->tw_mul = pl.Ra; *n_inst = pl.Ra;
+    a->big_tw = inverse ? 1 : 0;
+  }
+  a->swap = inverse;
+}
+
+}  // namespace smfft

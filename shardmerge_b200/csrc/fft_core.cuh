@@ -1,0 +1,265 @@
+// fft_core.cuh -- register butterflies and the Stockham stage used by every FFT kernel.
+//
+// Everything in this header is __host__ __device__ and free of CUDA intrinsics, so the
+// exact same index math / butterflies can be driven from a CPU loop in tests/hostemu
+// (one emulated CTA at a time) as well as from the sm_100a kernels in kernels_fft.cu.
+//
+// Conventions
+//   * forward transform only: X[k] = sum_n x[n] * exp(-2*pi*i*n*k/N).  The inverse is
+//     obtained by swapping re/im at the input and at the output of the forward engine
+//     (ifft(z) = swap(fft(swap(z))), unnormalised), so no second set of twiddles exists.
+//   * Stockham autosort, decimation in frequency: natural order in, natural order out.
+//   * twiddle tables hold W_M^j = (cos(2*pi*j/M), -sin(2*pi*j/M)) as float2, computed
+//     in double precision (kernels_fft.cu: k_init_twiddles).
+//
+// Replaces torch.fft.fft / fftn / ifft / ifftn as called by the reference at
+// shard/tensor/functions.py:55-58 and :70-73 (library calls into MKL / cuFFT there).
+#pragma once
+#include <cstdint>
+#include <type_traits>
+
+#if defined(__CUDACC__)
+#define SM_HD __host__ __device__ __forceinline__
+#else
+#define SM_HD inline
+#endif
+
+namespace smfft {
+
+struct cf { float x, y; };   // plain complex<float>, layout-compatible with float2
+
+// ---------------------------------------------------------------------------------
+// compile-time trigonometry (only used to bake small-radix constants into immediates)
+// ---------------------------------------------------------------------------------
+constexpr double kPi = 3.14159265358979323846264338327950288;
+
+constexpr double c_reduce(double x) {  // to [-pi, pi]
+  while (x > kPi) x -= 2.0 * kPi;
+  while (x < -kPi) x += 2.0 * kPi;
+  return x;
+}
+constexpr double c_sin(double x0) {
+  double x = c_reduce(x0), x2 = x * x, term = x, sum = x;
+  for (int i = 1; i < 20; ++i) { term *= -x2 / double((2 * i) * (2 * i + 1)); sum += term; }
+  return sum;
+}
+constexpr double c_cos(double x0) {
+  double x = c_reduce(x0), x2 = x * x, term = 1.0, sum = 1.0;
+  for (int i = 1; i < 20; ++i) { term *= -x2 / double((2 * i - 1) * (2 * i)); sum += term; }
+  return sum;
+}
+// cos / sin of 2*pi*k/n with the exact values at multiples of an eighth turn.
+constexpr double c_cos2pi(int k, int n) {
+  k %= n; if (k < 0) k += n;
+  if ((4 * k) % n == 0) { int q = (4 * k) / n; return q == 0 ? 1.0 : (q == 2 ? -1.0 : 0.0); }
+  if ((8 * k) % n == 0) { int q = (8 * k) / n; return (q == 1 || q == 7) ? 0.70710678118654752440 : -0.70710678118654752440; }
+  return c_cos(2.0 * kPi * double(k) / double(n));
+}
+constexpr double c_sin2pi(int k, int n) {
+  k %= n; if (k < 0) k += n;
+  if ((4 * k) % n == 0) { int q = (4 * k) / n; return q == 1 ? 1.0 : (q == 3 ? -1.0 : 0.0); }
+  if ((8 * k) % n == 0) { int q = (8 * k) / n; return (q == 1 || q == 3) ? 0.70710678118654752440 : -0.70710678118654752440; }
+  return c_sin(2.0 * kPi * double(k) / double(n));
+}
+
+template <int I, int N, class F>
+SM_HD void static_for(F&& f) {
+  if constexpr (I < N) {
+    f(std::integral_constant<int, I>{});
+    static_for<I + 1, N>(f);
+  }
+}
+
+// y = x * W_N^K, W_N = exp(-2*pi*i/N), K and N compile-time.
+template <int K, int N>
+SM_HD void twmul(float xr, float xi, float& yr, float& yi) {
+  constexpr int k = ((K % N) + N) % N;
+  if constexpr (k == 0) { yr = xr; yi = xi; }
+  else if constexpr (4 * k == N) { yr = xi; yi = -xr; }          // -i
+  else if constexpr (2 * k == N) { yr = -xr; yi = -xi; }         // -1
+  else if constexpr (4 * k == 3 * N) { yr = -xi; yi = xr; }      // +i
+  else {
+    constexpr float c = float(c_cos2pi(k, N));
+    constexpr float s = float(c_sin2pi(k, N));
+    // (xr + i xi)(c - i s)
+    yr = xr * c + xi * s;
+    yi = xi * c - xr * s;
+  }
+}
+
+SM_HD void cmul(float& xr, float& xi, float wr, float wi) {
+  float tr = xr * wr - xi * wi;
+  float ti = xr * wi + xi * wr;
+  xr = tr; xi = ti;
+}
+
+// ---------------------------------------------------------------------------------
+// in-register forward DFTs of small length
+// ---------------------------------------------------------------------------------
+template <int N> struct Dft;
+
+template <> struct Dft<1> {
+  static SM_HD void run(float (&)[1], float (&)[1]) {}
+};
+
+template <> struct Dft<2> {
+  static SM_HD void run(float (&re)[2], float (&im)[2]) {
+    float ar = re[0], ai = im[0], br = re[1], bi = im[1];
+    re[0] = ar + br; im[0] = ai + bi;
+    re[1] = ar - br; im[1] = ai - bi;
+  }
+};
+
+template <> struct Dft<4> {
+  static SM_HD void run(float (&re)[4], float (&im)[4]) {
+    float t0r = re[0] + re[2], t0i = im[0] + im[2];
+    float t1r = re[0] - re[2], t1i = im[0] - im[2];
+    float t2r = re[1] + re[3], t2i = im[1] + im[3];
+    float t3r = re[1] - re[3], t3i = im[1] - im[3];
+    re[0] = t0r + t2r; im[0] = t0i + t2i;
+    re[2] = t0r - t2r; im[2] = t0i - t2i;
+    // X1 = t1 - i*t3 ; X3 = t1 + i*t3
+    re[1] = t1r + t3i; im[1] = t1i - t3r;
+    re[3] = t1r - t3i; im[3] = t1i + t3r;
+  }
+};
+
+// odd prime length, symmetric (real cos/sin) formulation: (P-1)^2 FMAs.
+template <int P> struct DftPrime {
+  static SM_HD void run(float (&re)[P], float (&im)[P]) {
+    constexpr int H = (P - 1) / 2;
+    float sr[H], si[H], dr[H], di[H];
+    static_for<0, H>([&](auto j_) {
+      constexpr int j = decltype(j_)::value;
+      sr[j] = re[j + 1] + re[P - 1 - j]; si[j] = im[j + 1] + im[P - 1 - j];
+      dr[j] = re[j + 1] - re[P - 1 - j]; di[j] = im[j + 1] - im[P - 1 - j];
+    });
+    const float r0 = re[0], i0 = im[0];
+    float sumr = r0, sumi = i0;
+    static_for<0, H>([&](auto j_) { constexpr int j = decltype(j_)::value; sumr += sr[j]; sumi += si[j]; });
+    static_for<1, H + 1>([&](auto k_) {
+      constexpr int k = decltype(k_)::value;
+      float ar = r0, ai = i0, br = 0.f, bi = 0.f;
+      static_for<0, H>([&](auto j_) {
+        constexpr int j = decltype(j_)::value;
+        constexpr float c = float(c_cos2pi((j + 1) * k, P));
+        constexpr float s = float(c_sin2pi((j + 1) * k, P));
+        ar += c * sr[j]; ai += c * si[j];
+        br += s * dr[j]; bi += s * di[j];
+      });
+      // X[k] = a - i*b ; X[P-k] = a + i*b   with a=(ar,ai), b=(br,bi)
+      re[k] = ar + bi; im[k] = ai - br;
+      re[P - k] = ar - bi; im[P - k] = ai + br;
+    });
+    re[0] = sumr; im[0] = sumi;
+  }
+};
+template <> struct Dft<3> : DftPrime<3> {};
+template <> struct Dft<5> : DftPrime<5> {};
+template <> struct Dft<7> : DftPrime<7> {};
+template <> struct Dft<11> : DftPrime<11> {};
+template <> struct Dft<13> : DftPrime<13> {};
+
+// composite length A*B, one Cooley-Tukey level in registers.
+// input index n = B*a + b, output index k = ka + A*kb.
+template <int A, int B> struct DftCT {
+  static SM_HD void run(float (&re)[A * B], float (&im)[A * B]) {
+    float tr[A * B], ti[A * B];
+    static_for<0, B>([&](auto b_) {
+      constexpr int b = decltype(b_)::value;
+      float xr[A], xi[A];
+      static_for<0, A>([&](auto a_) { constexpr int a = decltype(a_)::value; xr[a] = re[B * a + b]; xi[a] = im[B * a + b]; });
+      Dft<A>::run(xr, xi);
+      static_for<0, A>([&](auto k_) {
+        constexpr int k = decltype(k_)::value;
+        twmul<b * k, A * B>(xr[k], xi[k], tr[k * B + b], ti[k * B + b]);
+      });
+    });
+    static_for<0, A>([&](auto k_) {
+      constexpr int k = decltype(k_)::value;
+      float zr[B], zi[B];
+      static_for<0, B>([&](auto b_) { constexpr int b = decltype(b_)::value; zr[b] = tr[k * B + b]; zi[b] = ti[k * B + b]; });
+      Dft<B>::run(zr, zi);
+      static_for<0, B>([&](auto q_) { constexpr int q = decltype(q_)::value; re[k + A * q] = zr[q]; im[k + A * q] = zi[q]; });
+    });
+  }
+};
+template <> struct Dft<8> : DftCT<4, 2> {};
+template <> struct Dft<16> : DftCT<4, 4> {};
+
+// ---------------------------------------------------------------------------------
+// one Stockham (DIF, autosort) butterfly of radix r
+//
+//   stage state: total length N, stride s = product of the radices of earlier stages.
+//   butterfly b in [0, N/r):  q = b % s, p = b / s
+//     reads   x[b + j*N/r]                 j = 0..r-1
+//     writes  y[q + s*(r*p + k)] * W_N^(s*p*k)   k = 0..r-1
+//   The twiddle table is W_M with M = N*tw_mul (so W_N^e = tab[e*tw_mul]).
+//   In the last stage (s*r == N) p is always 0 and the twiddles vanish (kLast).
+// ---------------------------------------------------------------------------------
+template <int r, bool kLast, class Src, class Dst>
+SM_HD void stockham_bfly(int b, int N, int s, int tw_mul, const cf* tw, const Src& src, const Dst& dst) {
+  float re[r], im[r];
+  const int Nr = N / r;
+  static_for<0, r>([&](auto j_) {
+    constexpr int j = decltype(j_)::value;
+    src.load(b + j * Nr, re[j], im[j]);
+  });
+  Dft<r>::run(re, im);
+  if constexpr (kLast) {
+    static_for<0, r>([&](auto k_) {
+      constexpr int k = decltype(k_)::value;
+      dst.store(b + k * s, re[k], im[k]);   // p == 0, q == b
+    });
+  } else {
+    const int p = b / s;
+    const int q = b - p * s;
+    const int obase = q + s * r * p;
+    const int tstep = s * p * tw_mul;
+    dst.store(obase, re[0], im[0]);
+    static_for<1, r>([&](auto k_) {
+      constexpr int k = decltype(k_)::value;
+      const cf w = tw[tstep * k];
+      float xr = re[k], xi = im[k];
+      cmul(xr, xi, w.x, w.y);
+      dst.store(obase + k * s, xr, xi);
+    });
+  }
+}
+
+// runtime-radix dispatch (the plan is data, the butterflies are code)
+template <bool kLast, class Src, class Dst>
+SM_HD void stockham_bfly_rt(int r, int b, int N, int s, int tw_mul, const cf* tw, const Src& src, const Dst& dst) {
+  switch (r) {
+    case 1:  stockham_bfly<1, kLast>(b, N, s, tw_mul, tw, src, dst); break;
+    case 2:  stockham_bfly<2, kLast>(b, N, s, tw_mul, tw, src, dst); break;
+    case 3:  stockham_bfly<3, kLast>(b, N, s, tw_mul, tw, src, dst); break;
+    case 4:  stockham_bfly<4, kLast>(b, N, s, tw_mul, tw, src, dst); break;
+    case 5:  stockham_bfly<5, kLast>(b, N, s, tw_mul, tw, src, dst); break;
+    case 7:  stockham_bfly<7, kLast>(b, N, s, tw_mul, tw, src, dst); break;
+    case 8:  stockham_bfly<8, kLast>(b, N, s, tw_mul, tw, src, dst); break;
+    case 11: stockham_bfly<11, kLast>(b, N, s, tw_mul, tw, src, dst); break;
+    case 13: stockham_bfly<13, kLast>(b, N, s, tw_mul, tw, src, dst); break;
+    case 16: stockham_bfly<16, kLast>(b, N, s, tw_mul, tw, src, dst); break;
+    default: break;
+  }
+}
+
+// ---------------------------------------------------------------------------------
+// bf16 helpers (bit-level, host/device identical)
+// ---------------------------------------------------------------------------------
+SM_HD float bf16_bits_to_f32(uint32_t hi16) {
+  union { uint32_t u; float f; } v; v.u = hi16 << 16; return v.f;
+}
+SM_HD uint32_t f32_bits(float f) { union { uint32_t u; float f; } v; v.f = f; return v.u; }
+SM_HD float bits_f32(uint32_t u) { union { uint32_t u; float f; } v; v.u = u; return v.f; }
+// round-to-nearest-even fp32 -> bf16 (same result as torch's .to(torch.bfloat16))
+SM_HD uint32_t f32_to_bf16_rne(float f) {
+  uint32_t u = f32_bits(f);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return (u >> 16) | 0x0040u;  // quiet NaN
+  uint32_t lsb = (u >> 16) & 1u;
+  u += 0x7fffu + lsb;
+  return u >> 16;
+}
+
+}  // namespace smfft
