@@ -1,0 +1,154 @@
+/* shardmerge_b200.h -- C ABI of libshardmerge_b200.so (sm_100a CUDA kernels).
+ *
+ * This is the drop-in boundary for the per-tensor spectral ("SLERP-FFT") merge hot path
+ * of 54rt1n/shardmerge.  The reference has no FFI of its own (it is pure Python over
+ * torch); every entry point below replaces a span of torch library calls at a
+ * reference call site, cited per function as `path:line` relative to the reference root.
+ * The host side (shardmerge_b200/tensor/functions.py, shardmerge_b200/merge/fast_fourier.py)
+ * binds these with ctypes and keeps the reference's Python signatures.
+ *
+ * Rules of the ABI
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless it is
+ *     marked "host"; `stream` is a cudaStream_t passed as void*.
+ *   - the library never allocates device memory: tables, spectra, workspaces and scalar
+ *     blocks are caller-provided (sizes from the sm_*_bytes queries).
+ *   - every call is asynchronous on `stream`; the only host synchronisation is whatever
+ *     the caller does to read scalars back.
+ *   - return value 0 = ok, negative = error; sm_last_error() gives the message.
+ *
+ * Spectrum layout ("half planar"): two fp32 planes re[R][P], im[R][P] holding the
+ * Hermitian half spectrum, columns 0..C/2 valid, row pitch P = sm_plan_pitch().  Rows are
+ * in *stored order*: stored row i holds frequency sm_plan_row_freq(plan, i) (identity
+ * unless the column FFT needed two sweeps).  Global statistics count a stored bin once
+ * for columns 0 and C/2 and twice otherwise (its mirror image is not stored).
+ */
+#ifndef SHARDMERGE_B200_H
+#define SHARDMERGE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sm_plan sm_plan;   /* opaque, host memory */
+
+int sm_version(void);
+const char* sm_last_error(void);
+
+/* ---- plans ------------------------------------------------------------------------ */
+/* Plan for tensors of shape [R][C] (R = 1 for 1-D tensors), C even, prime factors of C/2
+ * and R in {2,3,5,7,11,13}, R <= 65536.  Returns NULL if the shape is unsupported. */
+sm_plan* sm_plan_create(int R, int C);
+void sm_plan_destroy(sm_plan* plan);
+int sm_plan_pitch(const sm_plan* plan);                 /* P, in floats                       */
+int sm_plan_row_freq(const sm_plan* plan, int stored);  /* stored row -> frequency index      */
+int sm_plan_describe(const sm_plan* plan, char* buf, int buflen);   /* human-readable factorisation */
+size_t sm_plan_table_bytes(const sm_plan* plan);        /* device bytes for the twiddle tables */
+/* Fill the caller's table buffer (twiddles computed on the device in fp64, stored fp32). */
+int sm_plan_init_tables(const sm_plan* plan, void* tables, void* stream);
+
+/* ---- forward: delta + real 2-D FFT --------------------------------------------------
+ * Replaces get_delta_for_models (shard/merge/base.py:121-137: fp32(ft) - fp32(base)), the
+ * norm reduction of normalize_tensor (shard/tensor/functions.py:85) and the row half of
+ * fft_transform (shard/tensor/functions.py:55-58).
+ * sumsq (fp64, device) receives += sum(delta^2); the caller zeroes it beforehand. */
+int sm_fwd_rows_bf16(const sm_plan* plan, const void* tables, const void* base_bf16, const void* ft_bf16,
+                     float* re, float* im, double* sumsq, void* stream);
+/* Same for an fp32 input tensor x (already a delta / any real tensor); the transform is
+ * taken of (x*m1)*m2 (two fp32 roundings, as `a * norm_scale` / `b * weight_scale * norm_scale`
+ * at shard/merge/fast_fourier.py:228-230), sumsq accumulates sum(x^2). */
+int sm_fwd_rows_f32(const sm_plan* plan, const void* tables, const float* x, float m1, float m2,
+                    float* re, float* im, double* sumsq, void* stream);
+/* Column half of fft_transform, in place.  The spectrum is multiplied by *scale_dev (if
+ * non-NULL) else by scale_host: this is where `tensor / norm` of normalize_tensor
+ * (functions.py:88) is applied (the FFT is linear).  write_im = 0 skips storing the
+ * imaginary plane (the blend never reads Im X1). */
+int sm_fwd_cols(const sm_plan* plan, const void* tables, float* re, float* im,
+                const float* scale_dev, float scale_host, int write_im, void* stream);
+/* *out = 1/(float)sqrt(*sumsq), or 1 if the sum is 0 (normalize_tensor's `if norm != 0`). */
+int sm_inv_norm(const double* sumsq, float* out, void* stream);
+
+/* ---- order statistics ---------------------------------------------------------------
+ * Replace the two full torch.sort calls of interpolate_fft_components
+ * (shard/tensor/functions.py:113-122 cutoff, :138-148 cull): the element of 0-based rank
+ * `rank` of |plane0| (and |plane1| concatenated, if non-NULL) over the FULL spectrum,
+ * i.e. with the Hermitian multiplicities above.  Exact: the result is the bit pattern of
+ * an actual element.
+ *   mode 0 (fast): a random sample predicts a narrow window around the statistic, one
+ *          streaming pass counts what lies below it and collects what lies inside, a
+ *          radix select over the collected keys finishes.  If the window misses or the
+ *          candidate buffer overflows, state->status != 0 and *thr_out = NaN.
+ *   mode 1 (safe): window = everything; needs a workspace for all keys.
+ * sel_state: >= SM_SELECT_STATE_BYTES device bytes.  ws: sm_select_ws_bytes() device bytes.
+ * After completion (stream order) sel_state holds {u64 rank, u64 below, u32 prefix, u32 lo,
+ * u32 hi, u32 ncand, u32 cap, u32 status, f32 value}. */
+#define SM_SELECT_STATE_BYTES 64
+size_t sm_select_ws_bytes(const sm_plan* plan, int n_planes, int mode);
+int sm_select_kth_abs(const sm_plan* plan, const float* plane0, const float* plane1, uint64_t rank,
+                      int mode, void* sel_state, void* ws, size_t ws_bytes, float* thr_out, void* stream);
+
+/* ---- SLERP statistics and blend ------------------------------------------------------
+ * Masked sums for slerp() (shard/tensor/functions.py:36-41) over
+ * slerp_mask = sign(re0)==sign(re1) & ~(|re1| < thr_cut)  (functions.py:124-127; both
+ * "small" masks test re1 in the reference): sums3 += {sum re0^2, sum re1^2, sum re0*re1},
+ * fp64, Hermitian multiplicities applied.  *thr_cut is read on the device. */
+int sm_slerp_reduce(const sm_plan* plan, const float* re0, const float* re1, const float* thr_cut,
+                    double* sums3, void* stream);
+/* scal4 = {dot, cos(theta), sin(theta), max(||v1 - v0*dot||, 1e-12)} as fp32
+ * (functions.py:36-43; theta = acos(clamp(dot)) * t). */
+int sm_slerp_scalars(const double* sums3, double t, float* scal4, void* stream);
+/* Three-way masked blend of the real parts (functions.py:124-136); out may alias re0.
+ * mode 0: SLERP blend with *thr_cut, scal4, t_sum.
+ * mode 1: arithmetic blend of arithmetic_fft_components (functions.py:273-284):
+ *         sign agreement -> re0 + t*re1, else re1 (the reference's "larger" mask is always
+ *         False); agreement = 0 -> always re0 + t*re1.  t is passed in t_sum. */
+int sm_blend(const sm_plan* plan, int mode, int agreement, const float* re0, const float* re1,
+             const float* thr_cut, const float* scal4, float t_sum, float* out_re, void* stream);
+
+/* ---- inverse: cull + inverse 2-D FFT + epilogue ---------------------------------------
+ * Column half of ifft_transform (functions.py:70-73), in place; values of the real plane
+ * with |re| < *cull_thr are read as 0 (functions.py:146; cull_thr may be NULL). */
+int sm_inv_cols(const sm_plan* plan, const void* tables, float* re, float* im, const float* cull_thr,
+                void* stream);
+/* Row half of ifft_transform + everything after it:
+ *   x = ifft * 1/(R*C); NaN -> 0, count Inf            (functions.py:208-217)
+ *   x = x * scale  (scale = *scale_dev or scale_host)  (fast_fourier.py:243, target_norm)
+ *   y = fp32(base) + x; NaN -> 0, count Inf; bf16 RNE  (fast_fourier.py:269-276)
+ * flags4 += {nan after ifft, inf after ifft, nan final, inf final} (u32 counters).
+ * cull_thr is only honoured for 1-D plans (no column sweep).
+ * check_ifft = 0 skips the first NaN->0 / Inf step: task_arithmetic_fft2 (functions.py:224-254)
+ * returns the raw ifft, so a NaN there survives until the final check of _merge_layer. */
+int sm_inv_rows_bf16(const sm_plan* plan, const void* tables, const float* re, const float* im,
+                     const float* cull_thr, const void* base_bf16, void* out_bf16,
+                     const float* scale_dev, float scale_host, int check_ifft, uint32_t* flags4, void* stream);
+/* fp32 variant without the base add: out = ifft/(R*C) (NaN -> 0) * scale. */
+int sm_inv_rows_f32(const sm_plan* plan, const void* tables, const float* re, const float* im,
+                    const float* cull_thr, float* out, const float* scale_dev, float scale_host,
+                    int check_ifft, uint32_t* flags4, void* stream);
+
+/* ---- element-wise paths that need no FFT ------------------------------------------------
+ * out_bf16 = bf16(fp32(base_out) + (ca*(ft0-base0) + cb*(ft1-base1)) * scale), NaN -> 0, Inf
+ * counted in flags4[2..3].  Covers `merged = a + b` (fast_fourier.py:223-225), the
+ * single-model case (:256-257) and the small-norm early returns of
+ * merge_tensors_fft2_slerp (functions.py:184-190).  Any of ft1/base1 may be NULL (cb ignored). */
+int sm_delta_axpby_bf16(size_t n, const void* base_out, const void* base0, const void* ft0, float ca,
+                        const void* base1, const void* ft1, float cb, float scale, void* out_bf16,
+                        uint32_t* flags4, void* stream);
+/* pass-through copy with dtype cast to bf16 done by the writer: plain device copy of n bytes
+ * (is_input / is_output tensors, fast_fourier.py:104-130). */
+int sm_copy_bytes(void* dst, const void* src, size_t n, void* stream);
+
+/* ---- API-level format conversion (not on the timed path) --------------------------------
+ * Half planar (stored order) -> full complex64 [R][C] in natural order with the Hermitian
+ * mirror filled in: what fft_transform returns (functions.py:55-58). */
+int sm_expand_full(const sm_plan* plan, const float* re, const float* im, float* out_c64, void* stream);
+/* Full complex64 [R][C] natural order -> half planar stored order, Hermitian-projected
+ * ((Z[k] + conj(Z[-k]))/2), i.e. exactly the part `.real` of ifftn keeps (functions.py:73). */
+int sm_pack_half(const sm_plan* plan, const float* in_c64, float* re, float* im, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SHARDMERGE_B200_H */

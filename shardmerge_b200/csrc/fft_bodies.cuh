@@ -116,6 +116,7 @@ struct RowInvArgs {
   const uint16_t* base; uint16_t* out_bf16; float* out_f32;
   float inv_n;                           // 1/(R*C)
   const float* scale_ptr; float scale_host;
+  int check_ifft;                        // 1: NaN->0 / count Inf right after the ifft
   unsigned int* flags;                   // [0] nan after ifft [1] inf after ifft [2] nan final [3] inf final
 };
 
@@ -138,7 +139,7 @@ struct RowTangleSrc {          // stage-1 source of the inverse: Z'[k] from X[k]
 };
 
 struct RowEpilogueDst {        // last-stage sink of the inverse: element j is (x[2j], x[2j+1]) swapped
-  int out_mode; const uint32_t* base32; uint32_t* out32; cf* outf; float inv_n, scale;
+  int out_mode; const uint32_t* base32; uint32_t* out32; cf* outf; float inv_n, scale; int check;
   unsigned int* cnt;           // per-thread local counters [4]
   SM_HD float fin(float v, int which) const {
     uint32_t u = f32_bits(v) & 0x7fffffffu;
@@ -147,7 +148,8 @@ struct RowEpilogueDst {        // last-stage sink of the inverse: element j is (
     return v;
   }
   SM_HD void store(int j, float a, float b) const {
-    float x0 = fin(b * inv_n, 0), x1 = fin(a * inv_n, 0);
+    float x0 = b * inv_n, x1 = a * inv_n;
+    if (check) { x0 = fin(x0, 0); x1 = fin(x1, 0); }
     x0 *= scale; x1 *= scale;
     if (out_mode == 0) {
       uint32_t bb = base32[j];
@@ -175,7 +177,7 @@ SM_HD void row_inv_body(Exec& ex, const SmPlan& pl, int row, const RowInvArgs& a
   gdst.base32 = a.out_mode == 0 ? reinterpret_cast<const uint32_t*>(a.base + (size_t)row * pl.C) : nullptr;
   gdst.out32 = a.out_mode == 0 ? reinterpret_cast<uint32_t*>(a.out_bf16 + (size_t)row * pl.C) : nullptr;
   gdst.outf = a.out_mode != 0 ? reinterpret_cast<cf*>(a.out_f32 + (size_t)row * pl.C) : nullptr;
-  gdst.inv_n = a.inv_n;
+  gdst.inv_n = a.inv_n; gdst.check = a.check_ifft;
   gdst.scale = a.scale_ptr ? *a.scale_ptr : a.scale_host;
   gdst.cnt = cnt;
   int s = 1, cur = 0;

@@ -20,8 +20,10 @@
 
 #if defined(__CUDACC__)
 #define SM_HD __host__ __device__ __forceinline__
+#define SM_CX __host__ __device__ constexpr
 #else
 #define SM_HD inline
+#define SM_CX constexpr
 #endif
 
 namespace smfft {
@@ -33,29 +35,29 @@ struct cf { float x, y; };   // plain complex<float>, layout-compatible with flo
 // ---------------------------------------------------------------------------------
 constexpr double kPi = 3.14159265358979323846264338327950288;
 
-constexpr double c_reduce(double x) {  // to [-pi, pi]
+SM_CX double c_reduce(double x) {  // to [-pi, pi]
   while (x > kPi) x -= 2.0 * kPi;
   while (x < -kPi) x += 2.0 * kPi;
   return x;
 }
-constexpr double c_sin(double x0) {
+SM_CX double c_sin(double x0) {
   double x = c_reduce(x0), x2 = x * x, term = x, sum = x;
   for (int i = 1; i < 20; ++i) { term *= -x2 / double((2 * i) * (2 * i + 1)); sum += term; }
   return sum;
 }
-constexpr double c_cos(double x0) {
+SM_CX double c_cos(double x0) {
   double x = c_reduce(x0), x2 = x * x, term = 1.0, sum = 1.0;
   for (int i = 1; i < 20; ++i) { term *= -x2 / double((2 * i - 1) * (2 * i)); sum += term; }
   return sum;
 }
 // cos / sin of 2*pi*k/n with the exact values at multiples of an eighth turn.
-constexpr double c_cos2pi(int k, int n) {
+SM_CX double c_cos2pi(int k, int n) {
   k %= n; if (k < 0) k += n;
   if ((4 * k) % n == 0) { int q = (4 * k) / n; return q == 0 ? 1.0 : (q == 2 ? -1.0 : 0.0); }
   if ((8 * k) % n == 0) { int q = (8 * k) / n; return (q == 1 || q == 7) ? 0.70710678118654752440 : -0.70710678118654752440; }
   return c_cos(2.0 * kPi * double(k) / double(n));
 }
-constexpr double c_sin2pi(int k, int n) {
+SM_CX double c_sin2pi(int k, int n) {
   k %= n; if (k < 0) k += n;
   if ((4 * k) % n == 0) { int q = (4 * k) / n; return q == 1 ? 1.0 : (q == 3 ? -1.0 : 0.0); }
   if ((8 * k) % n == 0) { int q = (8 * k) / n; return (q == 1 || q == 3) ? 0.70710678118654752440 : -0.70710678118654752440; }

@@ -1,0 +1,260 @@
+// kernels_fft.cu -- sm_100a kernels for the delta + forward real 2-D FFT and the inverse
+// 2-D FFT + epilogue, and the plan part of the C ABI (include/shardmerge_b200.h).
+//
+// The arithmetic lives in fft_bodies.cuh (host/device); this file supplies the device
+// execution policy, the launch geometry and the reductions that need CUDA intrinsics.
+#include <cstdarg>
+#include <mutex>
+#include "fft_bodies.cuh"
+#include "sm_internal.h"
+
+using namespace smfft;
+
+// ------------------------------------------------------------------ error plumbing
+static thread_local char g_err[512] = "";
+void sm_set_error(const char* fmt, ...) {
+  va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap);
+}
+extern "C" const char* sm_last_error(void) { return g_err; }
+extern "C" int sm_version(void) { return 100; }
+
+// ------------------------------------------------------------------ device exec policy
+struct DeviceExec {
+  __device__ __forceinline__ int nthreads() const { return (int)blockDim.x; }
+  template <class F> __device__ __forceinline__ void phase(F&& f) { f((int)threadIdx.x); __syncthreads(); }
+};
+
+extern __shared__ float2 g_dyn_smem[];
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------ kernels
+__global__ void __launch_bounds__(512) k_row_fwd(SmPlan pl, RowFwdArgs a, const cf* __restrict__ twC,
+                                                 double* __restrict__ sumsq) {
+  DeviceExec ex;
+  double acc = 0.0;
+  row_fwd_body(ex, pl, (int)blockIdx.x, a, twC, reinterpret_cast<cf*>(g_dyn_smem), &acc);
+  __shared__ double wsum[16];
+  acc = warp_sum(acc);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) wsum[wid] = acc;
+  __syncthreads();
+  if (wid == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    double v = lane < nw ? wsum[lane] : 0.0;
+    v = warp_sum(v);
+    if (lane == 0) atomicAdd(sumsq, v);
+  }
+}
+
+__global__ void __launch_bounds__(512) k_row_inv(SmPlan pl, RowInvArgs a, const cf* __restrict__ twC) {
+  DeviceExec ex;
+  unsigned int cnt[4] = {0u, 0u, 0u, 0u};
+  row_inv_body(ex, pl, (int)blockIdx.x, a, twC, reinterpret_cast<cf*>(g_dyn_smem), cnt);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (cnt[i]) atomicAdd(a.flags + i, cnt[i]);
+}
+
+__global__ void __launch_bounds__(512) k_col(SmPlan pl, ColArgs a, const cf* __restrict__ twR) {
+  DeviceExec ex;
+  col_body(ex, pl, (int)blockIdx.x, (int)blockIdx.y, a, twR, reinterpret_cast<cf*>(g_dyn_smem));
+}
+
+// scale a 1-D spectrum (no column sweep exists to fold the normalisation into)
+__global__ void k_scale_row(float* re, float* im, int n, const float* scale_dev, float scale_host, int write_im) {
+  const float s = scale_dev ? *scale_dev : scale_host;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    re[i] *= s;
+    if (write_im) im[i] *= s;
+  }
+}
+
+__global__ void k_init_twiddles(cf* tw, int M) {
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < M; j += gridDim.x * blockDim.x) {
+    double s, c;
+    sincospi(2.0 * (double)j / (double)M, &s, &c);
+    cf w; w.x = (float)c; w.y = (float)(-s);
+    tw[j] = w;
+  }
+}
+
+__global__ void k_inv_norm(const double* sumsq, float* out) {
+  const double ss = *sumsq;
+  const float nrm = (float)sqrt(ss);
+  *out = (nrm != 0.f) ? (1.0f / nrm) : 1.0f;
+}
+
+// ------------------------------------------------------------------ host side
+static std::once_flag g_attr_once;
+static int g_attr_rc = 0;
+static int ensure_attrs() {
+  std::call_once(g_attr_once, [] {
+    const int kMax = 227 * 1024;
+    cudaError_t e;
+    e = cudaFuncSetAttribute(k_row_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_row_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_col, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax);
+    if (e != cudaSuccess) { sm_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); g_attr_rc = -100; }
+  });
+  return g_attr_rc;
+}
+
+extern "C" sm_plan* sm_plan_create(int R, int C) {
+  sm_plan* pl = new sm_plan;
+  int rc = sm_make_plan(R, C, &pl->p);
+  if (rc != 0) {
+    sm_set_error("unsupported tensor shape [%d][%d] for the sm_100a FFT (rc=%d): C must be even, "
+                 "C/2 and R must factor into {2,3,5,7,11,13}, R <= 65536", R, C, rc);
+    delete pl;
+    return nullptr;
+  }
+  return pl;
+}
+extern "C" void sm_plan_destroy(sm_plan* plan) { delete plan; }
+extern "C" int sm_plan_pitch(const sm_plan* plan) { return plan->p.P; }
+extern "C" int sm_plan_row_freq(const sm_plan* plan, int stored) { return sm_row_freq(&plan->p, stored); }
+extern "C" size_t sm_plan_table_bytes(const sm_plan* plan) {
+  return ((size_t)plan->p.C + (size_t)plan->p.R) * 8;
+}
+extern "C" int sm_plan_describe(const sm_plan* plan, char* buf, int buflen) {
+  const SmPlan& p = plan->p;
+  int n = snprintf(buf, buflen, "R=%d C=%d P=%d row[%d thr, smem %d/%d, pad %d]:", p.R, p.C, p.P,
+                   p.row_threads, p.row_smem_fwd, p.row_smem_inv, p.row_pad);
+  for (int i = 0; i < p.n_row && n < buflen; ++i) n += snprintf(buf + n, buflen - n, " %d", p.row_rad[i]);
+  if (n < buflen) n += snprintf(buf + n, buflen - n, " | col passes=%d Ra=%d[%d thr]:", p.col_passes, p.Ra, p.thrA);
+  for (int i = 0; i < p.nA && n < buflen; ++i) n += snprintf(buf + n, buflen - n, " %d", p.radA[i]);
+  if (p.col_passes == 2) {
+    if (n < buflen) n += snprintf(buf + n, buflen - n, " Rb=%d[%d thr]:", p.Rb, p.thrB);
+    for (int i = 0; i < p.nB && n < buflen; ++i) n += snprintf(buf + n, buflen - n, " %d", p.radB[i]);
+  }
+  return n;
+}
+
+extern "C" int sm_plan_init_tables(const sm_plan* plan, void* tables, void* stream) {
+  const SmPlan& p = plan->p;
+  cudaStream_t st = (cudaStream_t)stream;
+  cf* twC = reinterpret_cast<cf*>(tables);
+  cf* twR = reinterpret_cast<cf*>(reinterpret_cast<char*>(tables) + sm_tab_off_R(p));
+  k_init_twiddles<<<(p.C + 255) / 256, 256, 0, st>>>(twC, p.C);
+  SM_LAUNCH_CHECK();
+  k_init_twiddles<<<(p.R + 255) / 256, 256, 0, st>>>(twR, p.R);
+  SM_LAUNCH_CHECK();
+  return 0;
+}
+
+static const cf* tabC(const SmPlan&, const void* tables) { return reinterpret_cast<const cf*>(tables); }
+static const cf* tabR(const SmPlan& p, const void* tables) {
+  return reinterpret_cast<const cf*>(reinterpret_cast<const char*>(tables) + sm_tab_off_R(p));
+}
+
+static int launch_row_fwd(const SmPlan& p, const void* tables, const RowFwdArgs& a, double* sumsq, cudaStream_t st) {
+  if (ensure_attrs()) return -100;
+  k_row_fwd<<<p.R, p.row_threads, p.row_smem_fwd, st>>>(p, a, tabC(p, tables), sumsq);
+  SM_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sm_fwd_rows_bf16(const sm_plan* plan, const void* tables, const void* base_bf16, const void* ft_bf16,
+                                float* re, float* im, double* sumsq, void* stream) {
+  RowFwdArgs a{};
+  a.mode = 0; a.base = (const uint16_t*)base_bf16; a.ft = (const uint16_t*)ft_bf16;
+  a.m1 = 1.f; a.m2 = 1.f; a.re = re; a.im = im;
+  return launch_row_fwd(plan->p, tables, a, sumsq, (cudaStream_t)stream);
+}
+
+extern "C" int sm_fwd_rows_f32(const sm_plan* plan, const void* tables, const float* x, float m1, float m2,
+                               float* re, float* im, double* sumsq, void* stream) {
+  RowFwdArgs a{};
+  a.mode = 1; a.x32 = x; a.m1 = m1; a.m2 = m2; a.re = re; a.im = im;
+  return launch_row_fwd(plan->p, tables, a, sumsq, (cudaStream_t)stream);
+}
+
+static int launch_col(const SmPlan& p, const void* tables, int sweep, int inverse, float* re, float* im,
+                      const float* cull_thr, const float* scale_dev, float scale_host, int use_scale,
+                      int write_im, cudaStream_t st) {
+  if (ensure_attrs()) return -100;
+  ColArgs ca{};
+  int n_inst = 0;
+  sm_col_args(p, sweep, inverse, &ca, &n_inst);
+  ca.re = re; ca.im = im; ca.cull_thr = cull_thr;
+  ca.scale_ptr = scale_dev; ca.scale_host = scale_host; ca.use_scale = use_scale;
+  ca.write_im = write_im;
+  const int ntiles = (p.Ch + 1 + SM_COL_TILE - 1) / SM_COL_TILE;
+  const int threads = (sweep == 0) ? p.thrA : p.thrB;
+  const int smem = (sweep == 0) ? p.smemA : p.smemB;
+  k_col<<<dim3(ntiles, n_inst), threads, smem, st>>>(p, ca, tabR(p, tables));
+  SM_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sm_fwd_cols(const sm_plan* plan, const void* tables, float* re, float* im,
+                           const float* scale_dev, float scale_host, int write_im, void* stream) {
+  const SmPlan& p = plan->p;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (p.col_passes == 0) {
+    k_scale_row<<<(p.Ch + 1 + 255) / 256, 256, 0, st>>>(re, im, p.Ch + 1, scale_dev, scale_host, write_im);
+    SM_LAUNCH_CHECK();
+    return 0;
+  }
+  for (int sweep = 0; sweep < p.col_passes; ++sweep) {
+    const bool lastsweep = (sweep == p.col_passes - 1);
+    int rc = launch_col(p, tables, sweep, 0, re, im, nullptr, scale_dev, scale_host, lastsweep ? 1 : 0,
+                        lastsweep ? write_im : 1, st);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+extern "C" int sm_inv_norm(const double* sumsq, float* out, void* stream) {
+  k_inv_norm<<<1, 1, 0, (cudaStream_t)stream>>>(sumsq, out);
+  SM_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sm_inv_cols(const sm_plan* plan, const void* tables, float* re, float* im, const float* cull_thr,
+                           void* stream) {
+  const SmPlan& p = plan->p;
+  for (int i = 0; i < p.col_passes; ++i) {
+    const int sweep = p.col_passes - 1 - i;   // undo sweep B first, then sweep A
+    int rc = launch_col(p, tables, sweep, 1, re, im, i == 0 ? cull_thr : nullptr, nullptr, 1.f, 0, 1,
+                        (cudaStream_t)stream);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+static int launch_row_inv(const SmPlan& p, const void* tables, RowInvArgs& a, cudaStream_t st) {
+  if (ensure_attrs()) return -100;
+  a.inv_n = (float)(1.0 / ((double)p.R * (double)p.C));
+  if (p.col_passes != 0) a.cull_thr = nullptr;
+  k_row_inv<<<p.R, p.row_threads, p.row_smem_inv, st>>>(p, a, tabC(p, tables));
+  SM_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int sm_inv_rows_bf16(const sm_plan* plan, const void* tables, const float* re, const float* im,
+                                const float* cull_thr, const void* base_bf16, void* out_bf16,
+                                const float* scale_dev, float scale_host, int check_ifft, uint32_t* flags4,
+                                void* stream) {
+  RowInvArgs a{};
+  a.check_ifft = check_ifft;
+  a.re = re; a.im = im; a.cull_thr = cull_thr; a.out_mode = 0;
+  a.base = (const uint16_t*)base_bf16; a.out_bf16 = (uint16_t*)out_bf16;
+  a.scale_ptr = scale_dev; a.scale_host = scale_host; a.flags = flags4;
+  return launch_row_inv(plan->p, tables, a, (cudaStream_t)stream);
+}
+
+extern "C" int sm_inv_rows_f32(const sm_plan* plan, const void* tables, const float* re, const float* im,
+                               const float* cull_thr, float* out, const float* scale_dev, float scale_host,
+                               int check_ifft, uint32_t* flags4, void* stream) {
+  RowInvArgs a{};
+  a.check_ifft = check_ifft;
+  a.re = re; a.im = im; a.cull_thr = cull_thr; a.out_mode = 1; a.out_f32 = out;
+  a.scale_ptr = scale_dev; a.scale_host = scale_host; a.flags = flags4;
+  return launch_row_inv(plan->p, tables, a, (cudaStream_t)stream);
+}

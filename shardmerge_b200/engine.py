@@ -1,0 +1,331 @@
+"""Device-resident spectral merge pipeline on top of the C ABI (include/shardmerge_b200.h).
+
+This module owns plans, twiddle tables and workspaces (all torch-allocated: the C library
+never allocates) and strings the kernels together for one pair merge:
+
+    rows(A), rows(B)            delta + row FFT + sum of squares          (k_row_fwd)
+    -- one host read of the two sums: norms decide order / branch (fast_fourier.py:209-232)
+    cols(A), cols(B)            column sweeps, spectrum scaled by 1/norm  (k_col)
+    select(cutoff)              exact order statistic of |Re X0|,|Re X1|  (k_count_collect ...)
+    reduce + scalars            masked SLERP sums, dot/theta              (k_slerp_reduce)
+    blend                       three-way masked blend of the real parts  (k_blend)
+    select(cull)                exact order statistic of |Re R|
+    inverse cols + rows         cull on load, iFFT, x target_norm, + base, bf16 (k_col, k_row_inv)
+
+Tensors stay on the GPU from the bf16 inputs to the bf16 output; the reference's
+TensorDiskCache round trips (shard/merge/fast_fourier.py:46-77) have no equivalent here.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from dataclasses import dataclass, field
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+# offsets inside the per-workspace scalar block (bytes)
+_CTL_BYTES = 512
+_OFF_DBL, _OFF_FLT, _OFF_FLAGS, _OFF_SEL = 0, 64, 128, 192
+# float64 slots
+D_SUMSQ0, D_SUMSQ1, D_S00, D_S11, D_S01 = 0, 1, 2, 3, 4
+# float32 slots
+F_THR_CUT, F_THR_CULL, F_DOT, F_COS, F_SIN, F_RELNORM, F_INV0, F_INV1 = 0, 1, 2, 3, 4, 5, 6, 7
+
+
+class UnsupportedShape(ValueError):
+    pass
+
+
+def _require_cuda(device) -> torch.device:
+    dev = torch.device(device)
+    if dev.type != "cuda":
+        raise RuntimeError(
+            f"shardmerge_b200 only runs on CUDA devices (got device={device!r}); there is no CPU path"
+        )
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return dev
+
+
+def _stream(dev) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class Plan:
+    """FFT plan + twiddle tables for tensors of shape [R][C] on one device."""
+
+    def __init__(self, R: int, C: int, device):
+        self.lib = _lib.load()
+        self.device = _require_cuda(device)
+        self.R, self.C, self.Ch = R, C, C // 2
+        self.handle = self.lib.sm_plan_create(R, C)
+        if not self.handle:
+            raise UnsupportedShape(self.lib.sm_last_error().decode())
+        self.P = self.lib.sm_plan_pitch(self.handle)
+        with torch.cuda.device(self.device):
+            self.tables = torch.empty(self.lib.sm_plan_table_bytes(self.handle), dtype=torch.uint8, device=self.device)
+            _lib.check(self.lib.sm_plan_init_tables(self.handle, self.tables.data_ptr(), _stream(self.device)), "init_tables")
+
+    def describe(self) -> str:
+        buf = ctypes.create_string_buffer(1024)
+        self.lib.sm_plan_describe(self.handle, buf, 1024)
+        return buf.value.decode()
+
+    def row_freq(self) -> torch.Tensor:
+        """stored row -> frequency index (CPU int64 tensor)."""
+        return torch.tensor([self.lib.sm_plan_row_freq(self.handle, i) for i in range(self.R)], dtype=torch.int64)
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                self.lib.sm_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+class Workspace:
+    """Spectrum planes, scalar block and select scratch for one plan (re-used across tensors)."""
+
+    def __init__(self, plan: Plan, n_spectra: int = 2, safe_select: bool = False):
+        self.plan = plan
+        dev = plan.device
+        self.n_spectra = n_spectra
+        self.re = [torch.empty((plan.R, plan.P), dtype=torch.float32, device=dev) for _ in range(n_spectra)]
+        self.im = [torch.empty((plan.R, plan.P), dtype=torch.float32, device=dev) for _ in range(n_spectra)]
+        self.ctl = torch.zeros(_CTL_BYTES, dtype=torch.uint8, device=dev)
+        self.dbl = self.ctl[_OFF_DBL:_OFF_DBL + 64].view(torch.float64)
+        self.flt = self.ctl[_OFF_FLT:_OFF_FLT + 64].view(torch.float32)
+        self.flags = self.ctl[_OFF_FLAGS:_OFF_FLAGS + 16].view(torch.int32)
+        self.sel = self.ctl[_OFF_SEL:_OFF_SEL + 128]
+        self.safe_select = safe_select
+        mode = 1 if safe_select else 0
+        nbytes = max(plan.lib.sm_select_ws_bytes(plan.handle, 2, mode), plan.lib.sm_select_ws_bytes(plan.handle, 1, mode))
+        self.sel_ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        # pinned landing zone for the scalar block
+        self.ctl_host = torch.empty(_CTL_BYTES, dtype=torch.uint8).pin_memory()
+
+    # typed pointers into the scalar block
+    def dptr(self, slot): return self.dbl.data_ptr() + 8 * slot
+    def fptr(self, slot): return self.flt.data_ptr() + 4 * slot
+    def selptr(self, which): return self.sel.data_ptr() + 64 * which
+
+    def read_ctl(self):
+        """Synchronous read-back of the scalar block -> (float64[8], float32[16], int32[4], sel bytes)."""
+        self.ctl_host.copy_(self.ctl, non_blocking=True)
+        torch.cuda.current_stream(self.plan.device).synchronize()
+        h = self.ctl_host
+        return (h[_OFF_DBL:_OFF_DBL + 64].view(torch.float64), h[_OFF_FLT:_OFF_FLT + 64].view(torch.float32),
+                h[_OFF_FLAGS:_OFF_FLAGS + 16].view(torch.int32), h[_OFF_SEL:_OFF_SEL + 128])
+
+
+_plans: dict = {}
+_workspaces: dict = {}
+
+
+def get_plan(R: int, C: int, device) -> Plan:
+    dev = _require_cuda(device)
+    key = (dev.index, R, C)
+    pl = _plans.get(key)
+    if pl is None:
+        pl = _plans[key] = Plan(R, C, dev)
+    return pl
+
+
+def get_workspace(R: int, C: int, device, n_spectra: int = 2, safe_select: bool = False) -> Workspace:
+    dev = _require_cuda(device)
+    key = (dev.index, R, C, safe_select)
+    ws = _workspaces.get(key)
+    if ws is None or ws.n_spectra < n_spectra:
+        ws = _workspaces[key] = Workspace(get_plan(R, C, dev), n_spectra, safe_select)
+    return ws
+
+
+def clear_caches():
+    _workspaces.clear()
+    _plans.clear()
+
+
+def shape_rc(t: torch.Tensor):
+    if t.ndim == 1:
+        return 1, t.shape[0]
+    if t.ndim == 2:
+        return t.shape[0], t.shape[1]
+    raise UnsupportedShape(f"only 1-D and 2-D tensors are supported by the sm_100a FFT path, got {tuple(t.shape)}")
+
+
+# ------------------------------------------------------------------------------------------
+# sources: what a row pass can read
+# ------------------------------------------------------------------------------------------
+@dataclass
+class Source:
+    """Either a (base, finetune) pair of bf16 tensors (delta is formed in the kernel) or an
+    fp32 tensor that already is a delta / intermediate merge result."""
+    base: Optional[torch.Tensor] = None
+    ft: Optional[torch.Tensor] = None
+    x32: Optional[torch.Tensor] = None
+    weight: float = 1.0
+    name: str = ""
+    norm: float = float("nan")     # filled after the row pass
+
+    @property
+    def is_bf16(self) -> bool:
+        return self.x32 is None
+
+    def delta_f32(self) -> torch.Tensor:
+        """fp32 delta as a torch tensor (only used by the rare FFT-free fallbacks)."""
+        if self.x32 is not None:
+            return self.x32
+        return self.ft.to(torch.float32) - self.base.to(torch.float32)
+
+
+def make_source(base: Optional[torch.Tensor], ft: Optional[torch.Tensor], x32: Optional[torch.Tensor] = None,
+                weight: float = 1.0, name: str = "") -> Source:
+    if x32 is not None:
+        return Source(x32=x32.contiguous().to(torch.float32), weight=weight, name=name)
+    if base.dtype == torch.bfloat16 and ft.dtype == torch.bfloat16:
+        return Source(base=base.contiguous(), ft=ft.contiguous(), weight=weight, name=name)
+    # other storage dtypes: form the fp32 delta with torch (exact upcast + one rounding, base.py:128-132)
+    return Source(x32=(ft.to(torch.float32) - base.to(torch.float32)).contiguous(), weight=weight, name=name)
+
+
+# ------------------------------------------------------------------------------------------
+# kernel wrappers
+# ------------------------------------------------------------------------------------------
+def fwd_rows(ws: Workspace, slot: int, src: Source, sumsq_slot: int, m1: float = 1.0, m2: float = 1.0):
+    pl, lib = ws.plan, ws.plan.lib
+    st = _stream(pl.device)
+    if src.is_bf16:
+        rc = lib.sm_fwd_rows_bf16(pl.handle, pl.tables.data_ptr(), src.base.data_ptr(), src.ft.data_ptr(),
+                                  ws.re[slot].data_ptr(), ws.im[slot].data_ptr(), ws.dptr(sumsq_slot), st)
+    else:
+        rc = lib.sm_fwd_rows_f32(pl.handle, pl.tables.data_ptr(), src.x32.data_ptr(), m1, m2,
+                                 ws.re[slot].data_ptr(), ws.im[slot].data_ptr(), ws.dptr(sumsq_slot), st)
+    _lib.check(rc, "sm_fwd_rows")
+
+
+def fwd_cols(ws: Workspace, slot: int, scale: float = 1.0, scale_slot: Optional[int] = None, write_im: bool = True):
+    pl, lib = ws.plan, ws.plan.lib
+    rc = lib.sm_fwd_cols(pl.handle, pl.tables.data_ptr(), ws.re[slot].data_ptr(), ws.im[slot].data_ptr(),
+                         None if scale_slot is None else ws.fptr(scale_slot), float(scale), 1 if write_im else 0,
+                         _stream(pl.device))
+    _lib.check(rc, "sm_fwd_cols")
+
+
+def select_kth(ws: Workspace, plane0: torch.Tensor, plane1: Optional[torch.Tensor], rank: int, out_slot: int,
+               which: int = 0):
+    pl, lib = ws.plan, ws.plan.lib
+    rc = lib.sm_select_kth_abs(pl.handle, plane0.data_ptr(), _p(plane1), int(rank), 1 if ws.safe_select else 0,
+                               ws.selptr(which), ws.sel_ws.data_ptr(), ws.sel_ws.numel(), ws.fptr(out_slot),
+                               _stream(pl.device))
+    _lib.check(rc, "sm_select_kth_abs")
+
+
+def slerp_reduce(ws: Workspace, re0: torch.Tensor, re1: torch.Tensor):
+    pl, lib = ws.plan, ws.plan.lib
+    _lib.check(lib.sm_slerp_reduce(pl.handle, re0.data_ptr(), re1.data_ptr(), ws.fptr(F_THR_CUT), ws.dptr(D_S00),
+                                   _stream(pl.device)), "sm_slerp_reduce")
+
+
+def slerp_scalars(ws: Workspace, t: float):
+    pl, lib = ws.plan, ws.plan.lib
+    _lib.check(lib.sm_slerp_scalars(ws.dptr(D_S00), float(t), ws.fptr(F_DOT), _stream(pl.device)), "sm_slerp_scalars")
+
+
+def blend(ws: Workspace, mode: int, agreement: bool, re0: torch.Tensor, re1: torch.Tensor, t_sum: float,
+          out: torch.Tensor):
+    pl, lib = ws.plan, ws.plan.lib
+    _lib.check(lib.sm_blend(pl.handle, mode, 1 if agreement else 0, re0.data_ptr(), re1.data_ptr(), ws.fptr(F_THR_CUT),
+                            ws.fptr(F_DOT), float(t_sum), out.data_ptr(), _stream(pl.device)), "sm_blend")
+
+
+def inv_cols(ws: Workspace, re: torch.Tensor, im: torch.Tensor, cull: bool):
+    pl, lib = ws.plan, ws.plan.lib
+    _lib.check(lib.sm_inv_cols(pl.handle, pl.tables.data_ptr(), re.data_ptr(), im.data_ptr(),
+                               ws.fptr(F_THR_CULL) if cull else None, _stream(pl.device)), "sm_inv_cols")
+
+
+def inv_rows(ws: Workspace, re: torch.Tensor, im: torch.Tensor, cull: bool, scale: float,
+             base: Optional[torch.Tensor], out: torch.Tensor, check_ifft: bool = True):
+    pl, lib = ws.plan, ws.plan.lib
+    st = _stream(pl.device)
+    cptr = ws.fptr(F_THR_CULL) if cull else None
+    if out.dtype == torch.bfloat16:
+        rc = lib.sm_inv_rows_bf16(pl.handle, pl.tables.data_ptr(), re.data_ptr(), im.data_ptr(), cptr, base.data_ptr(),
+                                  out.data_ptr(), None, float(scale), 1 if check_ifft else 0, ws.flags.data_ptr(), st)
+    else:
+        rc = lib.sm_inv_rows_f32(pl.handle, pl.tables.data_ptr(), re.data_ptr(), im.data_ptr(), cptr, out.data_ptr(),
+                                 None, float(scale), 1 if check_ifft else 0, ws.flags.data_ptr(), st)
+    _lib.check(rc, "sm_inv_rows")
+
+
+def delta_axpby_bf16(base_out, s0: Source, ca: float, s1: Optional[Source], cb: float, scale: float,
+                     out: torch.Tensor, flags: torch.Tensor):
+    lib = _lib.load()
+    dev = out.device
+    rc = lib.sm_delta_axpby_bf16(out.numel(), base_out.data_ptr(), s0.base.data_ptr(), s0.ft.data_ptr(), float(ca),
+                                 None if s1 is None else s1.base.data_ptr(), None if s1 is None else s1.ft.data_ptr(),
+                                 float(cb), float(scale), out.data_ptr(), flags.data_ptr(), _stream(dev))
+    _lib.check(rc, "sm_delta_axpby_bf16")
+
+
+# ------------------------------------------------------------------------------------------
+# pair merge
+# ------------------------------------------------------------------------------------------
+def f32(x: float) -> float:
+    """round a Python float to fp32 (what torch does when a Python scalar meets an fp32 tensor)."""
+    return torch.tensor(x, dtype=torch.float32).item()
+
+
+def inv_norm_f32(norm: float) -> float:
+    """`tensor / norm` with a Python scalar on CUDA is tensor * (1/norm) evaluated in fp32."""
+    nf = f32(norm)
+    return f32(1.0 / nf) if nf != 0.0 else 1.0
+
+
+@dataclass
+class PairResult:
+    out: torch.Tensor
+    flags: Optional[torch.Tensor] = None     # int32[4] device counters (nan_ifft, inf_ifft, nan_final, inf_final)
+    branch: str = ""
+    scalars: dict = field(default_factory=dict)
+
+
+def spectral_pair(ws: Workspace, slot0: int, slot1: int, *, scale0: float, scale1: float, mode: str, t: float,
+                  t_sum: float = 1.0, cutoff_pct: float = 0.0, cull_pct: float = 0.0, agreement: bool = True,
+                  out_scale: float = 1.0, base: Optional[torch.Tensor] = None, out: torch.Tensor = None,
+                  check_ifft: bool = True):
+    """Everything after the row passes for one pair whose row spectra sit in slot0 (role v0) and
+    slot1 (role v1): column sweeps, statistics, blend, inverse, epilogue into `out`."""
+    pl = ws.plan
+    N = pl.R * pl.C
+    fwd_cols(ws, slot0, scale=scale0, write_im=True)
+    fwd_cols(ws, slot1, scale=scale1, write_im=False)
+    re0, im0, re1 = ws.re[slot0], ws.im[slot0], ws.re[slot1]
+    if mode == "slerp":
+        if cutoff_pct > 0:
+            # functions.py:113-120: sorted(cat(|re0|,|re1|))[int(2N*cutoff_pct)]
+            select_kth(ws, re0, re1, int((2 * N) * cutoff_pct), F_THR_CUT, which=0)
+        else:
+            ws.flt[F_THR_CUT] = 0.0
+        slerp_reduce(ws, re0, re1)
+        slerp_scalars(ws, t)
+        blend(ws, 0, True, re0, re1, t_sum, re0)
+        cull = cull_pct > 0
+        if cull:
+            # functions.py:138-141: sorted(|R.real|)[int(N*cull_pct)]
+            select_kth(ws, re0, None, int(N * cull_pct), F_THR_CULL, which=1)
+    elif mode == "arith":
+        blend(ws, 1, agreement, re0, re1, t, re0)
+        cull = False
+    else:
+        raise ValueError(mode)
+    inv_cols(ws, re0, im0, cull)
+    inv_rows(ws, re0, im0, cull, out_scale, base, out, check_ifft=check_ifft)

@@ -112,7 +112,7 @@ int emu_inverse(int R, int C, float* re, float* im, float cull_thr, int out_mode
   a.re = re; a.im = im; a.cull_thr = (pl.col_passes == 0) ? &cull_thr : nullptr;
   a.out_mode = out_mode; a.base = base; a.out_bf16 = out_bf16; a.out_f32 = out_f32;
   a.inv_n = (float)(1.0 / ((double)R * (double)C));
-  a.scale_ptr = nullptr; a.scale_host = scale; a.flags = flags4;
+  a.scale_ptr = nullptr; a.scale_host = scale; a.flags = flags4; a.check_ifft = 1;
   unsigned int cnt[4] = {0, 0, 0, 0};
   for (int row = 0; row < R; ++row) {
     HostExec ex{pl.row_threads};

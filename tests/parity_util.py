@@ -1,0 +1,39 @@
+"""Shared metrics for the parity tests (TEST INFRASTRUCTURE).
+
+The reference algorithm is discontinuous (sign masks, percentile thresholds, a cull that
+zeroes bins strictly below an order statistic), so two correct implementations whose FFTs
+differ in the last bit can disagree on a handful of spectrum bins ("flips").
+`flip_accounted` measures the relative L2 error after removing the K largest bins of the
+difference spectrum, and reports how much of the error energy those bins carried.
+"""
+import numpy as np
+
+
+def rel_l2(a, b):
+    a = np.asarray(a); b = np.asarray(b)
+    dt = np.complex128 if (np.iscomplexobj(a) or np.iscomplexobj(b)) else np.float64
+    a = a.astype(dt); b = b.astype(dt)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+
+def flip_accounted(ours, ref, k=16):
+    """-> (raw rel L2, residual rel L2 without the k largest difference bins, their energy share)."""
+    ours = np.asarray(ours, dtype=np.float64); ref = np.asarray(ref, dtype=np.float64)
+    d = ours - ref
+    D = np.fft.fftn(d) if d.ndim > 1 else np.fft.fft(d)
+    E = (np.abs(D) ** 2).ravel()
+    tot = float(E.sum())
+    refE = float(np.sum(np.abs(np.fft.fftn(ref) if ref.ndim > 1 else np.fft.fft(ref)) ** 2))
+    if tot == 0.0:
+        return 0.0, 0.0, 0.0
+    k = min(k, E.size)
+    top = float(np.partition(E, E.size - k)[E.size - k:].sum())
+    return float(np.sqrt(tot / refE)), float(np.sqrt(max(tot - top, 0.0) / refE)), top / tot
+
+
+def bf16_ulp_distance(a_bits, b_bits):
+    """ULP distance between two arrays of bf16 bit patterns (uint16)."""
+    def key(u):
+        u = u.astype(np.int32)
+        return np.where(u & 0x8000, 0x8000 - (u & 0x7FFF), u + 0x8000)
+    return np.abs(key(np.asarray(a_bits)) - key(np.asarray(b_bits)))
