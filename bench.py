@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the per-tensor spectral merge hot path (BASELINE.json metric:
+merged params/sec, weight GB/s; % of HBM roofline for the dominant kernel).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload llama8b|llama70b|tinyllama] [--layers L] [--finetunes M]
+
+A "step" is one pass of the hot path over the workload's merged tensors: for every
+`model.layers.*` tensor of the named architecture, base + M finetunes (synthetic random-init
+bf16) -> merged bf16 tensor, through FourierMerge.merge_sources (the body of
+`_merge_layer`).  Pass-through tensors (embed / norm / lm_head) are plain copies in the
+reference and are not part of the timed work.
+
+  value : whole-job merged params/s with inputs resident in HBM (device-timed, CUDA events,
+          max over ranks).  N > 1: every rank merges its own copy of the workload (tensors are
+          independent, no collective on the data path) -> weak scaling.
+  e2e   : same metric through FourierMerge._merge_layer with HOST (pinned) tensors: per tensor
+          the H2D copies of base + finetunes and the D2H copy of the result are inside the
+          timed region.
+  roofline : dominant kernel class (column FFT sweeps, k_col): algorithmic bytes / CUDA-event
+          time of its launches inside the timed region vs MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline : oracle/oracle_np.py (numpy port of the reference algorithm) timed on this
+          box's host cores on a bounded sample of the same workload.
+  --impl reference : the same port with all host threads (one tensor per thread), as its own arm.
+"""
+from __future__ import annotations
+
+import argparse
+import asyncio
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+ARCH = {
+    "tinyllama": dict(H=2048, I=5632, KV=256, L=22),
+    "llama8b": dict(H=4096, I=14336, KV=1024, L=32),
+    "llama70b": dict(H=8192, I=28672, KV=1024, L=80),
+}
+ALPHAS = (0.3, 0.5, 0.4, 0.2)
+SIGMAS = (0.002, 0.0026, 0.0023, 0.0029)
+
+
+def layer_tensors(a):
+    H, I, KV = a["H"], a["I"], a["KV"]
+    return [("self_attn.q_proj.weight", (H, H)), ("self_attn.k_proj.weight", (KV, H)),
+            ("self_attn.v_proj.weight", (KV, H)), ("self_attn.o_proj.weight", (H, H)),
+            ("mlp.gate_proj.weight", (I, H)), ("mlp.up_proj.weight", (I, H)), ("mlp.down_proj.weight", (H, I)),
+            ("input_layernorm.weight", (H,)), ("post_attention_layernorm.weight", (H,))]
+
+
+def numel(shape):
+    n = 1
+    for s in shape:
+        n *= s
+    return n
+
+
+def synth_tensor(torch, shape, idx, n_ft, device):
+    """SURVEY.md 8d synthetic weights, generated on `device`."""
+    g = torch.Generator(device=device).manual_seed(1234 + idx)
+    if len(shape) == 1:
+        base = (1.0 + 0.1 * torch.randn(shape, generator=g, device=device)).to(torch.bfloat16)
+        sig = [0.01 * (1 + 0.3 * k) for k in range(n_ft)]
+    else:
+        base = (0.02 * torch.randn(shape, generator=g, device=device)).to(torch.bfloat16)
+        sig = SIGMAS
+    fts = []
+    for k in range(n_ft):
+        gk = torch.Generator(device=device).manual_seed(100000 * (k + 1) + idx)
+        fts.append((base.float() + sig[k] * torch.randn(shape, generator=gk, device=device)).to(torch.bfloat16))
+    return base, fts
+
+
+class ClockSampler:
+    """nvidia-smi sampled every 200 ms during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu_index}",
+                 "--query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+# ------------------------------------------------------------------------------------------
+def cpu_port_rate(shape, n_ft, threads, repeats=1):
+    """oracle merge_layer on `threads` concurrent tensors of `shape` -> (params/s, seconds)."""
+    import numpy as np
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle_np as O
+
+    def make(i):
+        rng = np.random.default_rng(1234 + i)
+        base32 = (0.02 * rng.standard_normal(shape)).astype(np.float32)
+        base = O.f32_to_bf16(base32)
+        models = []
+        for k in range(n_ft):
+            ft = O.f32_to_bf16((O.bf16_to_f32(base) + SIGMAS[k] * rng.standard_normal(shape)).astype(np.float32))
+            models.append(dict(base=base, ft=ft, alpha=ALPHAS[k], name=f"m{k}"))
+        return base, models
+
+    jobs = [make(i) for i in range(threads)]
+    t0 = time.perf_counter()
+    for _ in range(repeats):
+        if threads == 1:
+            O.merge_layer(*jobs[0])
+        else:
+            with ThreadPoolExecutor(max_workers=threads) as ex:
+                list(ex.map(lambda j: O.merge_layer(*j), jobs))
+    dt = time.perf_counter() - t0
+    return threads * repeats * numel(shape) / dt, dt
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    a = ARCH[args.workload]
+    shape = (a["KV"], a["H"])
+    threads = max(1, min(os.cpu_count() or 1, 16))
+    for _ in range(min(args.warmup, 1)):
+        cpu_port_rate(shape, args.finetunes, threads)
+    rates, secs = [], []
+    for _ in range(args.steps):
+        r, dt = cpu_port_rate(shape, args.finetunes, threads)
+        rates.append(r); secs.append(dt)
+    value = sum(threads * numel(shape) for _ in secs) / sum(secs)
+    sample = f"{threads} x k_proj {shape[0]}x{shape[1]} per step (one tensor per host thread), numpy port of the reference"
+    line = dict(impl="reference", metric="merged_params_per_sec", value=value, unit="params/s", n_gpus=args.gpus,
+                steps=args.steps, warmup=args.warmup, ms_per_step=1000 * sum(secs) / len(secs), higher_is_better=True,
+                scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload=f"{args.workload}-shaped base + {args.finetunes} finetunes, alpha 0.3/0.5, SLERP-FFT merge",
+                            sample=sample),
+                cpu_baseline=dict(value=value, unit="params/s", cores=threads, kind="port", sample=sample),
+                e2e=dict(value=value, unit="params/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                gpu_launches=0)
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="llama8b", choices=sorted(ARCH))
+    ap.add_argument("--layers", type=int, default=0, help="layers resident per rank (0 = as many as fit, up to L)")
+    ap.add_argument("--finetunes", type=int, default=2)
+    ap.add_argument("--e2e-layers", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--profile-json", default="", help="write the per-kernel-class summary here")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl=ours) needs a CUDA device: shardmerge_b200 has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from shardmerge_b200 import engine as E
+    from shardmerge_b200.config import MergeConfig, MergeModel
+    from shardmerge_b200.index import InMemoryIndex
+    from shardmerge_b200.merge.fast_fourier import FourierMerge
+    from shardmerge_b200.writer import ShardLayer
+
+    a = ARCH[args.workload]
+    M = args.finetunes
+    per_layer = layer_tensors(a)
+    params_layer = sum(numel(s) for _, s in per_layer)
+    free_b, _ = torch.cuda.mem_get_info(dev)
+    bytes_layer = params_layer * 2 * (M + 2)                      # base + M finetunes + output, bf16
+    max_params = max(numel(s) for _, s in per_layer)
+    ws_bytes = 5 * 4 * 4 * max_params                             # workspaces of the distinct shapes (generous)
+    fit = int((free_b * 0.85 - ws_bytes) // bytes_layer)
+    L = a["L"] if args.layers <= 0 else min(args.layers, a["L"])
+    L = max(1, min(L, fit))
+
+    # ---- resident synthetic model -------------------------------------------------------
+    tensors = []                                                  # (name, base, [fts])
+    idx = 0
+    for layer in range(L):
+        for nm, shape in per_layer:
+            base, fts = synth_tensor(torch, shape, idx, M, dev)
+            tensors.append((f"model.layers.{layer}.{nm}", base, fts))
+            idx += 1
+    torch.cuda.synchronize(dev)
+    merged_params = L * params_layer
+
+    cfg = MergeConfig(finetune_merge=[MergeModel(model=f"synth/ft{k}", base="synth/base", alpha=ALPHAS[k],
+                                                 is_input=(k == 0), is_output=(k == 1)) for k in range(M)],
+                      output_base_model="synth/base", output_dir="/tmp/unused", device=str(dev))
+    fm = FourierMerge(cfg, index_manager=InMemoryIndex({}))
+    outputs = {}
+
+    def step():
+        outputs.clear()
+        for name, base, fts in tensors:
+            srcs = [E.make_source(base, ft, weight=ALPHAS[k], name=f"synth/ft{k}") for k, ft in enumerate(fts)]
+            outputs[name] = fm.merge_sources(srcs, base, dev, layer_name=name)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    E.PROFILER = E.Profiler(timing=True)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_wall0 = time.perf_counter()
+    for s0, s1 in ev:
+        s0.record(); step(); s1.record()
+    barrier()
+    wall = time.perf_counter() - t_wall0
+    prof = E.PROFILER
+    E.PROFILER = None
+    clocks = sampler.stop()
+    elapsed_ms = sum(s0.elapsed_time(s1) for s0, s1 in ev)
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    value = world * merged_params * args.steps / (elapsed_ms / 1000.0)
+
+    # ---- roofline of the dominant kernel class ---------------------------------------------
+    summ = prof.summary()
+    peaks_path = ROOT / "MEASURED_PEAKS.json"
+    if peaks_path.exists():
+        peak, peak_src = float(json.loads(peaks_path.read_text())["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    col_bytes = sum(summ[t]["bytes"] for t in ("col_fwd", "col_inv") if t in summ)
+    col_ms = sum(summ[t]["ms"] for t in ("col_fwd", "col_inv") if t in summ)
+    col_launch = sum(summ[t]["launches"] for t in ("col_fwd", "col_inv") if t in summ)
+    achieved = col_bytes / (col_ms / 1000.0) / 1e9 if col_ms else None
+    kernel_ms_total = sum(v["ms"] or 0.0 for v in summ.values())
+    roofline = dict(bound="hbm", kernel="k_col (column FFT sweeps, forward+inverse)", achieved=achieved, peak=peak,
+                    unit="GB/s", frac=(achieved / peak if achieved else None), traffic=None, peak_source=peak_src,
+                    bytes_per_launch=(col_bytes / col_launch if col_launch else None),
+                    share_of_kernel_time=(col_ms / kernel_ms_total if kernel_ms_total else None),
+                    per_class={k: dict(calls=v["calls"], launches=v["launches"], ms=v["ms"],
+                                       gbs=(v["bytes"] / (v["ms"] / 1000.0) / 1e9 if v["ms"] else None),
+                                       frac=(v["bytes"] / (v["ms"] / 1000.0) / 1e9 / peak if v["ms"] and v["bytes"] else None))
+                               for k, v in summ.items()})
+    gpu_launches = prof.launches
+
+    # ---- e2e: host tensors through _merge_layer ----------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        Le = max(1, min(args.e2e_layers, L))
+        host = {"synth/base": {}}
+        for k in range(M):
+            host[f"synth/ft{k}"] = {}
+        names = []
+        for name, base, fts in tensors[: Le * len(per_layer)]:
+            host["synth/base"][name] = base.cpu().pin_memory()
+            for k, ft in enumerate(fts):
+                host[f"synth/ft{k}"][name] = ft.cpu().pin_memory()
+            names.append(name)
+        fm2 = FourierMerge(cfg, index_manager=InMemoryIndex(host))
+        out_host = {n: torch.empty(host["synth/base"][n].shape, dtype=torch.bfloat16).pin_memory() for n in names}
+        h2d = sum(t.numel() * 2 for n in names for t in [host["synth/base"][n]] + [host[f"synth/ft{k}"][n] for k in range(M)])
+        d2h = sum(out_host[n].numel() * 2 for n in names)
+
+        async def e2e_step():
+            for i, n in enumerate(names):
+                out = await fm2._merge_layer(ShardLayer(i, "s", n, False), str(dev))
+                out_host[n].copy_(out, non_blocking=True)
+            torch.cuda.synchronize(dev)
+
+        loop = asyncio.new_event_loop()
+        for _ in range(min(args.warmup, 2)):
+            loop.run_until_complete(e2e_step())
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            loop.run_until_complete(e2e_step())
+        e1.record()
+        barrier()
+        ems = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ems], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ems = float(t.item())
+        e2e_params = sum(numel(host["synth/base"][n].shape) for n in names)
+        e2e = dict(value=world * e2e_params * args.steps / (ems / 1000.0), unit="params/s",
+                   h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, layers=Le,
+                   api="FourierMerge._merge_layer(shard_layer, 'cuda') with pinned host tensors")
+
+    # ---- CPU baseline (rank 0, N = 1 only) -----------------------------------------------------
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        shape = (a["KV"], a["H"])
+        r, dt = cpu_port_rate(shape, M, 1, repeats=2)
+        cpu_baseline = dict(value=r, unit="params/s", cores=1, kind="port",
+                            sample=f"2 x k_proj {shape[0]}x{shape[1]} through oracle/oracle_np.merge_layer "
+                                   f"(numpy, single thread), {dt:.1f} s")
+
+    if rank == 0:
+        line = dict(metric="merged_params_per_sec", value=value, unit="params/s", n_gpus=world, steps=args.steps,
+                    warmup=args.warmup, ms_per_step=elapsed_ms / args.steps, higher_is_better=True, scaling="weak",
+                    vs_baseline=None, dtype="f32", data="synthetic",
+                    merged_gb_per_s=value * 2 / 1e9,
+                    config=dict(workload=f"{args.workload}-shaped base + {M} finetunes (bf16), alpha "
+                                         f"{'/'.join(str(x) for x in ALPHAS[:M])}, SLERP-FFT merge of every model.layers.* tensor",
+                                layers_resident=L, layers_of_model=a["L"], merged_params_per_step_per_gpu=merged_params,
+                                tensors_per_step=len(tensors), l2="inputs per step (%.1f GB) exceed the 126 MB L2" %
+                                                                 (merged_params * 2 * (M + 1) / 1e9),
+                                partition="whole tensors per rank, no collective"),
+                    roofline=roofline, cpu_baseline=cpu_baseline, e2e=e2e, gpu_launches=gpu_launches, clocks=clocks,
+                    wall_s=wall)
+        print(json.dumps(line))
+        if args.profile_json:
+            Path(args.profile_json).parent.mkdir(parents=True, exist_ok=True)
+            Path(args.profile_json).write_text(json.dumps(dict(summary=summ, line=line), indent=1))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -44,6 +44,7 @@ sm_plan* sm_plan_create(int R, int C);
 void sm_plan_destroy(sm_plan* plan);
 int sm_plan_pitch(const sm_plan* plan);                 /* P, in floats                       */
 int sm_plan_row_freq(const sm_plan* plan, int stored);  /* stored row -> frequency index      */
+int sm_plan_col_passes(const sm_plan* plan);            /* column sweeps per transform: 0, 1, 2 */
 int sm_plan_describe(const sm_plan* plan, char* buf, int buflen);   /* human-readable factorisation */
 size_t sm_plan_table_bytes(const sm_plan* plan);        /* device bytes for the twiddle tables */
 /* Fill the caller's table buffer (twiddles computed on the device in fp64, stored fp32). */
@@ -83,7 +84,8 @@ int sm_inv_norm(const double* sumsq, float* out, void* stream);
  *   mode 1 (safe): window = everything; needs a workspace for all keys.
  * sel_state: >= SM_SELECT_STATE_BYTES device bytes.  ws: sm_select_ws_bytes() device bytes.
  * After completion (stream order) sel_state holds {u64 rank, u64 below, u32 prefix, u32 lo,
- * u32 hi, u32 ncand, u32 cap, u32 status, f32 value}. */
+ * u32 hi, u32 ncand, u32 cap, u32 status, f32 value, u32 sticky}; `sticky` ORs the status of
+ * every select that used this state since the caller last zeroed it. */
 #define SM_SELECT_STATE_BYTES 64
 size_t sm_select_ws_bytes(const sm_plan* plan, int n_planes, int mode);
 int sm_select_kth_abs(const sm_plan* plan, const float* plane0, const float* plane1, uint64_t rank,

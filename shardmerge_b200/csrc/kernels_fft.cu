@@ -117,6 +117,7 @@ extern "C" sm_plan* sm_plan_create(int R, int C) {
 }
 extern "C" void sm_plan_destroy(sm_plan* plan) { delete plan; }
 extern "C" int sm_plan_pitch(const sm_plan* plan) { return plan->p.P; }
+extern "C" int sm_plan_col_passes(const sm_plan* plan) { return plan->p.col_passes; }
 extern "C" int sm_plan_row_freq(const sm_plan* plan, int stored) { return sm_row_freq(&plan->p, stored); }
 extern "C" size_t sm_plan_table_bytes(const sm_plan* plan) {
   return ((size_t)plan->p.C + (size_t)plan->p.R) * 8;

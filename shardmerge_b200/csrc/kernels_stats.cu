@@ -24,7 +24,8 @@ struct SelState {              // must match SM_SELECT_STATE_BYTES / the header 
   unsigned int cap;
   unsigned int status;         // bit0: window missed the statistic, bit1: candidate overflow
   float value;
-  unsigned int pad[5];
+  unsigned int sticky;         // OR of every status this state has ended with (k_sel_init keeps it)
+  unsigned int pad[4];
 };
 static_assert(sizeof(SelState) == SM_SELECT_STATE_BYTES, "SelState layout");
 
@@ -175,6 +176,7 @@ __global__ void __launch_bounds__(1024) k_pick(unsigned int* __restrict__ hist, 
     } else if (action == PICK_FINISH) {
       const float val = (st->status == 0u) ? __uint_as_float(st->prefix) : __uint_as_float(0x7fc00000u);
       st->value = val;
+      st->sticky |= st->status;
       if (thr_out) *thr_out = val;
     }
   }

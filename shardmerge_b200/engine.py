@@ -58,6 +58,45 @@ def _p(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
+class Profiler:
+    """Optional per-kernel-class accounting: launch counts always, CUDA-event timing and
+    algorithmic bytes (SURVEY.md 8d / DESIGN.md) when `timing` is on.  bench.py uses it for the
+    `roofline` and `gpu_launches` fields; it is off (None) by default."""
+
+    def __init__(self, timing: bool = False):
+        self.timing = timing
+        self.launches = 0
+        self.calls: dict = {}          # tag -> [n_calls, n_launches, bytes, [(start, end), ...]]
+
+    def record(self, tag, launches, nbytes, dev, fn):
+        ent = self.calls.setdefault(tag, [0, 0, 0, []])
+        ent[0] += 1; ent[1] += launches; ent[2] += nbytes
+        self.launches += launches
+        if self.timing:
+            st = torch.cuda.current_stream(dev)
+            a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+            a.record(st); rc = fn(); b.record(st)
+            ent[3].append((a, b))
+            return rc
+        return fn()
+
+    def summary(self):
+        out = {}
+        for tag, (n, l, by, evs) in self.calls.items():
+            ms = sum(a.elapsed_time(b) for a, b in evs) if evs else None
+            out[tag] = dict(calls=n, launches=l, bytes=by, ms=ms)
+        return out
+
+
+PROFILER: Optional[Profiler] = None
+
+
+def _run(tag, launches, nbytes, dev, fn):
+    if PROFILER is None:
+        return fn()
+    return PROFILER.record(tag, launches, nbytes, dev, fn)
+
+
 class Plan:
     """FFT plan + twiddle tables for tensors of shape [R][C] on one device."""
 
@@ -201,55 +240,74 @@ def make_source(base: Optional[torch.Tensor], ft: Optional[torch.Tensor], x32: O
 # ------------------------------------------------------------------------------------------
 def fwd_rows(ws: Workspace, slot: int, src: Source, sumsq_slot: int, m1: float = 1.0, m2: float = 1.0):
     pl, lib = ws.plan, ws.plan.lib
+    fwd_rows_ptr(ws, slot, src, ws.dptr(sumsq_slot), m1, m2)
+
+
+def fwd_rows_ptr(ws: Workspace, slot: int, src: Source, sumsq_ptr: int, m1: float = 1.0, m2: float = 1.0):
+    pl, lib = ws.plan, ws.plan.lib
     st = _stream(pl.device)
+    N = pl.R * pl.C
     if src.is_bf16:
-        rc = lib.sm_fwd_rows_bf16(pl.handle, pl.tables.data_ptr(), src.base.data_ptr(), src.ft.data_ptr(),
-                                  ws.re[slot].data_ptr(), ws.im[slot].data_ptr(), ws.dptr(sumsq_slot), st)
+        rc = _run("row_fwd", 1, 8 * N, pl.device, lambda: lib.sm_fwd_rows_bf16(
+            pl.handle, pl.tables.data_ptr(), src.base.data_ptr(), src.ft.data_ptr(),
+            ws.re[slot].data_ptr(), ws.im[slot].data_ptr(), sumsq_ptr, st))
     else:
-        rc = lib.sm_fwd_rows_f32(pl.handle, pl.tables.data_ptr(), src.x32.data_ptr(), m1, m2,
-                                 ws.re[slot].data_ptr(), ws.im[slot].data_ptr(), ws.dptr(sumsq_slot), st)
+        rc = _run("row_fwd_f32", 1, 8 * N, pl.device, lambda: lib.sm_fwd_rows_f32(
+            pl.handle, pl.tables.data_ptr(), src.x32.data_ptr(), m1, m2,
+            ws.re[slot].data_ptr(), ws.im[slot].data_ptr(), sumsq_ptr, st))
     _lib.check(rc, "sm_fwd_rows")
 
 
 def fwd_cols(ws: Workspace, slot: int, scale: float = 1.0, scale_slot: Optional[int] = None, write_im: bool = True):
     pl, lib = ws.plan, ws.plan.lib
-    rc = lib.sm_fwd_cols(pl.handle, pl.tables.data_ptr(), ws.re[slot].data_ptr(), ws.im[slot].data_ptr(),
-                         None if scale_slot is None else ws.fptr(scale_slot), float(scale), 1 if write_im else 0,
-                         _stream(pl.device))
+    N = pl.R * pl.C
+    sweeps = max(1, pl.lib.sm_plan_col_passes(pl.handle))
+    nbytes = 8 * N * sweeps - (0 if write_im else 2 * N)
+    rc = _run("col_fwd", sweeps, nbytes, pl.device, lambda: lib.sm_fwd_cols(
+        pl.handle, pl.tables.data_ptr(), ws.re[slot].data_ptr(), ws.im[slot].data_ptr(),
+        None if scale_slot is None else ws.fptr(scale_slot), float(scale), 1 if write_im else 0, _stream(pl.device)))
     _lib.check(rc, "sm_fwd_cols")
 
 
 def select_kth(ws: Workspace, plane0: torch.Tensor, plane1: Optional[torch.Tensor], rank: int, out_slot: int,
                which: int = 0):
     pl, lib = ws.plan, ws.plan.lib
-    rc = lib.sm_select_kth_abs(pl.handle, plane0.data_ptr(), _p(plane1), int(rank), 1 if ws.safe_select else 0,
-                               ws.selptr(which), ws.sel_ws.data_ptr(), ws.sel_ws.numel(), ws.fptr(out_slot),
-                               _stream(pl.device))
+    N = pl.R * pl.C
+    rc = _run("select2" if plane1 is not None else "select1", 16, (4 if plane1 is not None else 2) * N, pl.device,
+              lambda: lib.sm_select_kth_abs(pl.handle, plane0.data_ptr(), _p(plane1), int(rank), 1 if ws.safe_select else 0,
+                                            ws.selptr(which), ws.sel_ws.data_ptr(), ws.sel_ws.numel(), ws.fptr(out_slot),
+                                            _stream(pl.device)))
     _lib.check(rc, "sm_select_kth_abs")
 
 
 def slerp_reduce(ws: Workspace, re0: torch.Tensor, re1: torch.Tensor):
     pl, lib = ws.plan, ws.plan.lib
-    _lib.check(lib.sm_slerp_reduce(pl.handle, re0.data_ptr(), re1.data_ptr(), ws.fptr(F_THR_CUT), ws.dptr(D_S00),
-                                   _stream(pl.device)), "sm_slerp_reduce")
+    _lib.check(_run("reduce", 1, 4 * pl.R * pl.C, pl.device, lambda: lib.sm_slerp_reduce(
+        pl.handle, re0.data_ptr(), re1.data_ptr(), ws.fptr(F_THR_CUT), ws.dptr(D_S00), _stream(pl.device))), "sm_slerp_reduce")
 
 
 def slerp_scalars(ws: Workspace, t: float):
     pl, lib = ws.plan, ws.plan.lib
-    _lib.check(lib.sm_slerp_scalars(ws.dptr(D_S00), float(t), ws.fptr(F_DOT), _stream(pl.device)), "sm_slerp_scalars")
+    _lib.check(_run("scalars", 1, 0, pl.device, lambda: lib.sm_slerp_scalars(
+        ws.dptr(D_S00), float(t), ws.fptr(F_DOT), _stream(pl.device))), "sm_slerp_scalars")
 
 
 def blend(ws: Workspace, mode: int, agreement: bool, re0: torch.Tensor, re1: torch.Tensor, t_sum: float,
           out: torch.Tensor):
     pl, lib = ws.plan, ws.plan.lib
-    _lib.check(lib.sm_blend(pl.handle, mode, 1 if agreement else 0, re0.data_ptr(), re1.data_ptr(), ws.fptr(F_THR_CUT),
-                            ws.fptr(F_DOT), float(t_sum), out.data_ptr(), _stream(pl.device)), "sm_blend")
+    _lib.check(_run("blend", 1, 6 * pl.R * pl.C, pl.device, lambda: lib.sm_blend(
+        pl.handle, mode, 1 if agreement else 0, re0.data_ptr(), re1.data_ptr(), ws.fptr(F_THR_CUT),
+        ws.fptr(F_DOT), float(t_sum), out.data_ptr(), _stream(pl.device))), "sm_blend")
 
 
 def inv_cols(ws: Workspace, re: torch.Tensor, im: torch.Tensor, cull: bool):
     pl, lib = ws.plan, ws.plan.lib
-    _lib.check(lib.sm_inv_cols(pl.handle, pl.tables.data_ptr(), re.data_ptr(), im.data_ptr(),
-                               ws.fptr(F_THR_CULL) if cull else None, _stream(pl.device)), "sm_inv_cols")
+    sweeps = pl.lib.sm_plan_col_passes(pl.handle)
+    if sweeps == 0:
+        return
+    _lib.check(_run("col_inv", sweeps, 8 * pl.R * pl.C * sweeps, pl.device, lambda: lib.sm_inv_cols(
+        pl.handle, pl.tables.data_ptr(), re.data_ptr(), im.data_ptr(),
+        ws.fptr(F_THR_CULL) if cull else None, _stream(pl.device))), "sm_inv_cols")
 
 
 def inv_rows(ws: Workspace, re: torch.Tensor, im: torch.Tensor, cull: bool, scale: float,
@@ -257,12 +315,15 @@ def inv_rows(ws: Workspace, re: torch.Tensor, im: torch.Tensor, cull: bool, scal
     pl, lib = ws.plan, ws.plan.lib
     st = _stream(pl.device)
     cptr = ws.fptr(F_THR_CULL) if cull else None
+    N = pl.R * pl.C
     if out.dtype == torch.bfloat16:
-        rc = lib.sm_inv_rows_bf16(pl.handle, pl.tables.data_ptr(), re.data_ptr(), im.data_ptr(), cptr, base.data_ptr(),
-                                  out.data_ptr(), None, float(scale), 1 if check_ifft else 0, ws.flags.data_ptr(), st)
+        rc = _run("row_inv", 1, 8 * N, pl.device, lambda: lib.sm_inv_rows_bf16(
+            pl.handle, pl.tables.data_ptr(), re.data_ptr(), im.data_ptr(), cptr, base.data_ptr(),
+            out.data_ptr(), None, float(scale), 1 if check_ifft else 0, ws.flags.data_ptr(), st))
     else:
-        rc = lib.sm_inv_rows_f32(pl.handle, pl.tables.data_ptr(), re.data_ptr(), im.data_ptr(), cptr, out.data_ptr(),
-                                 None, float(scale), 1 if check_ifft else 0, ws.flags.data_ptr(), st)
+        rc = _run("row_inv_f32", 1, 8 * N, pl.device, lambda: lib.sm_inv_rows_f32(
+            pl.handle, pl.tables.data_ptr(), re.data_ptr(), im.data_ptr(), cptr, out.data_ptr(),
+            None, float(scale), 1 if check_ifft else 0, ws.flags.data_ptr(), st))
     _lib.check(rc, "sm_inv_rows")
 
 
@@ -270,9 +331,10 @@ def delta_axpby_bf16(base_out, s0: Source, ca: float, s1: Optional[Source], cb: 
                      out: torch.Tensor, flags: torch.Tensor):
     lib = _lib.load()
     dev = out.device
-    rc = lib.sm_delta_axpby_bf16(out.numel(), base_out.data_ptr(), s0.base.data_ptr(), s0.ft.data_ptr(), float(ca),
-                                 None if s1 is None else s1.base.data_ptr(), None if s1 is None else s1.ft.data_ptr(),
-                                 float(cb), float(scale), out.data_ptr(), flags.data_ptr(), _stream(dev))
+    rc = _run("axpby", 1, out.numel() * (8 if s1 is None else 12), dev, lambda: lib.sm_delta_axpby_bf16(
+        out.numel(), base_out.data_ptr(), s0.base.data_ptr(), s0.ft.data_ptr(), float(ca),
+        None if s1 is None else s1.base.data_ptr(), None if s1 is None else s1.ft.data_ptr(),
+        float(cb), float(scale), out.data_ptr(), flags.data_ptr(), _stream(dev)))
     _lib.check(rc, "sm_delta_axpby_bf16")
 
 

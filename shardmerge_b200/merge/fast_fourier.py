@@ -1,0 +1,290 @@
+"""FourierMerge -- the SLERP-FFT merge strategy with the interface of
+shard/merge/fast_fourier.py (FourierMerge :79-276), device-resident.
+
+`_merge_layer(shard_layer, device)` keeps the reference's contract: embed / final norm /
+lm_head tensors are passed through from the is_input / is_output model (:104-130); every
+other tensor is the pairwise-tree spectral merge of the applicable finetunes' deltas
+(:132-257), added onto the output base, NaN -> 0, Inf -> ValueError, cast to bf16 (:269-276).
+
+What differs is where the bytes live: deltas are never materialised (the row-pass kernel
+subtracts bf16 base from bf16 finetune on load), spectra and tree intermediates stay in HBM,
+and the reference's TensorDiskCache round trips (:46-77, torch.save/torch.load of every delta
+and intermediate) have no equivalent.  `name_hash` is kept because the intermediate names show
+up in log lines.
+"""
+from __future__ import annotations
+
+import asyncio
+import hashlib
+import logging
+from typing import List, Optional
+
+import torch
+
+from .. import engine as E
+from ..config import MergeConfig, MergeModel
+from ..constants import INPUT_LAYER, OUTPUT_LAYER
+from ..tensor.functions import correlated_pairs
+from .base import MergeTensorsBase
+
+logger = logging.getLogger(__name__)
+
+
+def name_hash(name: str) -> str:
+    """First four characters of every '_'-separated part, '::', first 8 hex digits of sha256(name)
+    (shard/merge/fast_fourier.py:36-41)."""
+    short = "_".join(part[:4] for part in name.split("_"))
+    return f"{short}::{hashlib.sha256(name.encode()).hexdigest()[:8]}"
+
+
+def task_arithmetic(t0: torch.Tensor, t1: torch.Tensor) -> torch.Tensor:
+    """t0 + t1 where the signs agree, else t0 (shard/merge/fast_fourier.py:30-34; unused by the merge)."""
+    return torch.where(torch.sign(t0) == torch.sign(t1), t0 + t1, t0)
+
+
+def clamp(value: float, min_value: float, max_value: float) -> float:
+    return max(min_value, min(value, max_value))
+
+
+class FourierMerge(MergeTensorsBase):
+    def __init__(self, config: MergeConfig, task_add_models: Optional[List[str]] = None,
+                 target_norm_offset: float = 1e-10, cull_start_pct: float = 0.20, index_manager=None, **kwargs):
+        super().__init__(config, index_manager)
+        self.task_add_models = task_add_models or []
+        self.target_norm_offset = target_norm_offset
+        self.cull_start_pct = cull_start_pct
+        self.last_info: dict = {}
+
+    def get_readme(self) -> str:
+        models = "\n".join(f"- {m.model} (vs {m.base})" for m in self.config.finetune_merge)
+        return f"# SLERP-FFT Merged Model\nBase: {self.config.output_base_model}\nModels merged:\n{models}\n"
+
+    # -------------------------------------------------------------------------------------
+    async def _passthrough(self, shard_layer, device, attr: str) -> torch.Tensor:
+        chosen = next((m for m in self.config.finetune_merge if getattr(m, attr)), None)
+        source = chosen.model if chosen is not None else self.config.output_base_model
+        logger.info(f"Passthrough - {shard_layer.layer_name} from {source}")
+        return await self.index_manager.get_tensor(source, shard_layer.layer_name, device=device).get()
+
+    async def _merge_layer(self, shard_layer, device: str) -> torch.Tensor:
+        number = shard_layer.layer_number
+        if number == INPUT_LAYER:
+            return await self._passthrough(shard_layer, device, "is_input")
+        if number == OUTPUT_LAYER:
+            return await self._passthrough(shard_layer, device, "is_output")
+
+        dev = E._require_cuda(device)
+        name = shard_layer.layer_name
+        models = [m for m in self.config.finetune_merge if m.use_layer_index(number)]
+        preload = getattr(self.index_manager, "preload_tensor", None)
+        if preload is not None:
+            await asyncio.gather(*[preload(m.model, name) for m in models])
+
+        async def fetch(model_name):
+            return await self.index_manager.get_tensor(model_name, name, device=device).get()
+
+        base_cache: dict = {}
+        sources: List[E.Source] = []
+        for m in models:
+            if m.base not in base_cache:
+                base_cache[m.base] = await fetch(m.base)
+            sources.append(E.make_source(base_cache[m.base], await fetch(m.model), weight=m.alpha, name=m.model))
+        base_out = base_cache.get(self.config.output_base_model)
+        if base_out is None:
+            base_out = await fetch(self.config.output_base_model)
+        return self.merge_sources(sources, base_out, dev, layer_name=name)
+
+    # -------------------------------------------------------------------------------------
+    def merge_sources(self, sources: List[E.Source], base_out: torch.Tensor, dev, layer_name: str = "",
+                      safe_select: bool = False) -> torch.Tensor:
+        """The regular-layer part of _merge_layer (fast_fourier.py:147-276) on device tensors."""
+        if len(sources) == 0:
+            raise IndexError("list index out of range")      # what the reference does with no applicable model
+        R, C = E.shape_rc(base_out)
+        base_bf16 = base_out if base_out.dtype == torch.bfloat16 else None
+        ws = E.get_workspace(R, C, dev, n_spectra=max(2, len(sources)), safe_select=safe_select)
+        ws.ctl.zero_()
+        info = dict(branches=[], layer=layer_name)
+        self.last_info = info
+
+        # row passes of every model: delta, row FFT, sum of squares -> norms in one read-back
+        extra = torch.zeros(max(len(sources), 2), dtype=torch.float64, device=dev)
+        sumsq_ptrs = [extra.data_ptr() + 8 * i for i in range(len(sources))]
+        for i, s in enumerate(sources):
+            _rows_into(ws, i, s, sumsq_ptrs[i])
+        norms = [E.f32(v ** 0.5) for v in extra.to("cpu").tolist()[: len(sources)]]
+        for s, n in zip(sources, norms):
+            s.norm = n
+        info["norms"] = list(norms)
+        # torch.tensor(layer_norms).mean() is an fp32 mean (fast_fourier.py:165)
+        target_norm = torch.tensor(norms, dtype=torch.float32).mean().item() + self.target_norm_offset
+        info["target_norm"] = target_norm
+        cull_pct = self.cull_start_pct
+
+        if len(sources) == 1:
+            # loop skipped: result = raw delta, alpha ignored (fast_fourier.py:171,256-257)
+            return _finish_elementwise(sources[0], None, 1.0, 0.0, 1.0, base_out, ws)
+
+        # stack entries: (source, slot of its row spectrum or None)
+        stack = [(s, i) for i, s in enumerate(sources)]
+        weights = [s.weight for s in sources]
+        stale_norms = list(norms)
+        out_final: Optional[torch.Tensor] = None
+        while len(stack) > 1:
+            n = len(stack)
+            corr = torch.zeros((n, n), dtype=torch.float32)
+            for i in range(n):
+                for j in range(i + 1, n):
+                    # the reference multiplies the ORIGINAL layer_norms list (stale after round 1, :180-184)
+                    corr[i, j] = torch.tensor(stale_norms[i], dtype=torch.float32) * torch.tensor(stale_norms[j], dtype=torch.float32)
+            nxt, nxt_w = [], []
+            pairs = list(correlated_pairs(corr, way="least"))
+            n_pairs = sum(1 for _, y, _ in pairs if y >= 0)
+            last_round = (n_pairs == 1 and len(pairs) == 1)
+            for x, y, _ in pairs:
+                if y < 0:
+                    nxt.append(stack[x]); nxt_w.append(weights[x])
+                    continue
+                (sa, slot_a), (sb, slot_b) = stack[x], stack[y]
+                a_w, b_w = weights[x], weights[y]
+                # intermediates of an earlier round have no row spectrum yet: run their row pass into a
+                # slot nobody in the current stack still needs (norm_a/norm_b of :209-210 come with it)
+                busy = {sl for _, sl in stack if sl is not None} | {sl for _, sl in nxt if sl is not None}
+                if slot_a is None:
+                    slot_a = next(i for i in range(ws.n_spectra) if i not in busy)
+                    busy.add(slot_a)
+                    sa.norm = _rows_and_norm(ws, slot_a, sa)
+                if slot_b is None:
+                    slot_b = next(i for i in range(ws.n_spectra) if i not in busy)
+                    busy.add(slot_b)
+                    sb.norm = _rows_and_norm(ws, slot_b, sb)
+                na, nb = sa.norm, sb.norm
+                if abs(na) < abs(nb):                          # larger norm becomes `a`; weights stay put (:212-215)
+                    sa, sb, slot_a, slot_b, na, nb = sb, sa, slot_b, slot_a, nb, na
+                cnorm_a, cnorm_b = abs(na / target_norm), abs(nb / target_norm)
+                n_ratio = cnorm_b / (cnorm_a + 1e-10)
+                final = last_round
+                out = (torch.empty((R, C) if base_out.ndim == 2 else (C,), dtype=torch.bfloat16, device=dev)
+                       if (final and base_bf16 is not None)
+                       else torch.empty((R, C) if base_out.ndim == 2 else (C,), dtype=torch.float32, device=dev))
+                if cnorm_a < 1e-6:                             # :223-225  merged = a + b
+                    info["branches"].append("add")
+                    merged = _pair_elementwise(sa, sb, 1.0, 1.0, 1.0, final, base_out, ws, out)
+                elif cnorm_b < 1e-6 or n_ratio < 0.1:          # :226-232  arithmetic-FFT
+                    info["branches"].append("arith")
+                    norm_scale = target_norm / na
+                    weight_scale = b_w / (a_w + 1e-10)
+                    # FFT is linear: a*s and (b*w)*s scale the spectra instead of the inputs
+                    E.spectral_pair(ws, slot_a, slot_b, scale0=E.f32(norm_scale),
+                                    scale1=E.f32(E.f32(weight_scale) * E.f32(norm_scale)), mode="arith", t=1.0,
+                                    agreement=True, out_scale=1.0, base=base_bf16 if final else None, out=out,
+                                    check_ifft=False)
+                    merged = out
+                    logger.info(f"Arithmetic-FFT Merged {sb.name} x {weight_scale} on to {sa.name} x {norm_scale}")
+                else:                                          # :233-244  SLERP-FFT
+                    a_prop = a_w / (a_w + b_w)
+                    branch = _slerp_pair(ws, slot_a, slot_b, sa, sb, na, nb, a_prop, cull_pct, target_norm,
+                                         base_bf16 if final else None, out, final, base_out)
+                    info["branches"].append(branch)
+                    merged = out
+                    logger.info(f"SLERP-FFT Merged {sa.name} and {sb.name} with weight {a_prop}")
+                if final and merged.dtype == torch.bfloat16:
+                    out_final = merged
+                    nxt.append((None, None)); nxt_w.append((a_w + b_w) / 2.0)
+                else:
+                    inter = E.Source(x32=merged.reshape(R, C) if merged.ndim == 1 else merged,
+                                     weight=(a_w + b_w) / 2.0, name=name_hash(f"{sa.name}_{sb.name}"))
+                    nxt.append((inter, None)); nxt_w.append((a_w + b_w) / 2.0)
+            stack, weights = nxt, nxt_w
+            cull_pct = cull_pct / 2.0                          # :254
+
+        _, _, flags, sel = ws.read_ctl()
+        info["flags"] = [int(v) for v in flags]
+        sel32 = sel.view(torch.int32)
+        if (int(sel32[11]) | int(sel32[16 + 11])) != 0:
+            # the sampled window of a fast order-statistic select missed (or its candidate buffer
+            # overflowed): the thresholds are NaN.  Redo this tensor with the exhaustive select.
+            if safe_select:
+                raise RuntimeError(f"order-statistic select failed in safe mode for {layer_name}")
+            logger.warning(f"select window miss on {layer_name}; re-running with the exhaustive select")
+            return self.merge_sources(sources, base_out, dev, layer_name=layer_name, safe_select=True)
+        if int(flags[1]) > 0:
+            raise ValueError("Inf in ifft output")             # functions.py:215-217
+        if out_final is None:
+            # non-bf16 base or an FFT-free last pair: finish with torch ops exactly as :269-276
+            res = stack[0][0].x32.reshape(base_out.shape)
+            res = base_out.to(torch.float32) + res
+            res = torch.where(torch.isnan(res), torch.zeros_like(res), res)
+            if torch.any(torch.isinf(res)):
+                raise ValueError(f"Inf in merged tensor for {layer_name}")
+            return res.to(torch.bfloat16)
+        if int(flags[3]) > 0:
+            raise ValueError(f"Inf in merged tensor for {layer_name}")   # fast_fourier.py:273-274
+        return out_final.reshape(base_out.shape)
+
+
+# ------------------------------------------------------------------------------------------
+def _rows_into(ws: E.Workspace, slot: int, src: E.Source, sumsq_ptr: int):
+    E.fwd_rows_ptr(ws, slot, src, sumsq_ptr)
+
+
+def _rows_and_norm(ws: E.Workspace, slot: int, src: E.Source) -> float:
+    acc = torch.zeros(1, dtype=torch.float64, device=ws.plan.device)
+    _rows_into(ws, slot, src, acc.data_ptr())
+    return E.f32(acc.item() ** 0.5)
+
+
+def _slerp_pair(ws, slot_a, slot_b, sa, sb, na, nb, t, cull_pct, target_norm, base_bf16, out, final, base_out) -> str:
+    """merge_tensors_fft2_slerp as called at fast_fourier.py:235-243 (t_sum=1, cutoff 0.08), x target_norm."""
+    if nb < 1e-4 or na < 1e-4:
+        # functions.py:184-190: returns the normalised v0 unchanged
+        src = sa
+        scale = E.inv_norm_f32(na)
+        x = src.delta_f32() * scale if na != 0 else src.delta_f32()
+        res = x * E.f32(target_norm)
+        _store(res, final, base_out, out)
+        return "slerp-early"
+    ratio = nb / (na + 1e-10)
+    if ratio < 0.1:
+        # functions.py:199-202 (unreachable from _merge_layer, which required n_ratio >= 0.1)
+        x = sa.delta_f32() * E.inv_norm_f32(na) + (sb.delta_f32() * E.inv_norm_f32(nb)) * E.f32(t)
+        _store(x * E.f32(target_norm), final, base_out, out)
+        return "slerp-linear"
+    E.spectral_pair(ws, slot_a, slot_b, scale0=E.inv_norm_f32(na), scale1=E.inv_norm_f32(nb), mode="slerp", t=t,
+                    t_sum=1.0, cutoff_pct=0.08, cull_pct=cull_pct, out_scale=E.f32(target_norm),
+                    base=base_bf16, out=out, check_ifft=True)
+    return "slerp"
+
+
+def _store(res32: torch.Tensor, final: bool, base_out: torch.Tensor, out: torch.Tensor):
+    res32 = res32.reshape(out.shape)
+    if out.dtype == torch.bfloat16:
+        y = base_out.to(torch.float32).reshape(out.shape) + res32
+        y = torch.where(torch.isnan(y), torch.zeros_like(y), y)
+        if torch.any(torch.isinf(y)):
+            raise ValueError("Inf in merged tensor")
+        out.copy_(y.to(torch.bfloat16))
+    else:
+        out.copy_(res32)
+
+
+def _pair_elementwise(sa, sb, ca, cb, scale, final, base_out, ws, out):
+    """merged = ca*a + cb*b (FFT-free branches)."""
+    if final and out.dtype == torch.bfloat16 and sa.is_bf16 and sb.is_bf16:
+        E.delta_axpby_bf16(base_out, sa, ca, sb, cb, scale, out, ws.flags)
+        return out
+    res = (sa.delta_f32() * ca + sb.delta_f32() * cb) * scale
+    _store(res, final, base_out, out)
+    return out
+
+
+def _finish_elementwise(sa, sb, ca, cb, scale, base_out, ws):
+    out = torch.empty_like(base_out, dtype=torch.bfloat16)
+    if sa.is_bf16 and base_out.dtype == torch.bfloat16:
+        E.delta_axpby_bf16(base_out, sa, ca, None, 0.0, scale, out, ws.flags)
+        _, _, flags, _ = ws.read_ctl()
+        if int(flags[3]) > 0:
+            raise ValueError("Inf in merged tensor")
+        return out
+    _store(sa.delta_f32() * ca, True, base_out, out)
+    return out

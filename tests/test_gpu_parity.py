@@ -1,0 +1,392 @@
+"""GPU parity tests: the sm_100a kernels, called through the C ABI (ctypes), against the numpy
+oracle and the golden fixtures generated from the reference.  Run with `pytest -m gpu`.
+
+Tolerances (north_star): fp32 intermediates rel L2 <= 1e-5 per tensor, checked stage by stage
+with identical stage inputs; end to end additionally flip-accounted (tests/parity_util.py)
+because the reference's masks / order statistics are discontinuous; final bf16 within 1 ulp on
+>= 99.99 % of elements for the stages where that is well defined (epilogue given the same
+spectrum), with the end-to-end fraction reported and bounded more loosely.
+"""
+import glob
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle_np as O
+from tests.parity_util import bf16_ulp_distance, flip_accounted, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def E():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from shardmerge_b200 import engine
+    return engine
+
+
+def planes_to_numpy(ws, slot):
+    """half-planar stored order -> complex128 [R][Ch+1] in natural frequency order"""
+    pl = ws.plan
+    re = ws.re[slot][:, : pl.Ch + 1].double().cpu().numpy()
+    im = ws.im[slot][:, : pl.Ch + 1].double().cpu().numpy()
+    z = re + 1j * im
+    out = np.empty_like(z)
+    out[pl.row_freq().numpy()] = z
+    return out
+
+
+def numpy_to_planes(ws, slot, z):
+    """complex [R][Ch+1] natural order -> planes (stored order)"""
+    pl = ws.plan
+    zs = z[pl.row_freq().numpy()]
+    ws.re[slot].zero_(); ws.im[slot].zero_()
+    ws.re[slot][:, : pl.Ch + 1] = torch.from_numpy(np.ascontiguousarray(zs.real, dtype=np.float32)).to(DEV)
+    ws.im[slot][:, : pl.Ch + 1] = torch.from_numpy(np.ascontiguousarray(zs.imag, dtype=np.float32)).to(DEV)
+
+
+def half_weights(R, C):
+    w = np.full((R, C // 2 + 1), 2, dtype=np.int64)
+    w[:, 0] = 1; w[:, C // 2] = 1
+    return w
+
+
+def bits(t):
+    return t.contiguous().view(torch.int16).cpu().numpy().view(np.uint16)
+
+
+def from_bits(u16):
+    return torch.from_numpy(u16.view(np.int16).copy()).view(torch.bfloat16).to(DEV)
+
+
+SHAPES = [(1, 2), (1, 16), (1, 2048), (1, 8192), (2, 4), (8, 8), (32, 64), (96, 40), (352, 96), (143, 26),
+          (256, 2048), (1024, 512), (512, 5632), (2048, 2048), (1792, 1024)]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_forward_fft_matches_numpy(E, shape):
+    R, C = shape
+    g = torch.Generator(device=DEV).manual_seed(R * 7919 + C)
+    x = torch.randn((R, C), generator=g, device=DEV, dtype=torch.float32)
+    ws = E.get_workspace(R, C, DEV)
+    ws.ctl.zero_()
+    E.fwd_rows(ws, 0, E.Source(x32=x), E.D_SUMSQ0)
+    E.fwd_cols(ws, 0, scale=1.0)
+    got = planes_to_numpy(ws, 0)
+    xs = x.double().cpu().numpy()
+    ref = np.fft.rfft2(xs) if R > 1 else np.fft.rfft(xs, axis=1)
+    assert rel_l2(got, ref) < 1e-6
+    dbl, _, _, _ = ws.read_ctl()
+    assert abs(float(dbl[E.D_SUMSQ0]) / float((xs ** 2).sum()) - 1) < 1e-12
+    # inverse: back to the input (x 1/N inside the epilogue)
+    out = torch.empty((R, C), dtype=torch.float32, device=DEV)
+    E.inv_cols(ws, ws.re[0], ws.im[0], cull=False)
+    E.inv_rows(ws, ws.re[0], ws.im[0], False, 1.0, None, out, check_ifft=True)
+    assert rel_l2(out.cpu().numpy(), x.cpu().numpy()) < 1e-6
+
+
+def test_forward_bf16_delta(E):
+    R, C = 256, 2048
+    g = torch.Generator(device=DEV).manual_seed(5)
+    base = (0.02 * torch.randn((R, C), generator=g, device=DEV)).to(torch.bfloat16)
+    ft = (base.float() + 0.002 * torch.randn((R, C), generator=g, device=DEV)).to(torch.bfloat16)
+    ws = E.get_workspace(R, C, DEV)
+    ws.ctl.zero_()
+    E.fwd_rows(ws, 0, E.Source(base=base, ft=ft), E.D_SUMSQ0)
+    E.fwd_cols(ws, 0, scale=1.0)
+    delta = (ft.float() - base.float()).double().cpu().numpy()
+    assert rel_l2(planes_to_numpy(ws, 0), np.fft.rfft2(delta)) < 1e-6
+    dbl, _, _, _ = ws.read_ctl()
+    assert abs(float(dbl[E.D_SUMSQ0]) / float((delta ** 2).sum()) - 1) < 1e-12
+
+
+def _expanded_sorted(planes, R, C):
+    w = half_weights(R, C)
+    keys = np.concatenate([np.repeat(np.abs(p).ravel(), w.ravel()) for p in planes])
+    keys.sort(kind="stable")
+    return keys
+
+
+@pytest.mark.parametrize("shape,safe", [((64, 128), False), ((1, 4096), False), ((1024, 4096), False),
+                                        ((1024, 4096), True), ((2048, 2048), False)])
+def test_select_kth_exact(E, shape, safe):
+    """order statistics == sorted(cat(|re0|,|re1|))[k] with Hermitian multiplicities, bit exact."""
+    R, C = shape
+    ws = E.get_workspace(R, C, DEV, safe_select=safe)
+    g = torch.Generator(device=DEV).manual_seed(R + C)
+    for slot in (0, 1):
+        ws.re[slot].copy_(torch.randn(ws.re[slot].shape, generator=g, device=DEV) * (0.7 + 0.3 * slot))
+    Ch = C // 2
+    p0 = ws.re[0][:, : Ch + 1].cpu().numpy(); p1 = ws.re[1][:, : Ch + 1].cpu().numpy()
+    N = R * C
+    both = _expanded_sorted([p0, p1], R, C)
+    one = _expanded_sorted([p0], R, C)
+    for pct in (0.08, 0.2, 0.5, 0.0001, 0.999999):
+        ws.ctl.zero_()
+        k2 = int((2 * N) * pct); k1 = int(N * pct)
+        E.select_kth(ws, ws.re[0], ws.re[1], k2, E.F_THR_CUT, which=0)
+        E.select_kth(ws, ws.re[0], None, k1, E.F_THR_CULL, which=1)
+        _, flt, _, sel = ws.read_ctl()
+        status = sel.view(torch.int32)[9].item(), sel.view(torch.int32)[16 + 9].item()
+        assert status == (0, 0), (pct, status)
+        assert np.float32(flt[E.F_THR_CUT].item()) == both[k2], (pct, flt[E.F_THR_CUT].item(), both[k2])
+        assert np.float32(flt[E.F_THR_CULL].item()) == one[k1], (pct, flt[E.F_THR_CULL].item(), one[k1])
+
+
+def test_select_window_miss_is_reported(E):
+    """A degenerate distribution (most keys identical) must either give the exact answer or raise
+    the status flag -- never a silently wrong threshold."""
+    R, C = 2048, 4096
+    ws = E.get_workspace(R, C, DEV)
+    ws.re[0].fill_(1.0); ws.re[1].fill_(1.0)
+    ws.re[0][:, :64] = torch.randn((R, 64), device=DEV)
+    ws.ctl.zero_()
+    k = int(2 * R * C * 0.08)
+    E.select_kth(ws, ws.re[0], ws.re[1], k, E.F_THR_CUT, which=0)
+    _, flt, _, sel = ws.read_ctl()
+    status = sel.view(torch.int32)[9].item()
+    if status == 0:
+        assert flt[E.F_THR_CUT].item() == 1.0
+    else:
+        assert np.isnan(flt[E.F_THR_CUT].item())
+    ws2 = E.get_workspace(R, C, DEV, safe_select=True)
+    ws2.re[0].copy_(ws.re[0]); ws2.re[1].copy_(ws.re[1]); ws2.ctl.zero_()
+    E.select_kth(ws2, ws2.re[0], ws2.re[1], k, E.F_THR_CUT, which=0)
+    _, flt2, _, sel2 = ws2.read_ctl()
+    assert sel2.view(torch.int32)[9].item() == 0 and flt2[E.F_THR_CUT].item() == 1.0
+
+
+def _np_blend(re0, re1, thr, dot, ct, sn, rn, t_sum):
+    f = np.float32
+    same = np.sign(re0) == np.sign(re1)
+    small = np.abs(re1) < f(thr)
+    out = np.where(np.abs(re0) > np.abs(re1), re0, re1).astype(f)
+    sl = same & ~small
+    rel = (re1 - (re0 * f(dot)).astype(f)).astype(f)
+    val = ((re0 * f(ct)).astype(f) + ((rel / f(rn)).astype(f) * f(sn)).astype(f)).astype(f)
+    out[sl] = val[sl]
+    sm = same & small
+    out[sm] = (re0 + (f(t_sum) * re1).astype(f)).astype(f)[sm]
+    return out, sl
+
+
+@pytest.mark.parametrize("shape", [(1, 2048), (96, 40), (512, 1024)])
+def test_reduce_scalars_blend_bit_exact(E, shape):
+    R, C = shape
+    Ch = C // 2
+    ws = E.get_workspace(R, C, DEV)
+    g = torch.Generator(device=DEV).manual_seed(77)
+    ws.re[0].copy_(torch.randn(ws.re[0].shape, generator=g, device=DEV))
+    ws.re[1].copy_(0.6 * ws.re[0] + 0.8 * torch.randn(ws.re[0].shape, generator=g, device=DEV))
+    ws.re[0][0, 0] = 0.0; ws.re[1][0, 0] = 0.0            # sign(0) == sign(0) participates
+    ws.re[0][0, 1] = 0.0
+    re0 = ws.re[0][:, : Ch + 1].cpu().numpy(); re1 = ws.re[1][:, : Ch + 1].cpu().numpy()
+    ws.ctl.zero_()
+    thr = 0.1
+    ws.flt[E.F_THR_CUT] = thr
+    E.slerp_reduce(ws, ws.re[0], ws.re[1])
+    E.slerp_scalars(ws, 0.375)
+    out = torch.empty_like(ws.re[0])
+    E.blend(ws, 0, True, ws.re[0], ws.re[1], 1.0, out)
+    dbl, flt, _, _ = ws.read_ctl()
+    w = half_weights(R, C).astype(np.float64)
+    sl = (np.sign(re0) == np.sign(re1)) & ~(np.abs(re1) < np.float32(thr))
+    a, b = re0.astype(np.float64), re1.astype(np.float64)
+    s00, s11, s01 = (w * a * a)[sl].sum(), (w * b * b)[sl].sum(), (w * a * b)[sl].sum()
+    assert abs(float(dbl[E.D_S00]) / s00 - 1) < 1e-12 and abs(float(dbl[E.D_S11]) / s11 - 1) < 1e-12
+    assert abs(float(dbl[E.D_S01]) / s01 - 1) < 1e-11
+    dot, ct, sn, rn = (flt[i].item() for i in (E.F_DOT, E.F_COS, E.F_SIN, E.F_RELNORM))
+    dref = s01 / np.sqrt(s00 * s11)
+    assert abs(dot - dref) < 2e-7
+    assert abs(ct - np.cos(np.arccos(dref) * 0.375)) < 2e-7 and abs(sn - np.sin(np.arccos(dref) * 0.375)) < 2e-7
+    assert abs(rn / np.sqrt(s11 - 2 * dot * s01 + dot * dot * s00) - 1) < 1e-6
+    expect, _ = _np_blend(re0, re1, thr, dot, ct, sn, rn, 1.0)
+    got = out[:, : Ch + 1].cpu().numpy()
+    assert np.array_equal(got.view(np.uint32), expect.view(np.uint32))
+    # arithmetic functor (functions.py:273-284)
+    E.blend(ws, 1, True, ws.re[0], ws.re[1], 0.5, out)
+    exp2 = np.where(np.sign(re0) == np.sign(re1), (re0 + (np.float32(0.5) * re1).astype(np.float32)).astype(np.float32), re1)
+    assert np.array_equal(out[:, : Ch + 1].cpu().numpy().view(np.uint32), exp2.astype(np.float32).view(np.uint32))
+
+
+@pytest.mark.parametrize("shape", [(1, 4096), (256, 512), (352, 96), (1024, 2048)])
+def test_inverse_epilogue_bf16_within_1ulp(E, shape):
+    """Given the same spectrum, iFFT + x scale + base + bf16 RNE matches the oracle's epilogue on
+    >= 99.99 % of elements within 1 ulp (and the cull on load zeroes exactly |re| < thr)."""
+    R, C = shape
+    rng = np.random.default_rng(3)
+    m = (rng.standard_normal((R, C)) * 0.003).astype(np.float32)
+    base = O.f32_to_bf16((rng.standard_normal((R, C)) * 0.02).astype(np.float32))
+    Z = np.fft.rfft2(m.astype(np.float64)) if R > 1 else np.fft.rfft(m.astype(np.float64), axis=1)
+    thr = np.float32(np.quantile(np.abs(Z.real), 0.2))
+    Zc = np.where(np.abs(Z.real.astype(np.float32)) < thr, 0.0, Z.real.astype(np.float32)) + 1j * Z.imag.astype(np.float32)
+    # oracle: full-spectrum inverse of the culled Hermitian spectrum
+    mc = (np.fft.irfft2(Zc, s=(R, C)) if R > 1 else np.fft.irfft(Zc, n=C, axis=1)).astype(np.float32)
+    scale = np.float32(7.25)
+    expect = O.f32_to_bf16((O.bf16_to_f32(base) + (mc * scale).astype(np.float32)).astype(np.float32))
+    ws = E.get_workspace(R, C, DEV)
+    ws.ctl.zero_()
+    numpy_to_planes(ws, 0, Z)
+    ws.flt[E.F_THR_CULL] = float(thr)
+    out = torch.empty((R, C), dtype=torch.bfloat16, device=DEV)
+    E.inv_cols(ws, ws.re[0], ws.im[0], cull=True)
+    E.inv_rows(ws, ws.re[0], ws.im[0], True, float(scale), from_bits(base.reshape(R, C)), out, check_ifft=True)
+    u = bf16_ulp_distance(bits(out).reshape(R, C), expect)
+    assert float((u <= 1).mean()) >= 0.9999, float((u <= 1).mean())
+    assert float((u == 0).mean()) >= 0.995
+    _, _, flags, _ = ws.read_ctl()
+    assert [int(v) for v in flags] == [0, 0, 0, 0]
+
+
+def test_epilogue_nan_inf_policy(E):
+    R, C = 8, 64
+    ws = E.get_workspace(R, C, DEV)
+    ws.ctl.zero_()
+    Z = np.zeros((R, C // 2 + 1), dtype=np.complex128)
+    numpy_to_planes(ws, 0, Z)
+    base = torch.zeros((R, C), dtype=torch.bfloat16, device=DEV)
+    base[0, 0] = float("inf"); base[0, 1] = float("nan")
+    out = torch.empty((R, C), dtype=torch.bfloat16, device=DEV)
+    E.inv_cols(ws, ws.re[0], ws.im[0], cull=False)
+    E.inv_rows(ws, ws.re[0], ws.im[0], False, 1.0, base, out, check_ifft=True)
+    _, _, flags, _ = ws.read_ctl()
+    assert int(flags[2]) == 1 and int(flags[3]) == 1 and int(flags[0]) == 0
+    assert out[0, 1].item() == 0.0 and torch.isinf(out[0, 0])
+
+
+# ------------------------------------------------------------------------------------------
+# golden fixtures (reference outputs) and oracle, end to end
+# ------------------------------------------------------------------------------------------
+def _merger():
+    from shardmerge_b200.config import MergeConfig, MergeModel
+    from shardmerge_b200.index import InMemoryIndex
+    from shardmerge_b200.merge.fast_fourier import FourierMerge
+    cfg = MergeConfig(finetune_merge=[], output_base_model="org/base", output_dir="/tmp/unused")
+    return FourierMerge(cfg, index_manager=InMemoryIndex({}))
+
+
+def _run_layer_case(E, d, n_models=None):
+    fm = _merger()
+    alphas = d["alphas"][:n_models] if n_models else d["alphas"]
+    base = from_bits(d["base"])
+    srcs = [E.make_source(base, from_bits(d[f"ft{k}"]), weight=float(a), name=f"org/ft{k}") for k, a in enumerate(alphas)]
+    out = fm.merge_sources(srcs, base, torch.device(DEV), layer_name=str(d["layer"]))
+    return bits(out).reshape(d["base"].shape), fm.last_info
+
+
+@pytest.mark.parametrize("name,branches,min_within1", [
+    ("slerp_256x512", ["slerp"], 0.999), ("slerp_swapped_128x256", ["slerp"], 0.98),
+    ("slerp_a7b2_128x256", ["slerp"], 0.98), ("slerp_1d_2048", ["slerp"], 0.98), ("slerp_352x96", ["slerp"], 0.98),
+    ("arith_128x256", ["arith"], 0.9999), ("onezero_64x128", ["arith"], 0.9999),
+    ("single_64x128", [], 1.0), ("add_zero_64x128", ["add"], 1.0),
+])
+def test_golden_layer_cases(E, golden_dir, name, branches, min_within1):
+    """FourierMerge on the reference's own inputs vs the reference's bf16 outputs.  Small tensors
+    make a single flipped spectrum bin visible in a few % of the bf16 roundings, hence the
+    per-case floors; the flip-accounted residual of the fp32 delta is the tight check."""
+    d = np.load(golden_dir / f"layer_{name}.npz")
+    got, info = _run_layer_case(E, d)
+    assert info["branches"] == branches
+    u = bf16_ulp_distance(got, d["out"])
+    frac1 = float((u <= 1).mean())
+    assert frac1 >= min_within1, (name, frac1, int(u.max()))
+    if min_within1 == 1.0:
+        assert np.array_equal(got, d["out"])
+    if "slerp" in branches or "arith" in branches:
+        # same inputs through the oracle: ours and the oracle should bracket the reference alike
+        models = [dict(base=d["base"], ft=d[f"ft{k}"], alpha=float(a), name=f"org/ft{k}") for k, a in enumerate(d["alphas"])]
+        oo = O.merge_layer(d["base"], models)
+        basef = O.bf16_to_f32(d["base"])
+        raw, resid, share = flip_accounted(O.bf16_to_f32(got) - basef, O.bf16_to_f32(oo) - basef, k=8)
+        # bf16 quantisation of (base + delta) limits what the delta comparison can resolve
+        assert resid < 0.05, (name, raw, resid, share)
+
+
+def test_golden_layer_range(E, golden_dir):
+    d = np.load(golden_dir / "layer_layer_range_64x128.npz")
+    got, info = _run_layer_case(E, d, n_models=2)
+    u = bf16_ulp_distance(got, d["out"])
+    assert float((u <= 1).mean()) >= 0.98
+
+
+def test_golden_tensor_cases(E, golden_dir):
+    """merge_tensors_fft2_slerp (fp32 in, fp32 out) vs the reference's result: flip-accounted <= 1e-5."""
+    from shardmerge_b200.tensor import functions as F
+    for f in sorted(glob.glob(str(golden_dir / "tensor_*.npz"))):
+        d = np.load(f)
+        m, n0, n1 = F.merge_tensors_fft2_slerp(torch.from_numpy(d["v0"]), torch.from_numpy(d["v1"]), t=0.375, device=DEV,
+                                               t_sum=1.0, cutoff_pct=0.08, cull_pct=0.20)
+        assert abs(n0 / float(d["n0"]) - 1) < 1e-6 and abs(n1 / float(d["n1"]) - 1) < 1e-6
+        raw, resid, share = flip_accounted(m.numpy(), d["merged"], k=8)
+        assert resid < 1e-5, (f, raw, resid, share)
+        # forward transform vs the reference's (MKL) spectrum
+        X = F.fft_transform(torch.from_numpy(d["v0"]) / np.float32(d["n0"]), DEV).numpy()
+        assert rel_l2(X, d["fft0"]) < 2e-6
+
+
+@pytest.mark.parametrize("shape,seed", [((1024, 4096), 21), ((2048, 1024), 22), ((1, 8192), 23)])
+def test_pair_merge_vs_oracle_mid_size(E, shape, seed):
+    """Synthetic Llama-like tensors at sizes the oracle finishes in seconds."""
+    R, C = shape
+    g = torch.Generator(device=DEV).manual_seed(1234 + seed)
+    sh = (R, C) if R > 1 else (C,)
+    mean, bs, sig = (1.0, 0.1, (0.01, 0.013)) if R == 1 else (0.0, 0.02, (0.002, 0.0026))
+    base = (mean + bs * torch.randn(sh, generator=g, device=DEV)).to(torch.bfloat16)
+    fts = []
+    for k in range(2):
+        gk = torch.Generator(device=DEV).manual_seed(100000 * (k + 1) + seed)
+        fts.append((base.float() + sig[k] * torch.randn(sh, generator=gk, device=DEV)).to(torch.bfloat16))
+    fm = _merger()
+    srcs = [E.make_source(base, fts[k], weight=a, name=f"m{k}") for k, a in enumerate((0.3, 0.5))]
+    out = fm.merge_sources(srcs, base, torch.device(DEV), layer_name="model.layers.0.x")
+    assert fm.last_info["branches"] == ["slerp"]
+    models = [dict(base=bits(base), ft=bits(fts[k]), alpha=a, name=f"m{k}") for k, a in enumerate((0.3, 0.5))]
+    info = {}
+    oo = O.merge_layer(bits(base), models, info=info)
+    assert abs(fm.last_info["target_norm"] / info["target_norm"] - 1) < 1e-6
+    u = bf16_ulp_distance(bits(out), oo)
+    frac1 = float((u <= 1).mean())
+    print(f"\n[{shape}] bf16 exact {float((u == 0).mean()):.6f} within-1ulp {frac1:.6f} max-ulp {int(u.max())}")
+    assert frac1 >= 0.995
+
+
+@pytest.mark.parametrize("shape", [(4096, 4096), (14336, 4096), (4096, 14336), (1024, 4096)])
+def test_full_size_properties(E, shape):
+    """Llama-3.1-8B shapes, size-independent properties: FFT round trip, Parseval, linearity, exact
+    rank of the order statistic (by counting), bf16 output finite."""
+    R, C = shape
+    g = torch.Generator(device=DEV).manual_seed(R + 3 * C)
+    base = (0.02 * torch.randn((R, C), generator=g, device=DEV)).to(torch.bfloat16)
+    ft = (base.float() + 0.002 * torch.randn((R, C), generator=g, device=DEV)).to(torch.bfloat16)
+    delta = ft.float() - base.float()
+    ws = E.get_workspace(R, C, DEV)
+    ws.ctl.zero_()
+    E.fwd_rows(ws, 0, E.Source(base=base, ft=ft), E.D_SUMSQ0)
+    E.fwd_cols(ws, 0, scale=1.0)
+    Ch = C // 2
+    w = torch.full((Ch + 1,), 2.0, device=DEV, dtype=torch.float64); w[0] = 1; w[Ch] = 1
+    energy = ((ws.re[0][:, : Ch + 1].double() ** 2 + ws.im[0][:, : Ch + 1].double() ** 2) * w).sum().item()
+    ss = (delta.double() ** 2).sum().item()
+    dbl, _, _, _ = ws.read_ctl()
+    assert abs(float(dbl[E.D_SUMSQ0]) / ss - 1) < 1e-10
+    assert abs(energy / (ss * R * C) - 1) < 1e-5                      # Parseval
+    # exact rank by counting
+    N = R * C
+    k = int(N * 0.2)
+    E.select_kth(ws, ws.re[0], None, k, E.F_THR_CULL, which=1)
+    _, flt, _, sel = ws.read_ctl()
+    assert sel.view(torch.int32)[16 + 9].item() == 0
+    thr = flt[E.F_THR_CULL].item()
+    a = ws.re[0][:, : Ch + 1].abs()
+    below = ((a < thr).double() * w).sum().item(); upto = ((a <= thr).double() * w).sum().item()
+    assert below <= k < upto, (below, k, upto)
+    # round trip
+    out = torch.empty((R, C), dtype=torch.float32, device=DEV)
+    E.inv_cols(ws, ws.re[0], ws.im[0], cull=False)
+    E.inv_rows(ws, ws.re[0], ws.im[0], False, 1.0, None, out, check_ifft=True)
+    err = ((out.double() - delta.double()) ** 2).sum().sqrt().item() / ss ** 0.5
+    assert err < 1e-6, err
