@@ -74,12 +74,13 @@ def test_bf16_delta_and_epilogue(emu):
     re, im, ss = forward(emu, R, C, base=base, ft=ft)
     got = natural(emu, re[:, : C // 2 + 1] + 1j * im[:, : C // 2 + 1], R, C)
     assert rel_l2(got, np.fft.rfft2(delta.astype(np.float64))) < 5e-7
-    # inverse with the bf16 epilogue: base + delta*scale, RNE
+    # inverse with the bf16 epilogue: base + delta*scale, RNE (a non-dyadic scale: with a dyadic one
+    # base + delta*scale lands on exact bf16 rounding ties for ~2 % of these grid-valued inputs)
     out = np.zeros((R, C), np.uint16); fl = (ctypes.c_uint * 4)()
     rc = emu.emu_inverse(R, C, P(re, c_fp), P(im, c_fp), ctypes.c_float(0.0), 0, P(base, c_u16), P(out, c_u16), None,
-                         ctypes.c_float(3.0), fl)
+                         ctypes.c_float(1.2345), fl)
     assert rc == 0
-    expect = O.f32_to_bf16((O.bf16_to_f32(base) + (delta * np.float32(3.0)).astype(np.float32)).astype(np.float32))
+    expect = O.f32_to_bf16((O.bf16_to_f32(base) + (delta * np.float32(1.2345)).astype(np.float32)).astype(np.float32))
     u = bf16_ulp_distance(out, expect)
     # results that cancel to ~0 have a tiny ulp: allow a handful beyond 1 ulp, bound them absolutely
     assert float((u <= 1).mean()) >= 0.9995 and float((u == 0).mean()) > 0.995
