@@ -94,12 +94,20 @@ static std::once_flag g_attr_once;
 static int g_attr_rc = 0;
 static int ensure_attrs() {
   std::call_once(g_attr_once, [] {
-    const int kMax = 227 * 1024;
-    cudaError_t e;
-    e = cudaFuncSetAttribute(k_row_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_row_inv, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_col, cudaFuncAttributeMaxDynamicSharedMemorySize, kMax);
-    if (e != cudaSuccess) { sm_set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); g_attr_rc = -100; }
+    // opt in to the full 227 KB of shared memory per CTA (minus each kernel's static part)
+    int dev = 0, optin = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    auto set = [&](const void* fn) {
+      cudaFuncAttributes fa;
+      if (e == cudaSuccess) e = cudaFuncGetAttributes(&fa, fn);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes);
+    };
+    set((const void*)k_row_fwd);
+    set((const void*)k_row_inv);
+    set((const void*)k_col);
+    if (e != cudaSuccess) { sm_set_error("shared-memory opt-in failed: %s", cudaGetErrorString(e)); g_attr_rc = -100; }
   });
   return g_attr_rc;
 }

@@ -111,16 +111,49 @@ __global__ void __launch_bounds__(256) k_hist_flat(const unsigned int* __restric
     if (sh[i]) atomicAdd(&hist[i], sh[i]);
 }
 
-enum { PICK_NONE = 0, PICK_ADJUST = 1, PICK_TO_WINDOW = 2, PICK_FINISH = 3 };
+enum { PICK_NONE = 0, PICK_ADJUST = 1, PICK_FINISH = 3 };
 
-// single CTA, 1024 threads: locate the bin holding the remaining rank, extend the prefix
-__global__ void __launch_bounds__(1024) k_pick(unsigned int* __restrict__ hist, SelState* st, int pass, int action,
-                                               float eps, unsigned long long rank_full, float* thr_out) {
+// block of 1024 threads: find the bin of a 2048-bin histogram (global or shared) that holds 0-based
+// `rank`; returns through shared outputs.  The histogram is zeroed on the way.
+struct PickOut { int bin; unsigned long long rank_in_bin; };
+__device__ __forceinline__ void block_pick(unsigned int* hist, unsigned long long rank, PickOut* s_out /*shared*/) {
   __shared__ unsigned long long wtot[32];
-  __shared__ unsigned long long s_rank;
-  __shared__ int s_found;
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-  if (t == 0) {
+  if (t == 0) { s_out->bin = -1; s_out->rank_in_bin = 0ull; }
+  const unsigned int h0 = hist[2 * t], h1 = hist[2 * t + 1];
+  hist[2 * t] = 0u; hist[2 * t + 1] = 0u;
+  const unsigned long long v = (unsigned long long)h0 + h1;
+  unsigned long long incl = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long n = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += n;
+  }
+  if (lane == 31) wtot[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    const unsigned long long w = wtot[lane];
+    unsigned long long wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long n = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += n;
+    }
+    wtot[lane] = wi - w;                             // exclusive warp offsets
+  }
+  __syncthreads();
+  const unsigned long long excl = wtot[wid] + incl - v;
+  if (rank >= excl && rank < excl + h0) { s_out->bin = 2 * t; s_out->rank_in_bin = rank - excl; }
+  else if (rank >= excl + h0 && rank < excl + v) { s_out->bin = 2 * t + 1; s_out->rank_in_bin = rank - excl - h0; }
+  __syncthreads();
+}
+
+// single CTA, 1024 threads: extend the prefix of `st` by one radix digit
+__global__ void __launch_bounds__(1024) k_pick(unsigned int* __restrict__ hist, SelState* st, int pass, int action,
+                                               float* thr_out) {
+  __shared__ PickOut out;
+  __shared__ unsigned long long s_rank;
+  if (threadIdx.x == 0) {
     unsigned long long r = st->rank;
     if (action == PICK_ADJUST) {
       const unsigned long long below = st->below;
@@ -130,55 +163,62 @@ __global__ void __launch_bounds__(1024) k_pick(unsigned int* __restrict__ hist, 
       else r -= below;
       st->rank = r;
     }
-    s_rank = r; s_found = 0;
+    s_rank = r;
   }
   __syncthreads();
-  const unsigned long long rank = s_rank;
-  const unsigned int h0 = hist[2 * t], h1 = hist[2 * t + 1];
-  hist[2 * t] = 0u; hist[2 * t + 1] = 0u;           // leave the histogram clean for the next pass
-  unsigned long long v = (unsigned long long)h0 + h1, incl = v;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    unsigned long long n = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += n;
-  }
-  if (lane == 31) wtot[wid] = incl;
-  __syncthreads();
-  if (wid == 0) {
-    unsigned long long w = wtot[lane], wi = w;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      unsigned long long n = __shfl_up_sync(0xffffffffu, wi, o);
-      if (lane >= o) wi += n;
+  block_pick(hist, s_rank, &out);
+  if (threadIdx.x == 0) {
+    const int shift = pass == 0 ? 20 : (pass == 1 ? 10 : 0);
+    if (st->status == 0u) {
+      if (out.bin >= 0) { st->prefix |= (unsigned int)out.bin << shift; st->rank = out.rank_in_bin; }
+      else st->status |= 1u;
     }
-    wtot[lane] = wi - w;                             // exclusive warp offsets
-  }
-  __syncthreads();
-  const unsigned long long excl = wtot[wid] + incl - v;
-  const int shift = pass == 0 ? 20 : (pass == 1 ? 10 : 0);
-  if (st->status == 0u) {
-    if (rank >= excl && rank < excl + h0) {
-      st->prefix |= (unsigned int)(2 * t) << shift; st->rank = rank - excl; s_found = 1;
-    } else if (rank >= excl + h0 && rank < excl + v) {
-      st->prefix |= (unsigned int)(2 * t + 1) << shift; st->rank = rank - excl - h0; s_found = 1;
-    }
-  }
-  __syncthreads();
-  if (t == 0) {
-    if (!s_found && st->status == 0u) st->status |= 1u;
-    if (action == PICK_TO_WINDOW) {
-      const float vs = __uint_as_float(st->prefix);
-      float lo = vs * (1.f - eps), hi = vs * (1.f + eps);
-      unsigned int lob = __float_as_uint(lo), hib = __float_as_uint(hi);
-      if (!(hi < INFINITY)) hib = 0x7f7fffffu;
-      st->lo = lob; st->hi = hib;
-      st->rank = rank_full; st->below = 0ull; st->ncand = 0u; st->prefix = 0u;
-    } else if (action == PICK_FINISH) {
+    if (action == PICK_FINISH) {
       const float val = (st->status == 0u) ? __uint_as_float(st->prefix) : __uint_as_float(0x7fc00000u);
       st->value = val;
       st->sticky |= st->status;
       if (thr_out) *thr_out = val;
     }
+  }
+}
+
+// single CTA, 1024 threads: exact order statistics of the SAMPLE at ranks k_lo and k_hi give the key
+// window [lo, hi] that the full-data pass will count against / collect from.  k_lo < 0 -> lo = 0,
+// k_hi >= ns -> hi = all keys.
+__global__ void __launch_bounds__(1024) k_sample_window(const unsigned int* __restrict__ keys, unsigned int ns,
+                                                        SelState* st, long long k_lo, long long k_hi,
+                                                        unsigned long long rank_full) {
+  __shared__ unsigned int sh[kHistBins];
+  __shared__ PickOut out;
+  __shared__ unsigned int s_prefix;
+  unsigned int bounds[2] = {0u, 0x7fffffffu};
+  for (int which = 0; which < 2; ++which) {
+    const long long k = which == 0 ? k_lo : k_hi;
+    if (k < 0 || k >= (long long)ns) continue;       // uniform across the block
+    unsigned long long rank = (unsigned long long)k;
+    unsigned int prefix = 0u;
+    for (int pass = 0; pass < 3; ++pass) {
+      for (int i = threadIdx.x; i < kHistBins; i += blockDim.x) sh[i] = 0u;
+      __syncthreads();
+      for (unsigned int i = threadIdx.x; i < ns; i += blockDim.x) {
+        const unsigned int key = keys[i];
+        if (pass == 0) atomicAdd(&sh[key >> 20], 1u);
+        else if (pass == 1) { if ((key >> 20) == (prefix >> 20)) atomicAdd(&sh[(key >> 10) & 1023u], 1u); }
+        else { if ((key >> 10) == (prefix >> 10)) atomicAdd(&sh[key & 1023u], 1u); }
+      }
+      __syncthreads();
+      block_pick(sh, rank, &out);
+      const int shift = pass == 0 ? 20 : (pass == 1 ? 10 : 0);
+      if (threadIdx.x == 0) s_prefix = prefix | ((unsigned int)(out.bin < 0 ? 0 : out.bin) << shift);
+      __syncthreads();
+      prefix = s_prefix; rank = out.rank_in_bin;
+      __syncthreads();
+    }
+    bounds[which] = prefix;
+  }
+  if (threadIdx.x == 0) {
+    st->lo = bounds[0]; st->hi = bounds[1];
+    st->rank = rank_full; st->below = 0ull; st->ncand = 0u; st->prefix = 0u;
   }
 }
 
@@ -438,7 +478,7 @@ static unsigned int fast_cap(const SmPlan& p, int n_planes) {
   if (cap > 0xfffffff0ull) cap = 0xfffffff0ull;
   return (unsigned int)cap;
 }
-static const unsigned int kSampleN = 1u << 20;
+static const unsigned int kSampleN = 1u << 17;
 static bool use_safe(const SmPlan& p, int n_planes, int mode) {
   unsigned long long total = (unsigned long long)p.R * p.C * n_planes;
   return mode != 0 || total <= (4ull << 20);
@@ -477,26 +517,23 @@ extern "C" int sm_select_kth_abs(const sm_plan* plan, const float* plane0, const
   } else {
     unsigned int* sample = buf;
     cand = buf + kSampleN;
-    // rank inside the sample that corresponds to `rank` in the full key set
-    const unsigned long long ks = (unsigned long long)((long double)rank * (long double)kSampleN / (long double)total);
-    k_sel_init<<<1, 1, 0, s>>>(st, ks < kSampleN ? ks : kSampleN - 1, 0u, 0u, fast_cap(p, n_planes));
+    // sample ranks that bracket `rank` of the full key set with ~6 sigma of binomial noise
+    const double pq = (double)rank / (double)total;
+    const double ks = pq * (double)kSampleN;
+    const double delta = 6.0 * sqrt((double)kSampleN * pq * (1.0 - pq)) + 16.0;
+    k_sel_init<<<1, 1, 0, s>>>(st, rank, 0u, 0u, fast_cap(p, n_planes));
     SM_LAUNCH_CHECK();
-    k_sample<<<296, 256, 0, s>>>(p, plane0, plane1, n_planes, kSampleN, sample);
+    k_sample<<<148, 256, 0, s>>>(p, plane0, plane1, n_planes, kSampleN, sample);
     SM_LAUNCH_CHECK();
-    for (int pass = 0; pass < 3; ++pass) {
-      k_hist_flat<<<296, 256, 0, s>>>(sample, nullptr, kSampleN, st, pass, hist);
-      SM_LAUNCH_CHECK();
-      k_pick<<<1, 1024, 0, s>>>(hist, st, pass, pass == 2 ? PICK_TO_WINDOW : PICK_NONE, 1.0f / 32.0f, rank, nullptr);
-      SM_LAUNCH_CHECK();
-    }
+    k_sample_window<<<1, 1024, 0, s>>>(sample, kSampleN, st, (long long)floor(ks - delta), (long long)ceil(ks + delta), rank);
+    SM_LAUNCH_CHECK();
   }
   k_count_collect<<<eg, SM_EW_THREADS, 0, s>>>(p, plane0, plane1, st, cand);
   SM_LAUNCH_CHECK();
   for (int pass = 0; pass < 3; ++pass) {
     k_hist_flat<<<592, 256, 0, s>>>(cand, &st->ncand, 0u, st, pass, hist);
     SM_LAUNCH_CHECK();
-    k_pick<<<1, 1024, 0, s>>>(hist, st, pass, pass == 0 ? PICK_ADJUST : (pass == 2 ? PICK_FINISH : PICK_NONE), 0.f, 0ull,
-                              thr_out);
+    k_pick<<<1, 1024, 0, s>>>(hist, st, pass, pass == 0 ? PICK_ADJUST : (pass == 2 ? PICK_FINISH : PICK_NONE), thr_out);
     SM_LAUNCH_CHECK();
   }
   return 0;

@@ -85,6 +85,9 @@ class InMemoryIndex(_IndexBase):
         self._register(model_uri, {"metadata": {"total_size": sum(t.numel() * t.element_size() for t in tensors.values())},
                                    "weight_map": {n: self._shard_of(n) for n in tensors}})
 
+    def tensor_numels(self, model_uri: str) -> Dict[str, int]:
+        return {n: t.numel() for n, t in self.models[model_uri].items()}
+
     def get_tensor(self, model_uri: str, tensor_name: str, device: str = "cpu") -> TensorPromise:
         t = self.models[model_uri][tensor_name]
         return TensorPromise(model_uri, tensor_name, device, lambda: t if str(t.device) == str(device) else t.to(device))
@@ -111,6 +114,20 @@ class LocalSafetensorsIndex(_IndexBase):
             raise FileNotFoundError(f"{path} not found (shardmerge_b200 does not download models)")
         with open(path) as fh:
             self._register(model_uri, json.load(fh))
+
+    def tensor_numels(self, model_uri: str) -> Dict[str, int]:
+        """element counts from the safetensors headers (no tensor data is read)."""
+        from safetensors import safe_open
+        out: Dict[str, int] = {}
+        index = self.model_indexes[model_uri]
+        for shard in sorted(set(index["weight_map"].values())):
+            with safe_open(str(self.storage_dir / model_uri / shard), framework="pt") as f:
+                for key in f.keys():
+                    n = 1
+                    for d in f.get_slice(key).get_shape():
+                        n *= d
+                    out[key] = n
+        return out
 
     def get_tensor(self, model_uri: str, tensor_name: str, device: str = "cpu") -> TensorPromise:
         index = self.model_indexes[model_uri]

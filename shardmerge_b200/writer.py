@@ -152,11 +152,13 @@ class ModelWriter:
         if have >= self.shard_to_tensors[shard_name]:
             self._flush(shard_name)
 
-    def finalize(self):
+    def finalize(self, only_shards=None):
+        """Flush what is staged and verify completeness (shard/writer.py:151-161).  `only_shards`
+        restricts the check to the shards this process owns (multi-GPU merge, schedule.py)."""
         for shard_name in list(self._staged):
             self._flush(shard_name)
         missing = [(s, n) for s, names in self.shard_to_tensors.items() for n in names
-                   if (s, n) not in self.written_shard_layers]
+                   if (only_shards is None or s in only_shards) and (s, n) not in self.written_shard_layers]
         if missing:
             logger.error(f"Failed to write all layers. Missing: {missing}")
             raise RuntimeError(f"Incomplete model output: missing {len(missing)} layers")

@@ -1,0 +1,230 @@
+"""Host-side logic that needs no GPU: config schema, layer classification, canonical tensor order,
+writer (write-once shards, resume, finalize), pairing, name hashing, work partition, and a
+world_size-2 gloo run of the shard-granular multi-GPU merge driver with a CPU stand-in strategy."""
+import asyncio
+import json
+import os
+import subprocess
+import sys
+import textwrap
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle_np as O
+from shardmerge_b200 import schedule
+from shardmerge_b200.config import MergeConfig, MergeModel
+from shardmerge_b200.constants import INPUT_LAYER, OUTPUT_LAYER
+from shardmerge_b200.index import InMemoryIndex, LocalSafetensorsIndex, canonical_layer_order
+from shardmerge_b200.merge.fast_fourier import clamp, name_hash, task_arithmetic
+from shardmerge_b200.tensor.functions import correlated_pairs
+from shardmerge_b200.writer import ModelWriter, ShardLayer
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_config_yaml_roundtrip(tmp_path):
+    y = tmp_path / "c.yaml"
+    y.write_text(textwrap.dedent("""
+        output_base_model: "org/base"
+        finetune_merge:
+          - { model: "org/a", base: "org/base", alpha: 0.3, is_input: true }
+          - { model: "org/b", base: "org/base", alpha: 0.5, is_output: true, start_layer: 2, end_layer: 5 }
+        output_dir: "out"
+        device: "cuda"
+    """))
+    cfg = MergeConfig.from_yaml(y)
+    assert cfg.output_astype == torch.bfloat16 and cfg.device == "cuda"
+    assert cfg.input_model.model == "org/a" and cfg.output_model.model == "org/b"
+    b = cfg.finetune_merge[1]
+    assert [b.use_layer_index(i) for i in (1, 2, 5, 6)] == [False, True, True, False]
+    assert cfg.finetune_merge[0].use_layer_index(10**6)
+    cfg.update({"device": "cuda:1"}, cache_dir="x", bogus=1)
+    assert cfg.device == "cuda:1" and cfg.cache_dir == "x" and not hasattr(cfg, "bogus")
+    (tmp_path / "bad.yaml").write_text("output_dir: x\n")
+    with pytest.raises(ValueError):
+        MergeConfig.from_yaml(tmp_path / "bad.yaml")
+    with pytest.raises(TypeError):
+        MergeModel(model="a", base="b", unknown_key=1)
+
+
+def test_layer_number():
+    L = lambda n: ShardLayer(0, "s", n, False).layer_number
+    assert L("model.embed_tokens.weight") == INPUT_LAYER
+    assert L("model.norm.weight") == OUTPUT_LAYER and L("lm_head.weight") == OUTPUT_LAYER
+    assert L("model.layers.17.mlp.up_proj.weight") == 17
+    for bad in ("model.layers.07.x", "transformer.h.0.w"):
+        with pytest.raises(ValueError):
+            L(bad)
+
+
+def test_canonical_layer_order():
+    names = ["lm_head.weight", "model.layers.10.a.weight", "model.layers.2.b.weight", "model.layers.2.a.weight",
+             "model.layers.0.b.weight", "model.layers.0.a.weight", "model.layers.10.b.weight", "model.norm.weight",
+             "model.embed_tokens.weight", "rotary.inv_freq"]
+    assert canonical_layer_order(names) == [
+        "model.embed_tokens.weight", "model.layers.0.a.weight", "model.layers.0.b.weight", "model.layers.2.a.weight",
+        "model.layers.2.b.weight", "model.layers.10.a.weight", "model.layers.10.b.weight", "model.norm.weight",
+        "lm_head.weight", "rotary.inv_freq"]
+
+
+def test_name_hash_and_helpers():
+    h = name_hash("org/model-a_org/model-b")
+    assert h.startswith("org/_org/::") and len(h.split("::")[1]) == 8
+    assert name_hash("x") == name_hash("x") != name_hash("y")
+    assert clamp(5, 0, 3) == 3 and clamp(-1, 0, 3) == 0 and clamp(2, 0, 3) == 2
+    t = task_arithmetic(torch.tensor([1.0, -1.0, 2.0]), torch.tensor([2.0, 3.0, -1.0]))
+    assert t.tolist() == [3.0, -1.0, 2.0]
+
+
+def test_correlated_pairs_matches_oracle():
+    rng = np.random.default_rng(0)
+    for n in (2, 3, 4, 5, 7):
+        norms = rng.uniform(0.2, 0.9, n).astype(np.float32)
+        c = np.zeros((n, n), np.float32)
+        for i in range(n):
+            for j in range(i + 1, n):
+                c[i, j] = norms[i] * norms[j]
+        for way in ("least", "most"):
+            mine = [(x, y) for x, y, _ in correlated_pairs(torch.from_numpy(c), way)]
+            assert mine == [(x, y) for x, y, _ in O.correlated_pairs(c, way)]
+            used = [v for p in mine for v in p if v >= 0]
+            assert sorted(used) == list(range(n))
+    with pytest.raises(ValueError):
+        list(correlated_pairs(torch.zeros(3, 3), "sideways"))
+
+
+def _toy_model(seed, L=3, H=16):
+    g = torch.Generator().manual_seed(seed)
+    t = {"model.embed_tokens.weight": torch.randn(32, H, generator=g).to(torch.bfloat16),
+         "model.norm.weight": torch.randn(H, generator=g).to(torch.bfloat16),
+         "lm_head.weight": torch.randn(32, H, generator=g).to(torch.bfloat16)}
+    for i in range(L):
+        t[f"model.layers.{i}.mlp.up_proj.weight"] = torch.randn(2 * H, H, generator=g).to(torch.bfloat16)
+        t[f"model.layers.{i}.input_layernorm.weight"] = torch.randn(H, generator=g).to(torch.bfloat16)
+    return t
+
+
+def test_writer_write_once_resume_finalize(tmp_path):
+    from safetensors import safe_open
+    idx = InMemoryIndex({"m": _toy_model(0)})
+    asyncio.run(idx.add_model("m"))
+    order = idx.get_layer_order("m")
+    doc = idx.model_indexes["m"]
+    w = ModelWriter(base_index=doc, output_path=tmp_path / "out", layer_order=order, output_astype=torch.float16)
+    assert json.loads((tmp_path / "out" / "model.safetensors.index.json").read_text())["weight_map"] == doc["weight_map"]
+    groups = list(w.shard_layers())
+    assert [g[0].shard_name for g in groups] == sorted({v for v in doc["weight_map"].values()})
+    first = groups[0]
+    # nothing is written until the shard is complete
+    w.add_tensor(first[0].layer_name, idx.models["m"][first[0].layer_name])
+    assert not (tmp_path / "out" / first[0].shard_name).exists()
+    for sl in first[1:]:
+        w.add_tensor(sl.layer_name, idx.models["m"][sl.layer_name])
+    path = tmp_path / "out" / first[0].shard_name
+    assert path.exists()
+    with safe_open(path, framework="pt") as f:
+        assert set(f.keys()) == {sl.layer_name for sl in first} and f.metadata() == {"format": "pt"}
+        t = f.get_tensor(first[0].layer_name)
+        assert t.dtype == torch.float16
+        assert torch.equal(t, idx.models["m"][first[0].layer_name].to(torch.float16))
+    with pytest.raises(RuntimeError):
+        w.finalize()                                       # other shards are missing
+    # resume: a new writer sees the finished shard as written and skips it
+    w2 = ModelWriter(base_index=doc, output_path=tmp_path / "out", layer_order=order, output_astype=torch.float16)
+    assert all(sl.written for sl in list(w2.shard_layers())[0])
+    mtime = path.stat().st_mtime_ns
+    w2.add_tensor(first[0].layer_name, idx.models["m"][first[0].layer_name])
+    assert path.stat().st_mtime_ns == mtime
+    for g in list(w2.shard_layers())[1:]:
+        for sl in g:
+            w2.add_tensor(sl.layer_name, idx.models["m"][sl.layer_name])
+    w2.finalize()
+
+
+def test_local_safetensors_index(tmp_path):
+    from safetensors.torch import save_file
+    model = _toy_model(1)
+    d = tmp_path / "org" / "m"
+    d.mkdir(parents=True)
+    names = list(model)
+    shards = {"model-00001-of-00002.safetensors": names[:4], "model-00002-of-00002.safetensors": names[4:]}
+    wm = {}
+    for fn, ns in shards.items():
+        save_file({n: model[n] for n in ns}, str(d / fn), metadata={"format": "pt"})
+        wm.update({n: fn for n in ns})
+    (d / "model.safetensors.index.json").write_text(json.dumps({"metadata": {}, "weight_map": wm}))
+    idx = LocalSafetensorsIndex(tmp_path)
+    asyncio.run(idx.add_model("org/m"))
+    assert idx.get_model_keys("org/m") == set(names)
+    t = asyncio.run(idx.get_tensor("org/m", names[5]).get())
+    assert torch.equal(t, model[names[5]])
+    assert idx.tensor_numels("org/m") == {n: v.numel() for n, v in model.items()}
+    with pytest.raises(FileNotFoundError):
+        asyncio.run(idx.add_model("org/missing"))
+
+
+def test_lpt_partition_llama70b_balance():
+    H, I, KV, L = 8192, 28672, 1024, 80
+    numels = {}
+    for l in range(L):
+        for nm, n in (("q", H * H), ("k", KV * H), ("v", KV * H), ("o", H * H), ("gate", I * H), ("up", I * H),
+                      ("down", H * I), ("ln1", H), ("ln2", H)):
+            numels[f"model.layers.{l}.{nm}"] = n
+    parts = schedule.tensor_partition(numels, 8, n_models=2)
+    assert sorted(n for p in parts for n in p) == sorted(numels)
+    cost = {n: schedule.merge_cost(v, 2) for n, v in numels.items()}
+    assert schedule.imbalance(parts, cost) < 0.03          # < 3 %
+    assert schedule.tensor_partition(numels, 8, 2) == parts  # deterministic
+    assert schedule.lpt([("a", 3), ("b", 3), ("c", 2)], 2) == [["a", "c"], ["b"]]
+
+
+WORKER = textwrap.dedent("""
+    import asyncio, os, sys, torch, torch.distributed as dist
+    sys.path.insert(0, %(root)r)
+    from shardmerge_b200.config import MergeConfig, MergeModel
+    from shardmerge_b200.index import InMemoryIndex
+    from shardmerge_b200.merge.base import MergeTensorsBase
+    from shardmerge_b200 import schedule
+    sys.path.insert(0, os.path.join(%(root)r, "tests"))
+    from test_host_logic import _toy_model
+
+    class CpuStandIn(MergeTensorsBase):           # TEST stand-in: exercises partition + writer only
+        def get_readme(self): return "readme"
+        async def _merge_layer(self, shard_layer, device):
+            t = await self.index_manager.get_tensor("org/a", shard_layer.layer_name).get()
+            return (t.float() * 2).to(torch.bfloat16)
+
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%(port)d", rank=int(sys.argv[1]), world_size=2)
+    models = {"org/base": _toy_model(0, L=6), "org/a": _toy_model(1, L=6)}
+    cfg = MergeConfig(finetune_merge=[MergeModel(model="org/a", base="org/base")], output_base_model="org/base",
+                      output_dir=sys.argv[2])
+    m = CpuStandIn(cfg, index_manager=InMemoryIndex(models))
+    mine = asyncio.run(schedule.merge_distributed(m, "cpu", dist.get_rank(), 2, barrier=dist.barrier))
+    print("RANK", dist.get_rank(), "SHARDS", ",".join(mine))
+    dist.destroy_process_group()
+""")
+
+
+def test_merge_distributed_world2_gloo(tmp_path):
+    from safetensors import safe_open
+    port = 29500 + (os.getpid() % 2000)
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER % dict(root=str(ROOT), port=port))
+    out = tmp_path / "out"
+    procs = [subprocess.Popen([sys.executable, str(script), str(r), str(out)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    logs = [p.communicate(timeout=180)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), logs
+    owned = [set(l.split("SHARDS")[1].strip().split(",")) for l in logs]
+    assert owned[0] and owned[1] and not (owned[0] & owned[1])
+    ref = _toy_model(1, L=6)
+    seen = set()
+    for f in out.glob("*.safetensors"):
+        with safe_open(f, framework="pt") as sf:
+            for k in sf.keys():
+                assert torch.equal(sf.get_tensor(k), (ref[k].float() * 2).to(torch.bfloat16))
+                seen.add(k)
+    assert seen == set(ref) and (out / "README.md").read_text() == "readme"
