@@ -16,7 +16,22 @@
 #include "fft_core.cuh"
 #include "plan.h"
 
+// A phase is a plain loop over the CTA's threads followed by a barrier.  On the device the loop
+// runs exactly once (tid = threadIdx.x) and sync() is __syncthreads(); on the host it walks all
+// emulated threads.  (No lambdas here: closures that capture by reference end up in local memory
+// and turn every captured scalar into a generic load -- measured on k_row_inv, profiles/r01.)
+#define SM_FOR_THREADS(ex, tid) for (int tid = (ex).tid_begin(), tid##_end = (ex).tid_end(); tid < tid##_end; ++tid)
+
 namespace smfft {
+
+// counter bump that works on both sides (device: a rare global atomic; host: plain increment)
+SM_HD void sm_count(unsigned int* p) {
+#if defined(__CUDA_ARCH__)
+  atomicAdd(p, 1u);
+#else
+  *p += 1u;
+#endif
+}
 
 // ------------------------------------------------------------------ smem accessors
 struct RowSmem {               // one contiguous sequence, optional 1-in-16 padding
@@ -75,7 +90,7 @@ SM_HD void row_fwd_body(Exec& ex, const SmPlan& pl, int row, const RowFwdArgs& a
     const bool last = (st == pl.n_row - 1);
     RowSmem sin{smem + (size_t)(cur ^ 1) * bufstride, padmask};   // written by the previous stage
     RowSmem sout{smem + (size_t)cur * bufstride, padmask};
-    ex.phase([&](int tid) {
+    SM_FOR_THREADS(ex, tid) {
       for (int b = tid; b < nb; b += T) {
         if (st == 0) {
           if (last) stockham_bfly_rt<true>(r, b, Ch, s, 2, twC, gsrc, sout);
@@ -85,14 +100,15 @@ SM_HD void row_fwd_body(Exec& ex, const SmPlan& pl, int row, const RowFwdArgs& a
           else      stockham_bfly_rt<false>(r, b, Ch, s, 2, twC, sin, sout);
         }
       }
-    });
+    }
+    ex.sync();
     s *= r; cur ^= 1;
   }
   // untangle the packed transform into the Hermitian half spectrum X[0..Ch]
   RowSmem z{smem + (size_t)(cur ^ 1) * bufstride, padmask};
   float* ore = a.re + (size_t)row * pl.P;
   float* oim = a.im + (size_t)row * pl.P;
-  ex.phase([&](int tid) {
+  SM_FOR_THREADS(ex, tid) {
     for (int k = tid; k <= Ch; k += T) {
       const int k0 = (k == Ch) ? 0 : k;
       const int k1 = (k == 0 || k == Ch) ? 0 : Ch - k;
@@ -105,7 +121,8 @@ SM_HD void row_fwd_body(Exec& ex, const SmPlan& pl, int row, const RowFwdArgs& a
       ore[k] = er + (pr * w.x - qi * w.y);
       oim[k] = ei + (pr * w.y + qi * w.x);
     }
-  });
+  }
+  ex.sync();
 }
 
 // ------------------------------------------------------------------ row inverse
@@ -140,11 +157,13 @@ struct RowTangleSrc {          // stage-1 source of the inverse: Z'[k] from X[k]
 
 struct RowEpilogueDst {        // last-stage sink of the inverse: element j is (x[2j], x[2j+1]) swapped
   int out_mode; const uint32_t* base32; uint32_t* out32; cf* outf; float inv_n, scale; int check;
-  unsigned int* cnt;           // per-thread local counters [4]
+  unsigned int* flags;         // global counters [4]; NaN / Inf are exceptional, so a direct atomic is fine
   SM_HD float fin(float v, int which) const {
     uint32_t u = f32_bits(v) & 0x7fffffffu;
-    if (u > 0x7f800000u) { cnt[which] += 1; return 0.f; }
-    if (u == 0x7f800000u) cnt[which + 1] += 1;
+    if (u >= 0x7f800000u) {
+      if (u > 0x7f800000u) { sm_count(flags + which); return 0.f; }
+      sm_count(flags + which + 1);
+    }
     return v;
   }
   SM_HD void store(int j, float a, float b) const {
@@ -164,7 +183,7 @@ struct RowEpilogueDst {        // last-stage sink of the inverse: element j is (
 
 template <class Exec>
 SM_HD void row_inv_body(Exec& ex, const SmPlan& pl, int row, const RowInvArgs& a, const cf* twC,
-                        cf* smem, unsigned int* cnt) {
+                        cf* smem) {
   const int Ch = pl.Ch, T = ex.nthreads();
   const int bufstride = pl.row_pad ? (Ch + (Ch >> 4) + 1) : Ch;
   const int padmask = pl.row_pad ? ~0 : 0;
@@ -179,21 +198,22 @@ SM_HD void row_inv_body(Exec& ex, const SmPlan& pl, int row, const RowInvArgs& a
   gdst.outf = a.out_mode != 0 ? reinterpret_cast<cf*>(a.out_f32 + (size_t)row * pl.C) : nullptr;
   gdst.inv_n = a.inv_n; gdst.check = a.check_ifft;
   gdst.scale = a.scale_ptr ? *a.scale_ptr : a.scale_host;
-  gdst.cnt = cnt;
+  gdst.flags = a.flags;
   int s = 1, cur = 0;
   for (int st = 0; st < pl.n_row; ++st) {
     const int r = pl.row_rad[st], nb = Ch / r;
     const bool first = (st == 0), last = (st == pl.n_row - 1);
     RowSmem sin{smem + (size_t)(cur ^ 1) * bufstride, padmask};
     RowSmem sout{smem + (size_t)cur * bufstride, padmask};
-    ex.phase([&](int tid) {
+    SM_FOR_THREADS(ex, tid) {
       for (int b = tid; b < nb; b += T) {
         if (first && last)  stockham_bfly_rt<true>(r, b, Ch, s, 2, twC, gsrc, gdst);
         else if (first)     stockham_bfly_rt<false>(r, b, Ch, s, 2, twC, gsrc, sout);
         else if (last)      stockham_bfly_rt<true>(r, b, Ch, s, 2, twC, sin, gdst);
         else                stockham_bfly_rt<false>(r, b, Ch, s, 2, twC, sin, sout);
       }
-    });
+    }
+    ex.sync();
     s *= r; cur ^= 1;
   }
 }
@@ -247,7 +267,7 @@ SM_HD void col_body(Exec& ex, const SmPlan& pl, int tile, int inst, const ColArg
   for (int st = 0; st < a.n_rad; ++st) {
     const int r = a.rad[st], nb = L / r;
     const bool first = (st == 0), last = (st == a.n_rad - 1);
-    ex.phase([&](int tid) {
+    SM_FOR_THREADS(ex, tid) {
       const int lane = tid & 31, wid = tid >> 5;
       const int c = col0 + lane;
       const bool valid = (c <= pl.Ch);
@@ -264,7 +284,8 @@ SM_HD void col_body(Exec& ex, const SmPlan& pl, int tile, int inst, const ColArg
         else if (last)      stockham_bfly_rt<true>(r, b, L, s, a.tw_mul, twR, sin, gdst);
         else                stockham_bfly_rt<false>(r, b, L, s, a.tw_mul, twR, sin, sout);
       }
-    });
+    }
+    ex.sync();
     s *= r; cur ^= 1;
   }
 }

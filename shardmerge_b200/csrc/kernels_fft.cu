@@ -21,7 +21,9 @@ extern "C" int sm_version(void) { return 100; }
 // ------------------------------------------------------------------ device exec policy
 struct DeviceExec {
   __device__ __forceinline__ int nthreads() const { return (int)blockDim.x; }
-  template <class F> __device__ __forceinline__ void phase(F&& f) { f((int)threadIdx.x); __syncthreads(); }
+  __device__ __forceinline__ int tid_begin() const { return (int)threadIdx.x; }
+  __device__ __forceinline__ int tid_end() const { return (int)threadIdx.x + 1; }
+  __device__ __forceinline__ void sync() const { __syncthreads(); }
 };
 
 extern __shared__ float2 g_dyn_smem[];
@@ -33,7 +35,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 // ------------------------------------------------------------------ kernels
-__global__ void __launch_bounds__(512) k_row_fwd(SmPlan pl, RowFwdArgs a, const cf* __restrict__ twC,
+__global__ void __launch_bounds__(512) k_row_fwd(const __grid_constant__ SmPlan pl, const __grid_constant__ RowFwdArgs a, const cf* __restrict__ twC,
                                                  double* __restrict__ sumsq) {
   DeviceExec ex;
   double acc = 0.0;
@@ -51,16 +53,12 @@ __global__ void __launch_bounds__(512) k_row_fwd(SmPlan pl, RowFwdArgs a, const 
   }
 }
 
-__global__ void __launch_bounds__(512) k_row_inv(SmPlan pl, RowInvArgs a, const cf* __restrict__ twC) {
+__global__ void __launch_bounds__(512) k_row_inv(const __grid_constant__ SmPlan pl, const __grid_constant__ RowInvArgs a, const cf* __restrict__ twC) {
   DeviceExec ex;
-  unsigned int cnt[4] = {0u, 0u, 0u, 0u};
-  row_inv_body(ex, pl, (int)blockIdx.x, a, twC, reinterpret_cast<cf*>(g_dyn_smem), cnt);
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-    if (cnt[i]) atomicAdd(a.flags + i, cnt[i]);
+  row_inv_body(ex, pl, (int)blockIdx.x, a, twC, reinterpret_cast<cf*>(g_dyn_smem));
 }
 
-__global__ void __launch_bounds__(512) k_col(SmPlan pl, ColArgs a, const cf* __restrict__ twR) {
+__global__ void __launch_bounds__(512) k_col(const __grid_constant__ SmPlan pl, const __grid_constant__ ColArgs a, const cf* __restrict__ twR) {
   DeviceExec ex;
   col_body(ex, pl, (int)blockIdx.x, (int)blockIdx.y, a, twR, reinterpret_cast<cf*>(g_dyn_smem));
 }

@@ -116,12 +116,14 @@ enum { PICK_NONE = 0, PICK_ADJUST = 1, PICK_FINISH = 3 };
 // block of 1024 threads: find the bin of a 2048-bin histogram (global or shared) that holds 0-based
 // `rank`; returns through shared outputs.  The histogram is zeroed on the way.
 struct PickOut { int bin; unsigned long long rank_in_bin; };
-__device__ __forceinline__ void block_pick(unsigned int* hist, unsigned long long rank, PickOut* s_out /*shared*/) {
+__device__ __forceinline__ void block_pick(unsigned int* hist, unsigned long long rank, PickOut* s_out /*shared*/,
+                                           int nbins = kHistBins, bool zero = true) {
   __shared__ unsigned long long wtot[32];
   const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
   if (t == 0) { s_out->bin = -1; s_out->rank_in_bin = 0ull; }
-  const unsigned int h0 = hist[2 * t], h1 = hist[2 * t + 1];
-  hist[2 * t] = 0u; hist[2 * t + 1] = 0u;
+  const bool live = (2 * t + 1) < nbins;
+  const unsigned int h0 = live ? hist[2 * t] : 0u, h1 = live ? hist[2 * t + 1] : 0u;
+  if (zero && live) { hist[2 * t] = 0u; hist[2 * t + 1] = 0u; }
   const unsigned long long v = (unsigned long long)h0 + h1;
   unsigned long long incl = v;
 #pragma unroll
@@ -182,49 +184,52 @@ __global__ void __launch_bounds__(1024) k_pick(unsigned int* __restrict__ hist, 
   }
 }
 
-// single CTA, 1024 threads: exact order statistics of the SAMPLE at ranks k_lo and k_hi give the key
-// window [lo, hi] that the full-data pass will count against / collect from.  k_lo < 0 -> lo = 0,
-// k_hi >= ns -> hi = all keys.
+// single CTA, 1024 threads: order statistics of the SAMPLE at ranks k_lo and k_hi, resolved to 21 key
+// bits (two sweeps over the sample, both ranks per sweep), give the key window [lo, hi] that the
+// full-data pass will count against / collect from.  k_lo < 0 -> lo = 0, k_hi >= ns -> hi = all keys.
 __global__ void __launch_bounds__(1024) k_sample_window(const unsigned int* __restrict__ keys, unsigned int ns,
                                                         SelState* st, long long k_lo, long long k_hi,
                                                         unsigned long long rank_full) {
   __shared__ unsigned int sh[kHistBins];
-  __shared__ PickOut out;
-  __shared__ unsigned int s_prefix;
-  unsigned int bounds[2] = {0u, 0x7fffffffu};
-  for (int which = 0; which < 2; ++which) {
-    const long long k = which == 0 ? k_lo : k_hi;
-    if (k < 0 || k >= (long long)ns) continue;       // uniform across the block
-    unsigned long long rank = (unsigned long long)k;
-    unsigned int prefix = 0u;
-    for (int pass = 0; pass < 3; ++pass) {
-      for (int i = threadIdx.x; i < kHistBins; i += blockDim.x) sh[i] = 0u;
-      __syncthreads();
-      for (unsigned int i = threadIdx.x; i < ns; i += blockDim.x) {
-        const unsigned int key = keys[i];
-        if (pass == 0) atomicAdd(&sh[key >> 20], 1u);
-        else if (pass == 1) { if ((key >> 20) == (prefix >> 20)) atomicAdd(&sh[(key >> 10) & 1023u], 1u); }
-        else { if ((key >> 10) == (prefix >> 10)) atomicAdd(&sh[key & 1023u], 1u); }
-      }
-      __syncthreads();
-      block_pick(sh, rank, &out);
-      const int shift = pass == 0 ? 20 : (pass == 1 ? 10 : 0);
-      if (threadIdx.x == 0) s_prefix = prefix | ((unsigned int)(out.bin < 0 ? 0 : out.bin) << shift);
-      __syncthreads();
-      prefix = s_prefix; rank = out.rank_in_bin;
-      __syncthreads();
-    }
-    bounds[which] = prefix;
+  __shared__ PickOut out_a, out_b;
+  const bool want_a = (k_lo >= 0 && k_lo < (long long)ns), want_b = (k_hi >= 0 && k_hi < (long long)ns);
+  for (int i = threadIdx.x; i < kHistBins; i += blockDim.x) sh[i] = 0u;
+  __syncthreads();
+  for (unsigned int i = threadIdx.x; i < ns; i += blockDim.x) atomicAdd(&sh[keys[i] >> 20], 1u);
+  __syncthreads();
+  block_pick(sh, want_a ? (unsigned long long)k_lo : 0ull, &out_a, kHistBins, false);
+  block_pick(sh, want_b ? (unsigned long long)k_hi : 0ull, &out_b, kHistBins, true);
+  const unsigned int bin_a = (unsigned int)(out_a.bin < 0 ? 0 : out_a.bin);
+  const unsigned int bin_b = (unsigned int)(out_b.bin < 0 ? 0 : out_b.bin);
+  const unsigned long long ra = out_a.rank_in_bin, rb = out_b.rank_in_bin;
+  __syncthreads();
+  // second digit: two 1024-bin histograms in the two halves of sh
+  for (unsigned int i = threadIdx.x; i < ns; i += blockDim.x) {
+    const unsigned int key = keys[i], top = key >> 20, sub = (key >> 10) & 1023u;
+    if (top == bin_a) atomicAdd(&sh[sub], 1u);
+    if (top == bin_b) atomicAdd(&sh[1024 + sub], 1u);
   }
+  __syncthreads();
+  block_pick(sh, ra, &out_a, 1024, false);
+  block_pick(sh + 1024, rb, &out_b, 1024, false);
   if (threadIdx.x == 0) {
-    st->lo = bounds[0]; st->hi = bounds[1];
+    const unsigned int sub_a = (unsigned int)(out_a.bin < 0 ? 0 : out_a.bin);
+    const unsigned int sub_b = (unsigned int)(out_b.bin < 0 ? 1023 : out_b.bin);
+    st->lo = want_a ? ((bin_a << 20) | (sub_a << 10)) : 0u;
+    st->hi = want_b ? ((bin_b << 20) | (sub_b << 10) | 1023u) : 0x7fffffffu;
     st->rank = rank_full; st->below = 0ull; st->ncand = 0u; st->prefix = 0u;
   }
 }
 
 // ------------------------------------------------------------------ select: count below the window, collect inside
 constexpr int kStage = 8192;       // smem staging entries per CTA
-__global__ void __launch_bounds__(SM_EW_THREADS) k_count_collect(SmPlan pl, const float* __restrict__ p0,
+// kSafe = false (sampled window, candidates are ~1 % of the keys): a CTA stages everything it finds
+//         and flushes once at the end -- no barrier inside the streaming loop; if the stage overflows
+//         the select is flagged (status bit 1) and the caller falls back to the safe mode.
+// kSafe = true  (window = all keys): barrier + flush test after every row.
+template <bool kSafe>
+__global__ void __launch_bounds__(SM_EW_THREADS) k_count_collect(const __grid_constant__ SmPlan pl,
+                                                                 const float* __restrict__ p0,
                                                                  const float* __restrict__ p1, SelState* st,
                                                                  unsigned int* __restrict__ cand) {
   __shared__ unsigned int s_buf[kStage];
@@ -237,47 +242,66 @@ __global__ void __launch_bounds__(SM_EW_THREADS) k_count_collect(SmPlan pl, cons
   const bool active = (c0 <= pl.Ch);
   unsigned long long below = 0ull;
   const int n_planes = p1 ? 2 : 1;
-  for (int row = blockIdx.y; row < pl.R; row += gridDim.y) {
-    if (active) {
-      for (int pi = 0; pi < n_planes; ++pi) {
-        const float* pp = pi == 0 ? p0 : p1;
-        const float4 v = *reinterpret_cast<const float4*>(pp + (size_t)row * pl.P + c0);
-        const float e[4] = {v.x, v.y, v.z, v.w};
+  auto scan4 = [&](const float4 v) {
+    const float e[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int c = c0 + i;
-          if (c <= pl.Ch) {
-            const unsigned int w = (c == 0 || c == pl.Ch) ? 1u : 2u;
-            const unsigned int k = absbits(e[i]);
-            if (k < lo) below += w;
-            else if (k <= hi) {
-              const unsigned int pos = atomicAdd(&s_cnt, w);
-              s_buf[pos] = k;                        // pos + w <= kStage by the flush rule below
-              if (w == 2u) s_buf[pos + 1] = k;
-            }
-          }
+    for (int i = 0; i < 4; ++i) {
+      const int c = c0 + i;
+      if (c <= pl.Ch) {
+        const unsigned int w = (c == 0 || c == pl.Ch) ? 1u : 2u;
+        const unsigned int k = absbits(e[i]);
+        if (k < lo) below += w;
+        else if (k <= hi) {
+          const unsigned int pos = atomicAdd(&s_cnt, w);
+          if (pos + w <= (unsigned int)kStage) { s_buf[pos] = k; if (w == 2u) s_buf[pos + 1] = k; }
         }
       }
     }
-    __syncthreads();
-    const unsigned int cnt_now = s_cnt;
-    __syncthreads();                                 // everyone has read it before anyone appends again
-    // a CTA adds at most 256*4*2*2 = 4096 entries per row: flush once fewer than that remain
-    if (cnt_now > (unsigned int)(kStage - 4096)) {
-      const unsigned int cnt = cnt_now;
-      if (threadIdx.x == 0) s_base = atomicAdd(&st->ncand, cnt);
+  };
+  if (!kSafe) {
+    if (active) {
+      int row = blockIdx.y;
+      for (; row + gridDim.y < pl.R; row += 2 * gridDim.y) {          // two rows in flight per plane
+        float4 v[4];
+        for (int pi = 0; pi < n_planes; ++pi) {
+          const float* pp = pi == 0 ? p0 : p1;
+          v[2 * pi] = *reinterpret_cast<const float4*>(pp + (size_t)row * pl.P + c0);
+          v[2 * pi + 1] = *reinterpret_cast<const float4*>(pp + (size_t)(row + gridDim.y) * pl.P + c0);
+        }
+        for (int q = 0; q < 2 * n_planes; ++q) scan4(v[q]);
+      }
+      for (; row < pl.R; row += gridDim.y)
+        for (int pi = 0; pi < n_planes; ++pi)
+          scan4(*reinterpret_cast<const float4*>((pi == 0 ? p0 : p1) + (size_t)row * pl.P + c0));
+    }
+  } else {
+    for (int row = blockIdx.y; row < pl.R; row += gridDim.y) {
+      if (active)
+        for (int pi = 0; pi < n_planes; ++pi)
+          scan4(*reinterpret_cast<const float4*>((pi == 0 ? p0 : p1) + (size_t)row * pl.P + c0));
       __syncthreads();
-      const unsigned int base = s_base;
-      for (unsigned int i = threadIdx.x; i < cnt; i += blockDim.x)
-        if (base + i < cap) cand[base + i] = s_buf[i];
-      __syncthreads();
-      if (threadIdx.x == 0) s_cnt = 0u;
-      __syncthreads();
+      const unsigned int cnt_now = s_cnt;
+      __syncthreads();                               // everyone has read it before anyone appends again
+      // a CTA adds at most 256*4*2*2 = 4096 entries per row: flush once fewer than that remain
+      if (cnt_now > (unsigned int)(kStage - 4096)) {
+        if (threadIdx.x == 0) s_base = atomicAdd(&st->ncand, cnt_now);
+        __syncthreads();
+        const unsigned int base = s_base;
+        for (unsigned int i = threadIdx.x; i < cnt_now; i += blockDim.x)
+          if (base + i < cap) cand[base + i] = s_buf[i];
+        __syncthreads();
+        if (threadIdx.x == 0) s_cnt = 0u;
+        __syncthreads();
+      }
     }
   }
   __syncthreads();
   {
-    const unsigned int cnt = s_cnt;
+    unsigned int cnt = s_cnt;
+    if (cnt > (unsigned int)kStage) {                // only possible in the fast variant
+      if (threadIdx.x == 0) atomicOr(&st->status, 2u);
+      cnt = kStage;
+    }
     if (cnt) {
       if (threadIdx.x == 0) s_base = atomicAdd(&st->ncand, cnt);
       __syncthreads();
@@ -478,7 +502,7 @@ static unsigned int fast_cap(const SmPlan& p, int n_planes) {
   if (cap > 0xfffffff0ull) cap = 0xfffffff0ull;
   return (unsigned int)cap;
 }
-static const unsigned int kSampleN = 1u << 17;
+static const unsigned int kSampleN = 1u << 16;
 static bool use_safe(const SmPlan& p, int n_planes, int mode) {
   unsigned long long total = (unsigned long long)p.R * p.C * n_planes;
   return mode != 0 || total <= (4ull << 20);
@@ -528,7 +552,8 @@ extern "C" int sm_select_kth_abs(const sm_plan* plan, const float* plane0, const
     k_sample_window<<<1, 1024, 0, s>>>(sample, kSampleN, st, (long long)floor(ks - delta), (long long)ceil(ks + delta), rank);
     SM_LAUNCH_CHECK();
   }
-  k_count_collect<<<eg, SM_EW_THREADS, 0, s>>>(p, plane0, plane1, st, cand);
+  if (safe) k_count_collect<true><<<eg, SM_EW_THREADS, 0, s>>>(p, plane0, plane1, st, cand);
+  else k_count_collect<false><<<eg, SM_EW_THREADS, 0, s>>>(p, plane0, plane1, st, cand);
   SM_LAUNCH_CHECK();
   for (int pass = 0; pass < 3; ++pass) {
     k_hist_flat<<<592, 256, 0, s>>>(cand, &st->ncand, 0u, st, pass, hist);

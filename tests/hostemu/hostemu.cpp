@@ -16,7 +16,9 @@ using namespace smfft;
 struct HostExec {
   int T;
   int nthreads() const { return T; }
-  template <class F> void phase(F&& f) { for (int t = 0; t < T; ++t) f(t); }
+  int tid_begin() const { return 0; }
+  int tid_end() const { return T; }
+  void sync() const {}
 };
 
 static void make_tw(int M, std::vector<cf>& tw) {
@@ -113,12 +115,11 @@ int emu_inverse(int R, int C, float* re, float* im, float cull_thr, int out_mode
   a.out_mode = out_mode; a.base = base; a.out_bf16 = out_bf16; a.out_f32 = out_f32;
   a.inv_n = (float)(1.0 / ((double)R * (double)C));
   a.scale_ptr = nullptr; a.scale_host = scale; a.flags = flags4; a.check_ifft = 1;
-  unsigned int cnt[4] = {0, 0, 0, 0};
+  for (int i = 0; i < 4; ++i) flags4[i] = 0;
   for (int row = 0; row < R; ++row) {
     HostExec ex{pl.row_threads};
-    row_inv_body(ex, pl, row, a, twC.data(), smem.data(), cnt);
+    row_inv_body(ex, pl, row, a, twC.data(), smem.data());
   }
-  for (int i = 0; i < 4; ++i) flags4[i] = cnt[i];
   return 0;
 }
 
