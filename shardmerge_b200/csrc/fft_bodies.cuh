@@ -33,6 +33,20 @@ SM_HD void sm_count(unsigned int* p) {
 #endif
 }
 
+// NaN -> 0 (counted in flags[which]), Inf kept (counted in flags[which+1]): the exceptional path of
+// the epilogue, kept out of line so the hot loop stays small.
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__
+#else
+inline
+#endif
+float sm_fix_nonfinite(float v, unsigned int* flags, int which) {
+  const uint32_t u = f32_bits(v) & 0x7fffffffu;
+  if (u > 0x7f800000u) { sm_count(flags + which); return 0.f; }
+  if (u == 0x7f800000u) sm_count(flags + which + 1);
+  return v;
+}
+
 // ------------------------------------------------------------------ smem accessors
 struct RowSmem {               // one contiguous sequence, optional 1-in-16 padding
   cf* buf; int padmask;        // padmask = ~0 (padded) or 0
@@ -158,23 +172,18 @@ struct RowTangleSrc {          // stage-1 source of the inverse: Z'[k] from X[k]
 struct RowEpilogueDst {        // last-stage sink of the inverse: element j is (x[2j], x[2j+1]) swapped
   int out_mode; const uint32_t* base32; uint32_t* out32; cf* outf; float inv_n, scale; int check;
   unsigned int* flags;         // global counters [4]; NaN / Inf are exceptional, so a direct atomic is fine
-  SM_HD float fin(float v, int which) const {
-    uint32_t u = f32_bits(v) & 0x7fffffffu;
-    if (u >= 0x7f800000u) {
-      if (u > 0x7f800000u) { sm_count(flags + which); return 0.f; }
-      sm_count(flags + which + 1);
-    }
-    return v;
-  }
+  SM_HD float fin(float v, int which) const { return sm_fix_nonfinite(v, flags, which); }
   SM_HD void store(int j, float a, float b) const {
     float x0 = b * inv_n, x1 = a * inv_n;
-    if (check) { x0 = fin(x0, 0); x1 = fin(x1, 0); }
+    if (check) { if (not_finite(x0)) x0 = fin(x0, 0); if (not_finite(x1)) x1 = fin(x1, 0); }
     x0 *= scale; x1 *= scale;
     if (out_mode == 0) {
-      uint32_t bb = base32[j];
-      x0 = fin(bf16_bits_to_f32(bb & 0xffffu) + x0, 2);
-      x1 = fin(bf16_bits_to_f32(bb >> 16) + x1, 2);
-      out32[j] = f32_to_bf16_rne(x0) | (f32_to_bf16_rne(x1) << 16);
+      const uint32_t bb = base32[j];
+      x0 = bf16_bits_to_f32(bb & 0xffffu) + x0;
+      x1 = bits_f32(bb & 0xffff0000u) + x1;
+      if (not_finite(x0)) x0 = fin(x0, 2);
+      if (not_finite(x1)) x1 = fin(x1, 2);
+      out32[j] = pack_bf16x2_rne(x0, x1);
     } else {
       cf v; v.x = x0; v.y = x1; outf[j] = v;
     }
@@ -305,6 +314,179 @@ static inline void sm_col_args(const SmPlan& pl, int which, int inverse, ColArgs
     a->big_tw = inverse ? 1 : 0;
   }
   a->swap = inverse;
+}
+
+}  // namespace smfft
+
+// =====================================================================================
+// compile-time specialised sweeps (the hot shapes): all strides / trip counts fold to
+// immediates, scalars arrive by value, inverse = plane pointers swapped at the call site.
+// =====================================================================================
+namespace smfft {
+
+struct ColCtArgs {
+  float* p0; float* p1;        // forward: (re, im); inverse: (im, re)  -- i.e. already swapped
+  int P, Ch;                   // plane pitch / last valid column
+  int inst_mul, elem_mul;      // stored row of element i of instance g: g*inst_mul + i*elem_mul
+  int tw_mul;                  // W_L^e = twR[e * tw_mul]
+  const float* thr_ptr;        // inverse only, nullable: |re| < *thr_ptr -> 0 on load
+  const float* scale_ptr;      // nullable: outputs *= *scale_ptr, else *= scale
+  float scale;
+  int write_p1_fwd;            // forward: 0 -> do not store the imaginary plane
+};
+
+template <bool kInverse>
+struct ColCtSrc {
+  const float* p0; const float* p1; size_t row0; size_t estride; bool valid; float thr;
+  SM_HD void load(int i, float& a, float& b) const {
+    a = 0.f; b = 0.f;
+    if (valid) {
+      const size_t off = row0 + (size_t)i * estride;
+      a = p0[off]; b = p1[off];
+      if (kInverse) { if (b < thr && -b < thr) b = 0.f; }   // p1 is the real plane in the inverse
+    }
+  }
+};
+template <bool kBigTw>
+struct ColCtDst {
+  float* p0; float* p1; size_t row0; size_t estride; bool valid; const cf* twR; int inst; float scale; bool write_p1;
+  SM_HD void store(int k, float a, float b) const {
+    if (kBigTw) { if (inst != 0) { const cf w = twR[(size_t)inst * k]; cmul(a, b, w.x, w.y); } }
+    if (!valid) return;
+    const size_t off = row0 + (size_t)k * estride;
+    p0[off] = a * scale;
+    if (write_p1) p1[off] = b * scale;
+  }
+};
+
+// one CTA (NW warps) = one instance x 32 columns, L = R1*R2 (R2 == 1: single register stage)
+template <int R1, int R2, int NW, bool kInverse, bool kBigTw, class Exec>
+SM_HD void col_ct_body(Exec& ex, int tile, int inst, const ColCtArgs a, const cf* twR, cf* smem) {
+  constexpr int L = R1 * R2;
+  const int col0 = tile * SM_COL_TILE;
+  SM_FOR_THREADS(ex, tid) {
+    const int lane = tid & 31, wid = tid >> 5;
+    const int c = col0 + lane;
+    const bool valid = (c <= a.Ch);
+    const size_t row0 = (size_t)inst * a.inst_mul * a.P + c;
+    const size_t estride = (size_t)a.elem_mul * a.P;
+    const float thr = (kInverse && a.thr_ptr) ? *a.thr_ptr : 0.f;
+    const float scale = a.scale_ptr ? *a.scale_ptr : a.scale;
+    ColCtSrc<kInverse> gsrc{a.p0, a.p1, row0, estride, valid, thr};
+    ColCtDst<kBigTw> gdst{a.p0, a.p1, row0, estride, valid, twR, inst, scale, kInverse ? true : (a.write_p1_fwd != 0)};
+    if constexpr (R2 == 1) {
+      for (int b = wid; b < 1; b += NW) stockham_bfly<R1, true>(b, L, 1, a.tw_mul, twR, gsrc, gdst);
+    } else {
+      ColSmem sout{smem, lane};
+#pragma unroll
+      for (int b = wid; b < R2; b += NW) stockham_bfly<R1, false>(b, L, 1, a.tw_mul, twR, gsrc, sout);
+    }
+  }
+  if constexpr (R2 > 1) {
+    ex.sync();
+    SM_FOR_THREADS(ex, tid) {
+      const int lane = tid & 31, wid = tid >> 5;
+      const int c = col0 + lane;
+      const bool valid = (c <= a.Ch);
+      const size_t row0 = (size_t)inst * a.inst_mul * a.P + c;
+      const size_t estride = (size_t)a.elem_mul * a.P;
+      const float scale = a.scale_ptr ? *a.scale_ptr : a.scale;
+      ColCtDst<kBigTw> gdst{a.p0, a.p1, row0, estride, valid, twR, inst, scale, kInverse ? true : (a.write_p1_fwd != 0)};
+      ColSmem sin{smem, lane};
+#pragma unroll
+      for (int b = wid; b < R1; b += NW) stockham_bfly<R2, true>(b, L, R1, a.tw_mul, twR, sin, gdst);
+    }
+  }
+}
+
+}  // namespace smfft
+
+namespace smfft {
+
+// ------------------------------------------------------------------ specialised row passes
+// CH = R1*R2*R3*R4 (unused trailing radices = 1), T threads, padded smem when it fits.
+template <int CH, int S, int R, bool kLast, int T, class Src, class Dst, class Exec>
+SM_HD void row_ct_stage(Exec& ex, const cf* twC, const Src& src, const Dst& dst) {
+  constexpr int nb = CH / R;
+  SM_FOR_THREADS(ex, tid) {
+#pragma unroll
+    for (int b = tid; b < nb; b += T) stockham_bfly<R, kLast>(b, CH, S, 2, twC, src, dst);
+  }
+  ex.sync();
+}
+
+template <int R1, int R2, int R3, int R4, int T, bool kPad, class Exec>
+SM_HD void row_fwd_ct_body(Exec& ex, int row, int C, int P, const RowFwdArgs a, const cf* twC, cf* smem, double* acc) {
+  constexpr int CH = R1 * R2 * R3 * R4;
+  constexpr int bufstride = kPad ? (CH + (CH >> 4) + 1) : CH;
+  constexpr int padmask = kPad ? ~0 : 0;
+  RowDeltaSrc gsrc;
+  gsrc.mode = a.mode;
+  gsrc.b32 = a.mode == 0 ? reinterpret_cast<const uint32_t*>(a.base + (size_t)row * C) : nullptr;
+  gsrc.f32 = a.mode == 0 ? reinterpret_cast<const uint32_t*>(a.ft + (size_t)row * C) : nullptr;
+  gsrc.x32 = a.mode != 0 ? reinterpret_cast<const cf*>(a.x32 + (size_t)row * C) : nullptr;
+  gsrc.m1 = a.m1; gsrc.m2 = a.m2; gsrc.acc = acc;
+  RowSmem b0{smem, padmask}, b1{smem + bufstride, padmask};
+  constexpr int nst = (R2 > 1) + (R3 > 1) + (R4 > 1) + 1;
+  row_ct_stage<CH, 1, R1, nst == 1, T>(ex, twC, gsrc, b0);
+  if constexpr (nst >= 2) row_ct_stage<CH, R1, R2, nst == 2, T>(ex, twC, b0, b1);
+  if constexpr (nst >= 3) row_ct_stage<CH, R1 * R2, R3, nst == 3, T>(ex, twC, b1, b0);
+  if constexpr (nst >= 4) row_ct_stage<CH, R1 * R2 * R3, R4, true, T>(ex, twC, b0, b1);
+  const RowSmem z = (nst == 1 || nst == 3) ? b0 : b1;
+  float* ore = a.re + (size_t)row * P;
+  float* oim = a.im + (size_t)row * P;
+  SM_FOR_THREADS(ex, tid) {
+#pragma unroll 4
+    for (int k = tid; k <= CH; k += T) {
+      const int k0 = (k == CH) ? 0 : k;
+      const int k1 = (k == 0 || k == CH) ? 0 : CH - k;
+      float ar, ai, br, bi;
+      z.load(k0, ar, ai);
+      z.load(k1, br, bi);
+      const float er = 0.5f * (ar + br), ei = 0.5f * (ai - bi);
+      const float pr = 0.5f * (ai + bi), qi = -0.5f * (ar - br);
+      const cf w = twC[k];
+      ore[k] = er + (pr * w.x - qi * w.y);
+      oim[k] = ei + (pr * w.y + qi * w.x);
+    }
+  }
+  ex.sync();
+}
+
+template <int R1, int R2, int R3, int R4, int T, bool kPad, class Exec>
+SM_HD void row_inv_ct_body(Exec& ex, int row, int C, int P, const RowInvArgs a, const cf* twC, cf* smem) {
+  constexpr int CH = R1 * R2 * R3 * R4;
+  constexpr int bufstride = kPad ? (CH + (CH >> 4) + 1) : CH;
+  constexpr int padmask = kPad ? ~0 : 0;
+  RowTangleSrc gsrc;
+  gsrc.re = a.re + (size_t)row * P; gsrc.im = a.im + (size_t)row * P;
+  gsrc.twC = twC; gsrc.Ch = CH;
+  gsrc.thr = (a.cull_thr != nullptr) ? *a.cull_thr : 0.f;
+  RowEpilogueDst gdst;
+  gdst.out_mode = a.out_mode;
+  gdst.base32 = a.out_mode == 0 ? reinterpret_cast<const uint32_t*>(a.base + (size_t)row * C) : nullptr;
+  gdst.out32 = a.out_mode == 0 ? reinterpret_cast<uint32_t*>(a.out_bf16 + (size_t)row * C) : nullptr;
+  gdst.outf = a.out_mode != 0 ? reinterpret_cast<cf*>(a.out_f32 + (size_t)row * C) : nullptr;
+  gdst.inv_n = a.inv_n; gdst.check = a.check_ifft;
+  gdst.scale = a.scale_ptr ? *a.scale_ptr : a.scale_host;
+  gdst.flags = a.flags;
+  RowSmem b0{smem, padmask}, b1{smem + bufstride, padmask};
+  constexpr int nst = (R2 > 1) + (R3 > 1) + (R4 > 1) + 1;
+  if constexpr (nst == 1) {
+    row_ct_stage<CH, 1, R1, true, T>(ex, twC, gsrc, gdst);
+  } else if constexpr (nst == 2) {
+    row_ct_stage<CH, 1, R1, false, T>(ex, twC, gsrc, b0);
+    row_ct_stage<CH, R1, R2, true, T>(ex, twC, b0, gdst);
+  } else if constexpr (nst == 3) {
+    row_ct_stage<CH, 1, R1, false, T>(ex, twC, gsrc, b0);
+    row_ct_stage<CH, R1, R2, false, T>(ex, twC, b0, b1);
+    row_ct_stage<CH, R1 * R2, R3, true, T>(ex, twC, b1, gdst);
+  } else {
+    row_ct_stage<CH, 1, R1, false, T>(ex, twC, gsrc, b0);
+    row_ct_stage<CH, R1, R2, false, T>(ex, twC, b0, b1);
+    row_ct_stage<CH, R1 * R2, R3, false, T>(ex, twC, b1, b0);
+    row_ct_stage<CH, R1 * R2 * R3, R4, true, T>(ex, twC, b0, gdst);
+  }
 }
 
 }  // namespace smfft

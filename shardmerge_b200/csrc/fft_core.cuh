@@ -15,8 +15,12 @@
 // Replaces torch.fft.fft / fftn / ifft / ifftn as called by the reference at
 // shard/tensor/functions.py:55-58 and :70-73 (library calls into MKL / cuFFT there).
 #pragma once
+#include <cmath>
 #include <cstdint>
 #include <type_traits>
+#if defined(__CUDACC__)
+#include <cuda_bf16.h>
+#endif
 
 #if defined(__CUDACC__)
 #define SM_HD __host__ __device__ __forceinline__
@@ -263,5 +267,17 @@ SM_HD uint32_t f32_to_bf16_rne(float f) {
   u += 0x7fffu + lsb;
   return u >> 16;
 }
+
+// pack two fp32 values into bf16x2 (low half = a), round to nearest even
+SM_HD uint32_t pack_bf16x2_rne(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);     // one cvt.rn.bf16x2.f32
+  return *reinterpret_cast<uint32_t*>(&h);
+#else
+  return f32_to_bf16_rne(a) | (f32_to_bf16_rne(b) << 16);
+#endif
+}
+// true for NaN and +-Inf (one compare)
+SM_HD bool not_finite(float v) { return !(fabsf(v) <= 3.4028234663852886e38f); }
 
 }  // namespace smfft

@@ -63,6 +63,37 @@ __global__ void __launch_bounds__(512) k_col(const __grid_constant__ SmPlan pl, 
   col_body(ex, pl, (int)blockIdx.x, (int)blockIdx.y, a, twR, reinterpret_cast<cf*>(g_dyn_smem));
 }
 
+// ---- compile-time specialised kernels for the hot shapes (Llama / TinyLlama factorizations)
+template <int R1, int R2, int NW, bool kInverse, bool kBigTw>
+__global__ void __launch_bounds__(NW * 32, (R1 >= 11 || R2 >= 11) ? 3 : 4) k_col_ct(const ColCtArgs a, const cf* __restrict__ twR) {
+  DeviceExec ex;
+  col_ct_body<R1, R2, NW, kInverse, kBigTw>(ex, (int)blockIdx.x, (int)blockIdx.y, a, twR, reinterpret_cast<cf*>(g_dyn_smem));
+}
+
+template <int R1, int R2, int R3, int R4, int T, bool kPad>
+__global__ void __launch_bounds__(T) k_row_fwd_ct(int C, int P, const RowFwdArgs a, const cf* __restrict__ twC,
+                                                  double* __restrict__ sumsq) {
+  DeviceExec ex;
+  double acc = 0.0;
+  row_fwd_ct_body<R1, R2, R3, R4, T, kPad>(ex, (int)blockIdx.x, C, P, a, twC, reinterpret_cast<cf*>(g_dyn_smem), &acc);
+  __shared__ double wsum[16];
+  acc = warp_sum(acc);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) wsum[wid] = acc;
+  __syncthreads();
+  if (wid == 0) {
+    double v = lane < (T + 31) / 32 ? wsum[lane] : 0.0;
+    v = warp_sum(v);
+    if (lane == 0) atomicAdd(sumsq, v);
+  }
+}
+
+template <int R1, int R2, int R3, int R4, int T, bool kPad>
+__global__ void __launch_bounds__(T) k_row_inv_ct(int C, int P, const RowInvArgs a, const cf* __restrict__ twC) {
+  DeviceExec ex;
+  row_inv_ct_body<R1, R2, R3, R4, T, kPad>(ex, (int)blockIdx.x, C, P, a, twC, reinterpret_cast<cf*>(g_dyn_smem));
+}
+
 // scale a 1-D spectrum (no column sweep exists to fold the normalisation into)
 __global__ void k_scale_row(float* re, float* im, int n, const float* scale_dev, float scale_host, int write_im) {
   const float s = scale_dev ? *scale_dev : scale_host;
@@ -159,8 +190,99 @@ static const cf* tabR(const SmPlan& p, const void* tables) {
   return reinterpret_cast<const cf*>(reinterpret_cast<const char*>(tables) + sm_tab_off_R(p));
 }
 
+// ------------------------------------------------------------------ specialised dispatch
+static int g_optin_smem = 0;
+template <class K>
+static cudaError_t opt_in(K kernel, bool* done) {
+  if (*done) return cudaSuccess;
+  if (g_optin_smem == 0) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&g_optin_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (e != cudaSuccess) return e;
+  }
+  cudaFuncAttributes fa;
+  cudaError_t e = cudaFuncGetAttributes(&fa, (const void*)kernel);
+  if (e == cudaSuccess)
+    e = cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             g_optin_smem - (int)fa.sharedSizeBytes);
+  if (e == cudaSuccess) *done = true;
+  return e;
+}
+
+template <int R1, int R2, int NW>
+static int launch_col_ct_pair(bool inverse, bool big_tw, dim3 grid, const ColCtArgs& a, const cf* twR, cudaStream_t st) {
+  static bool done[4] = {false, false, false, false};
+  const int smem = (R2 > 1) ? R1 * R2 * SM_COL_TILE * 8 : 0;
+  cudaError_t e;
+#define SM_COL_CASE(INV, BIG, IDX)                                                        \
+  e = opt_in(k_col_ct<R1, R2, NW, INV, BIG>, &done[IDX]);                                 \
+  if (e != cudaSuccess) { sm_set_error("opt_in: %s", cudaGetErrorString(e)); return -100; } \
+  k_col_ct<R1, R2, NW, INV, BIG><<<grid, NW * 32, smem, st>>>(a, twR);
+  if (!inverse && big_tw) { SM_COL_CASE(false, true, 0) }
+  else if (!inverse) { SM_COL_CASE(false, false, 1) }
+  else if (big_tw) { SM_COL_CASE(true, true, 2) }
+  else { SM_COL_CASE(true, false, 3) }
+#undef SM_COL_CASE
+  SM_LAUNCH_CHECK();
+  return 0;
+}
+
+// returns 1 if no specialised kernel exists for this factorization
+static int try_col_ct(int n_rad, const int* rad, bool inverse, bool big_tw, dim3 grid, const ColCtArgs& a,
+                      const cf* twR, cudaStream_t st) {
+  if (n_rad != 2) return 1;
+  const int r1 = rad[0], r2 = rad[1];
+  if (r1 == 8 && r2 == 8) return launch_col_ct_pair<8, 8, 8>(inverse, big_tw, grid, a, twR, st);
+  if (r1 == 16 && r2 == 8) return launch_col_ct_pair<16, 8, 8>(inverse, big_tw, grid, a, twR, st);
+  if (r1 == 16 && r2 == 16) return launch_col_ct_pair<16, 16, 8>(inverse, big_tw, grid, a, twR, st);
+  if (r1 == 7 && r2 == 16) return launch_col_ct_pair<7, 16, 8>(inverse, big_tw, grid, a, twR, st);
+  if (r1 == 11 && r2 == 8) return launch_col_ct_pair<11, 8, 8>(inverse, big_tw, grid, a, twR, st);
+  if (r1 == 8 && r2 == 4) return launch_col_ct_pair<8, 4, 4>(inverse, big_tw, grid, a, twR, st);
+  return 1;
+}
+
+template <int R1, int R2, int R3, int R4, int T, bool kPad>
+static int launch_row_ct(bool inverse, const SmPlan& p, const RowFwdArgs* fa, const RowInvArgs* ia, const cf* twC,
+                         double* sumsq, cudaStream_t st) {
+  static bool done[2] = {false, false};
+  cudaError_t e;
+  if (!inverse) {
+    e = opt_in(k_row_fwd_ct<R1, R2, R3, R4, T, kPad>, &done[0]);
+    if (e != cudaSuccess) { sm_set_error("opt_in: %s", cudaGetErrorString(e)); return -100; }
+    k_row_fwd_ct<R1, R2, R3, R4, T, kPad><<<p.R, T, p.row_smem_fwd, st>>>(p.C, p.P, *fa, twC, sumsq);
+  } else {
+    e = opt_in(k_row_inv_ct<R1, R2, R3, R4, T, kPad>, &done[1]);
+    if (e != cudaSuccess) { sm_set_error("opt_in: %s", cudaGetErrorString(e)); return -100; }
+    k_row_inv_ct<R1, R2, R3, R4, T, kPad><<<p.R, T, p.row_smem_inv, st>>>(p.C, p.P, *ia, twC);
+  }
+  SM_LAUNCH_CHECK();
+  return 0;
+}
+
+static int try_row_ct(bool inverse, const SmPlan& p, const RowFwdArgs* fa, const RowInvArgs* ia, const cf* twC,
+                      double* sumsq, cudaStream_t st) {
+  auto is = [&](int n, int a, int b, int c, int d) {
+    if (p.n_row != n) return false;
+    const int want[4] = {a, b, c, d};
+    for (int i = 0; i < n; ++i) if (p.row_rad[i] != want[i]) return false;
+    return true;
+  };
+  if (is(3, 16, 8, 8, 1) && p.row_threads == 64 && p.row_pad) return launch_row_ct<16, 8, 8, 1, 64, true>(inverse, p, fa, ia, twC, sumsq, st);
+  if (is(3, 16, 16, 8, 1) && p.row_threads == 128 && p.row_pad) return launch_row_ct<16, 16, 8, 1, 128, true>(inverse, p, fa, ia, twC, sumsq, st);
+  if (is(3, 16, 16, 16, 1) && p.row_threads == 256 && p.row_pad) return launch_row_ct<16, 16, 16, 1, 256, true>(inverse, p, fa, ia, twC, sumsq, st);
+  if (is(3, 11, 16, 16, 1) && p.row_threads == 192 && p.row_pad) return launch_row_ct<11, 16, 16, 1, 192, true>(inverse, p, fa, ia, twC, sumsq, st);
+  if (is(4, 7, 16, 8, 8) && p.row_threads == 448 && p.row_pad) return launch_row_ct<7, 16, 8, 8, 448, true>(inverse, p, fa, ia, twC, sumsq, st);
+  if (is(4, 7, 16, 16, 8) && p.row_threads == 512 && !p.row_pad) return launch_row_ct<7, 16, 16, 8, 512, false>(inverse, p, fa, ia, twC, sumsq, st);
+  return 1;
+}
+
 static int launch_row_fwd(const SmPlan& p, const void* tables, const RowFwdArgs& a, double* sumsq, cudaStream_t st) {
   if (ensure_attrs()) return -100;
+  {
+    const int rc = try_row_ct(false, p, &a, nullptr, tabC(p, tables), sumsq, st);
+    if (rc <= 0) return rc;
+  }
   k_row_fwd<<<p.R, p.row_threads, p.row_smem_fwd, st>>>(p, a, tabC(p, tables), sumsq);
   SM_LAUNCH_CHECK();
   return 0;
@@ -192,6 +314,15 @@ static int launch_col(const SmPlan& p, const void* tables, int sweep, int invers
   ca.scale_ptr = scale_dev; ca.scale_host = scale_host; ca.use_scale = use_scale;
   ca.write_im = write_im;
   const int ntiles = (p.Ch + 1 + SM_COL_TILE - 1) / SM_COL_TILE;
+  {
+    ColCtArgs c{};
+    c.p0 = inverse ? im : re; c.p1 = inverse ? re : im;
+    c.P = p.P; c.Ch = p.Ch; c.inst_mul = ca.inst_mul; c.elem_mul = ca.elem_mul; c.tw_mul = ca.tw_mul;
+    c.thr_ptr = cull_thr; c.scale_ptr = use_scale ? scale_dev : nullptr;
+    c.scale = use_scale ? scale_host : 1.0f; c.write_p1_fwd = write_im;
+    const int rc = try_col_ct(ca.n_rad, ca.rad, inverse != 0, ca.big_tw != 0, dim3(ntiles, n_inst), c, tabR(p, tables), st);
+    if (rc <= 0) return rc;
+  }
   const int threads = (sweep == 0) ? p.thrA : p.thrB;
   const int smem = (sweep == 0) ? p.smemA : p.smemB;
   k_col<<<dim3(ntiles, n_inst), threads, smem, st>>>(p, ca, tabR(p, tables));
@@ -239,6 +370,10 @@ static int launch_row_inv(const SmPlan& p, const void* tables, RowInvArgs& a, cu
   if (ensure_attrs()) return -100;
   a.inv_n = (float)(1.0 / ((double)p.R * (double)p.C));
   if (p.col_passes != 0) a.cull_thr = nullptr;
+  {
+    const int rc = try_row_ct(true, p, nullptr, &a, tabC(p, tables), nullptr, st);
+    if (rc <= 0) return rc;
+  }
   k_row_inv<<<p.R, p.row_threads, p.row_smem_inv, st>>>(p, a, tabC(p, tables));
   SM_LAUNCH_CHECK();
   return 0;

@@ -104,8 +104,10 @@ static inline int sm_make_plan(int R, int C, SmPlan* pl) {
       int ra[SM_MAX_STAGES], rb[SM_MAX_STAGES];
       int na = sm_factor(a, ra), nb = sm_factor(b, rb);
       if (na < 0 || nb < 0) continue;
-      // fewest stages first, then the most balanced split
-      int cost = (na + nb) * 1024 + (a > b ? a - b : b - a);
+      // two register stages per sweep first (one smem exchange, and the shapes the specialised
+      // kernels cover), then the fewest stages, then the most balanced split
+      int off2 = (na > 2 ? na - 2 : 2 - na) + (nb > 2 ? nb - 2 : 2 - nb);
+      int cost = off2 * 65536 + (na + nb) * 1024 + (a > b ? a - b : b - a);
       if (cost < bestcost) { bestcost = cost; best = a; }
     }
     if (best < 0) return -5;
