@@ -250,7 +250,8 @@ def main():
         outputs.clear()
         for name, base, fts in tensors:
             srcs = [E.make_source(base, ft, weight=ALPHAS[k], name=f"synth/ft{k}") for k, ft in enumerate(fts)]
-            outputs[name] = fm.merge_sources(srcs, base, dev, layer_name=name)
+            outputs[name] = fm.merge_sources(srcs, base, dev, layer_name=name, defer=True)
+        fm.resolve_all()
 
     def barrier():
         if world > 1:

@@ -150,6 +150,73 @@ int sm_expand_full(const sm_plan* plan, const float* re, const float* im, float*
  * ((Z[k] + conj(Z[-k]))/2), i.e. exactly the part `.real` of ifftn keeps (functions.py:73). */
 int sm_pack_half(const sm_plan* plan, const float* in_c64, float* re, float* im, void* stream);
 
+
+/* ---- fused pair merge (no host synchronisation) ---------------------------------------------
+ * The regular-layer body of FourierMerge._merge_layer (shard/merge/fast_fourier.py:147-276) for two
+ * bf16 finetunes, issued as ONE stream-ordered chain from a single call: row passes -> device-side
+ * decisions (which model is `a`, :212-215; branch, :223-244; target_norm, :165) -> column sweeps ->
+ * cutoff statistic -> SLERP sums -> blend -> cull statistic -> inverse sweeps -> epilogue.
+ * The chain always runs the SLERP branch; afterwards the scalar block tells the caller whether that
+ * was right: ints[SM_I_BRANCH] != SM_BRANCH_SLERP, a non-zero `sticky` in either select state, or
+ * flags[1] / flags[3] (Inf) mean "redo this tensor on the step-by-step path / raise".
+ *
+ * Scalar block layout (SM_CTL_BYTES device bytes, zeroed by the call): */
+#define SM_CTL_BYTES   512
+#define SM_CTL_SUMSQ   0      /* double[2]  sum(delta^2) of model x, y                         */
+#define SM_CTL_SUMS    16     /* double[3]  masked SLERP sums s00, s11, s01                    */
+#define SM_CTL_FLT     64     /* float[16]  indexed by SM_F_*                                  */
+#define SM_CTL_FLAGS   128    /* u32[4]     nan/inf after ifft, nan/inf final                  */
+#define SM_CTL_INT     144    /* i32[4]     indexed by SM_I_*                                  */
+#define SM_CTL_TN      160    /* double     target_norm                                        */
+#define SM_CTL_SEL     192    /* 2 x SM_SELECT_STATE_BYTES: cutoff select, cull select         */
+#define SM_F_THR_CUT 0
+#define SM_F_THR_CULL 1
+#define SM_F_DOT 2            /* dot, cos, sin, relnorm follow (scal4 of sm_slerp_scalars)     */
+#define SM_F_SCALE_X 6
+#define SM_F_SCALE_Y 7
+#define SM_F_OUT_SCALE 8
+#define SM_F_NORM_X 9
+#define SM_F_NORM_Y 10
+#define SM_I_SWAP 0
+#define SM_I_BRANCH 1
+#define SM_BRANCH_SLERP 0
+#define SM_BRANCH_ADD 1
+#define SM_BRANCH_ARITH 2
+#define SM_BRANCH_EARLY 3
+#define SM_BRANCH_LINEAR 4
+
+typedef struct sm_pair_args {
+  const void* base0; const void* ft0;      /* bf16 [R][C]: model x and the base it is a delta of */
+  const void* base1; const void* ft1;      /* model y                                            */
+  const void* base_out; void* out_bf16;    /* output base (added back) and the merged result      */
+  float* re[3]; float* im[2];              /* planes: (re[0], im[0]) for x, (re[1], im[1]) for y, re[2] blend output */
+  void* ctl;                               /* scalar block, SM_CTL_BYTES                          */
+  void* sel_ws; size_t sel_ws_bytes;       /* select workspace (sm_select_ws_bytes, 2 planes)     */
+  double t;                                /* a_weight / (a_weight + b_weight), config order      */
+  float t_sum;
+  double cutoff_pct, cull_pct;
+  double target_norm_offset;
+  int select_mode;                         /* 0 fast (sampled window), 1 safe                     */
+} sm_pair_args;
+
+int sm_pair_merge_slerp_async(const sm_plan* plan, const void* tables, const sm_pair_args* args, void* stream);
+
+/* Per-kernel-class CUDA-event timing of the fused chain (bench.py roofline).  Classes: */
+#define SM_CLS_ROW_FWD 0
+#define SM_CLS_COL_FWD 1
+#define SM_CLS_SELECT2 2
+#define SM_CLS_REDUCE 3
+#define SM_CLS_SCALARS 4
+#define SM_CLS_BLEND 5
+#define SM_CLS_SELECT1 6
+#define SM_CLS_COL_INV 7
+#define SM_CLS_ROW_INV 8
+#define SM_CLS_COUNT 9
+int sm_profile_enable(int on);
+/* Synchronises the recorded events; per class: milliseconds, algorithmic bytes, kernel launches
+ * accumulated since the last collect (host arrays of n_classes entries). */
+int sm_profile_collect(double* ms, double* bytes, int* launches, int n_classes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -41,7 +41,22 @@ SIGNATURES = {
     "sm_copy_bytes": (_i, [_vp, _vp, _sz, _vp]),
     "sm_expand_full": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "sm_pack_half": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "sm_pair_merge_slerp_async": (_i, [_vp, _vp, _vp, _vp]),
+    "sm_profile_enable": (_i, [_i]),
+    "sm_profile_collect": (_i, [_vp, _vp, _vp, _i]),
 }
+
+
+class PairArgs(C.Structure):
+    """sm_pair_args of include/shardmerge_b200.h"""
+    _fields_ = [("base0", _vp), ("ft0", _vp), ("base1", _vp), ("ft1", _vp), ("base_out", _vp), ("out_bf16", _vp),
+                ("re", _vp * 3), ("im", _vp * 2), ("ctl", _vp), ("sel_ws", _vp), ("sel_ws_bytes", _sz),
+                ("t", _d), ("t_sum", _f), ("cutoff_pct", _d), ("cull_pct", _d), ("target_norm_offset", _d),
+                ("select_mode", _i)]
+
+
+CLS_NAMES = ["row_fwd", "col_fwd", "select2", "reduce", "scalars", "blend", "select1", "col_inv", "row_inv"]
+BRANCH_NAMES = {0: "slerp", 1: "add", 2: "arith", 3: "slerp-early", 4: "slerp-linear"}
 SELECT_STATE_BYTES = 64
 
 

@@ -69,18 +69,20 @@ struct RowFwdArgs {
 };
 
 struct RowDeltaSrc {           // stage-1 source: element idx is the packed pair (x[2idx], x[2idx+1])
-  int mode; const uint32_t* b32; const uint32_t* f32; const cf* x32; float m1, m2; double* acc;
+  int mode; const uint32_t* b32; const uint32_t* f32; const cf* x32; float m1, m2; float* acc;
+  // *acc is a per-thread fp32 partial over the <= 64 values one thread loads for one row; the
+  // caller widens it to fp64 per row, so the rounding of the partials averages out over rows.
   SM_HD void load(int i, float& re, float& im) const {
     float d0, d1;
     if (mode == 0) {
-      uint32_t bb = b32[i], ff = f32[i];
+      const uint32_t bb = ldg_u32(b32 + i), ff = ldg_u32(f32 + i);
       d0 = bf16_bits_to_f32(ff & 0xffffu) - bf16_bits_to_f32(bb & 0xffffu);
-      d1 = bf16_bits_to_f32(ff >> 16) - bf16_bits_to_f32(bb >> 16);
+      d1 = bits_f32(ff & 0xffff0000u) - bits_f32(bb & 0xffff0000u);
     } else {
-      cf v = x32[i];
+      const cf v = ldg_cf(x32 + i);
       d0 = v.x; d1 = v.y;
     }
-    *acc += double(d0) * double(d0) + double(d1) * double(d1);
+    *acc = fmaf(d0, d0, fmaf(d1, d1, *acc));
     if (mode != 0) { d0 = (d0 * m1) * m2; d1 = (d1 * m1) * m2; }
     re = d0; im = d1;
   }
@@ -88,7 +90,7 @@ struct RowDeltaSrc {           // stage-1 source: element idx is the packed pair
 
 template <class Exec>
 SM_HD void row_fwd_body(Exec& ex, const SmPlan& pl, int row, const RowFwdArgs& a, const cf* twC,
-                        cf* smem, double* acc) {
+                        cf* smem, float* acc) {
   const int Ch = pl.Ch, T = ex.nthreads();
   const int bufstride = pl.row_pad ? (Ch + (Ch >> 4) + 1) : Ch;
   const int padmask = pl.row_pad ? ~0 : 0;
@@ -131,7 +133,7 @@ SM_HD void row_fwd_body(Exec& ex, const SmPlan& pl, int row, const RowFwdArgs& a
       z.load(k1, br, bi);
       const float er = 0.5f * (ar + br), ei = 0.5f * (ai - bi);
       const float pr = 0.5f * (ai + bi), qi = -0.5f * (ar - br);
-      const cf w = twC[k];
+      const cf w = ldg_cf(twC + k);
       ore[k] = er + (pr * w.x - qi * w.y);
       oim[k] = ei + (pr * w.y + qi * w.x);
     }
@@ -142,6 +144,7 @@ SM_HD void row_fwd_body(Exec& ex, const SmPlan& pl, int row, const RowFwdArgs& a
 // ------------------------------------------------------------------ row inverse
 struct RowInvArgs {
   const float* re; const float* im;      // spectrum planes [R][P] (after the inverse column sweeps)
+  const float* im_alt; const int* sel;   // nullable: if *sel != 0 the imaginary plane is im_alt (device-side role pick)
   const float* cull_thr;                 // nullable; only used when R == 1 (no column sweep)
   int out_mode;                          // 0: bf16 = bf16(base + x*scale) ; 1: fp32 = x*scale
   const uint16_t* base; uint16_t* out_bf16; float* out_f32;
@@ -155,12 +158,12 @@ struct RowTangleSrc {          // stage-1 source of the inverse: Z'[k] from X[k]
   const float* re; const float* im; const cf* twC; int Ch; float thr;
   SM_HD float cull(float v) const { return (v < thr && -v < thr) ? 0.f : v; }   // |v| < thr, NaN kept
   SM_HD void load(int k, float& ore, float& oim) const {
-    float xr = cull(re[k]), xi = im[k];
-    float mr = cull(re[Ch - k]), mi = im[Ch - k];
+    float xr = cull(ldg_f32(re + k)), xi = ldg_f32(im + k);
+    float mr = cull(ldg_f32(re + Ch - k)), mi = ldg_f32(im + Ch - k);
     if (k == 0) { xi = 0.f; mi = 0.f; }    // .real semantics: bins 0 and Ch are real
     const float Ar = xr + mr, Ai = xi - mi;
     const float Br = xr - mr, Bi = xi + mi;
-    const cf w = twC[k];                  // (cos, -sin); conj(w) = (cos, +sin)
+    const cf w = ldg_cf(twC + k);         // (cos, -sin); conj(w) = (cos, +sin)
     const float br = Br * w.x + Bi * w.y; // B * conj(w), conj(w) = (w.x, -w.y)
     const float bi = Bi * w.x - Br * w.y;
     // Z' = A + i*B' ; hand it to the forward engine swapped
@@ -178,7 +181,7 @@ struct RowEpilogueDst {        // last-stage sink of the inverse: element j is (
     if (check) { if (not_finite(x0)) x0 = fin(x0, 0); if (not_finite(x1)) x1 = fin(x1, 0); }
     x0 *= scale; x1 *= scale;
     if (out_mode == 0) {
-      const uint32_t bb = base32[j];
+      const uint32_t bb = ldg_u32(base32 + j);
       x0 = bf16_bits_to_f32(bb & 0xffffu) + x0;
       x1 = bits_f32(bb & 0xffff0000u) + x1;
       if (not_finite(x0)) x0 = fin(x0, 2);
@@ -197,7 +200,8 @@ SM_HD void row_inv_body(Exec& ex, const SmPlan& pl, int row, const RowInvArgs& a
   const int bufstride = pl.row_pad ? (Ch + (Ch >> 4) + 1) : Ch;
   const int padmask = pl.row_pad ? ~0 : 0;
   RowTangleSrc gsrc;
-  gsrc.re = a.re + (size_t)row * pl.P; gsrc.im = a.im + (size_t)row * pl.P;
+  gsrc.re = a.re + (size_t)row * pl.P;
+  gsrc.im = ((a.sel != nullptr && *a.sel != 0) ? a.im_alt : a.im) + (size_t)row * pl.P;
   gsrc.twC = twC; gsrc.Ch = Ch;
   gsrc.thr = (a.cull_thr != nullptr) ? *a.cull_thr : 0.f;
   RowEpilogueDst gdst;
@@ -230,6 +234,7 @@ SM_HD void row_inv_body(Exec& ex, const SmPlan& pl, int row, const RowInvArgs& a
 // ------------------------------------------------------------------ column sweep
 struct ColArgs {
   float* re; float* im;        // planes [R][P], transformed in place
+  float* im_alt; const int* sel;   // nullable: if *sel != 0 the imaginary plane is im_alt
   int L; int n_rad; int rad[SM_MAX_STAGES];
   int inst_mul, elem_mul;      // stored row of element i of instance g: g*inst_mul + i*elem_mul
   int tw_mul;                  // W_L^e = twR[e * tw_mul], tw_mul = R / L
@@ -282,8 +287,9 @@ SM_HD void col_body(Exec& ex, const SmPlan& pl, int tile, int inst, const ColArg
       const bool valid = (c <= pl.Ch);
       const size_t row0 = (size_t)inst * a.inst_mul * pl.P + c;
       const size_t estride = (size_t)a.elem_mul * pl.P;
-      ColGlobalSrc gsrc{a.re, a.im, row0, estride, valid, a.swap, a.cull_thr ? *a.cull_thr : 0.f};
-      ColGlobalDst gdst{a.re, a.im, row0, estride, valid, a.swap, twR, a.big_tw ? inst : 0,
+      float* const imp = (a.sel != nullptr && *a.sel != 0) ? a.im_alt : a.im;
+      ColGlobalSrc gsrc{a.re, imp, row0, estride, valid, a.swap, a.cull_thr ? *a.cull_thr : 0.f};
+      ColGlobalDst gdst{a.re, imp, row0, estride, valid, a.swap, twR, a.big_tw ? inst : 0,
                         a.use_scale ? (a.scale_ptr ? *a.scale_ptr : a.scale_host) : 1.0f, a.write_im};
       ColSmem sin{smem + (size_t)(cur ^ 1) * L * SM_COL_TILE, lane};
       ColSmem sout{smem + (size_t)cur * L * SM_COL_TILE, lane};
@@ -326,6 +332,7 @@ namespace smfft {
 
 struct ColCtArgs {
   float* p0; float* p1;        // forward: (re, im); inverse: (im, re)  -- i.e. already swapped
+  float* p0_alt; const int* sel;   // nullable: if *sel != 0 use p0_alt instead of p0 (inverse: role pick of Im)
   int P, Ch;                   // plane pitch / last valid column
   int inst_mul, elem_mul;      // stored row of element i of instance g: g*inst_mul + i*elem_mul
   int tw_mul;                  // W_L^e = twR[e * tw_mul]
@@ -372,8 +379,9 @@ SM_HD void col_ct_body(Exec& ex, int tile, int inst, const ColCtArgs a, const cf
     const size_t estride = (size_t)a.elem_mul * a.P;
     const float thr = (kInverse && a.thr_ptr) ? *a.thr_ptr : 0.f;
     const float scale = a.scale_ptr ? *a.scale_ptr : a.scale;
-    ColCtSrc<kInverse> gsrc{a.p0, a.p1, row0, estride, valid, thr};
-    ColCtDst<kBigTw> gdst{a.p0, a.p1, row0, estride, valid, twR, inst, scale, kInverse ? true : (a.write_p1_fwd != 0)};
+    float* const p0 = (a.sel != nullptr && *a.sel != 0) ? a.p0_alt : a.p0;
+    ColCtSrc<kInverse> gsrc{p0, a.p1, row0, estride, valid, thr};
+    ColCtDst<kBigTw> gdst{p0, a.p1, row0, estride, valid, twR, inst, scale, kInverse ? true : (a.write_p1_fwd != 0)};
     if constexpr (R2 == 1) {
       for (int b = wid; b < 1; b += NW) stockham_bfly<R1, true>(b, L, 1, a.tw_mul, twR, gsrc, gdst);
     } else {
@@ -391,7 +399,8 @@ SM_HD void col_ct_body(Exec& ex, int tile, int inst, const ColCtArgs a, const cf
       const size_t row0 = (size_t)inst * a.inst_mul * a.P + c;
       const size_t estride = (size_t)a.elem_mul * a.P;
       const float scale = a.scale_ptr ? *a.scale_ptr : a.scale;
-      ColCtDst<kBigTw> gdst{a.p0, a.p1, row0, estride, valid, twR, inst, scale, kInverse ? true : (a.write_p1_fwd != 0)};
+      float* const p0 = (a.sel != nullptr && *a.sel != 0) ? a.p0_alt : a.p0;
+      ColCtDst<kBigTw> gdst{p0, a.p1, row0, estride, valid, twR, inst, scale, kInverse ? true : (a.write_p1_fwd != 0)};
       ColSmem sin{smem, lane};
 #pragma unroll
       for (int b = wid; b < R1; b += NW) stockham_bfly<R2, true>(b, L, R1, a.tw_mul, twR, sin, gdst);
@@ -416,7 +425,7 @@ SM_HD void row_ct_stage(Exec& ex, const cf* twC, const Src& src, const Dst& dst)
 }
 
 template <int R1, int R2, int R3, int R4, int T, bool kPad, class Exec>
-SM_HD void row_fwd_ct_body(Exec& ex, int row, int C, int P, const RowFwdArgs a, const cf* twC, cf* smem, double* acc) {
+SM_HD void row_fwd_ct_body(Exec& ex, int row, int C, int P, const RowFwdArgs a, const cf* twC, cf* smem, float* acc) {
   constexpr int CH = R1 * R2 * R3 * R4;
   constexpr int bufstride = kPad ? (CH + (CH >> 4) + 1) : CH;
   constexpr int padmask = kPad ? ~0 : 0;
@@ -445,7 +454,7 @@ SM_HD void row_fwd_ct_body(Exec& ex, int row, int C, int P, const RowFwdArgs a, 
       z.load(k1, br, bi);
       const float er = 0.5f * (ar + br), ei = 0.5f * (ai - bi);
       const float pr = 0.5f * (ai + bi), qi = -0.5f * (ar - br);
-      const cf w = twC[k];
+      const cf w = ldg_cf(twC + k);
       ore[k] = er + (pr * w.x - qi * w.y);
       oim[k] = ei + (pr * w.y + qi * w.x);
     }
@@ -459,7 +468,8 @@ SM_HD void row_inv_ct_body(Exec& ex, int row, int C, int P, const RowInvArgs a, 
   constexpr int bufstride = kPad ? (CH + (CH >> 4) + 1) : CH;
   constexpr int padmask = kPad ? ~0 : 0;
   RowTangleSrc gsrc;
-  gsrc.re = a.re + (size_t)row * P; gsrc.im = a.im + (size_t)row * P;
+  gsrc.re = a.re + (size_t)row * P;
+  gsrc.im = ((a.sel != nullptr && *a.sel != 0) ? a.im_alt : a.im) + (size_t)row * P;
   gsrc.twC = twC; gsrc.Ch = CH;
   gsrc.thr = (a.cull_thr != nullptr) ? *a.cull_thr : 0.f;
   RowEpilogueDst gdst;

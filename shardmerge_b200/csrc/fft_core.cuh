@@ -34,6 +34,30 @@ namespace smfft {
 
 struct cf { float x, y; };   // plain complex<float>, layout-compatible with float2
 
+// read-only global loads: ld.global.nc on the device lets the compiler hoist them above stores
+SM_HD cf ldg_cf(const cf* p) {
+#if defined(__CUDA_ARCH__)
+  const float2 v = __ldg(reinterpret_cast<const float2*>(p));
+  cf r; r.x = v.x; r.y = v.y; return r;
+#else
+  return *p;
+#endif
+}
+SM_HD float ldg_f32(const float* p) {
+#if defined(__CUDA_ARCH__)
+  return __ldg(p);
+#else
+  return *p;
+#endif
+}
+SM_HD uint32_t ldg_u32(const uint32_t* p) {
+#if defined(__CUDA_ARCH__)
+  return __ldg(p);
+#else
+  return *p;
+#endif
+}
+
 // ---------------------------------------------------------------------------------
 // compile-time trigonometry (only used to bake small-radix constants into immediates)
 // ---------------------------------------------------------------------------------
@@ -225,7 +249,7 @@ SM_HD void stockham_bfly(int b, int N, int s, int tw_mul, const cf* tw, const Sr
     dst.store(obase, re[0], im[0]);
     static_for<1, r>([&](auto k_) {
       constexpr int k = decltype(k_)::value;
-      const cf w = tw[tstep * k];
+      const cf w = ldg_cf(tw + tstep * k);
       float xr = re[k], xi = im[k];
       cmul(xr, xi, w.x, w.y);
       dst.store(obase + k * s, xr, xi);

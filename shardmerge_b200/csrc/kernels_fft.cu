@@ -38,10 +38,10 @@ __device__ __forceinline__ double warp_sum(double v) {
 __global__ void __launch_bounds__(512) k_row_fwd(const __grid_constant__ SmPlan pl, const __grid_constant__ RowFwdArgs a, const cf* __restrict__ twC,
                                                  double* __restrict__ sumsq) {
   DeviceExec ex;
-  double acc = 0.0;
-  row_fwd_body(ex, pl, (int)blockIdx.x, a, twC, reinterpret_cast<cf*>(g_dyn_smem), &acc);
+  float accf = 0.f;
+  row_fwd_body(ex, pl, (int)blockIdx.x, a, twC, reinterpret_cast<cf*>(g_dyn_smem), &accf);
   __shared__ double wsum[16];
-  acc = warp_sum(acc);
+  double acc = warp_sum((double)accf);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   if (lane == 0) wsum[wid] = acc;
   __syncthreads();
@@ -74,10 +74,10 @@ template <int R1, int R2, int R3, int R4, int T, bool kPad>
 __global__ void __launch_bounds__(T) k_row_fwd_ct(int C, int P, const RowFwdArgs a, const cf* __restrict__ twC,
                                                   double* __restrict__ sumsq) {
   DeviceExec ex;
-  double acc = 0.0;
-  row_fwd_ct_body<R1, R2, R3, R4, T, kPad>(ex, (int)blockIdx.x, C, P, a, twC, reinterpret_cast<cf*>(g_dyn_smem), &acc);
+  float accf = 0.f;
+  row_fwd_ct_body<R1, R2, R3, R4, T, kPad>(ex, (int)blockIdx.x, C, P, a, twC, reinterpret_cast<cf*>(g_dyn_smem), &accf);
   __shared__ double wsum[16];
-  acc = warp_sum(acc);
+  double acc = warp_sum((double)accf);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   if (lane == 0) wsum[wid] = acc;
   __syncthreads();
@@ -305,18 +305,19 @@ extern "C" int sm_fwd_rows_f32(const sm_plan* plan, const void* tables, const fl
 
 static int launch_col(const SmPlan& p, const void* tables, int sweep, int inverse, float* re, float* im,
                       const float* cull_thr, const float* scale_dev, float scale_host, int use_scale,
-                      int write_im, cudaStream_t st) {
+                      int write_im, cudaStream_t st, float* im_alt = nullptr, const int* sel = nullptr) {
   if (ensure_attrs()) return -100;
   ColArgs ca{};
   int n_inst = 0;
   sm_col_args(p, sweep, inverse, &ca, &n_inst);
-  ca.re = re; ca.im = im; ca.cull_thr = cull_thr;
+  ca.re = re; ca.im = im; ca.cull_thr = cull_thr; ca.im_alt = im_alt; ca.sel = sel;
   ca.scale_ptr = scale_dev; ca.scale_host = scale_host; ca.use_scale = use_scale;
   ca.write_im = write_im;
   const int ntiles = (p.Ch + 1 + SM_COL_TILE - 1) / SM_COL_TILE;
   {
     ColCtArgs c{};
     c.p0 = inverse ? im : re; c.p1 = inverse ? re : im;
+    c.p0_alt = inverse ? im_alt : nullptr; c.sel = inverse ? sel : nullptr;
     c.P = p.P; c.Ch = p.Ch; c.inst_mul = ca.inst_mul; c.elem_mul = ca.elem_mul; c.tw_mul = ca.tw_mul;
     c.thr_ptr = cull_thr; c.scale_ptr = use_scale ? scale_dev : nullptr;
     c.scale = use_scale ? scale_host : 1.0f; c.write_p1_fwd = write_im;
@@ -354,16 +355,21 @@ extern "C" int sm_inv_norm(const double* sumsq, float* out, void* stream) {
   return 0;
 }
 
-extern "C" int sm_inv_cols(const sm_plan* plan, const void* tables, float* re, float* im, const float* cull_thr,
-                           void* stream) {
+int sm_inv_cols_sel(const sm_plan* plan, const void* tables, float* re, float* im, float* im_alt, const int* sel,
+                    const float* cull_thr, void* stream) {
   const SmPlan& p = plan->p;
   for (int i = 0; i < p.col_passes; ++i) {
     const int sweep = p.col_passes - 1 - i;   // undo sweep B first, then sweep A
     int rc = launch_col(p, tables, sweep, 1, re, im, i == 0 ? cull_thr : nullptr, nullptr, 1.f, 0, 1,
-                        (cudaStream_t)stream);
+                        (cudaStream_t)stream, im_alt, sel);
     if (rc) return rc;
   }
   return 0;
+}
+
+extern "C" int sm_inv_cols(const sm_plan* plan, const void* tables, float* re, float* im, const float* cull_thr,
+                           void* stream) {
+  return sm_inv_cols_sel(plan, tables, re, im, nullptr, nullptr, cull_thr, stream);
 }
 
 static int launch_row_inv(const SmPlan& p, const void* tables, RowInvArgs& a, cudaStream_t st) {
@@ -377,6 +383,18 @@ static int launch_row_inv(const SmPlan& p, const void* tables, RowInvArgs& a, cu
   k_row_inv<<<p.R, p.row_threads, p.row_smem_inv, st>>>(p, a, tabC(p, tables));
   SM_LAUNCH_CHECK();
   return 0;
+}
+
+int sm_inv_rows_bf16_sel(const sm_plan* plan, const void* tables, const float* re, const float* im,
+                         const float* im_alt, const int* sel, const float* cull_thr, const void* base_bf16,
+                         void* out_bf16, const float* scale_dev, float scale_host, int check_ifft, uint32_t* flags4,
+                         void* stream) {
+  RowInvArgs a{};
+  a.check_ifft = check_ifft; a.im_alt = im_alt; a.sel = sel;
+  a.re = re; a.im = im; a.cull_thr = cull_thr; a.out_mode = 0;
+  a.base = (const uint16_t*)base_bf16; a.out_bf16 = (uint16_t*)out_bf16;
+  a.scale_ptr = scale_dev; a.scale_host = scale_host; a.flags = flags4;
+  return launch_row_inv(plan->p, tables, a, (cudaStream_t)stream);
 }
 
 extern "C" int sm_inv_rows_bf16(const sm_plan* plan, const void* tables, const float* re, const float* im,

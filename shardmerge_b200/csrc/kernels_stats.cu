@@ -321,11 +321,14 @@ __global__ void __launch_bounds__(SM_EW_THREADS) k_count_collect(const __grid_co
 }
 
 // ------------------------------------------------------------------ SLERP masked sums
-__global__ void __launch_bounds__(SM_EW_THREADS) k_slerp_reduce(SmPlan pl, const float* __restrict__ re0,
-                                                                const float* __restrict__ re1,
+__global__ void __launch_bounds__(SM_EW_THREADS) k_slerp_reduce(SmPlan pl, const float* __restrict__ reX,
+                                                                const float* __restrict__ reY, const int* sel,
                                                                 const float* __restrict__ thr_cut,
                                                                 double* __restrict__ sums3) {
   __shared__ double s_part[3][SM_EW_THREADS / 32];
+  const bool sw = (sel != nullptr && *sel != 0);      // device-side role pick: v0 is the larger-norm model
+  const float* __restrict__ re0 = sw ? reY : reX;
+  const float* __restrict__ re1 = sw ? reX : reY;
   const float thr = *thr_cut;
   const int c0 = blockIdx.x * SM_EW_COLS + threadIdx.x * 4;
   double s00 = 0.0, s11 = 0.0, s01 = 0.0;
@@ -381,13 +384,15 @@ __global__ void k_slerp_scalars(const double* __restrict__ sums3, double t, floa
 
 // ------------------------------------------------------------------ blend
 __global__ void __launch_bounds__(SM_EW_THREADS) k_blend(SmPlan pl, int mode, int agreement,
-                                                         const float* __restrict__ re0,
-                                                         const float* __restrict__ re1,
+                                                         const float* reX, const float* reY, const int* sel,
                                                          const float* __restrict__ thr_cut,
                                                          const float* __restrict__ scal4, float t_sum,
-                                                         float* __restrict__ out) {
+                                                         float* out) {
   const int c0 = blockIdx.x * SM_EW_COLS + threadIdx.x * 4;
   if (c0 > pl.Ch) return;
+  const bool sw = (sel != nullptr && *sel != 0);
+  const float* re0 = sw ? reY : reX;
+  const float* re1 = sw ? reX : reY;
   float thr = 0.f, dot = 0.f, ct = 0.f, sn = 0.f, rn = 1.f;
   if (mode == 0) { thr = *thr_cut; dot = scal4[0]; ct = scal4[1]; sn = scal4[2]; rn = scal4[3]; }
   for (int row = blockIdx.y; row < pl.R; row += gridDim.y) {
@@ -564,12 +569,16 @@ extern "C" int sm_select_kth_abs(const sm_plan* plan, const float* plane0, const
   return 0;
 }
 
-extern "C" int sm_slerp_reduce(const sm_plan* plan, const float* re0, const float* re1, const float* thr_cut,
-                               double* sums3, void* stream) {
+int sm_slerp_reduce_sel(const sm_plan* plan, const float* reX, const float* reY, const int* sel,
+                        const float* thr_cut, double* sums3, void* stream) {
   const SmPlan& p = plan->p;
-  k_slerp_reduce<<<ew_grid(p, ew_max_y(p)), SM_EW_THREADS, 0, (cudaStream_t)stream>>>(p, re0, re1, thr_cut, sums3);
+  k_slerp_reduce<<<ew_grid(p, ew_max_y(p)), SM_EW_THREADS, 0, (cudaStream_t)stream>>>(p, reX, reY, sel, thr_cut, sums3);
   SM_LAUNCH_CHECK();
   return 0;
+}
+extern "C" int sm_slerp_reduce(const sm_plan* plan, const float* re0, const float* re1, const float* thr_cut,
+                               double* sums3, void* stream) {
+  return sm_slerp_reduce_sel(plan, re0, re1, nullptr, thr_cut, sums3, stream);
 }
 
 extern "C" int sm_slerp_scalars(const double* sums3, double t, float* scal4, void* stream) {
@@ -578,14 +587,18 @@ extern "C" int sm_slerp_scalars(const double* sums3, double t, float* scal4, voi
   return 0;
 }
 
-extern "C" int sm_blend(const sm_plan* plan, int mode, int agreement, const float* re0, const float* re1,
-                        const float* thr_cut, const float* scal4, float t_sum, float* out_re, void* stream) {
+int sm_blend_sel(const sm_plan* plan, int mode, int agreement, const float* reX, const float* reY, const int* sel,
+                 const float* thr_cut, const float* scal4, float t_sum, float* out_re, void* stream) {
   const SmPlan& p = plan->p;
   if (mode == 0 && (!thr_cut || !scal4)) { sm_set_error("blend: SLERP mode needs thr_cut and scal4"); return -2; }
-  k_blend<<<ew_grid(p, ew_max_y(p)), SM_EW_THREADS, 0, (cudaStream_t)stream>>>(p, mode, agreement, re0, re1, thr_cut,
-                                                                               scal4, t_sum, out_re);
+  k_blend<<<ew_grid(p, ew_max_y(p)), SM_EW_THREADS, 0, (cudaStream_t)stream>>>(p, mode, agreement, reX, reY, sel,
+                                                                               thr_cut, scal4, t_sum, out_re);
   SM_LAUNCH_CHECK();
   return 0;
+}
+extern "C" int sm_blend(const sm_plan* plan, int mode, int agreement, const float* re0, const float* re1,
+                        const float* thr_cut, const float* scal4, float t_sum, float* out_re, void* stream) {
+  return sm_blend_sel(plan, mode, agreement, re0, re1, nullptr, thr_cut, scal4, t_sum, out_re, stream);
 }
 
 extern "C" int sm_delta_axpby_bf16(size_t n, const void* base_out, const void* base0, const void* ft0, float ca,

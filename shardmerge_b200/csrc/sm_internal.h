@@ -36,3 +36,16 @@ static inline size_t sm_tab_off_R(const SmPlan& p) { return (size_t)p.C * 8; }
 // iteration space of the element-wise / statistics kernels over the valid half spectrum
 #define SM_EW_THREADS 256
 #define SM_EW_COLS (SM_EW_THREADS * 4)
+
+// internal (C++ linkage) variants with a device-side role pick: `sel` points at an int in device
+// memory; if it is non-zero the two models swap roles (v0 = larger-norm model, fast_fourier.py:212-215)
+int sm_slerp_reduce_sel(const sm_plan* plan, const float* reX, const float* reY, const int* sel,
+                        const float* thr_cut, double* sums3, void* stream);
+int sm_blend_sel(const sm_plan* plan, int mode, int agreement, const float* reX, const float* reY, const int* sel,
+                 const float* thr_cut, const float* scal4, float t_sum, float* out_re, void* stream);
+int sm_inv_cols_sel(const sm_plan* plan, const void* tables, float* re, float* im, float* im_alt, const int* sel,
+                    const float* cull_thr, void* stream);
+int sm_inv_rows_bf16_sel(const sm_plan* plan, const void* tables, const float* re, const float* im,
+                         const float* im_alt, const int* sel, const float* cull_thr, const void* base_bf16,
+                         void* out_bf16, const float* scale_dev, float scale_host, int check_ifft, uint32_t* flags4,
+                         void* stream);

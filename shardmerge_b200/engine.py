@@ -66,7 +66,9 @@ class Profiler:
     def __init__(self, timing: bool = False):
         self.timing = timing
         self.launches = 0
+        self.fused_calls = 0
         self.calls: dict = {}          # tag -> [n_calls, n_launches, bytes, [(start, end), ...]]
+        _lib.load().sm_profile_enable(1 if timing else 0)
 
     def record(self, tag, launches, nbytes, dev, fn):
         ent = self.calls.setdefault(tag, [0, 0, 0, []])
@@ -85,6 +87,18 @@ class Profiler:
         for tag, (n, l, by, evs) in self.calls.items():
             ms = sum(a.elapsed_time(b) for a, b in evs) if evs else None
             out[tag] = dict(calls=n, launches=l, bytes=by, ms=ms)
+        # classes timed inside the fused C chain (sm_profile_collect)
+        lib = _lib.load()
+        n = len(_lib.CLS_NAMES)
+        ms = (ctypes.c_double * n)(); by = (ctypes.c_double * n)(); la = (ctypes.c_int * n)()
+        lib.sm_profile_collect(ms, by, la, n)
+        for i, name in enumerate(_lib.CLS_NAMES):
+            if la[i] == 0:
+                continue
+            ent = out.setdefault(name, dict(calls=0, launches=0, bytes=0, ms=0.0))
+            ent["calls"] += self.fused_calls
+            ent["launches"] += int(la[i]); ent["bytes"] += float(by[i])
+            ent["ms"] = (ent["ms"] or 0.0) + float(ms[i])
         return out
 
 
@@ -139,6 +153,7 @@ class Workspace:
         self.n_spectra = n_spectra
         self.re = [torch.empty((plan.R, plan.P), dtype=torch.float32, device=dev) for _ in range(n_spectra)]
         self.im = [torch.empty((plan.R, plan.P), dtype=torch.float32, device=dev) for _ in range(n_spectra)]
+        self.re_out = torch.empty((plan.R, plan.P), dtype=torch.float32, device=dev)   # blend output of the fused chain
         self.ctl = torch.zeros(_CTL_BYTES, dtype=torch.uint8, device=dev)
         self.dbl = self.ctl[_OFF_DBL:_OFF_DBL + 64].view(torch.float64)
         self.flt = self.ctl[_OFF_FLT:_OFF_FLT + 64].view(torch.float32)
@@ -391,3 +406,75 @@ def spectral_pair(ws: Workspace, slot0: int, slot1: int, *, scale0: float, scale
         raise ValueError(mode)
     inv_cols(ws, re0, im0, cull)
     inv_rows(ws, re0, im0, cull, out_scale, base, out, check_ifft=check_ifft)
+
+
+# ------------------------------------------------------------------------------------------
+# fused, host-sync-free pair merge (csrc/pipeline.cu)
+# ------------------------------------------------------------------------------------------
+class _PinnedRing:
+    """Pinned landing slots for scalar blocks whose check is deferred."""
+
+    def __init__(self, slots: int = 1024):
+        self.buf = torch.empty((slots, _CTL_BYTES), dtype=torch.uint8).pin_memory()
+        self.slots, self.next = slots, 0
+
+    def take(self) -> torch.Tensor:
+        t = self.buf[self.next]
+        self.next = (self.next + 1) % self.slots
+        return t
+
+
+_ring: Optional[_PinnedRing] = None
+
+
+class PendingPair:
+    """Result of pair_merge_async: the output tensor is already enqueued; `resolve()` waits for the
+    scalar block, and reports what the device decided."""
+
+    def __init__(self, out, host_ctl, event, layer_name=""):
+        self.out, self.host_ctl, self.event, self.layer_name = out, host_ctl, event, layer_name
+        self.redo = None
+        self.info: dict = {}
+
+    def resolve(self) -> dict:
+        self.event.synchronize()
+        h = self.host_ctl
+        dbl = h[0:64].view(torch.float64); flt = h[64:128].view(torch.float32)
+        flags = h[128:144].view(torch.int32); ints = h[144:160].view(torch.int32)
+        sel32 = h[192:320].view(torch.int32)
+        self.info = dict(norms=[float(flt[9]), float(flt[10])], target_norm=float(h[160:168].view(torch.float64)[0]),
+                         swap=int(ints[0]), branch=_lib.BRANCH_NAMES.get(int(ints[1]), "?"),
+                         select_sticky=int(sel32[11]) | int(sel32[16 + 11]), flags=[int(v) for v in flags],
+                         thr_cut=float(flt[0]), thr_cull=float(flt[1]), dot=float(flt[2]))
+        return self.info
+
+
+def pair_merge_async(ws: Workspace, s0: Source, s1: Source, base_out: torch.Tensor, out: torch.Tensor, *, t: float,
+                     t_sum: float = 1.0, cutoff_pct: float = 0.08, cull_pct: float = 0.20,
+                     target_norm_offset: float = 1e-10, layer_name: str = "") -> PendingPair:
+    global _ring
+    pl, lib = ws.plan, ws.plan.lib
+    dev = pl.device
+    a = _lib.PairArgs()
+    a.base0, a.ft0, a.base1, a.ft1 = s0.base.data_ptr(), s0.ft.data_ptr(), s1.base.data_ptr(), s1.ft.data_ptr()
+    a.base_out, a.out_bf16 = base_out.data_ptr(), out.data_ptr()
+    a.re[0], a.re[1], a.re[2] = ws.re[0].data_ptr(), ws.re[1].data_ptr(), ws.re_out.data_ptr()
+    a.im[0], a.im[1] = ws.im[0].data_ptr(), ws.im[1].data_ptr()
+    a.ctl = ws.ctl.data_ptr()
+    a.sel_ws, a.sel_ws_bytes = ws.sel_ws.data_ptr(), ws.sel_ws.numel()
+    a.t, a.t_sum, a.cutoff_pct, a.cull_pct = float(t), float(t_sum), float(cutoff_pct), float(cull_pct)
+    a.target_norm_offset = float(target_norm_offset)
+    a.select_mode = 1 if ws.safe_select else 0
+    sweeps = lib.sm_plan_col_passes(pl.handle)
+    if PROFILER is not None:
+        PROFILER.launches += 2 + 1 + 2 * max(sweeps, 1) + 11 * ((cutoff_pct > 0) + (cull_pct > 0)) + 3 + sweeps + 1
+        PROFILER.fused_calls += 1
+    _lib.check(lib.sm_pair_merge_slerp_async(pl.handle, pl.tables.data_ptr(), ctypes.byref(a), _stream(dev)),
+               "sm_pair_merge_slerp_async")
+    if _ring is None:
+        _ring = _PinnedRing()
+    host = _ring.take()
+    host.copy_(ws.ctl, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(dev))
+    return PendingPair(out, host, ev, layer_name)

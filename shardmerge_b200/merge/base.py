@@ -76,19 +76,41 @@ class MergeTensorsBase(ABC):
         await self.initialize()
         layer_order = self.index_manager.get_layer_order(self.config.output_base_model)
         writer = self.get_writer(layer_order)
-        for group in writer.shard_layers():
-            await self._process_layers(writer, [sl for sl in group if not sl.written], device)
+        if self.pipeline_depth > 0:
+            self.defer_checks = True
+        try:
+            for group in writer.shard_layers():
+                await self._process_layers(writer, [sl for sl in group if not sl.written], device)
+        finally:
+            self.defer_checks = False
         writer.finalize()
         readme = self.get_readme() or "No README defined"
         with open(self.config.output_path / "README.md", "w") as fh:
             fh.write(readme)
         logger.info(f"Merge complete. Output saved to {self.config.output_path}")
 
+    # Strategies whose _merge_layer only ENQUEUES device work (FourierMerge's fused chain) set
+    # pipeline_depth > 0: the loop then keeps that many tensors in flight before it settles the
+    # oldest one (waits for its device-side status) and hands it to the writer, so the GPU never
+    # drains between tensors.  depth 0 = the reference's strictly sequential behaviour.
+    pipeline_depth = 0
+
+    def _settle(self, keep: int = 0):
+        """Make every result except the newest `keep` final (override where results are deferred)."""
+
     async def _process_layers(self, writer: ModelWriter, shard_layers: List[ShardLayer], device: str):
         current = None
+        in_flight = []
         try:
             for current in shard_layers:
-                writer.add_tensor(current.layer_name, await self._merge_layer(current, device))
+                in_flight.append((current, await self._merge_layer(current, device)))
+                while len(in_flight) > self.pipeline_depth:
+                    self._settle(keep=len(in_flight) - 1)
+                    done, tensor = in_flight.pop(0)
+                    writer.add_tensor(done.layer_name, tensor)
+            self._settle(keep=0)
+            for done, tensor in in_flight:
+                writer.add_tensor(done.layer_name, tensor)
         except Exception as exc:
             logger.error(f"Error processing {getattr(current, 'layer_name', '?')}: {exc}")
             raise

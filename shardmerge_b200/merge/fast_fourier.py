@@ -47,6 +47,8 @@ def clamp(value: float, min_value: float, max_value: float) -> float:
 
 
 class FourierMerge(MergeTensorsBase):
+    pipeline_depth = 1           # merge(): one tensor stays in flight while the previous one is settled / written
+
     def __init__(self, config: MergeConfig, task_add_models: Optional[List[str]] = None,
                  target_norm_offset: float = 1e-10, cull_start_pct: float = 0.20, index_manager=None, **kwargs):
         super().__init__(config, index_manager)
@@ -54,6 +56,8 @@ class FourierMerge(MergeTensorsBase):
         self.target_norm_offset = target_norm_offset
         self.cull_start_pct = cull_start_pct
         self.last_info: dict = {}
+        self.pending: list = []          # deferred checks of fused pair merges (resolve_all)
+        self.defer_checks = False        # True inside merge(): _merge_layer returns before the check
 
     def get_readme(self) -> str:
         models = "\n".join(f"- {m.model} (vs {m.base})" for m in self.config.finetune_merge)
@@ -92,12 +96,65 @@ class FourierMerge(MergeTensorsBase):
         base_out = base_cache.get(self.config.output_base_model)
         if base_out is None:
             base_out = await fetch(self.config.output_base_model)
-        return self.merge_sources(sources, base_out, dev, layer_name=name)
+        return self.merge_sources(sources, base_out, dev, layer_name=name, defer=self.defer_checks)
+
+    def _settle(self, keep: int = 0):
+        n = max(len(self.pending) - keep, 0)
+        head, self.pending = self.pending[:n], self.pending[n:]
+        for pend in head:
+            self._resolve(pend)
 
     # -------------------------------------------------------------------------------------
     def merge_sources(self, sources: List[E.Source], base_out: torch.Tensor, dev, layer_name: str = "",
-                      safe_select: bool = False) -> torch.Tensor:
-        """The regular-layer part of _merge_layer (fast_fourier.py:147-276) on device tensors."""
+                      safe_select: bool = False, defer: bool = False) -> torch.Tensor:
+        """The regular-layer part of _merge_layer (fast_fourier.py:147-276) on device tensors.
+
+        Two bf16 finetunes on a bf16 base take the fused chain (csrc/pipeline.cu): everything is
+        enqueued from one C call and no host synchronisation happens until the scalar block is
+        checked -- right away (defer=False) or later through resolve_all() (defer=True: the returned
+        tensor is valid once resolve_all() has returned)."""
+        fused_ok = (len(sources) == 2 and not safe_select and base_out.dtype == torch.bfloat16
+                    and sources[0].is_bf16 and sources[1].is_bf16 and base_out.ndim in (1, 2))
+        if not fused_ok:
+            return self._merge_sources_steps(sources, base_out, dev, layer_name, safe_select)
+        R, C = E.shape_rc(base_out)
+        ws = E.get_workspace(R, C, dev, n_spectra=2)
+        out = torch.empty(base_out.shape, dtype=torch.bfloat16, device=dev)
+        a_w, b_w = sources[0].weight, sources[1].weight
+        pend = E.pair_merge_async(ws, sources[0], sources[1], base_out.contiguous(), out, t=a_w / (a_w + b_w), t_sum=1.0,
+                                  cutoff_pct=0.08, cull_pct=self.cull_start_pct,
+                                  target_norm_offset=self.target_norm_offset, layer_name=layer_name)
+        pend.redo = lambda: self._merge_sources_steps(sources, base_out, dev, layer_name, False)
+        if defer:
+            self.pending.append(pend)
+            return out
+        self._resolve(pend)
+        return out
+
+    def _resolve(self, pend):
+        info = pend.resolve()
+        if info["branch"] != "slerp" or info["select_sticky"] != 0:
+            # the device found another branch (or a select window missed): the step-by-step path decides
+            if info["select_sticky"] != 0:
+                logger.warning(f"select window miss on {pend.layer_name}; re-running step by step")
+            pend.out.copy_(pend.redo().reshape(pend.out.shape))
+            return
+        self.last_info = dict(branches=["slerp"], layer=pend.layer_name, norms=info["norms"],
+                              target_norm=info["target_norm"], flags=info["flags"], swap=info["swap"])
+        if info["flags"][1] > 0:
+            raise ValueError("Inf in ifft output")                          # functions.py:215-217
+        if info["flags"][3] > 0:
+            raise ValueError(f"Inf in merged tensor for {pend.layer_name}")  # fast_fourier.py:273-274
+
+    def resolve_all(self):
+        """Check every deferred fused merge (one wait per tensor, all already in flight)."""
+        pending, self.pending = self.pending, []
+        for pend in pending:
+            self._resolve(pend)
+
+    def _merge_sources_steps(self, sources: List[E.Source], base_out: torch.Tensor, dev, layer_name: str = "",
+                             safe_select: bool = False) -> torch.Tensor:
+        """Step-by-step path: any number of models, any branch, host decisions between the stages."""
         if len(sources) == 0:
             raise IndexError("list index out of range")      # what the reference does with no applicable model
         R, C = E.shape_rc(base_out)
@@ -207,7 +264,7 @@ class FourierMerge(MergeTensorsBase):
             if safe_select:
                 raise RuntimeError(f"order-statistic select failed in safe mode for {layer_name}")
             logger.warning(f"select window miss on {layer_name}; re-running with the exhaustive select")
-            return self.merge_sources(sources, base_out, dev, layer_name=layer_name, safe_select=True)
+            return self._merge_sources_steps(sources, base_out, dev, layer_name=layer_name, safe_select=True)
         if int(flags[1]) > 0:
             raise ValueError("Inf in ifft output")             # functions.py:215-217
         if out_final is None:

@@ -62,7 +62,9 @@ int emu_forward(int R, int C, int mode, const uint16_t* base, const uint16_t* ft
   double acc = 0.0;
   for (int row = 0; row < R; ++row) {
     HostExec ex{pl.row_threads};
-    row_fwd_body(ex, pl, row, a, twC.data(), smem.data(), &acc);
+    float part = 0.f;                      // the device widens one fp32 partial per thread; here per row
+    row_fwd_body(ex, pl, row, a, twC.data(), smem.data(), &part);
+    acc += (double)part;
   }
   *sumsq = acc;
   for (int sweep = 0; sweep < pl.col_passes; ++sweep) {

@@ -81,7 +81,7 @@ def test_forward_fft_matches_numpy(E, shape):
     ref = np.fft.rfft2(xs) if R > 1 else np.fft.rfft(xs, axis=1)
     assert rel_l2(got, ref) < 1e-6
     dbl, _, _, _ = ws.read_ctl()
-    assert abs(float(dbl[E.D_SUMSQ0]) / float((xs ** 2).sum()) - 1) < 1e-12
+    assert abs(float(dbl[E.D_SUMSQ0]) / float((xs ** 2).sum()) - 1) < 5e-7     # fp32 per-thread partials, fp64 across
     # inverse: back to the input (x 1/N inside the epilogue)
     out = torch.empty((R, C), dtype=torch.float32, device=DEV)
     E.inv_cols(ws, ws.re[0], ws.im[0], cull=False)
@@ -101,7 +101,7 @@ def test_forward_bf16_delta(E):
     delta = (ft.float() - base.float()).double().cpu().numpy()
     assert rel_l2(planes_to_numpy(ws, 0), np.fft.rfft2(delta)) < 1e-6
     dbl, _, _, _ = ws.read_ctl()
-    assert abs(float(dbl[E.D_SUMSQ0]) / float((delta ** 2).sum()) - 1) < 1e-12
+    assert abs(float(dbl[E.D_SUMSQ0]) / float((delta ** 2).sum()) - 1) < 5e-7
 
 
 def _expanded_sorted(planes, R, C):
@@ -372,7 +372,7 @@ def test_full_size_properties(E, shape):
     energy = ((ws.re[0][:, : Ch + 1].double() ** 2 + ws.im[0][:, : Ch + 1].double() ** 2) * w).sum().item()
     ss = (delta.double() ** 2).sum().item()
     dbl, _, _, _ = ws.read_ctl()
-    assert abs(float(dbl[E.D_SUMSQ0]) / ss - 1) < 1e-10
+    assert abs(float(dbl[E.D_SUMSQ0]) / ss - 1) < 1e-7
     assert abs(energy / (ss * R * C) - 1) < 1e-5                      # Parseval
     # exact rank by counting
     N = R * C
@@ -390,3 +390,61 @@ def test_full_size_properties(E, shape):
     E.inv_rows(ws, ws.re[0], ws.im[0], False, 1.0, None, out, check_ifft=True)
     err = ((out.double() - delta.double()) ** 2).sum().sqrt().item() / ss ** 0.5
     assert err < 1e-6, err
+
+
+@pytest.mark.parametrize("shape", [(1, 4096), (256, 512), (1024, 4096), (2048, 5632)])
+def test_fused_chain_matches_step_path(E, shape):
+    """The host-sync-free fused chain (csrc/pipeline.cu: device-side role / branch / target_norm
+    decisions) gives the same tensor as the step-by-step path with host decisions, both ways round
+    (model 0 larger and model 1 larger)."""
+    R, C = shape
+    sh = (R, C) if R > 1 else (C,)
+    for sig in ((0.002, 0.0026), (0.0026, 0.002)):
+        g = torch.Generator(device=DEV).manual_seed(R + C)
+        base = (0.02 * torch.randn(sh, generator=g, device=DEV)).to(torch.bfloat16)
+        fts = [(base.float() + s * torch.randn(sh, generator=g, device=DEV)).to(torch.bfloat16) for s in sig]
+        fm = _merger()
+        mk = lambda: [E.make_source(base, ft, weight=a, name=f"m{k}") for k, (ft, a) in enumerate(zip(fts, (0.3, 0.5)))]
+        fused = fm.merge_sources(mk(), base, torch.device(DEV), layer_name="model.layers.0.x")
+        info_f = dict(fm.last_info)
+        steps = fm._merge_sources_steps(mk(), base, torch.device(DEV), layer_name="model.layers.0.x")
+        assert info_f["branches"] == ["slerp"] and fm.last_info["branches"] == ["slerp"]
+        assert info_f["swap"] == (1 if sig[1] > sig[0] else 0)
+        assert abs(info_f["target_norm"] / fm.last_info["target_norm"] - 1) < 1e-7
+        u = bf16_ulp_distance(bits(fused), bits(steps))
+        assert float((u == 0).mean()) >= 0.9999 and int(u.max()) <= 1, (float((u == 0).mean()), int(u.max()))
+
+
+def test_fused_chain_falls_back_on_other_branches(E):
+    """Device-side branch detection: a near-zero second delta (arithmetic branch) and identical
+    models (add branch) are re-run on the step path and match the reference fixtures."""
+    import numpy as np
+    from pathlib import Path
+    gd = Path(__file__).resolve().parent / "golden"
+    for name, branch in (("arith_128x256", "arith"), ("add_zero_64x128", "add"), ("onezero_64x128", "arith")):
+        d = np.load(gd / f"layer_{name}.npz")
+        got, info = _run_layer_case(E, d)
+        assert info["branches"] == [branch]
+        u = bf16_ulp_distance(got, d["out"])
+        assert float((u <= 1).mean()) >= 0.9999
+
+
+def test_deferred_checks_pipeline(E):
+    """defer=True: several tensors enqueued back to back, settled afterwards."""
+    fm = _merger()
+    outs, refs = [], []
+    for i, (R, C) in enumerate([(256, 512), (128, 256), (256, 512), (1, 2048)]):
+        sh = (R, C) if R > 1 else (C,)
+        g = torch.Generator(device=DEV).manual_seed(50 + i)
+        base = (0.02 * torch.randn(sh, generator=g, device=DEV)).to(torch.bfloat16)
+        fts = [(base.float() + s * torch.randn(sh, generator=g, device=DEV)).to(torch.bfloat16) for s in (0.002, 0.0026)]
+        mk = lambda: [E.make_source(base, ft, weight=a, name=f"m{k}") for k, (ft, a) in enumerate(zip(fts, (0.3, 0.5)))]
+        outs.append(fm.merge_sources(mk(), base, torch.device(DEV), layer_name=f"model.layers.{i}.x", defer=True))
+        refs.append((mk, base))
+    assert len(fm.pending) == 4
+    fm.resolve_all()
+    assert not fm.pending
+    for out, (mk, base) in zip(outs, refs):
+        steps = fm._merge_sources_steps(mk(), base, torch.device(DEV), layer_name="x")
+        u = bf16_ulp_distance(bits(out), bits(steps))
+        assert int(u.max()) <= 1 and float((u == 0).mean()) >= 0.9999

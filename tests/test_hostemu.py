@@ -58,7 +58,8 @@ def test_forward_and_roundtrip(emu, shape):
     ref = np.fft.rfft2(x.astype(np.float64)) if R > 1 else np.fft.rfft(x.astype(np.float64), axis=1)
     got = natural(emu, re[:, : Ch + 1] + 1j * im[:, : Ch + 1], R, C)
     assert rel_l2(got, ref) < 5e-7
-    assert abs(ss / float((x.astype(np.float64) ** 2).sum()) - 1) < 1e-12
+    # fp32 partial sums (per thread on the device, per row in the emulation), widened to fp64
+    assert abs(ss / float((x.astype(np.float64) ** 2).sum()) - 1) < 2e-6
     out = np.zeros((R, C), np.float32); fl = (ctypes.c_uint * 4)()
     rc = emu.emu_inverse(R, C, P(re, c_fp), P(im, c_fp), ctypes.c_float(0.0), 1, None, None, P(out, c_fp), ctypes.c_float(1.0), fl)
     assert rc == 0 and list(fl) == [0, 0, 0, 0]
