@@ -113,6 +113,12 @@ class FourierMerge(MergeTensorsBase):
         enqueued from one C call and no host synchronisation happens until the scalar block is
         checked -- right away (defer=False) or later through resolve_all() (defer=True: the returned
         tensor is valid once resolve_all() has returned)."""
+        for src in sources:
+            shp = tuple(src.x32.shape) if src.x32 is not None else tuple(src.base.shape)
+            if src.x32 is None and tuple(src.ft.shape) != shp:
+                raise ValueError(f"finetune / base shape mismatch for {layer_name}: {tuple(src.ft.shape)} vs {shp}")
+            if int(torch.tensor(shp).prod()) != base_out.numel():
+                raise ValueError(f"tensor shape mismatch for {layer_name}: {shp} vs output base {tuple(base_out.shape)}")
         fused_ok = (len(sources) == 2 and not safe_select and base_out.dtype == torch.bfloat16
                     and sources[0].is_bf16 and sources[1].is_bf16 and base_out.ndim in (1, 2))
         if not fused_ok:

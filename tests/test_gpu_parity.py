@@ -438,7 +438,8 @@ def test_deferred_checks_pipeline(E):
         g = torch.Generator(device=DEV).manual_seed(50 + i)
         base = (0.02 * torch.randn(sh, generator=g, device=DEV)).to(torch.bfloat16)
         fts = [(base.float() + s * torch.randn(sh, generator=g, device=DEV)).to(torch.bfloat16) for s in (0.002, 0.0026)]
-        mk = lambda: [E.make_source(base, ft, weight=a, name=f"m{k}") for k, (ft, a) in enumerate(zip(fts, (0.3, 0.5)))]
+        mk = lambda base=base, fts=fts: [E.make_source(base, ft, weight=a, name=f"m{k}")
+                                         for k, (ft, a) in enumerate(zip(fts, (0.3, 0.5)))]
         outs.append(fm.merge_sources(mk(), base, torch.device(DEV), layer_name=f"model.layers.{i}.x", defer=True))
         refs.append((mk, base))
     assert len(fm.pending) == 4
@@ -448,3 +449,12 @@ def test_deferred_checks_pipeline(E):
         steps = fm._merge_sources_steps(mk(), base, torch.device(DEV), layer_name="x")
         u = bf16_ulp_distance(bits(out), bits(steps))
         assert int(u.max()) <= 1 and float((u == 0).mean()) >= 0.9999
+
+
+def test_shape_mismatch_is_refused(E):
+    fm = _merger()
+    base = torch.zeros((64, 128), dtype=torch.bfloat16, device=DEV)
+    other = torch.zeros((2048,), dtype=torch.bfloat16, device=DEV)
+    srcs = [E.make_source(other, other, weight=0.3), E.make_source(other, other, weight=0.5)]
+    with pytest.raises(ValueError):
+        fm.merge_sources(srcs, base, torch.device(DEV), layer_name="model.layers.0.x")
