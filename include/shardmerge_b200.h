@@ -109,6 +109,28 @@ int sm_slerp_scalars(const double* sums3, double t, float* scal4, void* stream);
 int sm_blend(const sm_plan* plan, int mode, int agreement, const float* re0, const float* re1,
              const float* thr_cut, const float* scal4, float t_sum, float* out_re, void* stream);
 
+/* ---- fused statistics (what the pair-merge chain uses for tensors of more than 2^20 elements) ----------
+ * sm_fstats_cutoff = sm_select_kth_abs(re0, re1, rank) + sm_slerp_reduce + sm_slerp_scalars in ONE streaming
+ * pass over the two real planes (functions.py:113-129, :36-43): thr_cut_out, scal4_out (and sums3_out, if
+ * non-NULL) are written on the device.  `sel` (nullable, device int): non-zero swaps the roles, i.e.
+ * (re0, re1) = (reY, reX).
+ * sm_fstats_blend_cull = sm_blend(mode 0) + sm_select_kth_abs(out, rank) in one pass (functions.py:131-141).
+ * Both use a sampled key window; fs_state (SM_FS_STATE_BYTES device bytes, zero before the first use) holds a
+ * u32 at byte SM_FS_STATUS_OFF that is non-zero afterwards if the window missed / was too wide / a bucket
+ * overflowed -- the thresholds are NaN then and the caller redoes the tensor with the step-by-step kernels
+ * (sm_select_kth_abs mode 1).  ws: sm_fstats_ws_bytes() device bytes.  sm_fstats_supported() == 0: tensor
+ * too small (launch bound; use the step-by-step kernels) or too large (>= 2^31 elements). */
+#define SM_FS_STATE_BYTES 128
+#define SM_FS_STATUS_OFF 28
+int sm_fstats_supported(const sm_plan* plan);
+size_t sm_fstats_ws_bytes(const sm_plan* plan);
+int sm_fstats_cutoff(const sm_plan* plan, const float* reX, const float* reY, const int* sel, uint64_t rank,
+                     double t, void* fs_state, void* ws, size_t ws_bytes, float* thr_cut_out,
+                     float* scal4_out, double* sums3_out, void* stream);
+int sm_fstats_blend_cull(const sm_plan* plan, const float* reX, const float* reY, const int* sel,
+                         const float* thr_cut, const float* scal4, float t_sum, float* out_re, uint64_t rank,
+                         void* fs_state, void* ws, size_t ws_bytes, float* thr_cull_out, void* stream);
+
 /* ---- inverse: cull + inverse 2-D FFT + epilogue ---------------------------------------
  * Column half of ifft_transform (functions.py:70-73), in place; values of the real plane
  * with |re| < *cull_thr are read as 0 (functions.py:146; cull_thr may be NULL). */
@@ -157,18 +179,20 @@ int sm_pack_half(const sm_plan* plan, const float* in_c64, float* re, float* im,
  * decisions (which model is `a`, :212-215; branch, :223-244; target_norm, :165) -> column sweeps ->
  * cutoff statistic -> SLERP sums -> blend -> cull statistic -> inverse sweeps -> epilogue.
  * The chain always runs the SLERP branch; afterwards the scalar block tells the caller whether that
- * was right: ints[SM_I_BRANCH] != SM_BRANCH_SLERP, a non-zero `sticky` in either select state, or
- * flags[1] / flags[3] (Inf) mean "redo this tensor on the step-by-step path / raise".
+ * was right: ints[SM_I_BRANCH] != SM_BRANCH_SLERP, a non-zero status in either fused-statistics state
+ * (SM_CTL_FS + k * SM_FS_STATE_BYTES + SM_FS_STATUS_OFF) or a non-zero `sticky` in either select state
+ * (small tensors), or flags[1] / flags[3] (Inf) mean "redo this tensor on the step-by-step path / raise".
  *
  * Scalar block layout (SM_CTL_BYTES device bytes, zeroed by the call): */
-#define SM_CTL_BYTES   512
+#define SM_CTL_BYTES   1024
 #define SM_CTL_SUMSQ   0      /* double[2]  sum(delta^2) of model x, y                         */
 #define SM_CTL_SUMS    16     /* double[3]  masked SLERP sums s00, s11, s01                    */
 #define SM_CTL_FLT     64     /* float[16]  indexed by SM_F_*                                  */
 #define SM_CTL_FLAGS   128    /* u32[4]     nan/inf after ifft, nan/inf final                  */
 #define SM_CTL_INT     144    /* i32[4]     indexed by SM_I_*                                  */
 #define SM_CTL_TN      160    /* double     target_norm                                        */
-#define SM_CTL_SEL     192    /* 2 x SM_SELECT_STATE_BYTES: cutoff select, cull select         */
+#define SM_CTL_SEL     192    /* 2 x SM_SELECT_STATE_BYTES: cutoff select, cull select (step-by-step path) */
+#define SM_CTL_FS      512    /* 2 x SM_FS_STATE_BYTES: fused cutoff statistics, fused blend + cull   */
 #define SM_F_THR_CUT 0
 #define SM_F_THR_CULL 1
 #define SM_F_DOT 2            /* dot, cos, sin, relnorm follow (scal4 of sm_slerp_scalars)     */
@@ -191,7 +215,7 @@ typedef struct sm_pair_args {
   const void* base_out; void* out_bf16;    /* output base (added back) and the merged result      */
   float* re[3]; float* im[2];              /* planes: (re[0], im[0]) for x, (re[1], im[1]) for y, re[2] blend output */
   void* ctl;                               /* scalar block, SM_CTL_BYTES                          */
-  void* sel_ws; size_t sel_ws_bytes;       /* select workspace (sm_select_ws_bytes, 2 planes)     */
+  void* sel_ws; size_t sel_ws_bytes;       /* statistics workspace: max(sm_fstats_ws_bytes, sm_select_ws_bytes for 2 planes) */
   double t;                                /* a_weight / (a_weight + b_weight), config order      */
   float t_sum;
   double cutoff_pct, cull_pct;

@@ -34,6 +34,10 @@ SIGNATURES = {
     "sm_slerp_reduce": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "sm_slerp_scalars": (_i, [_vp, _d, _vp, _vp]),
     "sm_blend": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp, _f, _vp, _vp]),
+    "sm_fstats_supported": (_i, [_vp]),
+    "sm_fstats_ws_bytes": (_sz, [_vp]),
+    "sm_fstats_cutoff": (_i, [_vp, _vp, _vp, _vp, _u64, _d, _vp, _vp, _sz, _vp, _vp, _vp, _vp]),
+    "sm_fstats_blend_cull": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _u64, _vp, _vp, _sz, _vp, _vp]),
     "sm_inv_cols": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "sm_inv_rows_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _vp, _vp]),
     "sm_inv_rows_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _vp, _vp]),
@@ -55,9 +59,10 @@ class PairArgs(C.Structure):
                 ("select_mode", _i)]
 
 
-CLS_NAMES = ["row_fwd", "col_fwd", "select2", "reduce", "scalars", "blend", "select1", "col_inv", "row_inv"]
+CLS_NAMES = ["row_fwd", "col_fwd", "stats_cutoff", "reduce", "scalars", "blend_cull", "select1", "col_inv", "row_inv"]
 BRANCH_NAMES = {0: "slerp", 1: "add", 2: "arith", 3: "slerp-early", 4: "slerp-linear"}
 SELECT_STATE_BYTES = 64
+FS_STATE_BYTES, FS_STATUS_OFF, CTL_FS_OFF, CTL_BYTES = 128, 28, 512, 1024
 
 
 class ShardMergeLibraryError(RuntimeError):

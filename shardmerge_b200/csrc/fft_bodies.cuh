@@ -89,7 +89,7 @@ struct RowDeltaSrc {           // stage-1 source: element idx is the packed pair
 };
 
 template <class Exec>
-SM_HD void row_fwd_body(Exec& ex, const SmPlan& pl, int row, const RowFwdArgs& a, const cf* twC,
+SM_HD void row_fwd_body(Exec& ex, const SmPlan& pl, int row, const RowFwdArgs& a, const cf* twC, const cf* twQ,
                         cf* smem, float* acc) {
   const int Ch = pl.Ch, T = ex.nthreads();
   const int bufstride = pl.row_pad ? (Ch + (Ch >> 4) + 1) : Ch;
@@ -110,7 +110,7 @@ SM_HD void row_fwd_body(Exec& ex, const SmPlan& pl, int row, const RowFwdArgs& a
       for (int b = tid; b < nb; b += T) {
         if (st == 0) {
           if (last) stockham_bfly_rt<true>(r, b, Ch, s, 2, twC, gsrc, sout);
-          else      stockham_bfly_rt<false>(r, b, Ch, s, 2, twC, gsrc, sout);
+          else      stockham_bfly_first_rt(r, b, Ch, twQ, gsrc, sout);
         } else {
           if (last) stockham_bfly_rt<true>(r, b, Ch, s, 2, twC, sin, sout);
           else      stockham_bfly_rt<false>(r, b, Ch, s, 2, twC, sin, sout);
@@ -194,7 +194,7 @@ struct RowEpilogueDst {        // last-stage sink of the inverse: element j is (
 };
 
 template <class Exec>
-SM_HD void row_inv_body(Exec& ex, const SmPlan& pl, int row, const RowInvArgs& a, const cf* twC,
+SM_HD void row_inv_body(Exec& ex, const SmPlan& pl, int row, const RowInvArgs& a, const cf* twC, const cf* twQ,
                         cf* smem) {
   const int Ch = pl.Ch, T = ex.nthreads();
   const int bufstride = pl.row_pad ? (Ch + (Ch >> 4) + 1) : Ch;
@@ -221,7 +221,7 @@ SM_HD void row_inv_body(Exec& ex, const SmPlan& pl, int row, const RowInvArgs& a
     SM_FOR_THREADS(ex, tid) {
       for (int b = tid; b < nb; b += T) {
         if (first && last)  stockham_bfly_rt<true>(r, b, Ch, s, 2, twC, gsrc, gdst);
-        else if (first)     stockham_bfly_rt<false>(r, b, Ch, s, 2, twC, gsrc, sout);
+        else if (first)     stockham_bfly_first_rt(r, b, Ch, twQ, gsrc, sout);
         else if (last)      stockham_bfly_rt<true>(r, b, Ch, s, 2, twC, sin, gdst);
         else                stockham_bfly_rt<false>(r, b, Ch, s, 2, twC, sin, sout);
       }
@@ -415,35 +415,95 @@ namespace smfft {
 // ------------------------------------------------------------------ specialised row passes
 // CH = R1*R2*R3*R4 (unused trailing radices = 1), T threads, padded smem when it fits.
 template <int CH, int S, int R, bool kLast, int T, class Src, class Dst, class Exec>
-SM_HD void row_ct_stage(Exec& ex, const cf* twC, const Src& src, const Dst& dst) {
+SM_HD void row_ct_stage(Exec& ex, const cf* twC, const cf* twQ, const Src& src, const Dst& dst) {
   constexpr int nb = CH / R;
   SM_FOR_THREADS(ex, tid) {
 #pragma unroll
-    for (int b = tid; b < nb; b += T) stockham_bfly<R, kLast>(b, CH, S, 2, twC, src, dst);
+    for (int b = tid; b < nb; b += T) {
+      if constexpr (S == 1 && !kLast) stockham_bfly_first<R>(b, CH, twQ, src, dst);
+      else stockham_bfly<R, kLast>(b, CH, S, 2, twC, src, dst);
+    }
   }
   ex.sync();
 }
 
-template <int R1, int R2, int R3, int R4, int T, bool kPad, class Exec>
-SM_HD void row_fwd_ct_body(Exec& ex, int row, int C, int P, const RowFwdArgs a, const cf* twC, cf* smem, float* acc) {
+// stage-1 sources that read a row staged in shared memory by a bulk async copy (kernels_fft.cu:
+// k_row_fwd_tma / k_row_inv_tma); same arithmetic as RowDeltaSrc / RowTangleSrc, plain loads
+struct RowDeltaStagedSrc {
+  int mode; const uint32_t* b32; const uint32_t* f32; const cf* x32; float m1, m2; float* acc;
+  SM_HD void load(int i, float& re, float& im) const {
+    float d0, d1;
+    if (mode == 0) {
+      const uint32_t bb = b32[i], ff = f32[i];
+      d0 = bf16_bits_to_f32(ff & 0xffffu) - bf16_bits_to_f32(bb & 0xffffu);
+      d1 = bits_f32(ff & 0xffff0000u) - bits_f32(bb & 0xffff0000u);
+    } else {
+      const cf v = x32[i];
+      d0 = v.x; d1 = v.y;
+    }
+    *acc = fmaf(d0, d0, fmaf(d1, d1, *acc));
+    if (mode != 0) { d0 = (d0 * m1) * m2; d1 = (d1 * m1) * m2; }
+    re = d0; im = d1;
+  }
+};
+
+struct RowTangleStagedSrc {
+  const float* re; const float* im; const cf* twC; int Ch; float thr;
+  SM_HD float cull(float v) const { return (v < thr && -v < thr) ? 0.f : v; }
+  SM_HD void load(int k, float& ore, float& oim) const {
+    float xr = cull(re[k]), xi = im[k];
+    float mr = cull(re[Ch - k]), mi = im[Ch - k];
+    if (k == 0) { xi = 0.f; mi = 0.f; }
+    const float Ar = xr + mr, Ai = xi - mi;
+    const float Br = xr - mr, Bi = xi + mi;
+    const cf w = ldg_cf(twC + k);
+    const float br = Br * w.x + Bi * w.y;
+    const float bi = Bi * w.x - Br * w.y;
+    const float zr = Ar - bi, zi = Ai + br;
+    ore = zi; oim = zr;
+  }
+};
+
+struct RowEpilogueStagedDst {   // RowEpilogueDst with the base row read from shared memory
+  int out_mode; const uint32_t* base32; uint32_t* out32; cf* outf; float inv_n, scale; int check;
+  unsigned int* flags;
+  SM_HD float fin(float v, int which) const { return sm_fix_nonfinite(v, flags, which); }
+  SM_HD void store(int j, float a, float b) const {
+    float x0 = b * inv_n, x1 = a * inv_n;
+    if (check) { if (not_finite(x0)) x0 = fin(x0, 0); if (not_finite(x1)) x1 = fin(x1, 0); }
+    x0 *= scale; x1 *= scale;
+    if (out_mode == 0) {
+      const uint32_t bb = base32[j];
+      x0 = bf16_bits_to_f32(bb & 0xffffu) + x0;
+      x1 = bits_f32(bb & 0xffff0000u) + x1;
+      if (not_finite(x0)) x0 = fin(x0, 2);
+      if (not_finite(x1)) x1 = fin(x1, 2);
+      out32[j] = pack_bf16x2_rne(x0, x1);
+    } else {
+      cf v; v.x = x0; v.y = x1; outf[j] = v;
+    }
+  }
+};
+
+// forward row: stages + untangle, stage-1 source supplied by the caller
+struct NoHook { SM_HD void after_first_stage() const {} };
+
+// `hook.after_first_stage()` runs once the stage-1 barrier has passed, i.e. when the stage-1 source
+// (a staging buffer in the bulk-copy kernels) may be refilled.
+template <int R1, int R2, int R3, int R4, int T, bool kPad, class Src, class Hook, class Exec>
+SM_HD void row_fwd_ct_stages(Exec& ex, const Src& gsrc, float* ore, float* oim, const cf* twC, const cf* twQ, cf* smem,
+                             const Hook& hook) {
   constexpr int CH = R1 * R2 * R3 * R4;
   constexpr int bufstride = kPad ? (CH + (CH >> 4) + 1) : CH;
   constexpr int padmask = kPad ? ~0 : 0;
-  RowDeltaSrc gsrc;
-  gsrc.mode = a.mode;
-  gsrc.b32 = a.mode == 0 ? reinterpret_cast<const uint32_t*>(a.base + (size_t)row * C) : nullptr;
-  gsrc.f32 = a.mode == 0 ? reinterpret_cast<const uint32_t*>(a.ft + (size_t)row * C) : nullptr;
-  gsrc.x32 = a.mode != 0 ? reinterpret_cast<const cf*>(a.x32 + (size_t)row * C) : nullptr;
-  gsrc.m1 = a.m1; gsrc.m2 = a.m2; gsrc.acc = acc;
   RowSmem b0{smem, padmask}, b1{smem + bufstride, padmask};
   constexpr int nst = (R2 > 1) + (R3 > 1) + (R4 > 1) + 1;
-  row_ct_stage<CH, 1, R1, nst == 1, T>(ex, twC, gsrc, b0);
-  if constexpr (nst >= 2) row_ct_stage<CH, R1, R2, nst == 2, T>(ex, twC, b0, b1);
-  if constexpr (nst >= 3) row_ct_stage<CH, R1 * R2, R3, nst == 3, T>(ex, twC, b1, b0);
-  if constexpr (nst >= 4) row_ct_stage<CH, R1 * R2 * R3, R4, true, T>(ex, twC, b0, b1);
+  row_ct_stage<CH, 1, R1, nst == 1, T>(ex, twC, twQ, gsrc, b0);
+  hook.after_first_stage();
+  if constexpr (nst >= 2) row_ct_stage<CH, R1, R2, nst == 2, T>(ex, twC, twQ, b0, b1);
+  if constexpr (nst >= 3) row_ct_stage<CH, R1 * R2, R3, nst == 3, T>(ex, twC, twQ, b1, b0);
+  if constexpr (nst >= 4) row_ct_stage<CH, R1 * R2 * R3, R4, true, T>(ex, twC, twQ, b0, b1);
   const RowSmem z = (nst == 1 || nst == 3) ? b0 : b1;
-  float* ore = a.re + (size_t)row * P;
-  float* oim = a.im + (size_t)row * P;
   SM_FOR_THREADS(ex, tid) {
 #pragma unroll 4
     for (int k = tid; k <= CH; k += T) {
@@ -463,10 +523,49 @@ SM_HD void row_fwd_ct_body(Exec& ex, int row, int C, int P, const RowFwdArgs a, 
 }
 
 template <int R1, int R2, int R3, int R4, int T, bool kPad, class Exec>
-SM_HD void row_inv_ct_body(Exec& ex, int row, int C, int P, const RowInvArgs a, const cf* twC, cf* smem) {
+SM_HD void row_fwd_ct_body(Exec& ex, int row, int C, int P, const RowFwdArgs a, const cf* twC, const cf* twQ, cf* smem, float* acc) {
+  RowDeltaSrc gsrc;
+  gsrc.mode = a.mode;
+  gsrc.b32 = a.mode == 0 ? reinterpret_cast<const uint32_t*>(a.base + (size_t)row * C) : nullptr;
+  gsrc.f32 = a.mode == 0 ? reinterpret_cast<const uint32_t*>(a.ft + (size_t)row * C) : nullptr;
+  gsrc.x32 = a.mode != 0 ? reinterpret_cast<const cf*>(a.x32 + (size_t)row * C) : nullptr;
+  gsrc.m1 = a.m1; gsrc.m2 = a.m2; gsrc.acc = acc;
+  row_fwd_ct_stages<R1, R2, R3, R4, T, kPad>(ex, gsrc, a.re + (size_t)row * P, a.im + (size_t)row * P, twC, twQ, smem, NoHook{});
+}
+
+// inverse row: stages with caller-supplied stage-1 source and last-stage sink
+template <int R1, int R2, int R3, int R4, int T, bool kPad, class Src, class Dst, class Hook, class Exec>
+SM_HD void row_inv_ct_stages(Exec& ex, const Src& gsrc, const Dst& gdst, const cf* twC, const cf* twQ, cf* smem,
+                             const Hook& hook) {
   constexpr int CH = R1 * R2 * R3 * R4;
   constexpr int bufstride = kPad ? (CH + (CH >> 4) + 1) : CH;
   constexpr int padmask = kPad ? ~0 : 0;
+  RowSmem b0{smem, padmask}, b1{smem + bufstride, padmask};
+  constexpr int nst = (R2 > 1) + (R3 > 1) + (R4 > 1) + 1;
+  if constexpr (nst == 1) {
+    row_ct_stage<CH, 1, R1, true, T>(ex, twC, twQ, gsrc, gdst);
+    hook.after_first_stage();
+  } else if constexpr (nst == 2) {
+    row_ct_stage<CH, 1, R1, false, T>(ex, twC, twQ, gsrc, b0);
+    hook.after_first_stage();
+    row_ct_stage<CH, R1, R2, true, T>(ex, twC, twQ, b0, gdst);
+  } else if constexpr (nst == 3) {
+    row_ct_stage<CH, 1, R1, false, T>(ex, twC, twQ, gsrc, b0);
+    hook.after_first_stage();
+    row_ct_stage<CH, R1, R2, false, T>(ex, twC, twQ, b0, b1);
+    row_ct_stage<CH, R1 * R2, R3, true, T>(ex, twC, twQ, b1, gdst);
+  } else {
+    row_ct_stage<CH, 1, R1, false, T>(ex, twC, twQ, gsrc, b0);
+    hook.after_first_stage();
+    row_ct_stage<CH, R1, R2, false, T>(ex, twC, twQ, b0, b1);
+    row_ct_stage<CH, R1 * R2, R3, false, T>(ex, twC, twQ, b1, b0);
+    row_ct_stage<CH, R1 * R2 * R3, R4, true, T>(ex, twC, twQ, b0, gdst);
+  }
+}
+
+template <int R1, int R2, int R3, int R4, int T, bool kPad, class Exec>
+SM_HD void row_inv_ct_body(Exec& ex, int row, int C, int P, const RowInvArgs a, const cf* twC, const cf* twQ, cf* smem) {
+  constexpr int CH = R1 * R2 * R3 * R4;
   RowTangleSrc gsrc;
   gsrc.re = a.re + (size_t)row * P;
   gsrc.im = ((a.sel != nullptr && *a.sel != 0) ? a.im_alt : a.im) + (size_t)row * P;
@@ -480,23 +579,7 @@ SM_HD void row_inv_ct_body(Exec& ex, int row, int C, int P, const RowInvArgs a, 
   gdst.inv_n = a.inv_n; gdst.check = a.check_ifft;
   gdst.scale = a.scale_ptr ? *a.scale_ptr : a.scale_host;
   gdst.flags = a.flags;
-  RowSmem b0{smem, padmask}, b1{smem + bufstride, padmask};
-  constexpr int nst = (R2 > 1) + (R3 > 1) + (R4 > 1) + 1;
-  if constexpr (nst == 1) {
-    row_ct_stage<CH, 1, R1, true, T>(ex, twC, gsrc, gdst);
-  } else if constexpr (nst == 2) {
-    row_ct_stage<CH, 1, R1, false, T>(ex, twC, gsrc, b0);
-    row_ct_stage<CH, R1, R2, true, T>(ex, twC, b0, gdst);
-  } else if constexpr (nst == 3) {
-    row_ct_stage<CH, 1, R1, false, T>(ex, twC, gsrc, b0);
-    row_ct_stage<CH, R1, R2, false, T>(ex, twC, b0, b1);
-    row_ct_stage<CH, R1 * R2, R3, true, T>(ex, twC, b1, gdst);
-  } else {
-    row_ct_stage<CH, 1, R1, false, T>(ex, twC, gsrc, b0);
-    row_ct_stage<CH, R1, R2, false, T>(ex, twC, b0, b1);
-    row_ct_stage<CH, R1 * R2, R3, false, T>(ex, twC, b1, b0);
-    row_ct_stage<CH, R1 * R2 * R3, R4, true, T>(ex, twC, b0, gdst);
-  }
+  row_inv_ct_stages<R1, R2, R3, R4, T, kPad>(ex, gsrc, gdst, twC, twQ, smem, NoHook{});
 }
 
 }  // namespace smfft

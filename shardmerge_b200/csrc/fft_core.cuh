@@ -257,6 +257,84 @@ SM_HD void stockham_bfly(int b, int N, int s, int tw_mul, const cf* tw, const Sr
   }
 }
 
+// ---------------------------------------------------------------------------------
+// first stage of a row pass (s == 1, p == b): every butterfly needs its own r-1 twiddles
+// W_N^(b*k).  Looked up one by one in the W table they are 32 scattered sectors per warp
+// request (measured: 90 % of the L1 traffic of k_row_fwd, profiles/r01).  Instead each
+// butterfly reads one 32-byte "quad" {W^b, W^2b, W^4b, W^8b} (coalesced: 1 KB per warp)
+// and forms the other powers as products of at most three table values.
+// ---------------------------------------------------------------------------------
+SM_HD void ldg_quad(const cf* quad, int b, cf (&q)[4]) {
+#if defined(__CUDA_ARCH__)
+  const float4 lo = __ldg(reinterpret_cast<const float4*>(quad + 4 * (size_t)b));
+  const float4 hi = __ldg(reinterpret_cast<const float4*>(quad + 4 * (size_t)b) + 1);
+  q[0].x = lo.x; q[0].y = lo.y; q[1].x = lo.z; q[1].y = lo.w;
+  q[2].x = hi.x; q[2].y = hi.y; q[3].x = hi.z; q[3].y = hi.w;
+#else
+  for (int i = 0; i < 4; ++i) q[i] = quad[4 * (size_t)b + i];
+#endif
+}
+
+SM_CX int c_top_bit(int k) { int t = 1; while (2 * t <= k) t *= 2; return t; }
+
+template <int r>
+SM_HD void quad_twiddles(const cf* quad, int b, float (&wr)[r], float (&wi)[r]) {
+  cf q[4];
+  ldg_quad(quad, b, q);
+  wr[0] = 1.f; wi[0] = 0.f;
+  if constexpr (r > 1) { wr[1] = q[0].x; wi[1] = q[0].y; }
+  if constexpr (r > 2) { wr[2] = q[1].x; wi[2] = q[1].y; }
+  if constexpr (r > 4) { wr[4] = q[2].x; wi[4] = q[2].y; }
+  if constexpr (r > 8) { wr[8] = q[3].x; wi[8] = q[3].y; }
+  static_for<3, r>([&](auto k_) {
+    constexpr int k = decltype(k_)::value;
+    constexpr int t = c_top_bit(k);
+    if constexpr (t != k) {
+      float xr = wr[t], xi = wi[t];
+      cmul(xr, xi, wr[k - t], wi[k - t]);
+      wr[k] = xr; wi[k] = xi;
+    }
+  });
+}
+
+// non-last first stage: s == 1, so q == 0, p == b, outputs go to r*b + k
+template <int r, class Src, class Dst>
+SM_HD void stockham_bfly_first(int b, int N, const cf* quad, const Src& src, const Dst& dst) {
+  float re[r], im[r];
+  const int Nr = N / r;
+  static_for<0, r>([&](auto j_) {
+    constexpr int j = decltype(j_)::value;
+    src.load(b + j * Nr, re[j], im[j]);
+  });
+  float wr[r], wi[r];
+  quad_twiddles<r>(quad, b, wr, wi);
+  Dft<r>::run(re, im);
+  const int obase = r * b;
+  dst.store(obase, re[0], im[0]);
+  static_for<1, r>([&](auto k_) {
+    constexpr int k = decltype(k_)::value;
+    float xr = re[k], xi = im[k];
+    cmul(xr, xi, wr[k], wi[k]);
+    dst.store(obase + k, xr, xi);
+  });
+}
+
+template <class Src, class Dst>
+SM_HD void stockham_bfly_first_rt(int r, int b, int N, const cf* quad, const Src& src, const Dst& dst) {
+  switch (r) {
+    case 2:  stockham_bfly_first<2>(b, N, quad, src, dst); break;
+    case 3:  stockham_bfly_first<3>(b, N, quad, src, dst); break;
+    case 4:  stockham_bfly_first<4>(b, N, quad, src, dst); break;
+    case 5:  stockham_bfly_first<5>(b, N, quad, src, dst); break;
+    case 7:  stockham_bfly_first<7>(b, N, quad, src, dst); break;
+    case 8:  stockham_bfly_first<8>(b, N, quad, src, dst); break;
+    case 11: stockham_bfly_first<11>(b, N, quad, src, dst); break;
+    case 13: stockham_bfly_first<13>(b, N, quad, src, dst); break;
+    case 16: stockham_bfly_first<16>(b, N, quad, src, dst); break;
+    default: break;
+  }
+}
+
 // runtime-radix dispatch (the plan is data, the butterflies are code)
 template <bool kLast, class Src, class Dst>
 SM_HD void stockham_bfly_rt(int r, int b, int N, int s, int tw_mul, const cf* tw, const Src& src, const Dst& dst) {

@@ -26,7 +26,7 @@ struct DeviceExec {
   __device__ __forceinline__ void sync() const { __syncthreads(); }
 };
 
-extern __shared__ float2 g_dyn_smem[];
+extern __shared__ __align__(128) float2 g_dyn_smem[];
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -36,10 +36,10 @@ __device__ __forceinline__ double warp_sum(double v) {
 
 // ------------------------------------------------------------------ kernels
 __global__ void __launch_bounds__(512) k_row_fwd(const __grid_constant__ SmPlan pl, const __grid_constant__ RowFwdArgs a, const cf* __restrict__ twC,
-                                                 double* __restrict__ sumsq) {
+                                                 const cf* __restrict__ twQ, double* __restrict__ sumsq) {
   DeviceExec ex;
   float accf = 0.f;
-  row_fwd_body(ex, pl, (int)blockIdx.x, a, twC, reinterpret_cast<cf*>(g_dyn_smem), &accf);
+  row_fwd_body(ex, pl, (int)blockIdx.x, a, twC, twQ, reinterpret_cast<cf*>(g_dyn_smem), &accf);
   __shared__ double wsum[16];
   double acc = warp_sum((double)accf);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -53,9 +53,10 @@ __global__ void __launch_bounds__(512) k_row_fwd(const __grid_constant__ SmPlan 
   }
 }
 
-__global__ void __launch_bounds__(512) k_row_inv(const __grid_constant__ SmPlan pl, const __grid_constant__ RowInvArgs a, const cf* __restrict__ twC) {
+__global__ void __launch_bounds__(512) k_row_inv(const __grid_constant__ SmPlan pl, const __grid_constant__ RowInvArgs a, const cf* __restrict__ twC,
+                                                 const cf* __restrict__ twQ) {
   DeviceExec ex;
-  row_inv_body(ex, pl, (int)blockIdx.x, a, twC, reinterpret_cast<cf*>(g_dyn_smem));
+  row_inv_body(ex, pl, (int)blockIdx.x, a, twC, twQ, reinterpret_cast<cf*>(g_dyn_smem));
 }
 
 __global__ void __launch_bounds__(512) k_col(const __grid_constant__ SmPlan pl, const __grid_constant__ ColArgs a, const cf* __restrict__ twR) {
@@ -72,10 +73,10 @@ __global__ void __launch_bounds__(NW * 32, (R1 >= 11 || R2 >= 11) ? 3 : 4) k_col
 
 template <int R1, int R2, int R3, int R4, int T, bool kPad>
 __global__ void __launch_bounds__(T) k_row_fwd_ct(int C, int P, const RowFwdArgs a, const cf* __restrict__ twC,
-                                                  double* __restrict__ sumsq) {
+                                                  const cf* __restrict__ twQ, double* __restrict__ sumsq) {
   DeviceExec ex;
   float accf = 0.f;
-  row_fwd_ct_body<R1, R2, R3, R4, T, kPad>(ex, (int)blockIdx.x, C, P, a, twC, reinterpret_cast<cf*>(g_dyn_smem), &accf);
+  row_fwd_ct_body<R1, R2, R3, R4, T, kPad>(ex, (int)blockIdx.x, C, P, a, twC, twQ, reinterpret_cast<cf*>(g_dyn_smem), &accf);
   __shared__ double wsum[16];
   double acc = warp_sum((double)accf);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -89,9 +90,149 @@ __global__ void __launch_bounds__(T) k_row_fwd_ct(int C, int P, const RowFwdArgs
 }
 
 template <int R1, int R2, int R3, int R4, int T, bool kPad>
-__global__ void __launch_bounds__(T) k_row_inv_ct(int C, int P, const RowInvArgs a, const cf* __restrict__ twC) {
+__global__ void __launch_bounds__(T) k_row_inv_ct(int C, int P, const RowInvArgs a, const cf* __restrict__ twC,
+                                                  const cf* __restrict__ twQ) {
   DeviceExec ex;
-  row_inv_ct_body<R1, R2, R3, R4, T, kPad>(ex, (int)blockIdx.x, C, P, a, twC, reinterpret_cast<cf*>(g_dyn_smem));
+  row_inv_ct_body<R1, R2, R3, R4, T, kPad>(ex, (int)blockIdx.x, C, P, a, twC, twQ, reinterpret_cast<cf*>(g_dyn_smem));
+}
+
+// ---- persistent row passes fed by bulk asynchronous copies (TMA 1-D, cp.async.bulk + mbarrier) ----
+// One CTA walks rows blockIdx.x, blockIdx.x + gridDim.x, ...  The row it will transform next is
+// copied global -> shared by the copy engine while it computes the current one: one elected thread
+// issues the copy as soon as the stage-1 barrier has released the staging buffer, every thread waits
+// on the mbarrier before stage 1 of the next row.  No thread ever stalls on a global load.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!ok);
+}
+
+struct FwdStageHook {          // refill the input staging buffer with the CTA's next row
+  const RowFwdArgs* a; int next_row, R, C; char* stage; uint64_t* bar;
+  __device__ __forceinline__ void after_first_stage() const {
+    if (threadIdx.x == 0 && next_row < R) {
+      if (a->mode == 0) {
+        mbar_expect_tx(bar, 4u * (uint32_t)C);
+        bulk_g2s(stage, a->base + (size_t)next_row * C, 2u * (uint32_t)C, bar);
+        bulk_g2s(stage + 2 * (size_t)C, a->ft + (size_t)next_row * C, 2u * (uint32_t)C, bar);
+      } else {
+        mbar_expect_tx(bar, 4u * (uint32_t)C);
+        bulk_g2s(stage, a->x32 + (size_t)next_row * C, 4u * (uint32_t)C, bar);
+      }
+    }
+  }
+};
+
+template <int R1, int R2, int R3, int R4, int T, bool kPad>
+__global__ void __launch_bounds__(T) k_row_fwd_tma(int R, int C, int P, const __grid_constant__ RowFwdArgs a,
+                                                   const cf* __restrict__ twC, const cf* __restrict__ twQ,
+                                                   double* __restrict__ sumsq, int work_bytes) {
+  DeviceExec ex;
+  __shared__ uint64_t full;
+  __shared__ double wsum[16];
+  cf* work = reinterpret_cast<cf*>(g_dyn_smem);
+  char* stage = reinterpret_cast<char*>(g_dyn_smem) + work_bytes;
+  if (threadIdx.x == 0) { mbar_init(&full, 1); mbar_fence_init(); }
+  __syncthreads();
+  FwdStageHook hook{&a, (int)blockIdx.x, R, C, stage, &full};
+  hook.after_first_stage();                       // first row of this CTA
+  uint32_t phase = 0;
+  double accd = 0.0;
+  for (int row = blockIdx.x; row < R; row += gridDim.x) {
+    mbar_wait(&full, phase); phase ^= 1u;
+    float accf = 0.f;
+    RowDeltaStagedSrc src;
+    src.mode = a.mode;
+    src.b32 = reinterpret_cast<const uint32_t*>(stage);
+    src.f32 = reinterpret_cast<const uint32_t*>(stage + 2 * (size_t)C);
+    src.x32 = reinterpret_cast<const cf*>(stage);
+    src.m1 = a.m1; src.m2 = a.m2; src.acc = &accf;
+    hook.next_row = row + gridDim.x;
+    row_fwd_ct_stages<R1, R2, R3, R4, T, kPad>(ex, src, a.re + (size_t)row * P, a.im + (size_t)row * P, twC, twQ, work, hook);
+    accd += (double)accf;                          // fp32 over one row's share, fp64 across rows
+  }
+  double acc = warp_sum(accd);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) wsum[wid] = acc;
+  __syncthreads();
+  if (wid == 0) {
+    double v = lane < (T + 31) / 32 ? wsum[lane] : 0.0;
+    v = warp_sum(v);
+    if (lane == 0) atomicAdd(sumsq, v);
+  }
+}
+
+struct InvStageHook {          // refill the spectrum staging (re, im rows) with the CTA's next row
+  const float* re; const float* im; int next_row, R, P; char* st_re; char* st_im; uint64_t* bar;
+  __device__ __forceinline__ void after_first_stage() const {
+    if (threadIdx.x == 0 && next_row < R) {
+      mbar_expect_tx(bar, 8u * (uint32_t)P);
+      bulk_g2s(st_re, re + (size_t)next_row * P, 4u * (uint32_t)P, bar);
+      bulk_g2s(st_im, im + (size_t)next_row * P, 4u * (uint32_t)P, bar);
+    }
+  }
+};
+
+template <int R1, int R2, int R3, int R4, int T, bool kPad>
+__global__ void __launch_bounds__(T) k_row_inv_tma(int R, int C, int P, const __grid_constant__ RowInvArgs a,
+                                                   const cf* __restrict__ twC, const cf* __restrict__ twQ, int work_bytes) {
+  constexpr int CH = R1 * R2 * R3 * R4;
+  DeviceExec ex;
+  __shared__ uint64_t full_spec, full_base;
+  cf* work = reinterpret_cast<cf*>(g_dyn_smem);
+  char* st_re = reinterpret_cast<char*>(g_dyn_smem) + work_bytes;
+  char* st_im = st_re + 4 * (size_t)P;
+  char* st_base = st_im + 4 * (size_t)P;
+  if (threadIdx.x == 0) { mbar_init(&full_spec, 1); mbar_init(&full_base, 1); mbar_fence_init(); }
+  __syncthreads();
+  const float* im = (a.sel != nullptr && *a.sel != 0) ? a.im_alt : a.im;
+  InvStageHook hook{a.re, im, (int)blockIdx.x, R, P, st_re, st_im, &full_spec};
+  hook.after_first_stage();
+  auto load_base = [&](int row) {
+    if (threadIdx.x == 0 && row < R && a.out_mode == 0) {
+      mbar_expect_tx(&full_base, 2u * (uint32_t)C);
+      bulk_g2s(st_base, a.base + (size_t)row * C, 2u * (uint32_t)C, &full_base);
+    }
+  };
+  load_base((int)blockIdx.x);
+  RowTangleStagedSrc gsrc;
+  gsrc.re = reinterpret_cast<const float*>(st_re); gsrc.im = reinterpret_cast<const float*>(st_im);
+  gsrc.twC = twC; gsrc.Ch = CH;
+  gsrc.thr = (a.cull_thr != nullptr) ? *a.cull_thr : 0.f;
+  RowEpilogueStagedDst gdst;
+  gdst.out_mode = a.out_mode;
+  gdst.base32 = reinterpret_cast<const uint32_t*>(st_base);
+  gdst.inv_n = a.inv_n; gdst.check = a.check_ifft;
+  gdst.scale = a.scale_ptr ? *a.scale_ptr : a.scale_host;
+  gdst.flags = a.flags;
+  uint32_t phase = 0;
+  for (int row = blockIdx.x; row < R; row += gridDim.x) {
+    gdst.out32 = a.out_mode == 0 ? reinterpret_cast<uint32_t*>(a.out_bf16 + (size_t)row * C) : nullptr;
+    gdst.outf = a.out_mode != 0 ? reinterpret_cast<cf*>(a.out_f32 + (size_t)row * C) : nullptr;
+    mbar_wait(&full_spec, phase);
+    if (a.out_mode == 0) mbar_wait(&full_base, phase);
+    phase ^= 1u;
+    hook.next_row = row + gridDim.x;
+    row_inv_ct_stages<R1, R2, R3, R4, T, kPad>(ex, gsrc, gdst, twC, twQ, work, hook);
+    load_base(row + gridDim.x);                    // the last stage (the only reader of the base row) has passed its barrier
+  }
 }
 
 // scale a 1-D spectrum (no column sweep exists to fold the normalisation into)
@@ -109,6 +250,17 @@ __global__ void k_init_twiddles(cf* tw, int M) {
     sincospi(2.0 * (double)j / (double)M, &s, &c);
     cf w; w.x = (float)c; w.y = (float)(-s);
     tw[j] = w;
+  }
+}
+
+// quad[b] = {W^b, W^2b, W^4b, W^8b}, W = exp(-2*pi*i/N): first-stage twiddles of the row passes
+__global__ void k_init_quads(cf* quad, int n_b, int N) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 4 * n_b; i += gridDim.x * blockDim.x) {
+    const long long e = ((long long)(i >> 2) << (i & 3)) % N;
+    double s, c;
+    sincospi(2.0 * (double)e / (double)N, &s, &c);
+    cf w; w.x = (float)c; w.y = (float)(-s);
+    quad[i] = w;
   }
 }
 
@@ -157,7 +309,7 @@ extern "C" int sm_plan_pitch(const sm_plan* plan) { return plan->p.P; }
 extern "C" int sm_plan_col_passes(const sm_plan* plan) { return plan->p.col_passes; }
 extern "C" int sm_plan_row_freq(const sm_plan* plan, int stored) { return sm_row_freq(&plan->p, stored); }
 extern "C" size_t sm_plan_table_bytes(const sm_plan* plan) {
-  return ((size_t)plan->p.C + (size_t)plan->p.R) * 8;
+  return sm_tab_off_Q(plan->p) + 32 * (size_t)sm_quad_count(plan->p) + 32;
 }
 extern "C" int sm_plan_describe(const sm_plan* plan, char* buf, int buflen) {
   const SmPlan& p = plan->p;
@@ -182,10 +334,19 @@ extern "C" int sm_plan_init_tables(const sm_plan* plan, void* tables, void* stre
   SM_LAUNCH_CHECK();
   k_init_twiddles<<<(p.R + 255) / 256, 256, 0, st>>>(twR, p.R);
   SM_LAUNCH_CHECK();
+  cf* twQ = reinterpret_cast<cf*>(reinterpret_cast<char*>(tables) + sm_tab_off_Q(p));
+  const int nq = sm_quad_count(p);
+  if (nq > 0) {
+    k_init_quads<<<(4 * nq + 255) / 256, 256, 0, st>>>(twQ, nq, p.Ch);
+    SM_LAUNCH_CHECK();
+  }
   return 0;
 }
 
 static const cf* tabC(const SmPlan&, const void* tables) { return reinterpret_cast<const cf*>(tables); }
+static const cf* tabQ(const SmPlan& p, const void* tables) {
+  return reinterpret_cast<const cf*>(reinterpret_cast<const char*>(tables) + sm_tab_off_Q(p));
+}
 static const cf* tabR(const SmPlan& p, const void* tables) {
   return reinterpret_cast<const cf*>(reinterpret_cast<const char*>(tables) + sm_tab_off_R(p));
 }
@@ -242,48 +403,92 @@ static int try_col_ct(int n_rad, const int* rad, bool inverse, bool big_tw, dim3
   return 1;
 }
 
+static int g_num_sms = 0;
+static int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+static bool g_use_tma = true;     // SM_ROW_TMA=0 falls back to the one-CTA-per-row kernels (debug / A-B timing)
+static bool use_tma() {
+  static int init = 0;
+  if (!init) { const char* e = getenv("SM_ROW_TMA"); if (e && e[0] == '0') g_use_tma = false; init = 1; }
+  return g_use_tma;
+}
+
 template <int R1, int R2, int R3, int R4, int T, bool kPad>
 static int launch_row_ct(bool inverse, const SmPlan& p, const RowFwdArgs* fa, const RowInvArgs* ia, const cf* twC,
-                         double* sumsq, cudaStream_t st) {
-  static bool done[2] = {false, false};
+                         const cf* twQ, double* sumsq, cudaStream_t st) {
+  static bool done[4] = {false, false, false, false};
+  static int occ[2] = {0, 0};
+  constexpr int CH = R1 * R2 * R3 * R4;
+  constexpr int nst = (R2 > 1) + (R3 > 1) + (R4 > 1) + 1;
+  constexpr int bufstride = kPad ? (CH + (CH >> 4) + 1) : CH;
   cudaError_t e;
+  // persistent bulk-copy variant: rows must start 16-byte aligned and the staging must fit next to the work buffers
+  const int work_bytes = (((!inverse ? (nst >= 2 ? 2 : 1) : (nst >= 3 ? 2 : 1)) * bufstride * 8) + 127) / 128 * 128;
+  const int stage_bytes = !inverse ? 4 * p.C : 8 * p.P + ((ia->out_mode == 0) ? 2 * p.C : 0);
+  const bool aligned = (p.C % 8 == 0);
+  if (use_tma() && aligned && work_bytes + stage_bytes <= 227 * 1024 - 256 && p.R >= 2) {
+    const int smem = work_bytes + stage_bytes;
+    const int which = inverse ? 1 : 0;
+    if (!inverse) {
+      e = opt_in(k_row_fwd_tma<R1, R2, R3, R4, T, kPad>, &done[2]);
+      if (e == cudaSuccess && occ[0] == 0)
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], k_row_fwd_tma<R1, R2, R3, R4, T, kPad>, T, smem);
+    } else {
+      e = opt_in(k_row_inv_tma<R1, R2, R3, R4, T, kPad>, &done[3]);
+      if (e == cudaSuccess && occ[1] == 0)
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], k_row_inv_tma<R1, R2, R3, R4, T, kPad>, T, smem);
+    }
+    if (e != cudaSuccess) { sm_set_error("row tma setup: %s", cudaGetErrorString(e)); return -100; }
+    int grid = num_sms() * (occ[which] > 0 ? occ[which] : 1);
+    if (grid > p.R) grid = p.R;
+    if (!inverse) k_row_fwd_tma<R1, R2, R3, R4, T, kPad><<<grid, T, smem, st>>>(p.R, p.C, p.P, *fa, twC, twQ, sumsq, work_bytes);
+    else k_row_inv_tma<R1, R2, R3, R4, T, kPad><<<grid, T, smem, st>>>(p.R, p.C, p.P, *ia, twC, twQ, work_bytes);
+    SM_LAUNCH_CHECK();
+    return 0;
+  }
   if (!inverse) {
     e = opt_in(k_row_fwd_ct<R1, R2, R3, R4, T, kPad>, &done[0]);
     if (e != cudaSuccess) { sm_set_error("opt_in: %s", cudaGetErrorString(e)); return -100; }
-    k_row_fwd_ct<R1, R2, R3, R4, T, kPad><<<p.R, T, p.row_smem_fwd, st>>>(p.C, p.P, *fa, twC, sumsq);
+    k_row_fwd_ct<R1, R2, R3, R4, T, kPad><<<p.R, T, p.row_smem_fwd, st>>>(p.C, p.P, *fa, twC, twQ, sumsq);
   } else {
     e = opt_in(k_row_inv_ct<R1, R2, R3, R4, T, kPad>, &done[1]);
     if (e != cudaSuccess) { sm_set_error("opt_in: %s", cudaGetErrorString(e)); return -100; }
-    k_row_inv_ct<R1, R2, R3, R4, T, kPad><<<p.R, T, p.row_smem_inv, st>>>(p.C, p.P, *ia, twC);
+    k_row_inv_ct<R1, R2, R3, R4, T, kPad><<<p.R, T, p.row_smem_inv, st>>>(p.C, p.P, *ia, twC, twQ);
   }
   SM_LAUNCH_CHECK();
   return 0;
 }
 
 static int try_row_ct(bool inverse, const SmPlan& p, const RowFwdArgs* fa, const RowInvArgs* ia, const cf* twC,
-                      double* sumsq, cudaStream_t st) {
+                      const cf* twQ, double* sumsq, cudaStream_t st) {
   auto is = [&](int n, int a, int b, int c, int d) {
     if (p.n_row != n) return false;
     const int want[4] = {a, b, c, d};
     for (int i = 0; i < n; ++i) if (p.row_rad[i] != want[i]) return false;
     return true;
   };
-  if (is(3, 16, 8, 8, 1) && p.row_threads == 64 && p.row_pad) return launch_row_ct<16, 8, 8, 1, 64, true>(inverse, p, fa, ia, twC, sumsq, st);
-  if (is(3, 16, 16, 8, 1) && p.row_threads == 128 && p.row_pad) return launch_row_ct<16, 16, 8, 1, 128, true>(inverse, p, fa, ia, twC, sumsq, st);
-  if (is(3, 16, 16, 16, 1) && p.row_threads == 256 && p.row_pad) return launch_row_ct<16, 16, 16, 1, 256, true>(inverse, p, fa, ia, twC, sumsq, st);
-  if (is(3, 11, 16, 16, 1) && p.row_threads == 192 && p.row_pad) return launch_row_ct<11, 16, 16, 1, 192, true>(inverse, p, fa, ia, twC, sumsq, st);
-  if (is(4, 7, 16, 8, 8) && p.row_threads == 448 && p.row_pad) return launch_row_ct<7, 16, 8, 8, 448, true>(inverse, p, fa, ia, twC, sumsq, st);
-  if (is(4, 7, 16, 16, 8) && p.row_threads == 512 && !p.row_pad) return launch_row_ct<7, 16, 16, 8, 512, false>(inverse, p, fa, ia, twC, sumsq, st);
+  if (is(3, 16, 8, 8, 1) && p.row_threads == 64 && p.row_pad) return launch_row_ct<16, 8, 8, 1, 64, true>(inverse, p, fa, ia, twC, twQ, sumsq, st);
+  if (is(3, 16, 16, 8, 1) && p.row_threads == 128 && p.row_pad) return launch_row_ct<16, 16, 8, 1, 128, true>(inverse, p, fa, ia, twC, twQ, sumsq, st);
+  if (is(3, 16, 16, 16, 1) && p.row_threads == 256 && p.row_pad) return launch_row_ct<16, 16, 16, 1, 256, true>(inverse, p, fa, ia, twC, twQ, sumsq, st);
+  if (is(3, 11, 16, 16, 1) && p.row_threads == 192 && p.row_pad) return launch_row_ct<11, 16, 16, 1, 192, true>(inverse, p, fa, ia, twC, twQ, sumsq, st);
+  if (is(4, 7, 16, 8, 8) && p.row_threads == 448 && p.row_pad) return launch_row_ct<7, 16, 8, 8, 448, true>(inverse, p, fa, ia, twC, twQ, sumsq, st);
+  if (is(4, 7, 16, 16, 8) && p.row_threads == 512 && !p.row_pad) return launch_row_ct<7, 16, 16, 8, 512, false>(inverse, p, fa, ia, twC, twQ, sumsq, st);
   return 1;
 }
 
 static int launch_row_fwd(const SmPlan& p, const void* tables, const RowFwdArgs& a, double* sumsq, cudaStream_t st) {
   if (ensure_attrs()) return -100;
   {
-    const int rc = try_row_ct(false, p, &a, nullptr, tabC(p, tables), sumsq, st);
+    const int rc = try_row_ct(false, p, &a, nullptr, tabC(p, tables), tabQ(p, tables), sumsq, st);
     if (rc <= 0) return rc;
   }
-  k_row_fwd<<<p.R, p.row_threads, p.row_smem_fwd, st>>>(p, a, tabC(p, tables), sumsq);
+  k_row_fwd<<<p.R, p.row_threads, p.row_smem_fwd, st>>>(p, a, tabC(p, tables), tabQ(p, tables), sumsq);
   SM_LAUNCH_CHECK();
   return 0;
 }
@@ -377,10 +582,10 @@ static int launch_row_inv(const SmPlan& p, const void* tables, RowInvArgs& a, cu
   a.inv_n = (float)(1.0 / ((double)p.R * (double)p.C));
   if (p.col_passes != 0) a.cull_thr = nullptr;
   {
-    const int rc = try_row_ct(true, p, nullptr, &a, tabC(p, tables), nullptr, st);
+    const int rc = try_row_ct(true, p, nullptr, &a, tabC(p, tables), tabQ(p, tables), nullptr, st);
     if (rc <= 0) return rc;
   }
-  k_row_inv<<<p.R, p.row_threads, p.row_smem_inv, st>>>(p, a, tabC(p, tables));
+  k_row_inv<<<p.R, p.row_threads, p.row_smem_inv, st>>>(p, a, tabC(p, tables), tabQ(p, tables));
   SM_LAUNCH_CHECK();
   return 0;
 }

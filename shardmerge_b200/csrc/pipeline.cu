@@ -110,32 +110,46 @@ extern "C" int sm_pair_merge_slerp_async(const sm_plan* plan, const void* tables
     if ((rc = sm_fwd_cols(plan, tables, a->re[0], a->im[0], flt + SM_F_SCALE_X, 1.f, 1, st))) return rc;
     if ((rc = sm_fwd_cols(plan, tables, a->re[1], a->im[1], flt + SM_F_SCALE_Y, 1.f, 1, st))) return rc;
   }
-  if (a->cutoff_pct > 0) {
-    Scope s(st, SM_CLS_SELECT2, 4.0 * N, 11);
-    // functions.py:113-120: sorted(cat(|re0|,|re1|))[int(2N*cutoff_pct)]  (Python float arithmetic)
-    const uint64_t rank = (uint64_t)((2.0 * N) * a->cutoff_pct);
-    if ((rc = sm_select_kth_abs(plan, a->re[0], a->re[1], rank, a->select_mode, sel0, a->sel_ws, a->sel_ws_bytes,
-                                flt + SM_F_THR_CUT, st))) return rc;
-  }
-  {
-    Scope s(st, SM_CLS_REDUCE, 4.0 * N, 1);
-    if ((rc = sm_slerp_reduce_sel(plan, a->re[0], a->re[1], swap, flt + SM_F_THR_CUT, dbl + 2, st))) return rc;
-  }
-  {
-    Scope s(st, SM_CLS_SCALARS, 0.0, 1);
-    if ((rc = sm_slerp_scalars(dbl + 2, a->t, flt + SM_F_DOT, st))) return rc;
-  }
-  {
-    Scope s(st, SM_CLS_BLEND, 6.0 * N, 1);
-    if ((rc = sm_blend_sel(plan, 0, 1, a->re[0], a->re[1], swap, flt + SM_F_THR_CUT, flt + SM_F_DOT, a->t_sum, a->re[2], st)))
-      return rc;
-  }
+  void* fs0 = ctl + SM_CTL_FS;
+  void* fs1 = ctl + SM_CTL_FS + SM_FS_STATE_BYTES;
   const bool cull = a->cull_pct > 0;
-  if (cull) {
-    Scope s(st, SM_CLS_SELECT1, 2.0 * N, 11);
-    const uint64_t rank = (uint64_t)(N * a->cull_pct);          // functions.py:140
-    if ((rc = sm_select_kth_abs(plan, a->re[2], nullptr, rank, a->select_mode, sel1, a->sel_ws, a->sel_ws_bytes,
-                                flt + SM_F_THR_CULL, st))) return rc;
+  const bool fused_stats = sm_fstats_supported(plan) && a->select_mode == 0;
+  // functions.py:113-120: sorted(cat(|re0|,|re1|))[int(2N*cutoff_pct)]  (Python float arithmetic); :140 for the cull
+  const uint64_t rank_cut = (uint64_t)((2.0 * N) * a->cutoff_pct);
+  const uint64_t rank_cull = (uint64_t)(N * a->cull_pct);
+  if (fused_stats && a->cutoff_pct > 0) {
+    // cutoff statistic + SLERP sums + scalars: one pass over Re X, Re Y (kernels_fstats.cu)
+    Scope s(st, SM_CLS_SELECT2, 4.0 * N, 2);
+    if ((rc = sm_fstats_cutoff(plan, a->re[0], a->re[1], swap, rank_cut, a->t, fs0, a->sel_ws, a->sel_ws_bytes,
+                               flt + SM_F_THR_CUT, flt + SM_F_DOT, dbl + 2, st))) return rc;
+  } else {
+    if (a->cutoff_pct > 0) {
+      Scope s(st, SM_CLS_SELECT2, 4.0 * N, 11);
+      if ((rc = sm_select_kth_abs(plan, a->re[0], a->re[1], rank_cut, a->select_mode, sel0, a->sel_ws, a->sel_ws_bytes,
+                                  flt + SM_F_THR_CUT, st))) return rc;
+    }
+    {
+      Scope s(st, SM_CLS_REDUCE, 4.0 * N, 2);
+      if ((rc = sm_slerp_reduce_sel(plan, a->re[0], a->re[1], swap, flt + SM_F_THR_CUT, dbl + 2, st))) return rc;
+      if ((rc = sm_slerp_scalars(dbl + 2, a->t, flt + SM_F_DOT, st))) return rc;
+    }
+  }
+  if (fused_stats && cull) {
+    // blend + cull statistic of its output: one pass
+    Scope s(st, SM_CLS_BLEND, 6.0 * N, 2);
+    if ((rc = sm_fstats_blend_cull(plan, a->re[0], a->re[1], swap, flt + SM_F_THR_CUT, flt + SM_F_DOT, a->t_sum, a->re[2],
+                                   rank_cull, fs1, a->sel_ws, a->sel_ws_bytes, flt + SM_F_THR_CULL, st))) return rc;
+  } else {
+    {
+      Scope s(st, SM_CLS_BLEND, 6.0 * N, 1);
+      if ((rc = sm_blend_sel(plan, 0, 1, a->re[0], a->re[1], swap, flt + SM_F_THR_CUT, flt + SM_F_DOT, a->t_sum, a->re[2], st)))
+        return rc;
+    }
+    if (cull) {
+      Scope s(st, SM_CLS_SELECT1, 2.0 * N, 11);
+      if ((rc = sm_select_kth_abs(plan, a->re[2], nullptr, rank_cull, a->select_mode, sel1, a->sel_ws, a->sel_ws_bytes,
+                                  flt + SM_F_THR_CULL, st))) return rc;
+    }
   }
   if (sweeps > 0) {
     Scope s(st, SM_CLS_COL_INV, 8.0 * N * sweeps, sweeps);

@@ -30,8 +30,11 @@ void sm_set_error(const char* fmt, ...);
     }                                                                                  \
   } while (0)
 
-// table layout inside the caller's buffer: [W_C : C entries][W_R : R entries] of float2
+// table layout inside the caller's buffer: [W_C : C entries][W_R : R entries][quads : 4 * (Ch / row_rad[0])]
+// of float2; the quad table (fft_core.cuh: first-stage twiddles) starts 32-byte aligned.
 static inline size_t sm_tab_off_R(const SmPlan& p) { return (size_t)p.C * 8; }
+static inline size_t sm_tab_off_Q(const SmPlan& p) { return (((size_t)p.C + (size_t)p.R) * 8 + 31) / 32 * 32; }
+static inline int sm_quad_count(const SmPlan& p) { return p.n_row > 1 ? p.Ch / p.row_rad[0] : 0; }
 
 // iteration space of the element-wise / statistics kernels over the valid half spectrum
 #define SM_EW_THREADS 256

@@ -27,7 +27,7 @@ import torch
 from . import _lib
 
 # offsets inside the per-workspace scalar block (bytes)
-_CTL_BYTES = 512
+_CTL_BYTES = _lib.CTL_BYTES
 _OFF_DBL, _OFF_FLT, _OFF_FLAGS, _OFF_SEL = 0, 64, 128, 192
 # float64 slots
 D_SUMSQ0, D_SUMSQ1, D_S00, D_S11, D_S01 = 0, 1, 2, 3, 4
@@ -161,7 +161,8 @@ class Workspace:
         self.sel = self.ctl[_OFF_SEL:_OFF_SEL + 128]
         self.safe_select = safe_select
         mode = 1 if safe_select else 0
-        nbytes = max(plan.lib.sm_select_ws_bytes(plan.handle, 2, mode), plan.lib.sm_select_ws_bytes(plan.handle, 1, mode))
+        nbytes = max(plan.lib.sm_select_ws_bytes(plan.handle, 2, mode), plan.lib.sm_select_ws_bytes(plan.handle, 1, mode),
+                     plan.lib.sm_fstats_ws_bytes(plan.handle))
         self.sel_ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         # pinned landing zone for the scalar block
         self.ctl_host = torch.empty(_CTL_BYTES, dtype=torch.uint8).pin_memory()
@@ -170,6 +171,14 @@ class Workspace:
     def dptr(self, slot): return self.dbl.data_ptr() + 8 * slot
     def fptr(self, slot): return self.flt.data_ptr() + 4 * slot
     def selptr(self, which): return self.sel.data_ptr() + 64 * which
+    def fsptr(self, which): return self.ctl.data_ptr() + _lib.CTL_FS_OFF + _lib.FS_STATE_BYTES * which
+
+    def fs_status(self):
+        """(status of the fused cutoff state, status of the fused blend/cull state) -- synchronous."""
+        h = self.ctl.cpu()
+        o = _lib.CTL_FS_OFF + _lib.FS_STATUS_OFF
+        return (int(h[o:o + 4].view(torch.int32)[0]),
+                int(h[o + _lib.FS_STATE_BYTES:o + _lib.FS_STATE_BYTES + 4].view(torch.int32)[0]))
 
     def read_ctl(self):
         """Synchronous read-back of the scalar block -> (float64[8], float32[16], int32[4], sel bytes)."""
@@ -315,6 +324,25 @@ def blend(ws: Workspace, mode: int, agreement: bool, re0: torch.Tensor, re1: tor
         ws.fptr(F_DOT), float(t_sum), out.data_ptr(), _stream(pl.device))), "sm_blend")
 
 
+def fstats_cutoff(ws: Workspace, reX: torch.Tensor, reY: torch.Tensor, rank: int, t: float, sel_ptr: Optional[int] = None):
+    """Fused cutoff statistic + SLERP sums + scalars (csrc/kernels_fstats.cu): writes F_THR_CUT, F_DOT.., D_S00.."""
+    pl, lib = ws.plan, ws.plan.lib
+    _lib.check(_run("stats_cutoff", 3, 4 * pl.R * pl.C, pl.device, lambda: lib.sm_fstats_cutoff(
+        pl.handle, reX.data_ptr(), reY.data_ptr(), sel_ptr, int(rank), float(t),
+        ws.fsptr(0), ws.sel_ws.data_ptr(), ws.sel_ws.numel(), ws.fptr(F_THR_CUT), ws.fptr(F_DOT), ws.dptr(D_S00),
+        _stream(pl.device))), "sm_fstats_cutoff")
+
+
+def fstats_blend_cull(ws: Workspace, reX: torch.Tensor, reY: torch.Tensor, t_sum: float, out: torch.Tensor, rank: int,
+                      sel_ptr: Optional[int] = None):
+    """Fused SLERP blend + cull statistic of its output: writes `out` and F_THR_CULL."""
+    pl, lib = ws.plan, ws.plan.lib
+    _lib.check(_run("blend_cull", 3, 6 * pl.R * pl.C, pl.device, lambda: lib.sm_fstats_blend_cull(
+        pl.handle, reX.data_ptr(), reY.data_ptr(), sel_ptr, ws.fptr(F_THR_CUT), ws.fptr(F_DOT), float(t_sum),
+        out.data_ptr(), int(rank), ws.fsptr(1), ws.sel_ws.data_ptr(), ws.sel_ws.numel(),
+        ws.fptr(F_THR_CULL), _stream(pl.device))), "sm_fstats_blend_cull")
+
+
 def inv_cols(ws: Workspace, re: torch.Tensor, im: torch.Tensor, cull: bool):
     pl, lib = ws.plan, ws.plan.lib
     sweeps = pl.lib.sm_plan_col_passes(pl.handle)
@@ -441,10 +469,13 @@ class PendingPair:
         h = self.host_ctl
         dbl = h[0:64].view(torch.float64); flt = h[64:128].view(torch.float32)
         flags = h[128:144].view(torch.int32); ints = h[144:160].view(torch.int32)
+        fs = _lib.CTL_FS_OFF + _lib.FS_STATUS_OFF
         sel32 = h[192:320].view(torch.int32)
+        st0 = int(h[fs:fs + 4].view(torch.int32)[0]) | int(sel32[11])
+        st1 = int(h[fs + _lib.FS_STATE_BYTES:fs + _lib.FS_STATE_BYTES + 4].view(torch.int32)[0]) | int(sel32[16 + 11])
         self.info = dict(norms=[float(flt[9]), float(flt[10])], target_norm=float(h[160:168].view(torch.float64)[0]),
                          swap=int(ints[0]), branch=_lib.BRANCH_NAMES.get(int(ints[1]), "?"),
-                         select_sticky=int(sel32[11]) | int(sel32[16 + 11]), flags=[int(v) for v in flags],
+                         select_sticky=st0 | st1, flags=[int(v) for v in flags],
                          thr_cut=float(flt[0]), thr_cull=float(flt[1]), dot=float(flt[2]))
         return self.info
 
@@ -467,7 +498,8 @@ def pair_merge_async(ws: Workspace, s0: Source, s1: Source, base_out: torch.Tens
     a.select_mode = 1 if ws.safe_select else 0
     sweeps = lib.sm_plan_col_passes(pl.handle)
     if PROFILER is not None:
-        PROFILER.launches += 2 + 1 + 2 * max(sweeps, 1) + 11 * ((cutoff_pct > 0) + (cull_pct > 0)) + 3 + sweeps + 1
+        fs = lib.sm_fstats_supported(pl.handle) and not ws.safe_select
+        PROFILER.launches += 2 + 1 + 2 * max(sweeps, 1) + ((2 + 2) if fs else (11 + 2 + 1 + 11)) + sweeps + 1
         PROFILER.fused_calls += 1
     _lib.check(lib.sm_pair_merge_slerp_async(pl.handle, pl.tables.data_ptr(), ctypes.byref(a), _stream(dev)),
                "sm_pair_merge_slerp_async")

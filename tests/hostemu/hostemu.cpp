@@ -36,6 +36,17 @@ static void make_tw(int M, std::vector<cf>& tw) {
   }
 }
 
+static void make_quads(const SmPlan& pl, std::vector<cf>& q) {
+  const int nb = pl.n_row > 1 ? pl.Ch / pl.row_rad[0] : 0, N = pl.Ch;
+  q.resize(4 * (size_t)nb + 4);
+  for (int b = 0; b < nb; ++b)
+    for (int j = 0; j < 4; ++j) {
+      const long long e = ((long long)b << j) % N;
+      const double a = 2.0 * M_PI * (double)e / (double)N;
+      q[4 * (size_t)b + j].x = (float)std::cos(a); q[4 * (size_t)b + j].y = (float)(-std::sin(a));
+    }
+}
+
 extern "C" {
 
 int emu_plan(int R, int C, int* out /* >= 64 ints */) {
@@ -54,8 +65,8 @@ int emu_forward(int R, int C, int mode, const uint16_t* base, const uint16_t* ft
   SmPlan pl;
   int rc = sm_make_plan(R, C, &pl);
   if (rc) return rc;
-  std::vector<cf> twC, twR;
-  make_tw(C, twC); make_tw(R, twR);
+  std::vector<cf> twC, twR, twQ;
+  make_tw(C, twC); make_tw(R, twR); make_quads(pl, twQ);
   std::vector<cf> smem(2 * (size_t)(pl.Ch + (pl.Ch >> 4) + 1) + 16);
   RowFwdArgs a{};
   a.mode = mode; a.base = base; a.ft = ft; a.x32 = x32; a.m1 = m1; a.m2 = m2; a.re = re; a.im = im;
@@ -63,7 +74,7 @@ int emu_forward(int R, int C, int mode, const uint16_t* base, const uint16_t* ft
   for (int row = 0; row < R; ++row) {
     HostExec ex{pl.row_threads};
     float part = 0.f;                      // the device widens one fp32 partial per thread; here per row
-    row_fwd_body(ex, pl, row, a, twC.data(), smem.data(), &part);
+    row_fwd_body(ex, pl, row, a, twC.data(), twQ.data(), smem.data(), &part);
     acc += (double)part;
   }
   *sumsq = acc;
@@ -94,8 +105,8 @@ int emu_inverse(int R, int C, float* re, float* im, float cull_thr, int out_mode
   SmPlan pl;
   int rc = sm_make_plan(R, C, &pl);
   if (rc) return rc;
-  std::vector<cf> twC, twR;
-  make_tw(C, twC); make_tw(R, twR);
+  std::vector<cf> twC, twR, twQ;
+  make_tw(C, twC); make_tw(R, twR); make_quads(pl, twQ);
   for (int i = 0; i < pl.col_passes; ++i) {
     int sweep = pl.col_passes - 1 - i;       // B first, then A
     ColArgs ca{};
@@ -120,7 +131,7 @@ int emu_inverse(int R, int C, float* re, float* im, float cull_thr, int out_mode
   for (int i = 0; i < 4; ++i) flags4[i] = 0;
   for (int row = 0; row < R; ++row) {
     HostExec ex{pl.row_threads};
-    row_inv_body(ex, pl, row, a, twC.data(), smem.data());
+    row_inv_body(ex, pl, row, a, twC.data(), twQ.data(), smem.data());
   }
   return 0;
 }

@@ -213,6 +213,72 @@ def test_reduce_scalars_blend_bit_exact(E, shape):
     assert np.array_equal(out[:, : Ch + 1].cpu().numpy().view(np.uint32), exp2.astype(np.float32).view(np.uint32))
 
 
+@pytest.mark.parametrize("shape", [(1024, 4096), (2048, 2048), (512, 5632), (4096, 4096)])
+def test_fused_stats_match_separate_kernels(E, shape, safe=False):
+    """kernels_fstats.cu (one pass: cutoff statistic + SLERP sums + scalars; one pass: blend + cull statistic)
+    against the exact sort and against the step-by-step kernels: thresholds bit-exact, sums to 1e-12,
+    blend output bit-exact."""
+    R, C = shape
+    Ch = C // 2
+    ws = E.get_workspace(R, C, DEV, safe_select=safe)
+    g = torch.Generator(device=DEV).manual_seed(R * 3 + C)
+    ws.re[0].copy_(torch.randn(ws.re[0].shape, generator=g, device=DEV) * 0.7)
+    ws.re[1].copy_(0.5 * ws.re[0] + 0.6 * torch.randn(ws.re[0].shape, generator=g, device=DEV))
+    ws.re[0][0, 0] = 0.0; ws.re[1][0, 0] = 0.0
+    N = R * C
+    re0 = ws.re[0][:, : Ch + 1].cpu().numpy(); re1 = ws.re[1][:, : Ch + 1].cpu().numpy()
+    for cutoff, cullp in ((0.08, 0.20), (0.5, 0.10), (0.02, 0.05)):
+        ws.ctl.zero_()
+        k2 = int((2 * N) * cutoff); k1 = int(N * cullp)
+        E.fstats_cutoff(ws, ws.re[0], ws.re[1], k2, 0.375)
+        out = torch.empty_like(ws.re[0])
+        E.fstats_blend_cull(ws, ws.re[0], ws.re[1], 1.0, out, k1)
+        dbl, flt, _, _ = ws.read_ctl()
+        assert ws.fs_status() == (0, 0), (cutoff, ws.fs_status())
+        thr = np.float32(flt[E.F_THR_CUT].item())
+        both = _expanded_sorted([re0, re1], R, C)
+        assert thr == both[k2], (cutoff, thr, both[k2])
+        w = half_weights(R, C).astype(np.float64)
+        sl = (np.sign(re0) == np.sign(re1)) & ~(np.abs(re1) < thr)
+        a, b = re0.astype(np.float64), re1.astype(np.float64)
+        s00, s11, s01 = (w * a * a)[sl].sum(), (w * b * b)[sl].sum(), (w * a * b)[sl].sum()
+        # fp32 products / 4-element fp32 partials inside the streaming pass, fp64 across
+        assert abs(float(dbl[E.D_S00]) / s00 - 1) < 2e-7 and abs(float(dbl[E.D_S11]) / s11 - 1) < 2e-7
+        assert abs(float(dbl[E.D_S01]) - s01) < 2e-7 * np.sqrt(s00 * s11)
+        scal = [float(flt[E.F_DOT + i].item()) for i in range(4)]
+        # the same scalars from the step-by-step kernel given the fused sums
+        ws2 = E.Workspace(E.get_plan(R, C, DEV), 2, False)
+        ws2.ctl.zero_()
+        ws2.dbl[E.D_S00:E.D_S00 + 3] = torch.tensor([float(dbl[E.D_S00]), float(dbl[E.D_S11]), float(dbl[E.D_S01])],
+                                                    dtype=torch.float64, device=DEV)
+        ws2.flt[E.F_THR_CUT] = float(thr)
+        E.slerp_scalars(ws2, 0.375)
+        out2 = torch.empty_like(ws.re[0])
+        E.blend(ws2, 0, True, ws.re[0], ws.re[1], 1.0, out2)
+        _, flt2, _, _ = ws2.read_ctl()
+        assert scal == [float(flt2[E.F_DOT + i].item()) for i in range(4)]
+        o1 = out[:, : Ch + 1].cpu().numpy(); o2 = out2[:, : Ch + 1].cpu().numpy()
+        assert np.array_equal(o1.view(np.uint32), o2.view(np.uint32))
+        one = _expanded_sorted([o2], R, C)
+        assert np.float32(flt[E.F_THR_CULL].item()) == one[k1], (cullp, flt[E.F_THR_CULL].item(), one[k1])
+
+
+def test_fused_stats_window_miss_is_reported(E):
+    """Degenerate distribution: either the exact answer or a raised status, never a silently wrong threshold."""
+    R, C = 2048, 4096
+    ws = E.get_workspace(R, C, DEV)
+    ws.re[0].fill_(1.0); ws.re[1].fill_(1.0)
+    ws.re[0][:, :64] = torch.randn((R, 64), device=DEV)
+    ws.ctl.zero_()
+    E.fstats_cutoff(ws, ws.re[0], ws.re[1], int(2 * R * C * 0.08), 0.375)
+    _, flt, _, _ = ws.read_ctl()
+    st = ws.fs_status()[0]
+    if st == 0:
+        assert flt[E.F_THR_CUT].item() == 1.0
+    else:
+        assert np.isnan(flt[E.F_THR_CUT].item())
+
+
 @pytest.mark.parametrize("shape", [(1, 4096), (256, 512), (352, 96), (1024, 2048)])
 def test_inverse_epilogue_bf16_within_1ulp(E, shape):
     """Given the same spectrum, iFFT + x scale + base + bf16 RNE matches the oracle's epilogue on
@@ -348,10 +414,27 @@ def test_pair_merge_vs_oracle_mid_size(E, shape, seed):
     info = {}
     oo = O.merge_layer(bits(base), models, info=info)
     assert abs(fm.last_info["target_norm"] / info["target_norm"] - 1) < 1e-6
+    # (a) fp32 intermediates: the merged delta of the tensor function vs the oracle on identical fp32 deltas.
+    #     north_star tolerance: rel L2 <= 1e-5 -- met outright when no decision flips, and by the residual
+    #     once the <= 8 flipped Hermitian bin pairs are set aside (discontinuous algorithm).
+    from shardmerge_b200.tensor import functions as F
+    d0 = fts[0].float() - base.float(); d1 = fts[1].float() - base.float()
+    n0, n1 = float(d0.norm()), float(d1.norm())
+    a_, b_ = (d0, d1) if n0 >= n1 else (d1, d0)
+    m, _, _ = F.merge_tensors_fft2_slerp(a_, b_, t=0.3 / 0.8, device=DEV, t_sum=1.0, cutoff_pct=0.08, cull_pct=0.20)
+    mo, _, _ = O.merge_tensors_fft2_slerp(a_.cpu().numpy(), b_.cpu().numpy(), 0.3 / 0.8, t_sum=1.0, cutoff_pct=0.08,
+                                          cull_pct=0.20, interp_imag=False)
+    raw, resid, share = flip_accounted(m.cpu().numpy().reshape(sh), np.asarray(mo).reshape(sh), k=16)
+    print(f"\n[{shape}] fp32 merged delta: raw rel-L2 {raw:.3e}, flip-accounted {resid:.3e} (top-16 bins carry {share:.4f})")
+    assert resid <= 1e-5, (raw, resid, share)
+    # (b) final bf16: within 1 ulp on >= 99.99 % when nothing flipped; one flipped bin pair is a sinusoid of
+    #     ~3 % of a typical bf16 ulp over the whole tensor, which moves ~0.5 % of the near-zero elements by > 1 ulp.
     u = bf16_ulp_distance(bits(out), oo)
     frac1 = float((u <= 1).mean())
-    print(f"\n[{shape}] bf16 exact {float((u == 0).mean()):.6f} within-1ulp {frac1:.6f} max-ulp {int(u.max())}")
-    assert frac1 >= 0.995
+    absd = np.abs(O.bf16_to_f32(bits(out)) - O.bf16_to_f32(oo))
+    print(f"[{shape}] bf16 exact {float((u == 0).mean()):.6f} within-1ulp {frac1:.6f} max-abs-diff {absd.max():.3e}")
+    assert frac1 >= (0.9999 if raw <= 1e-5 else 0.985), (frac1, raw)
+    assert absd.max() <= 2.0 ** -7 * np.abs(O.bf16_to_f32(oo)).max() + 1e-4   # never more than one bf16 ulp of the largest value
 
 
 @pytest.mark.parametrize("shape", [(4096, 4096), (14336, 4096), (4096, 14336), (1024, 4096)])
