@@ -80,48 +80,52 @@ def synth_tensor(torch, shape, idx, n_ft, device):
 
 
 class ClockSampler:
-    """nvidia-smi sampled every 200 ms during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and clock-event (throttle) reasons sampled through NVML every 10 ms during the timed region
+    (B200_PROFILING.md recipe; nvidia-smi -lms is too coarse for a region of a few hundred ms)."""
+
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, gpu_index):
-        self.rows = []
-        self.proc = None
         self.gpu_index = gpu_index
+        self.sm, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+
+    def _loop(self, nv, h):
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons", None)
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                if get_reasons is not None:
+                    bits = int(get_reasons(h))
+                    for bit, name in self.REASONS.items():
+                        if bits & bit:
+                            self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.01)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.gpu_index}",
-                 "--query-gpu=clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-                 "clocks_event_reasons.sw_power_cap", "--format=csv,noheader,nounits", "-lms", "200"],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
+            import pynvml as nv
+            nv.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.gpu_index]) if vis and vis.split(",")[self.gpu_index].isdigit() else self.gpu_index
+            h = nv.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self._thread = threading.Thread(target=self._loop, args=(nv, h), daemon=True)
+            self._thread.start()
         except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self._thread = None
 
     def stop(self):
-        if self.proc is not None:
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=2)
-            except Exception:
-                self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-                for nm, v in zip(names, r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nm)
-            except Exception:
-                pass
-        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None,
-                    reasons=sorted(reasons), samples=len(sm))
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=1)
+        return dict(sm_mhz=statistics.median(self.sm) if self.sm else None, sm_max_mhz=self.max_mhz,
+                    reasons=sorted(self.reasons), samples=len(self.sm))
 
 
 # ------------------------------------------------------------------------------------------

@@ -27,6 +27,7 @@
 // Only tensors with more than 2^20 elements come here (sm_fstats_supported); smaller ones are launch
 // bound and use the step-by-step kernels.
 #include <cstddef>
+#include <cstdlib>
 #include "sm_internal.h"
 
 namespace {
@@ -261,7 +262,8 @@ __global__ void __launch_bounds__(1024) k_fs_sample(const __grid_constant__ SmPl
     const unsigned int sub_a = (unsigned int)(out_a.bin < 0 ? 0 : out_a.bin);
     const unsigned int sub_b = (unsigned int)(out_b.bin < 0 ? 2047 : out_b.bin);
     const unsigned int lo = want_a ? ((ea << 19) | (sub_a << 8)) : 0u;
-    const unsigned int hi = want_b ? ((eb << 19) | (sub_b << 8) | 255u) : 0x7fffffffu;
+    unsigned int hi = want_b ? ((eb << 19) | (sub_b << 8) | 255u) : 0x7f800000u;
+    if (hi > 0x7f800000u) hi = 0x7f800000u;           // NaN keys stay above every window
     unsigned int status = 0u;
     const unsigned long long width = hi >= lo ? (unsigned long long)hi - lo + 1ull : 0ull;
     if (width == 0ull) status |= 4u;
@@ -282,6 +284,7 @@ constexpr int kCandStage = 2048, kCandFlush = 1024;   // staged per CTA; flushed
 constexpr int kSideStage = 512, kSideFlush = 256;
 
 struct PassCtx {
+  float lo_f, hi_f;                  // the window as floats: for non-NaN keys, float order == bit-pattern order
   unsigned int lo, span, shift, bcap, scap;
   unsigned long long* hc; unsigned int* bkt;
   unsigned int* scnt; float4* sbkt; double* hs;
@@ -289,66 +292,68 @@ struct PassCtx {
 
 // one key of multiplicity w: count it below the window, or stage it for its bucket (a shared-memory atomic; the
 // global bucket append -- a returning L2 atomic -- is batched in fs_flush so that no warp stalls on it per key)
-__device__ __forceinline__ void fs_key(const PassCtx& x, unsigned int k, unsigned int w, unsigned int& below,
-                                       unsigned int* s_cand, unsigned int* s_ncand) {
-  if (k < x.lo) below += w;
-  if (k - x.lo <= x.span) {                              // unsigned wrap: k < lo is far above span
-    const unsigned int pos = atomicAdd(s_ncand, 1u);
-    if (pos < (unsigned int)kCandStage) s_cand[pos] = k | ((w - 1u) << 31);
-  }
-}
+// CTA staging of the pass kernel, at namespace scope so that the out-of-line push helpers need no pointer arguments
+__shared__ unsigned int g_fs_hist[kBins];               // streaming phase: staged candidates; last CTA: bucket histogram
+__shared__ float4 g_fs_side[kSideStage];
+__shared__ unsigned int g_fs_ncand, g_fs_nside;
+static_assert(kCandStage <= kBins, "candidate staging aliases the histogram");
 
+__device__ __noinline__ void fs_push_cand(unsigned int e) {
+  const unsigned int pos = atomicAdd(&g_fs_ncand, 1u);
+  if (pos < (unsigned int)kCandStage) g_fs_hist[pos] = e;
+}
+__device__ __noinline__ void fs_push_side(float a, float b, float wf) {
+  const unsigned int pos = atomicAdd(&g_fs_nside, 1u);
+  if (pos < (unsigned int)kSideStage) g_fs_side[pos] = make_float4(a, b, wf, 0.f);
+}
 // torch.sign(a) == torch.sign(b) (sign(+-0) = sign(NaN) = 0).  A non-zero product decides it at once; the exact
-// comparison only runs for zeros, NaNs and products that underflow.
+// comparison only runs for zeros, NaNs and products that underflow (a rarely taken, warp-coherent branch).
 __device__ __forceinline__ bool same_sign(float a, float b) {
   const float p = a * b;
-  if (p > 0.f) return true;
-  if (p < 0.f) return false;
-  return sgn(a) == sgn(b);
+  bool same = p > 0.f;
+  if (!(p > 0.f) && !(p < 0.f)) same = (sgn(a) == sgn(b));
+  return same;
 }
 
-// one element pair (MODE 0: statistics, MODE 1: blend); kEdge: column bounds / multiplicity checks
+// one element pair (MODE 0: statistics, MODE 1: blend), multiplicity w (0 for the zero-filled padding columns).
+// The common work is predicated / select based -- the three masks split a warp roughly 46 / 4 / 50 %, so branching
+// on them would run every side for every warp anyway -- and only the rare events (a key or an element inside the
+// window) branch, out of line.  Window tests are float compares on |v| (free abs modifier); NaN keys compare
+// false everywhere, i.e. they sit above the window like their bit patterns do.
 template <int MODE>
-__device__ __forceinline__ float fs_elem(const PassCtx& x, unsigned int hi, const BlendScal& bs, float a, float b, unsigned int w,
-                                         unsigned int& below, float& p00, float& p11, float& p01, unsigned int* s_cand,
-                                         unsigned int* s_ncand, float4* s_side, unsigned int* s_nside) {
+__device__ __forceinline__ float fs_elem(const PassCtx& x, const BlendScal& bs, float a, float b, unsigned int w,
+                                         unsigned int& below, float& p00, float& p11, float& p01) {
+  const bool same = same_sign(a, b);
   if (MODE == 0) {
-    const unsigned int ka = absbits(a), kb = absbits(b);
-    fs_key(x, ka, w, below, s_cand, s_ncand);
-    fs_key(x, kb, w, below, s_cand, s_ncand);
-    if (kb >= x.lo && same_sign(a, b)) {
-      const float wf = (float)w;
-      if (kb > hi) {                                     // |re1| >= thr for every thr in the window (NaN: never < thr)
-        p00 = fmaf(wf * a, a, p00); p11 = fmaf(wf * b, b, p11); p01 = fmaf(wf * a, b, p01);
-      } else {                                           // undecided until the exact threshold is known
-        const unsigned int pos = atomicAdd(s_nside, 1u);
-        if (pos < (unsigned int)kSideStage) s_side[pos] = make_float4(a, b, wf, 0.f);
-      }
+    below += (fabsf(a) < x.lo_f ? w : 0u) + (fabsf(b) < x.lo_f ? w : 0u);
+    if (fabsf(a) >= x.lo_f && fabsf(a) <= x.hi_f && w) fs_push_cand(absbits(a) | ((w - 1u) << 31));
+    const bool b_in_window = fabsf(b) >= x.lo_f && fabsf(b) <= x.hi_f && w;
+    if (b_in_window) fs_push_cand(absbits(b) | ((w - 1u) << 31));
+    const float wf = (float)w;
+    if (same && !(fabsf(b) <= x.hi_f)) {                 // |re1| >= thr for every thr in the window (NaN: never < thr)
+      p00 = fmaf(wf * a, a, p00); p11 = fmaf(wf * b, b, p11); p01 = fmaf(wf * a, b, p01);
     }
+    if (same && b_in_window) fs_push_side(a, b, wf);                // undecided until the exact threshold is known
     return 0.f;
   } else {
-    float o;
-    if (same_sign(a, b)) {
-      if (!(fabsf(b) < bs.thr)) {
-        const float rel = __fsub_rn(b, __fmul_rn(a, bs.dot));
-        o = __fadd_rn(__fmul_rn(a, bs.ct), __fmul_rn(__fdiv_rn(rel, bs.rn), bs.sn));
-      } else {
-        o = __fadd_rn(a, __fmul_rn(bs.t_sum, b));
-      }
-    } else {
-      o = (fabsf(a) > fabsf(b)) ? a : b;
-    }
-    fs_key(x, absbits(o), w, below, s_cand, s_ncand);
+    // functions.py:134-136, one rounding per torch op (same arithmetic as blend1 / k_blend)
+    const float rel = __fsub_rn(b, __fmul_rn(a, bs.dot));
+    const float o_slerp = __fadd_rn(__fmul_rn(a, bs.ct), __fmul_rn(__fdiv_rn(rel, bs.rn), bs.sn));
+    const float o_sum = __fadd_rn(a, __fmul_rn(bs.t_sum, b));
+    const float o_big = (fabsf(a) > fabsf(b)) ? a : b;
+    const float o = same ? ((fabsf(b) < bs.thr) ? o_sum : o_slerp) : o_big;
+    below += fabsf(o) < x.lo_f ? w : 0u;
+    if (fabsf(o) >= x.lo_f && fabsf(o) <= x.hi_f && w) fs_push_cand(absbits(o) | ((w - 1u) << 31));
     return o;
   }
 }
 
 // all threads of the CTA: append the staged entries to their global buckets; returns the overflow flag
 template <int MODE>
-__device__ unsigned int fs_flush(const PassCtx& x, unsigned int* s_cand, unsigned int* s_ncand, float4* s_side,
-                                 unsigned int* s_nside) {
+__device__ unsigned int fs_flush(const PassCtx& x) {
+  unsigned int* s_cand = g_fs_hist; float4* s_side = g_fs_side;
   unsigned int ovf = 0u;
-  unsigned int nc = *s_ncand, nsd = (MODE == 0) ? *s_nside : 0u;
+  unsigned int nc = g_fs_ncand, nsd = (MODE == 0) ? g_fs_nside : 0u;
   if (nc > (unsigned int)kCandStage) { nc = kCandStage; ovf = 2u; }
   if (nsd > (unsigned int)kSideStage) { nsd = kSideStage; ovf = 2u; }
   for (unsigned int i = threadIdx.x; i < nc; i += blockDim.x) {
@@ -369,88 +374,89 @@ __device__ unsigned int fs_flush(const PassCtx& x, unsigned int* s_cand, unsigne
     }
   }
   __syncthreads();
-  if (threadIdx.x == 0) { *s_ncand = 0u; *s_nside = 0u; }
+  if (threadIdx.x == 0) { g_fs_ncand = 0u; g_fs_nside = 0u; }
   __syncthreads();
   return ovf;
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(SM_EW_THREADS) k_fs_pass(const __grid_constant__ SmPlan pl, const __grid_constant__ FsCommon c,
+__global__ void __launch_bounds__(SM_EW_THREADS, 4) k_fs_pass(const __grid_constant__ SmPlan pl, const __grid_constant__ FsCommon c,
                                                            FsState* st, const __grid_constant__ FsWs ws, float* out,
                                                            double t, float* thr_out, float* scal4, double* sums_out) {
   __shared__ unsigned long long s_below[SM_EW_THREADS / 32];
   __shared__ double s_red[32];
-  __shared__ unsigned int s_hist[kBins];                 // streaming phase: candidate staging; last CTA: bucket histogram
-  __shared__ float4 s_side[MODE == 0 ? kSideStage : 1];
-  __shared__ unsigned int s_ncand, s_nside;
   __shared__ Pick pick;
   __shared__ unsigned long long s_rank;
   __shared__ int s_ok;
-  static_assert(kCandStage <= kBins, "candidate staging aliases the histogram");
-  unsigned int* s_cand = s_hist;
-  if (threadIdx.x == 0) { s_ncand = 0u; s_nside = 0u; }
+  unsigned int* const s_hist = g_fs_hist;
+  if (threadIdx.x == 0) { g_fs_ncand = 0u; g_fs_nside = 0u; }
   __syncthreads();
   const bool sw = (c.sel != nullptr && *c.sel != 0);
   const float* __restrict__ re0 = sw ? c.reY : c.reX;
   const float* __restrict__ re1 = sw ? c.reX : c.reY;
   PassCtx x;
   x.lo = st->lo; x.span = st->hi - x.lo; x.shift = st->shift; x.bcap = ws.bcap; x.scap = ws.scap;
+  x.lo_f = __uint_as_float(x.lo); x.hi_f = __uint_as_float(st->hi);       // hi <= +inf (k_fs_sample)
   x.hc = ws.hc; x.bkt = ws.bkt; x.scnt = ws.scnt; x.sbkt = ws.sbkt; x.hs = ws.hs;
-  const unsigned int hi = st->hi;
   const bool dead = st->status != 0u;
   BlendScal bs{};
   if (MODE == 1) { bs.thr = *c.thr_cut; bs.dot = c.scal4[0]; bs.ct = c.scal4[1]; bs.sn = c.scal4[2]; bs.rn = c.scal4[3]; bs.t_sum = c.t_sum; }
-  const int c0 = blockIdx.x * SM_EW_COLS + threadIdx.x * 4;
   const int Ch = pl.Ch;
-  const bool active = (c0 <= Ch);
-  const bool interior = (c0 > 0 && c0 + 3 < Ch);          // four valid columns of multiplicity 2: no per-element checks
   unsigned int below32 = 0u;
   unsigned int ovf = 0u;
   double d00 = 0.0, d11 = 0.0, d01 = 0.0;
+  // Work items are float4 column groups, numbered row-major over rows x G groups (G covers columns 0..Ch); the grid
+  // strides over them so every thread gets the same share (no idle column blocks, no tail wave), two items in flight.
+  const unsigned int G = (unsigned int)(Ch + 4) / 4u;
+  const unsigned int total = (unsigned int)pl.R * G;
+  const unsigned int stride = gridDim.x * blockDim.x;
+  const unsigned int step_row = stride / G, step_g = stride - step_row * G;
   if (!dead) {
     int it = 0;
-    for (int row0 = blockIdx.y; row0 < pl.R; row0 += 2 * gridDim.y, ++it) {      // trip count is uniform over the CTA
-      if (active) {
-        const int row1 = row0 + gridDim.y;
-        const bool two = row1 < pl.R;
-        const size_t off0 = (size_t)row0 * pl.P + c0, off1 = (size_t)(two ? row1 : row0) * pl.P + c0;
-        float4 a4[2], b4[2];
-        a4[0] = *reinterpret_cast<const float4*>(re0 + off0); b4[0] = *reinterpret_cast<const float4*>(re1 + off0);
-        a4[1] = *reinterpret_cast<const float4*>(re0 + off1); b4[1] = *reinterpret_cast<const float4*>(re1 + off1);
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-          if (r == 1 && !two) break;
-          const float a[4] = {a4[r].x, a4[r].y, a4[r].z, a4[r].w}, b[4] = {b4[r].x, b4[r].y, b4[r].z, b4[r].w};
+    unsigned int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned int row = idx / G, g = idx - row * G;
+    for (unsigned int base = blockIdx.x * blockDim.x; base < total; base += 2u * stride, ++it) {   // uniform trip count
+      // second item of this iteration: one grid stride further
+      unsigned int row1 = row + step_row, g1 = g + step_g;
+      if (g1 >= G) { g1 -= G; ++row1; }
+      const int n_item = idx < total ? (idx + stride < total ? 2 : 1) : 0;
+      if (n_item > 0) {
+        const size_t off[2] = {(size_t)row * pl.P + 4u * g, n_item == 2 ? (size_t)row1 * pl.P + 4u * g1 : (size_t)row * pl.P + 4u * g};
+        float4 a4[2], b4[2];                             // both items in flight before the first is consumed
+        a4[0] = *reinterpret_cast<const float4*>(re0 + off[0]); b4[0] = *reinterpret_cast<const float4*>(re1 + off[0]);
+        a4[1] = *reinterpret_cast<const float4*>(re0 + off[1]); b4[1] = *reinterpret_cast<const float4*>(re1 + off[1]);
+#pragma unroll 1
+        for (int r = 0; r < n_item; ++r) {               // rolled: one copy of the element code keeps the loop in the I-cache
+          const float4 av = r == 0 ? a4[0] : a4[1], bv = r == 0 ? b4[0] : b4[1];
+          const int c0 = 4 * (int)(r == 0 ? g : g1);
+          const float a[4] = {av.x, av.y, av.z, av.w}, b[4] = {bv.x, bv.y, bv.z, bv.w};
           float p00 = 0.f, p11 = 0.f, p01 = 0.f;         // fp32 over one float4, fp64 across
           float o[4];
-          if (interior) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-              o[i] = fs_elem<MODE>(x, hi, bs, a[i], b[i], 2u, below32, p00, p11, p01, s_cand, &s_ncand, s_side, &s_nside);
-          } else {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int col = c0 + i;
-              o[i] = 0.f;
-              if (col <= Ch)
-                o[i] = fs_elem<MODE>(x, hi, bs, a[i], b[i], (col == 0 || col == Ch) ? 1u : 2u, below32, p00, p11, p01, s_cand,
-                                     &s_ncand, s_side, &s_nside);
-              else if (MODE == 1) o[i] = blend1(a[i], b[i], bs);             // padding columns: same values as sm_blend writes
-            }
+          for (int i = 0; i < 4; ++i) {
+            // multiplicity: 1 at columns 0 and Ch, 2 inside, 0 for the padding (zero-filled by the plane allocator and
+            // never written by any kernel, so padding elements contribute nothing)
+            const int col = c0 + i;
+            const unsigned int w = col > Ch ? 0u : ((col == 0 || col == Ch) ? 1u : 2u);
+            o[i] = fs_elem<MODE>(x, bs, a[i], b[i], w, below32, p00, p11, p01);
           }
           if (MODE == 0) { d00 += (double)p00; d11 += (double)p11; d01 += (double)p01; }
-          else *reinterpret_cast<float4*>(out + (r == 0 ? off0 : off1)) = make_float4(o[0], o[1], o[2], o[3]);
+          else *reinterpret_cast<float4*>(out + (r == 0 ? off[0] : off[1])) = make_float4(o[0], o[1], o[2], o[3]);
         }
       }
+      // advance this thread by two grid strides
+      idx += 2u * stride;
+      row = row1 + step_row; g = g1 + step_g;
+      if (g >= G) { g -= G; ++row; }
       if ((it & 7) == 7) {                               // every 8 iterations: flush the staging if it is half full
         __syncthreads();
-        if (s_ncand >= (unsigned int)kCandFlush || s_nside >= (unsigned int)kSideFlush)
-          ovf |= fs_flush<MODE>(x, s_cand, &s_ncand, s_side, &s_nside);
+        if (g_fs_ncand >= (unsigned int)kCandFlush || g_fs_nside >= (unsigned int)kSideFlush)
+          ovf |= fs_flush<MODE>(x);
         else __syncthreads();                            // nobody appends before everybody has read the counters
       }
     }
     __syncthreads();
-    ovf |= fs_flush<MODE>(x, s_cand, &s_ncand, s_side, &s_nside);
+    ovf |= fs_flush<MODE>(x);
   }
   unsigned long long below = below32;
   if (ovf) atomicOr(&st->status, ovf);
@@ -555,11 +561,14 @@ __global__ void __launch_bounds__(SM_EW_THREADS) k_fs_pass(const __grid_constant
 }
 
 inline dim3 fs_grid(const SmPlan& p) {
-  const int gx = (p.Ch + 1 + SM_EW_COLS - 1) / SM_EW_COLS;
-  int gy = (148 * 6 + gx - 1) / gx;                      // ~6 CTAs of 256 threads per SM, each walks its rows two at a time
-  if (gy > (p.R + 1) / 2) gy = (p.R + 1) / 2;
-  if (gy < 1) gy = 1;
-  return dim3(gx, gy);
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long items = (long long)p.R * ((p.Ch + 4) / 4);
+  long long ctas = (long long)sms * 4;                   // one resident wave at 4 CTAs of 256 threads per SM (launch bounds)
+  const long long need = (items + 2 * SM_EW_THREADS - 1) / (2 * SM_EW_THREADS);
+  if (ctas > need) ctas = need;
+  if (ctas < 1) ctas = 1;
+  return dim3((unsigned int)ctas, 1);
 }
 
 void fs_sample_ranks(unsigned long long rank, unsigned long long total, long long* k_lo, long long* k_hi) {

@@ -151,9 +151,11 @@ class Workspace:
         self.plan = plan
         dev = plan.device
         self.n_spectra = n_spectra
-        self.re = [torch.empty((plan.R, plan.P), dtype=torch.float32, device=dev) for _ in range(n_spectra)]
-        self.im = [torch.empty((plan.R, plan.P), dtype=torch.float32, device=dev) for _ in range(n_spectra)]
-        self.re_out = torch.empty((plan.R, plan.P), dtype=torch.float32, device=dev)   # blend output of the fused chain
+        # zero-filled: no kernel writes the padding columns (Ch+1 .. P-1) with anything but blend(0, 0) = 0, and the
+        # fused statistics pass relies on them being zero
+        self.re = [torch.zeros((plan.R, plan.P), dtype=torch.float32, device=dev) for _ in range(n_spectra)]
+        self.im = [torch.zeros((plan.R, plan.P), dtype=torch.float32, device=dev) for _ in range(n_spectra)]
+        self.re_out = torch.zeros((plan.R, plan.P), dtype=torch.float32, device=dev)   # blend output of the fused chain
         self.ctl = torch.zeros(_CTL_BYTES, dtype=torch.uint8, device=dev)
         self.dbl = self.ctl[_OFF_DBL:_OFF_DBL + 64].view(torch.float64)
         self.flt = self.ctl[_OFF_FLT:_OFF_FLT + 64].view(torch.float32)
