@@ -193,7 +193,7 @@ def main():
     ap.add_argument("--workload", default="llama8b", choices=sorted(ARCH))
     ap.add_argument("--layers", type=int, default=0, help="layers resident per rank (0 = as many as fit, up to L)")
     ap.add_argument("--finetunes", type=int, default=2)
-    ap.add_argument("--e2e-layers", type=int, default=1)
+    ap.add_argument("--e2e-layers", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profile-json", default="", help="write the per-kernel-class summary here")
@@ -324,10 +324,36 @@ def main():
         h2d = sum(t.numel() * 2 for n in names for t in [host["synth/base"][n]] + [host[f"synth/ft{k}"][n] for k in range(M)])
         d2h = sum(out_host[n].numel() * 2 for n in names)
 
+        class HostSink:
+            """Stands in for ModelWriter.add_tensor (shard/writer.py:115-149) without the file write: every result
+            is copied device -> pinned host on a side stream, like ModelWriter._stage does."""
+
+            def __init__(self):
+                self.stream = torch.cuda.Stream(device=dev)
+                self.events = []
+
+            def add_tensor(self, name, tensor):
+                produced = torch.cuda.current_stream(dev).record_event()
+                with torch.cuda.stream(self.stream):
+                    self.stream.wait_event(produced)
+                    out_host[name].copy_(tensor, non_blocking=True)
+                    tensor.record_stream(self.stream)
+                    self.events.append(self.stream.record_event())
+
+            def wait(self):
+                for ev in self.events:
+                    ev.synchronize()
+                self.events.clear()
+
+        sink = HostSink()
+        layers_e2e = [ShardLayer(i, "s", n, False) for i, n in enumerate(names)]
+        fm2.defer_checks = True                    # what MergeTensorsBase.merge() sets: checks settle one tensor behind
+
         async def e2e_step():
-            for i, n in enumerate(names):
-                out = await fm2._merge_layer(ShardLayer(i, "s", n, False), str(dev))
-                out_host[n].copy_(out, non_blocking=True)
+            # the reference's hot loop (shard/merge/base.py:212-223): _merge_layer + writer.add_tensor per tensor;
+            # here the next tensor's upload, this tensor's kernels and the previous tensor's download overlap
+            await fm2._process_layers(sink, layers_e2e, str(dev))
+            sink.wait()
             torch.cuda.synchronize(dev)
 
         loop = asyncio.new_event_loop()
@@ -348,7 +374,8 @@ def main():
         e2e_params = sum(numel(host["synth/base"][n].shape) for n in names)
         e2e = dict(value=world * e2e_params * args.steps / (ems / 1000.0), unit="params/s",
                    h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, layers=Le,
-                   api="FourierMerge._merge_layer(shard_layer, 'cuda') with pinned host tensors")
+                   api="MergeTensorsBase._process_layers (FourierMerge._merge_layer + writer.add_tensor per tensor) on "
+                       "pinned host tensors: H2D of base + finetunes and D2H of the merged tensor inside the timed region")
 
     # ---- CPU baseline (rank 0, N = 1 only) -----------------------------------------------------
     cpu_baseline = None

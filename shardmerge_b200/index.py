@@ -54,6 +54,8 @@ class _IndexBase:
     def __init__(self):
         self.model_indexes: Dict[str, dict] = {}
         self._order: Dict[str, List[str]] = {}
+        self._prefetched: dict = {}
+        self._copy_streams: dict = {}
 
     def _register(self, model_uri: str, index: dict):
         self.model_indexes[model_uri] = index
@@ -67,6 +69,44 @@ class _IndexBase:
 
     async def preload_tensor(self, model_uri: str, tensor_name: str):
         return None
+
+    # ---- one-tensor-ahead upload ------------------------------------------------------
+    # The reference loads a tensor when _merge_layer asks for it, synchronously (shard/index.py:238-270), so the
+    # GPU idles during every host-to-device copy.  prefetch() starts the copy of a tensor the merge loop will ask
+    # for next on a dedicated copy stream; the matching get_tensor(...).get() hands the device tensor over after
+    # making the caller's stream wait for the copy.
+    def _host_tensor(self, model_uri: str, tensor_name: str) -> torch.Tensor:
+        raise NotImplementedError
+
+    def prefetch(self, model_uri: str, tensor_name: str, device: str):
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            return
+        key = (model_uri, tensor_name, str(dev))
+        if key in self._prefetched:
+            return
+        host = self._host_tensor(model_uri, tensor_name)
+        if host.device.type == "cuda":
+            return
+        if not host.is_pinned():
+            host = host.pin_memory()
+        stream = self._copy_streams.get(str(dev))
+        if stream is None:
+            stream = self._copy_streams[str(dev)] = torch.cuda.Stream(device=dev)
+        with torch.cuda.stream(stream):
+            t = host.to(dev, non_blocking=True)
+            ev = stream.record_event()
+        self._prefetched[key] = (t, ev, host)
+
+    def _take_prefetched(self, model_uri: str, tensor_name: str, device: str):
+        ent = self._prefetched.pop((model_uri, tensor_name, str(torch.device(device))), None)
+        if ent is None:
+            return None
+        t, ev, _host = ent
+        cur = torch.cuda.current_stream(t.device)
+        cur.wait_event(ev)
+        t.record_stream(cur)
+        return t
 
 
 class InMemoryIndex(_IndexBase):
@@ -88,9 +128,19 @@ class InMemoryIndex(_IndexBase):
     def tensor_numels(self, model_uri: str) -> Dict[str, int]:
         return {n: t.numel() for n, t in self.models[model_uri].items()}
 
+    def _host_tensor(self, model_uri: str, tensor_name: str) -> torch.Tensor:
+        return self.models[model_uri][tensor_name]
+
     def get_tensor(self, model_uri: str, tensor_name: str, device: str = "cpu") -> TensorPromise:
         t = self.models[model_uri][tensor_name]
-        return TensorPromise(model_uri, tensor_name, device, lambda: t if str(t.device) == str(device) else t.to(device))
+
+        def load():
+            if str(t.device) == str(device):
+                return t
+            pre = self._take_prefetched(model_uri, tensor_name, device)
+            return pre if pre is not None else t.to(device, non_blocking=t.is_pinned())
+
+        return TensorPromise(model_uri, tensor_name, device, load)
 
 
 def _default_shard_of(name: str) -> str:
@@ -136,11 +186,18 @@ class LocalSafetensorsIndex(_IndexBase):
         shard = self.storage_dir / model_uri / index["weight_map"][tensor_name]
 
         def load():
-            from safetensors import safe_open
-            with safe_open(str(shard), framework="pt") as f:
-                t = f.get_tensor(tensor_name)
             if torch.device(device).type == "cuda":
-                return t.pin_memory().to(device, non_blocking=True)
-            return t
+                pre = self._take_prefetched(model_uri, tensor_name, device)
+                if pre is not None:
+                    return pre
+                return self._host_tensor(model_uri, tensor_name).pin_memory().to(device, non_blocking=True)
+            return self._host_tensor(model_uri, tensor_name)
 
         return TensorPromise(model_uri, tensor_name, device, load)
+
+    def _host_tensor(self, model_uri: str, tensor_name: str) -> torch.Tensor:
+        from safetensors import safe_open
+        index = self.model_indexes[model_uri]
+        shard = self.storage_dir / model_uri / index["weight_map"][tensor_name]
+        with safe_open(str(shard), framework="pt") as f:
+            return f.get_tensor(tensor_name)

@@ -98,11 +98,19 @@ class MergeTensorsBase(ABC):
     def _settle(self, keep: int = 0):
         """Make every result except the newest `keep` final (override where results are deferred)."""
 
+    def prefetch_layer(self, shard_layer: ShardLayer, device: str):
+        """Start the host-to-device copies of the tensors `_merge_layer(shard_layer)` will ask for (override per
+        strategy; needs an index manager with `prefetch`, see shardmerge_b200/index.py)."""
+
     async def _process_layers(self, writer: ModelWriter, shard_layers: List[ShardLayer], device: str):
         current = None
         in_flight = []
         try:
-            for current in shard_layers:
+            for i, current in enumerate(shard_layers):
+                if i == 0:
+                    self.prefetch_layer(current, device)
+                if i + 1 < len(shard_layers):
+                    self.prefetch_layer(shard_layers[i + 1], device)      # its upload overlaps this tensor's kernels
                 in_flight.append((current, await self._merge_layer(current, device)))
                 while len(in_flight) > self.pipeline_depth:
                     self._settle(keep=len(in_flight) - 1)

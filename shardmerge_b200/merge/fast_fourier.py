@@ -70,6 +70,23 @@ class FourierMerge(MergeTensorsBase):
         logger.info(f"Passthrough - {shard_layer.layer_name} from {source}")
         return await self.index_manager.get_tensor(source, shard_layer.layer_name, device=device).get()
 
+    def prefetch_layer(self, shard_layer, device: str):
+        prefetch = getattr(self.index_manager, "prefetch", None)
+        if prefetch is None or not str(device).startswith("cuda"):
+            return
+        number, name = shard_layer.layer_number, shard_layer.layer_name
+        if number in (INPUT_LAYER, OUTPUT_LAYER):
+            attr = "is_input" if number == INPUT_LAYER else "is_output"
+            chosen = next((m for m in self.config.finetune_merge if getattr(m, attr)), None)
+            prefetch(chosen.model if chosen is not None else self.config.output_base_model, name, device)
+            return
+        wanted = [self.config.output_base_model]
+        for m in self.config.finetune_merge:
+            if m.use_layer_index(number):
+                wanted += [m.base, m.model]
+        for uri in dict.fromkeys(wanted):
+            prefetch(uri, name, device)
+
     async def _merge_layer(self, shard_layer, device: str) -> torch.Tensor:
         number = shard_layer.layer_number
         if number == INPUT_LAYER:
