@@ -48,6 +48,11 @@ ALPHAS = (0.3, 0.5, 0.4, 0.2)
 SIGMAS = (0.002, 0.0026, 0.0023, 0.0029)
 
 
+def workload_name(workload, n_ft):
+    return (f"{workload}-shaped base + {n_ft} finetunes (bf16), alpha {'/'.join(str(x) for x in ALPHAS[:n_ft])}, "
+            "SLERP-FFT merge of every model.layers.* tensor")
+
+
 def layer_tensors(a):
     H, I, KV = a["H"], a["I"], a["KV"]
     return [("self_attn.q_proj.weight", (H, H)), ("self_attn.k_proj.weight", (KV, H)),
@@ -163,7 +168,7 @@ def run_reference_arm(args):
         return
     a = ARCH[args.workload]
     shape = (a["KV"], a["H"])
-    threads = max(1, min(os.cpu_count() or 1, 16))
+    threads = max(1, min(os.cpu_count() or 1, 64))      # one tensor per host thread (numpy's FFT / sort are single-threaded)
     for _ in range(min(args.warmup, 1)):
         cpu_port_rate(shape, args.finetunes, threads)
     rates, secs = [], []
@@ -175,8 +180,7 @@ def run_reference_arm(args):
     line = dict(impl="reference", metric="merged_params_per_sec", value=value, unit="params/s", n_gpus=args.gpus,
                 steps=args.steps, warmup=args.warmup, ms_per_step=1000 * sum(secs) / len(secs), higher_is_better=True,
                 scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-                config=dict(workload=f"{args.workload}-shaped base + {args.finetunes} finetunes, alpha 0.3/0.5, SLERP-FFT merge",
-                            sample=sample),
+                config=dict(workload=workload_name(args.workload, args.finetunes), sample=sample),
                 cpu_baseline=dict(value=value, unit="params/s", cores=threads, kind="port", sample=sample),
                 e2e=dict(value=value, unit="params/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0)
@@ -391,8 +395,7 @@ def main():
                     warmup=args.warmup, ms_per_step=elapsed_ms / args.steps, higher_is_better=True, scaling="weak",
                     vs_baseline=None, dtype="f32", data="synthetic",
                     merged_gb_per_s=value * 2 / 1e9,
-                    config=dict(workload=f"{args.workload}-shaped base + {M} finetunes (bf16), alpha "
-                                         f"{'/'.join(str(x) for x in ALPHAS[:M])}, SLERP-FFT merge of every model.layers.* tensor",
+                    config=dict(workload=workload_name(args.workload, M),
                                 layers_resident=L, layers_of_model=a["L"], merged_params_per_step_per_gpu=merged_params,
                                 tensors_per_step=len(tensors), l2="inputs per step (%.1f GB) exceed the 126 MB L2" %
                                                                  (merged_params * 2 * (M + 1) / 1e9),

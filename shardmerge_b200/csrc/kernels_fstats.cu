@@ -55,11 +55,15 @@ struct FsWs {                        // carved out of the caller's workspace
   unsigned long long* hc;            // [kBins]  hi 32 bits: keys (with multiplicity), lo 32 bits: bucket entries
   unsigned int* scnt;                // [kBins]  side bucket entries
   double* hs;                        // [kBins][3] per-bin partial SLERP sums of the side entries
-  unsigned int* sample;              // [kNS]
+  unsigned int* shist;               // [kSampleBins] sample histogram (zeroed by a memset node before k_fs_sample)
   unsigned int* bkt;                 // [kBins][bcap]  key | (multiplicity - 1) << 31
   float4* sbkt;                      // [kBins][scap]  (re0, re1, multiplicity, -)
   unsigned int bcap, scap;
+  unsigned long long* dbg;           // development: per-CTA phase timestamps (NULL in production)
 };
+
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define FS_STAMP(slot) do { if (ws.dbg && threadIdx.x == 0) ws.dbg[(blockIdx.x) * 8 + (slot)] = gtimer(); } while (0)
 
 __device__ __forceinline__ unsigned int absbits(float v) { return __float_as_uint(v) & 0x7fffffffu; }
 __device__ __forceinline__ int sgn(float v) { return (v > 0.f) - (v < 0.f); }
@@ -190,12 +194,22 @@ struct FsCommon {
   const float* thr_cut; const float* scal4; float t_sum;  // MODE 1 only
 };
 
+constexpr int kSampleShift = 18;                         // sample histogram digit: key bits [30:18] (exponent + 5 mantissa bits)
+constexpr int kSampleBins = 1 << (31 - kSampleShift);    // 8192
+
+struct LoadGlobal32 { const unsigned int* h; __device__ unsigned long long operator()(int b) const { return __ldcg(h + b); } };
+
+// 64 K random keys of the full (mirrored) spectrum are histogrammed by their top 14 key bits with global
+// reductions (spread over the L2 slices, no single-SM bottleneck); the last CTA to finish copies the 8 K bins to
+// shared memory (all loads in flight at once: single-CTA epilogues must not chain L2 round trips), finds the bins
+// holding the sample ranks k_lo / k_hi and takes their outer edges as the key window: at most one bin (3 % of the
+// key value) wider per side than the exact sample statistics would give.
 template <int MODE>
 __global__ void __launch_bounds__(1024) k_fs_sample(const __grid_constant__ SmPlan pl, const __grid_constant__ FsCommon c,
                                                     FsState* st, const __grid_constant__ FsWs ws, unsigned long long rank,
                                                     long long k_lo, long long k_hi) {
-  __shared__ unsigned int sh[4096];
   __shared__ Pick out_a, out_b;
+  __shared__ unsigned int s_h[kSampleBins];
   const unsigned int ns = kNS;
   const unsigned long long per_plane = (unsigned long long)pl.R * (unsigned long long)pl.C;
   const unsigned long long total = per_plane * (MODE == 0 ? 2ull : 1ull);
@@ -205,7 +219,11 @@ __global__ void __launch_bounds__(1024) k_fs_sample(const __grid_constant__ SmPl
   BlendScal bs{};
   if (MODE == 1) { bs.thr = *c.thr_cut; bs.dot = c.scal4[0]; bs.ct = c.scal4[1]; bs.sn = c.scal4[2]; bs.rn = c.scal4[3]; bs.t_sum = c.t_sum; }
   const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
-  // this kernel also zeroes the histograms / bucket counters of the pass that follows
+  FS_STAMP(0);
+#pragma unroll
+  for (int j = 0; j < kSampleBins / 1024; ++j) s_h[threadIdx.x + 1024 * j] = 0u;
+  __syncthreads();
+  // this kernel also zeroes the bucket counters / per-bin sums of the pass that follows
   for (unsigned int z = i; z < (unsigned int)kBins; z += gridDim.x * blockDim.x) {
     ws.hc[z] = 0ull; ws.scnt[z] = 0u; ws.hs[3 * z] = 0.0; ws.hs[3 * z + 1] = 0.0; ws.hs[3 * z + 2] = 0.0;
   }
@@ -217,53 +235,39 @@ __global__ void __launch_bounds__(1024) k_fs_sample(const __grid_constant__ SmPl
     unsigned int col = (unsigned int)(j - (unsigned long long)row * pl.C);
     if (col > (unsigned int)pl.Ch) col = pl.C - col;
     const size_t off = (size_t)row * pl.P + col;
-    ws.sample[i] = (MODE == 0) ? absbits(pp[off]) : absbits(blend1(re0[off], re1[off], bs));
+    const unsigned int key = (MODE == 0) ? absbits(pp[off]) : absbits(blend1(re0[off], re1[off], bs));
+    // CTA-local histogram first: the populated bins are few, and same-address reductions serialise in L2
+    // (measured: 64 K direct global REDs took 12-17 us; one RED per CTA and non-empty bin takes < 1 us)
+    atomicAdd(&s_h[key >> kSampleShift], 1u);
   }
-  if (!fs_last_block(st)) return;
-  // ---- last CTA: the sample's order statistics at ranks k_lo / k_hi, resolved to 23 key bits in two digits.
-  // Digit 1 = key bits [30:19] (exponent + 4 mantissa bits): the populated exponents spread over enough bins
-  // that plain shared atomics see little same-address contention.  Loads are batched 16 deep so that a sweep
-  // costs a handful of L2 round trips instead of one per key.
+  __syncthreads();
+  FS_STAMP(1);
+#pragma unroll
+  for (int j = 0; j < kSampleBins / 1024; ++j) {
+    const unsigned int v = s_h[threadIdx.x + 1024 * j];
+    if (v) atomicAdd(ws.shist + threadIdx.x + 1024 * j, v);
+  }
+  FS_STAMP(2);
+  const bool last = fs_last_block(st);
+  FS_STAMP(3);
+  if (!last) return;
   const bool want_a = (k_lo >= 0 && k_lo < (long long)ns), want_b = (k_hi >= 0 && k_hi < (long long)ns);
-  for (int b = threadIdx.x; b < 4096; b += blockDim.x) sh[b] = 0u;
-  __syncthreads();
-  for (unsigned int q0 = threadIdx.x; q0 < ns; q0 += 16u * blockDim.x) {      // ns is a multiple of 16 * blockDim.x
-    unsigned int kk[16];
+  {
+    unsigned int v[kSampleBins / 1024];
 #pragma unroll
-    for (int u = 0; u < 16; ++u) kk[u] = __ldcg(ws.sample + q0 + u * blockDim.x);
+    for (int j = 0; j < kSampleBins / 1024; ++j) v[j] = __ldcg(ws.shist + threadIdx.x + 1024 * j);
 #pragma unroll
-    for (int u = 0; u < 16; ++u) atomicAdd(&sh[kk[u] >> 19], 1u);
+    for (int j = 0; j < kSampleBins / 1024; ++j) s_h[threadIdx.x + 1024 * j] = v[j];
   }
   __syncthreads();
-  block_pick<1024>(LoadSmem32{sh}, 4096, want_a ? (unsigned long long)k_lo : 0ull, &out_a);
-  block_pick<1024>(LoadSmem32{sh}, 4096, want_b ? (unsigned long long)k_hi : 0ull, &out_b);
-  const unsigned int ea = (unsigned int)(out_a.bin < 0 ? 0 : out_a.bin);
-  const unsigned int eb = (unsigned int)(out_b.bin < 0 ? 0 : out_b.bin);
-  const unsigned long long ra = out_a.rank_in_bin, rb = out_b.rank_in_bin;
+  block_pick<1024>(LoadSmem32{s_h}, kSampleBins, want_a ? (unsigned long long)k_lo : 0ull, &out_a);
+  block_pick<1024>(LoadSmem32{s_h}, kSampleBins, want_b ? (unsigned long long)k_hi : 0ull, &out_b);
+  const int bin_a = out_a.bin, bin_b = out_b.bin;
   __syncthreads();
-  // digit 2 = key bits [18:8] inside the two selected digit-1 bins
-  for (int b = threadIdx.x; b < 2 * kBins; b += blockDim.x) sh[b] = 0u;
-  __syncthreads();
-  for (unsigned int q0 = threadIdx.x; q0 < ns; q0 += 16u * blockDim.x) {
-    unsigned int kk[16];
-#pragma unroll
-    for (int u = 0; u < 16; ++u) kk[u] = __ldcg(ws.sample + q0 + u * blockDim.x);
-#pragma unroll
-    for (int u = 0; u < 16; ++u) {
-      const unsigned int key = kk[u], e = key >> 19, sub = (key >> 8) & 2047u;
-      if (e == ea) atomicAdd(&sh[sub], 1u);
-      if (e == eb) atomicAdd(&sh[kBins + sub], 1u);
-    }
-  }
-  __syncthreads();
-  block_pick<1024>(LoadSmem32{sh}, kBins, ra, &out_a);
-  block_pick<1024>(LoadSmem32{sh + kBins}, kBins, rb, &out_b);
   if (threadIdx.x == 0) {
-    const unsigned int sub_a = (unsigned int)(out_a.bin < 0 ? 0 : out_a.bin);
-    const unsigned int sub_b = (unsigned int)(out_b.bin < 0 ? 2047 : out_b.bin);
-    const unsigned int lo = want_a ? ((ea << 19) | (sub_a << 8)) : 0u;
-    unsigned int hi = want_b ? ((eb << 19) | (sub_b << 8) | 255u) : 0x7f800000u;
-    if (hi > 0x7f800000u) hi = 0x7f800000u;           // NaN keys stay above every window
+    const unsigned int lo = (want_a && bin_a >= 0) ? ((unsigned int)bin_a << kSampleShift) : 0u;
+    unsigned int hi = (want_b && bin_b >= 0) ? ((((unsigned int)bin_b + 1u) << kSampleShift) - 1u) : 0x7f800000u;
+    if (hi > 0x7f800000u) hi = 0x7f800000u;             // NaN keys stay above every window
     unsigned int status = 0u;
     const unsigned long long width = hi >= lo ? (unsigned long long)hi - lo + 1ull : 0ull;
     if (width == 0ull) status |= 4u;
@@ -275,6 +279,7 @@ __global__ void __launch_bounds__(1024) k_fs_sample(const __grid_constant__ SmPl
     st->s_in[0] = 0.0; st->s_in[1] = 0.0; st->s_in[2] = 0.0;
     st->ticket = 0u;
   }
+  FS_STAMP(4);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -391,6 +396,7 @@ __global__ void __launch_bounds__(SM_EW_THREADS, 4) k_fs_pass(const __grid_const
   unsigned int* const s_hist = g_fs_hist;
   if (threadIdx.x == 0) { g_fs_ncand = 0u; g_fs_nside = 0u; }
   __syncthreads();
+  FS_STAMP(0);
   const bool sw = (c.sel != nullptr && *c.sel != 0);
   const float* __restrict__ re0 = sw ? c.reY : c.reX;
   const float* __restrict__ re1 = sw ? c.reX : c.reY;
@@ -456,7 +462,9 @@ __global__ void __launch_bounds__(SM_EW_THREADS, 4) k_fs_pass(const __grid_const
       }
     }
     __syncthreads();
+    FS_STAMP(1);
     ovf |= fs_flush<MODE>(x);
+    FS_STAMP(2);
   }
   unsigned long long below = below32;
   if (ovf) atomicOr(&st->status, ovf);
@@ -477,7 +485,10 @@ __global__ void __launch_bounds__(SM_EW_THREADS, 4) k_fs_pass(const __grid_const
       atomicAdd(&st->s_in[0], r0); atomicAdd(&st->s_in[1], r1); atomicAdd(&st->s_in[2], r2);
     }
   }
-  if (!fs_last_block(st)) return;
+  FS_STAMP(3);
+  const bool last_cta = fs_last_block(st);
+  FS_STAMP(4);
+  if (!last_cta) return;
 
   // ---- last CTA: bin of the statistic -> exact key inside that bucket -> (MODE 0) close the sums
   constexpr int NT = SM_EW_THREADS;
@@ -493,7 +504,15 @@ __global__ void __launch_bounds__(SM_EW_THREADS, 4) k_fs_pass(const __grid_const
   unsigned int key = 0u;
   int bstar = -1;
   if (ok) {
-    block_pick<NT>(LoadGlobalHi{ws.hc}, kBins, s_rank, &pick);
+    {  // key counts per bucket -> shared memory, every load in flight at once
+      unsigned long long v[kBins / NT];
+#pragma unroll
+      for (int j = 0; j < kBins / NT; ++j) v[j] = __ldcg(ws.hc + threadIdx.x + NT * j);
+#pragma unroll
+      for (int j = 0; j < kBins / NT; ++j) s_hist[threadIdx.x + NT * j] = (unsigned int)(v[j] >> 32);
+    }
+    __syncthreads();
+    block_pick<NT>(LoadSmem32{s_hist}, kBins, s_rank, &pick);
     bstar = pick.bin;
     if (bstar < 0) ok = false;                            // rank beyond the window: the sample window missed
   }
@@ -525,8 +544,16 @@ __global__ void __launch_bounds__(SM_EW_THREADS, 4) k_fs_pass(const __grid_const
   if (MODE == 0 && ok) {
     // side entries: bins above the statistic's bin are "in" (per-bin partial sums); inside the bin decide per entry
     double acc[3] = {0.0, 0.0, 0.0};
-    for (int b = threadIdx.x; b < kBins; b += NT) {
-      if (b > bstar) { acc[0] += __ldcg(ws.hs + 3 * b); acc[1] += __ldcg(ws.hs + 3 * b + 1); acc[2] += __ldcg(ws.hs + 3 * b + 2); }
+    {
+      double h[kBins / NT][3];
+#pragma unroll
+      for (int j = 0; j < kBins / NT; ++j) {
+        const int b = threadIdx.x + NT * j;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) h[j][q] = (b > bstar) ? __ldcg(ws.hs + 3 * b + q) : 0.0;
+      }
+#pragma unroll
+      for (int j = 0; j < kBins / NT; ++j) { acc[0] += h[j][0]; acc[1] += h[j][1]; acc[2] += h[j][2]; }
     }
     unsigned int ns_b = __ldcg(ws.scnt + bstar);
     if (ns_b > x.scap) ns_b = x.scap;
@@ -558,6 +585,7 @@ __global__ void __launch_bounds__(SM_EW_THREADS, 4) k_fs_pass(const __grid_const
       }
     }
   }
+  FS_STAMP(5);
 }
 
 inline dim3 fs_grid(const SmPlan& p) {
@@ -602,10 +630,10 @@ extern "C" int sm_fstats_supported(const sm_plan* plan) {
 extern "C" size_t sm_fstats_ws_bytes(const sm_plan* plan) {
   const SmPlan& p = plan->p;
   if (!sm_fstats_supported(plan)) return 256;
-  size_t b = (size_t)kBins * (8 + 24 + 4) + (size_t)kNS * 4;
+  size_t b = (size_t)kBins * (8 + 24 + 4) + (size_t)(1 << 13) * 4;
   b += (size_t)kBins * fs_scap(p) * 16;
   b += (size_t)kBins * fs_bcap(p) * 4;
-  return b + 512;
+  return b + 512 + 65536;        // + development timestamps (SM_FS_STAMPS)
 }
 
 static int fs_carve(const sm_plan* plan, void* wsp, size_t ws_bytes, FsWs* w) {
@@ -617,10 +645,13 @@ static int fs_carve(const sm_plan* plan, void* wsp, size_t ws_bytes, FsWs* w) {
   w->hc = reinterpret_cast<unsigned long long*>(b); b += (size_t)kBins * 8;
   w->hs = reinterpret_cast<double*>(b); b += (size_t)kBins * 3 * 8;
   w->scnt = reinterpret_cast<unsigned int*>(b); b += (size_t)kBins * 4;
-  w->sample = reinterpret_cast<unsigned int*>(b); b += (size_t)kNS * 4;
+  w->shist = reinterpret_cast<unsigned int*>(b); b += (size_t)(1 << 13) * 4;
   w->bcap = fs_bcap(p); w->scap = fs_scap(p);
   w->sbkt = reinterpret_cast<float4*>(b); b += (size_t)kBins * w->scap * 16;
   w->bkt = reinterpret_cast<unsigned int*>(b);
+  b += (size_t)kBins * w->bcap * 4;
+  b = reinterpret_cast<char*>(((uintptr_t)b + 63) / 64 * 64);
+  w->dbg = getenv("SM_FS_STAMPS") ? reinterpret_cast<unsigned long long*>(b) : nullptr;   // development only
   return 0;
 }
 
@@ -639,8 +670,10 @@ extern "C" int sm_fstats_cutoff(const sm_plan* plan, const float* reX, const flo
   FsCommon c{reX, reY, sel, nullptr, nullptr, 1.f};
   long long k_lo = 0, k_hi = 0;
   fs_sample_ranks(rank, total, &k_lo, &k_hi);
+  SM_CUDA_CHECK(cudaMemsetAsync(w.shist, 0, (size_t)kSampleBins * 4, s));
   k_fs_sample<0><<<(int)(kNS / 1024), 1024, 0, s>>>(p, c, st, w, rank, k_lo, k_hi);
   SM_LAUNCH_CHECK();
+  if (getenv("SM_FS_ONLY_SAMPLE")) return 0;
   k_fs_pass<0><<<fs_grid(p), SM_EW_THREADS, 0, s>>>(p, c, st, w, nullptr, t, thr_cut_out, scal4_out, sums3_out);
   SM_LAUNCH_CHECK();
   return 0;
@@ -661,6 +694,7 @@ extern "C" int sm_fstats_blend_cull(const sm_plan* plan, const float* reX, const
   FsCommon c{reX, reY, sel, thr_cut, scal4, t_sum};
   long long k_lo = 0, k_hi = 0;
   fs_sample_ranks(rank, total, &k_lo, &k_hi);
+  SM_CUDA_CHECK(cudaMemsetAsync(w.shist, 0, (size_t)kSampleBins * 4, s));
   k_fs_sample<1><<<(int)(kNS / 1024), 1024, 0, s>>>(p, c, st, w, rank, k_lo, k_hi);
   SM_LAUNCH_CHECK();
   k_fs_pass<1><<<fs_grid(p), SM_EW_THREADS, 0, s>>>(p, c, st, w, out_re, 0.0, thr_cull_out, nullptr, nullptr);

@@ -165,7 +165,7 @@ class Workspace:
         mode = 1 if safe_select else 0
         nbytes = max(plan.lib.sm_select_ws_bytes(plan.handle, 2, mode), plan.lib.sm_select_ws_bytes(plan.handle, 1, mode),
                      plan.lib.sm_fstats_ws_bytes(plan.handle))
-        self.sel_ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        self.sel_ws = torch.zeros(nbytes, dtype=torch.uint8, device=dev)   # sm_fstats_* wants it zero-filled once
         # pinned landing zone for the scalar block
         self.ctl_host = torch.empty(_CTL_BYTES, dtype=torch.uint8).pin_memory()
 
