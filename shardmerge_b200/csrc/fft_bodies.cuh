@@ -349,7 +349,7 @@ struct ColCtSrc {
     a = 0.f; b = 0.f;
     if (valid) {
       const size_t off = row0 + (size_t)i * estride;
-      a = p0[off]; b = p1[off];
+      a = ldcg_f32(p0 + off); b = ldcg_f32(p1 + off);
       if (kInverse) { if (b < thr && -b < thr) b = 0.f; }   // p1 is the real plane in the inverse
     }
   }

@@ -50,6 +50,15 @@ SM_HD float ldg_f32(const float* p) {
   return *p;
 #endif
 }
+// streaming load that never allocates in L1 (ld.global.cg): the column sweeps read data another CTA of the same
+// launch may have just written (fused two-sweep kernel), so a stale L1 line must not be hit
+SM_HD float ldcg_f32(const float* p) {
+#if defined(__CUDA_ARCH__)
+  return __ldcg(p);
+#else
+  return *p;
+#endif
+}
 SM_HD uint32_t ldg_u32(const uint32_t* p) {
 #if defined(__CUDA_ARCH__)
   return __ldg(p);

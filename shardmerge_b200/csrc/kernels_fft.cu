@@ -71,6 +71,56 @@ __global__ void __launch_bounds__(NW * 32, (R1 >= 11 || R2 >= 11) ? 3 : 4) k_col
   col_ct_body<R1, R2, NW, kInverse, kBigTw>(ex, (int)blockIdx.x, (int)blockIdx.y, a, twR, reinterpret_cast<cf*>(g_dyn_smem));
 }
 
+// ---- both column sweeps of a four-step transform in ONE launch, the second one fed from L2 ----------------
+// A separate launch per sweep streams the whole spectrum through DRAM twice (16N bytes per transform).  Here the
+// CTAs of both sweeps share one 1-D grid, ordered so that the second-sweep CTAs of column tile t are dispatched
+// `lag` tiles after its first-sweep CTAs: by then those have finished (a per-tile counter makes that a guarantee,
+// not an assumption), and the tile's R x 32 complex values -- a few MB times `lag` -- are still in the 126 MB L2.
+// Block order is the dependency order, so a waiting CTA only ever waits for CTAs that were dispatched before it.
+struct Col2Sched { int ntiles, n1, n2, lag; unsigned int* cnt; unsigned int* done; };
+
+__device__ __forceinline__ void col2_decode(const Col2Sched& s, unsigned int b, int* phase, int* tile, int* inst) {
+  const unsigned int head = (unsigned int)s.lag * s.n1;
+  if (b < head) { *phase = 0; *tile = b / s.n1; *inst = b % s.n1; return; }
+  b -= head;
+  const unsigned int per = s.n1 + s.n2, mid = (unsigned int)(s.ntiles - s.lag) * per;
+  if (b < mid) {
+    const unsigned int g = b / per, r = b % per;
+    if (r < (unsigned int)s.n1) { *phase = 0; *tile = s.lag + g; *inst = r; }
+    else { *phase = 1; *tile = g; *inst = r - s.n1; }
+    return;
+  }
+  b -= mid;
+  *phase = 1; *tile = (s.ntiles - s.lag) + b / s.n2; *inst = b % s.n2;
+}
+
+// P = first sweep (R1 x R2), Q = second sweep (S1 x S2); forward: P has the inter-sweep twiddle, inverse: P has it too
+// (the inverse undoes sweep B first, which carries the big twiddle there -- fft_bodies.cuh: sm_col_args)
+template <int R1, int R2, int S1, int S2, int NW, bool kInverse>
+__global__ void __launch_bounds__(NW * 32, (R1 >= 11 || R2 >= 11 || S1 >= 11 || S2 >= 11) ? 3 : 4)
+k_col2_ct(const __grid_constant__ ColCtArgs a1, const __grid_constant__ ColCtArgs a2, const __grid_constant__ Col2Sched s,
+          const cf* __restrict__ twR) {
+  DeviceExec ex;
+  int phase, tile, inst;
+  col2_decode(s, blockIdx.x, &phase, &tile, &inst);
+  cf* smem = reinterpret_cast<cf*>(g_dyn_smem);
+  if (phase == 0) {
+    col_ct_body<R1, R2, NW, kInverse, true>(ex, tile, inst, a1, twR, smem);
+    __syncthreads();
+    if (threadIdx.x == 0) { __threadfence(); atomicAdd(s.cnt + tile, 1u); }
+  } else {
+    if (threadIdx.x == 0) {
+      while (*((volatile unsigned int*)(s.cnt + tile)) < (unsigned int)s.n1) __nanosleep(64);
+      __threadfence();
+    }
+    __syncthreads();
+    col_ct_body<S1, S2, NW, kInverse, false>(ex, tile, inst, a2, twR, smem);
+    if (threadIdx.x == 0) {                      // the last second-sweep CTA of the tile re-arms its counters
+      if (atomicAdd(s.done + tile, 1u) == (unsigned int)s.n2 - 1u) { s.cnt[tile] = 0u; s.done[tile] = 0u; }
+    }
+  }
+}
+
 template <int R1, int R2, int R3, int R4, int T, bool kPad>
 __global__ void __launch_bounds__(T) k_row_fwd_ct(int C, int P, const RowFwdArgs a, const cf* __restrict__ twC,
                                                   const cf* __restrict__ twQ, double* __restrict__ sumsq) {
@@ -309,7 +359,7 @@ extern "C" int sm_plan_pitch(const sm_plan* plan) { return plan->p.P; }
 extern "C" int sm_plan_col_passes(const sm_plan* plan) { return plan->p.col_passes; }
 extern "C" int sm_plan_row_freq(const sm_plan* plan, int stored) { return sm_row_freq(&plan->p, stored); }
 extern "C" size_t sm_plan_table_bytes(const sm_plan* plan) {
-  return sm_tab_off_Q(plan->p) + 32 * (size_t)sm_quad_count(plan->p) + 32;
+  return sm_tab_bytes(plan->p);
 }
 extern "C" int sm_plan_describe(const sm_plan* plan, char* buf, int buflen) {
   const SmPlan& p = plan->p;
@@ -340,6 +390,7 @@ extern "C" int sm_plan_init_tables(const sm_plan* plan, void* tables, void* stre
     k_init_quads<<<(4 * nq + 255) / 256, 256, 0, st>>>(twQ, nq, p.Ch);
     SM_LAUNCH_CHECK();
   }
+  SM_CUDA_CHECK(cudaMemsetAsync(reinterpret_cast<char*>(tables) + sm_tab_off_K(p), 0, 8 * (size_t)sm_col_tiles(p), st));
   return 0;
 }
 
@@ -417,6 +468,64 @@ static bool use_tma() {
   static int init = 0;
   if (!init) { const char* e = getenv("SM_ROW_TMA"); if (e && e[0] == '0') g_use_tma = false; init = 1; }
   return g_use_tma;
+}
+
+// Measured (profiles/r01, 4096x4096): the fused launch takes 63 us against 28 + 22 us for two launches -- the
+// sweeps are latency / issue bound, not DRAM bound, and the second launch already reads mostly from L2 -- so it is
+// OFF by default (SM_COL_FUSED=1 enables it for A-B timing).
+static bool g_use_col2 = false;
+static bool use_col2() {
+  static int init = 0;
+  if (!init) { const char* e = getenv("SM_COL_FUSED"); if (e && e[0] == '1') g_use_col2 = true; init = 1; }
+  return g_use_col2;
+}
+
+template <int R1, int R2, int S1, int S2, int NW>
+static int launch_col2(bool inverse, const ColCtArgs& a1, const ColCtArgs& a2, Col2Sched s, const cf* twR, cudaStream_t st) {
+  static bool done[2] = {false, false};
+  static int occ[2] = {0, 0};
+  const int smem1 = (R2 > 1) ? R1 * R2 * SM_COL_TILE * 8 : 0, smem2 = (S2 > 1) ? S1 * S2 * SM_COL_TILE * 8 : 0;
+  const int smem = smem1 > smem2 ? smem1 : smem2;
+  cudaError_t e;
+  const int w = inverse ? 1 : 0;
+  if (!inverse) {
+    e = opt_in(k_col2_ct<R1, R2, S1, S2, NW, false>, &done[0]);
+    if (e == cudaSuccess && occ[0] == 0) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], k_col2_ct<R1, R2, S1, S2, NW, false>, NW * 32, smem);
+  } else {
+    e = opt_in(k_col2_ct<R1, R2, S1, S2, NW, true>, &done[1]);
+    if (e == cudaSuccess && occ[1] == 0) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], k_col2_ct<R1, R2, S1, S2, NW, true>, NW * 32, smem);
+  }
+  if (e != cudaSuccess) { sm_set_error("col2 setup: %s", cudaGetErrorString(e)); return -100; }
+  const int slots = num_sms() * (occ[w] > 0 ? occ[w] : 1);
+  int lag = (2 * slots + s.n1 - 1) / s.n1 + 1;
+  if (lag < 2) lag = 2;
+  if (lag > s.ntiles) lag = s.ntiles;
+  s.lag = lag;
+  const unsigned int grid = (unsigned int)s.ntiles * (unsigned int)(s.n1 + s.n2);
+  if (!inverse) k_col2_ct<R1, R2, S1, S2, NW, false><<<grid, NW * 32, smem, st>>>(a1, a2, s, twR);
+  else k_col2_ct<R1, R2, S1, S2, NW, true><<<grid, NW * 32, smem, st>>>(a1, a2, s, twR);
+  SM_LAUNCH_CHECK();
+  return 0;
+}
+
+// returns 1 if the pair of factorizations has no fused kernel
+static int try_col2_ct(const int* p_rad, int p_n, const int* q_rad, int q_n, bool inverse, const ColCtArgs& a1, const ColCtArgs& a2,
+                       const Col2Sched& s, const cf* twR, cudaStream_t st) {
+  if (p_n != 2 || q_n != 2) return 1;
+  const int r1 = p_rad[0], r2 = p_rad[1], s1 = q_rad[0], s2 = q_rad[1];
+#define SM_COL2_CASE(A, B, C_, D)                                                                                   \
+  if (r1 == A && r2 == B && s1 == C_ && s2 == D) return launch_col2<A, B, C_, D, 8>(inverse, a1, a2, s, twR, st);
+  SM_COL2_CASE(8, 8, 8, 8)        // R = 4096
+  SM_COL2_CASE(7, 16, 16, 8)      // R = 14336 forward (112 x 128)
+  SM_COL2_CASE(16, 8, 7, 16)      // R = 14336 inverse
+  SM_COL2_CASE(8, 8, 16, 8)       // R = 8192 (64 x 128)
+  SM_COL2_CASE(16, 8, 8, 8)
+  SM_COL2_CASE(7, 16, 16, 16)     // R = 28672 (112 x 256)
+  SM_COL2_CASE(16, 16, 7, 16)
+  SM_COL2_CASE(11, 8, 8, 8)       // R = 5632 (88 x 64)
+  SM_COL2_CASE(8, 8, 11, 8)
+#undef SM_COL2_CASE
+  return 1;
 }
 
 template <int R1, int R2, int R3, int R4, int T, bool kPad>
@@ -536,10 +645,44 @@ static int launch_col(const SmPlan& p, const void* tables, int sweep, int invers
   return 0;
 }
 
+// both sweeps of a two-sweep plan in one launch (k_col2_ct); returns 1 if this plan has no fused kernel
+static int launch_col2_pair(const SmPlan& p, const void* tables, int inverse, float* re, float* im, const float* cull_thr,
+                            const float* scale_dev, float scale_host, int write_im, cudaStream_t st,
+                            float* im_alt = nullptr, const int* sel = nullptr) {
+  if (p.col_passes != 2 || !use_col2()) return 1;
+  ColArgs ca[2];
+  int n_inst[2];
+  ColCtArgs c[2];
+  for (int k = 0; k < 2; ++k) {                  // k-th sweep in execution order
+    const int sweep = inverse ? 1 - k : k;
+    ca[k] = ColArgs{};
+    sm_col_args(p, sweep, inverse, &ca[k], &n_inst[k]);
+    const bool lastk = (k == 1);
+    c[k] = ColCtArgs{};
+    c[k].p0 = inverse ? im : re; c[k].p1 = inverse ? re : im;
+    c[k].p0_alt = inverse ? im_alt : nullptr; c[k].sel = inverse ? sel : nullptr;
+    c[k].P = p.P; c[k].Ch = p.Ch; c[k].inst_mul = ca[k].inst_mul; c[k].elem_mul = ca[k].elem_mul; c[k].tw_mul = ca[k].tw_mul;
+    c[k].thr_ptr = (inverse && k == 0) ? cull_thr : nullptr;                    // cull on the first inverse load
+    const bool use_scale = (!inverse && lastk);                                  // 1/||delta|| on the last forward store
+    c[k].scale_ptr = use_scale ? scale_dev : nullptr;
+    c[k].scale = use_scale ? scale_host : 1.0f;
+    c[k].write_p1_fwd = (!inverse && lastk) ? write_im : 1;
+  }
+  Col2Sched s{};
+  s.ntiles = sm_col_tiles(p); s.n1 = n_inst[0]; s.n2 = n_inst[1];
+  s.cnt = reinterpret_cast<unsigned int*>(const_cast<char*>(reinterpret_cast<const char*>(tables)) + sm_tab_off_K(p));
+  s.done = s.cnt + s.ntiles;
+  return try_col2_ct(ca[0].rad, ca[0].n_rad, ca[1].rad, ca[1].n_rad, inverse != 0, c[0], c[1], s, tabR(p, tables), st);
+}
+
 extern "C" int sm_fwd_cols(const sm_plan* plan, const void* tables, float* re, float* im,
                            const float* scale_dev, float scale_host, int write_im, void* stream) {
   const SmPlan& p = plan->p;
   cudaStream_t st = (cudaStream_t)stream;
+  {
+    const int rc = launch_col2_pair(p, tables, 0, re, im, nullptr, scale_dev, scale_host, write_im, st);
+    if (rc <= 0) return rc;
+  }
   if (p.col_passes == 0) {
     k_scale_row<<<(p.Ch + 1 + 255) / 256, 256, 0, st>>>(re, im, p.Ch + 1, scale_dev, scale_host, write_im);
     SM_LAUNCH_CHECK();
@@ -563,6 +706,10 @@ extern "C" int sm_inv_norm(const double* sumsq, float* out, void* stream) {
 int sm_inv_cols_sel(const sm_plan* plan, const void* tables, float* re, float* im, float* im_alt, const int* sel,
                     const float* cull_thr, void* stream) {
   const SmPlan& p = plan->p;
+  {
+    const int rc = launch_col2_pair(p, tables, 1, re, im, cull_thr, nullptr, 1.f, 1, (cudaStream_t)stream, im_alt, sel);
+    if (rc <= 0) return rc;
+  }
   for (int i = 0; i < p.col_passes; ++i) {
     const int sweep = p.col_passes - 1 - i;   // undo sweep B first, then sweep A
     int rc = launch_col(p, tables, sweep, 1, re, im, i == 0 ? cull_thr : nullptr, nullptr, 1.f, 0, 1,

@@ -35,6 +35,10 @@ void sm_set_error(const char* fmt, ...);
 static inline size_t sm_tab_off_R(const SmPlan& p) { return (size_t)p.C * 8; }
 static inline size_t sm_tab_off_Q(const SmPlan& p) { return (((size_t)p.C + (size_t)p.R) * 8 + 31) / 32 * 32; }
 static inline int sm_quad_count(const SmPlan& p) { return p.n_row > 1 ? p.Ch / p.row_rad[0] : 0; }
+// after the quads: 2 x ntiles u32 tile counters of the fused two-sweep column kernel (zero between launches)
+static inline int sm_col_tiles(const SmPlan& p) { return (p.Ch + 1 + SM_COL_TILE - 1) / SM_COL_TILE; }
+static inline size_t sm_tab_off_K(const SmPlan& p) { return (sm_tab_off_Q(p) + 32 * (size_t)sm_quad_count(p) + 63) / 64 * 64; }
+static inline size_t sm_tab_bytes(const SmPlan& p) { return sm_tab_off_K(p) + 8 * (size_t)sm_col_tiles(p) + 64; }
 
 // iteration space of the element-wise / statistics kernels over the valid half spectrum
 #define SM_EW_THREADS 256
