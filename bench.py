@@ -269,16 +269,17 @@ def main():
     for _ in range(args.warmup):
         step()
     barrier()
+    # ---- timed region: production configuration (consecutive tensors spread over fm.lanes streams) -------------
     sampler = ClockSampler(local_rank)
     sampler.start()
-    E.PROFILER = E.Profiler(timing=True)
+    E.PROFILER = E.Profiler(timing=False)                          # counts launches only
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     t_wall0 = time.perf_counter()
     for s0, s1 in ev:
         s0.record(); step(); s1.record()
     barrier()
     wall = time.perf_counter() - t_wall0
-    prof = E.PROFILER
+    gpu_launches = E.PROFILER.launches
     E.PROFILER = None
     clocks = sampler.stop()
     elapsed_ms = sum(s0.elapsed_time(s1) for s0, s1 in ev)
@@ -287,6 +288,24 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed_ms = float(t.item())
     value = world * merged_params * args.steps / (elapsed_ms / 1000.0)
+
+    # ---- per-kernel pass: the same steps on ONE stream with a CUDA-event pair around every kernel class ----------
+    # (with several lanes the kernels of different tensors overlap, and an event pair around one of them would also
+    # time its neighbours; the roofline figures therefore come from this serial pass, `value` from the region above)
+    lanes_used = fm.lanes
+    fm.lanes = 1
+    step()
+    barrier()
+    E.PROFILER = E.Profiler(timing=True)
+    pv = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for s0, s1 in pv:
+        s0.record(); step(); s1.record()
+    barrier()
+    prof = E.PROFILER
+    E.PROFILER = None
+    fm.lanes = lanes_used
+    serial_ms = sum(s0.elapsed_time(s1) for s0, s1 in pv)
+    value_serial = merged_params * args.steps / (serial_ms / 1000.0)
 
     # ---- roofline of the dominant kernel class ---------------------------------------------
     summ = prof.summary()
@@ -304,11 +323,13 @@ def main():
                     unit="GB/s", frac=(achieved / peak if achieved else None), traffic=None, peak_source=peak_src,
                     bytes_per_launch=(col_bytes / col_launch if col_launch else None),
                     share_of_kernel_time=(col_ms / kernel_ms_total if kernel_ms_total else None),
+                    measured="CUDA events around every kernel class during a serial (one stream) pass of the same steps "
+                             "inside this run; the timed region overlaps kernels of consecutive tensors on several streams",
+                    serial_pass=dict(ms_per_step=serial_ms / args.steps, params_per_s_per_gpu=value_serial),
                     per_class={k: dict(calls=v["calls"], launches=v["launches"], ms=v["ms"],
                                        gbs=(v["bytes"] / (v["ms"] / 1000.0) / 1e9 if v["ms"] else None),
                                        frac=(v["bytes"] / (v["ms"] / 1000.0) / 1e9 / peak if v["ms"] and v["bytes"] else None))
                                for k, v in summ.items()})
-    gpu_launches = prof.launches
 
     # ---- e2e: host tensors through _merge_layer ----------------------------------------------
     e2e = None
@@ -399,7 +420,7 @@ def main():
                                 layers_resident=L, layers_of_model=a["L"], merged_params_per_step_per_gpu=merged_params,
                                 tensors_per_step=len(tensors), l2="inputs per step (%.1f GB) exceed the 126 MB L2" %
                                                                  (merged_params * 2 * (M + 1) / 1e9),
-                                partition="whole tensors per rank, no collective"),
+                                partition="whole tensors per rank, no collective", streams_per_gpu=lanes_used),
                     roofline=roofline, cpu_baseline=cpu_baseline, e2e=e2e, gpu_launches=gpu_launches, clocks=clocks,
                     wall_s=wall)
         print(json.dumps(line))

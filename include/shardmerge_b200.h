@@ -122,6 +122,7 @@ int sm_blend(const sm_plan* plan, int mode, int agreement, const float* re0, con
  * too small (launch bound; use the step-by-step kernels) or too large (>= 2^31 elements). */
 #define SM_FS_STATE_BYTES 128
 #define SM_FS_STATUS_OFF 28
+#define SM_FS_STICKY_OFF 72      /* u32: OR of the status of every call that used this state since it was zeroed */
 int sm_fstats_supported(const sm_plan* plan);
 size_t sm_fstats_ws_bytes(const sm_plan* plan);
 int sm_fstats_cutoff(const sm_plan* plan, const float* reX, const float* reY, const int* sel, uint64_t rank,

@@ -62,7 +62,7 @@ class PairArgs(C.Structure):
 CLS_NAMES = ["row_fwd", "col_fwd", "stats_cutoff", "reduce", "scalars", "blend_cull", "select1", "col_inv", "row_inv"]
 BRANCH_NAMES = {0: "slerp", 1: "add", 2: "arith", 3: "slerp-early", 4: "slerp-linear"}
 SELECT_STATE_BYTES = 64
-FS_STATE_BYTES, FS_STATUS_OFF, CTL_FS_OFF, CTL_BYTES = 128, 28, 512, 1024
+FS_STATE_BYTES, FS_STATUS_OFF, FS_STICKY_OFF, CTL_FS_OFF, CTL_BYTES = 128, 28, 72, 512, 1024
 
 
 class ShardMergeLibraryError(RuntimeError):

@@ -46,10 +46,12 @@ struct FsState {                     // SM_FS_STATE_BYTES device bytes
   float value;
   unsigned int bstar;
   double s_in[3];                    // decided part of the SLERP sums (s00, s11, s01)
-  unsigned int pad[14];
+  unsigned int sticky;               // OR of every status this state has ended with (kernels never clear it)   (SM_FS_STICKY_OFF)
+  unsigned int pad[13];
 };
 static_assert(sizeof(FsState) == SM_FS_STATE_BYTES, "FsState layout");
 static_assert(offsetof(FsState, status) == SM_FS_STATUS_OFF, "FsState status offset");
+static_assert(offsetof(FsState, sticky) == SM_FS_STICKY_OFF, "FsState sticky offset");
 
 struct FsWs {                        // carved out of the caller's workspace
   unsigned long long* hc;            // [kBins]  hi 32 bits: keys (with multiplicity), lo 32 bits: bucket entries
@@ -571,6 +573,7 @@ __global__ void __launch_bounds__(SM_EW_THREADS, 4) k_fs_pass(const __grid_const
   __syncthreads();
   if (threadIdx.x == 0) {
     if (!ok && st->status == 0u) st->status = 1u;
+    st->sticky |= st->status;
     st->ticket = 0u;
     if (st->status != 0u) {
       st->value = __uint_as_float(0x7fc00000u);

@@ -178,7 +178,7 @@ class Workspace:
     def fs_status(self):
         """(status of the fused cutoff state, status of the fused blend/cull state) -- synchronous."""
         h = self.ctl.cpu()
-        o = _lib.CTL_FS_OFF + _lib.FS_STATUS_OFF
+        o = _lib.CTL_FS_OFF + _lib.FS_STICKY_OFF
         return (int(h[o:o + 4].view(torch.int32)[0]),
                 int(h[o + _lib.FS_STATE_BYTES:o + _lib.FS_STATE_BYTES + 4].view(torch.int32)[0]))
 
@@ -204,9 +204,11 @@ def get_plan(R: int, C: int, device) -> Plan:
     return pl
 
 
-def get_workspace(R: int, C: int, device, n_spectra: int = 2, safe_select: bool = False) -> Workspace:
+def get_workspace(R: int, C: int, device, n_spectra: int = 2, safe_select: bool = False, lane: int = 0) -> Workspace:
+    """Workspaces are cached per (device, shape, select mode, lane); a lane is one of the streams FourierMerge
+    spreads consecutive tensors over, and two tensors in flight must not share planes."""
     dev = _require_cuda(device)
-    key = (dev.index, R, C, safe_select)
+    key = (dev.index, R, C, safe_select, lane)
     ws = _workspaces.get(key)
     if ws is None or ws.n_spectra < n_spectra:
         ws = _workspaces[key] = Workspace(get_plan(R, C, dev), n_spectra, safe_select)
@@ -416,7 +418,15 @@ def spectral_pair(ws: Workspace, slot0: int, slot1: int, *, scale0: float, scale
     fwd_cols(ws, slot0, scale=scale0, write_im=True)
     fwd_cols(ws, slot1, scale=scale1, write_im=False)
     re0, im0, re1 = ws.re[slot0], ws.im[slot0], ws.re[slot1]
-    if mode == "slerp":
+    fused_stats = (mode == "slerp" and not ws.safe_select and cutoff_pct > 0 and cull_pct > 0
+                   and pl.lib.sm_fstats_supported(pl.handle))
+    if fused_stats:
+        # one pass for the cutoff statistic + SLERP sums + scalars, one for the blend + cull statistic
+        # (csrc/kernels_fstats.cu); a missed window shows up in ws.fs_status() and the caller redoes the tensor
+        fstats_cutoff(ws, re0, re1, int((2 * N) * cutoff_pct), t)
+        fstats_blend_cull(ws, re0, re1, t_sum, re0, int(N * cull_pct))
+        cull = True
+    elif mode == "slerp":
         if cutoff_pct > 0:
             # functions.py:113-120: sorted(cat(|re0|,|re1|))[int(2N*cutoff_pct)]
             select_kth(ws, re0, re1, int((2 * N) * cutoff_pct), F_THR_CUT, which=0)
@@ -471,7 +481,7 @@ class PendingPair:
         h = self.host_ctl
         dbl = h[0:64].view(torch.float64); flt = h[64:128].view(torch.float32)
         flags = h[128:144].view(torch.int32); ints = h[144:160].view(torch.int32)
-        fs = _lib.CTL_FS_OFF + _lib.FS_STATUS_OFF
+        fs = _lib.CTL_FS_OFF + _lib.FS_STICKY_OFF
         sel32 = h[192:320].view(torch.int32)
         st0 = int(h[fs:fs + 4].view(torch.int32)[0]) | int(sel32[11])
         st1 = int(h[fs + _lib.FS_STATE_BYTES:fs + _lib.FS_STATE_BYTES + 4].view(torch.int32)[0]) | int(sel32[16 + 11])

@@ -17,6 +17,7 @@ from __future__ import annotations
 import asyncio
 import hashlib
 import logging
+import os
 from typing import List, Optional
 
 import torch
@@ -48,6 +49,10 @@ def clamp(value: float, min_value: float, max_value: float) -> float:
 
 class FourierMerge(MergeTensorsBase):
     pipeline_depth = 1           # merge(): one tensor stays in flight while the previous one is settled / written
+    # Consecutive tensors alternate between `lanes` CUDA streams (each with its own workspace): every kernel of the
+    # chain has a latency-bound prologue / epilogue (single-CTA statistics epilogues, launch gaps, tail waves) that
+    # a second tensor's kernels fill.  The reference merges strictly one tensor at a time (shard/merge/base.py:215-220).
+    lanes = max(1, int(os.environ.get("SHARDMERGE_LANES", "3")))
 
     def __init__(self, config: MergeConfig, task_add_models: Optional[List[str]] = None,
                  target_norm_offset: float = 1e-10, cull_start_pct: float = 0.20, index_manager=None, **kwargs):
@@ -58,6 +63,8 @@ class FourierMerge(MergeTensorsBase):
         self.last_info: dict = {}
         self.pending: list = []          # deferred checks of fused pair merges (resolve_all)
         self.defer_checks = False        # True inside merge(): _merge_layer returns before the check
+        self._lane_streams: dict = {}    # device index -> [streams]
+        self._lane_next = 0
 
     def get_readme(self) -> str:
         models = "\n".join(f"- {m.model} (vs {m.base})" for m in self.config.finetune_merge)
@@ -141,12 +148,29 @@ class FourierMerge(MergeTensorsBase):
         if not fused_ok:
             return self._merge_sources_steps(sources, base_out, dev, layer_name, safe_select)
         R, C = E.shape_rc(base_out)
-        ws = E.get_workspace(R, C, dev, n_spectra=2)
         out = torch.empty(base_out.shape, dtype=torch.bfloat16, device=dev)
         a_w, b_w = sources[0].weight, sources[1].weight
-        pend = E.pair_merge_async(ws, sources[0], sources[1], base_out.contiguous(), out, t=a_w / (a_w + b_w), t_sum=1.0,
-                                  cutoff_pct=0.08, cull_pct=self.cull_start_pct,
-                                  target_norm_offset=self.target_norm_offset, layer_name=layer_name)
+        base_c = base_out.contiguous()
+        kwargs = dict(t=a_w / (a_w + b_w), t_sum=1.0, cutoff_pct=0.08, cull_pct=self.cull_start_pct,
+                      target_norm_offset=self.target_norm_offset, layer_name=layer_name)
+        if self.lanes > 1 and defer:
+            # the chain runs on this tensor's lane; the caller's stream is not made to wait for it -- whoever
+            # consumes `out` does so after resolve (a host-side wait for the lane's last event)
+            streams = self._lane_streams.get(dev.index)
+            if streams is None:
+                streams = self._lane_streams[dev.index] = [torch.cuda.Stream(device=dev) for _ in range(self.lanes)]
+            lane_i = self._lane_next % self.lanes
+            self._lane_next += 1
+            lane = streams[lane_i]
+            ws = E.get_workspace(R, C, dev, n_spectra=2, lane=lane_i)
+            lane.wait_event(torch.cuda.current_stream(dev).record_event())      # inputs are ready on the caller's stream
+            with torch.cuda.stream(lane):
+                pend = E.pair_merge_async(ws, sources[0], sources[1], base_c, out, **kwargs)
+            for t_ in (out, base_c, sources[0].base, sources[0].ft, sources[1].base, sources[1].ft):
+                t_.record_stream(lane)
+        else:
+            ws = E.get_workspace(R, C, dev, n_spectra=2)
+            pend = E.pair_merge_async(ws, sources[0], sources[1], base_c, out, **kwargs)
         pend.redo = lambda: self._merge_sources_steps(sources, base_out, dev, layer_name, False)
         if defer:
             self.pending.append(pend)
@@ -281,7 +305,10 @@ class FourierMerge(MergeTensorsBase):
         _, _, flags, sel = ws.read_ctl()
         info["flags"] = [int(v) for v in flags]
         sel32 = sel.view(torch.int32)
-        if (int(sel32[11]) | int(sel32[16 + 11])) != 0:
+        fs_off = E._lib.CTL_FS_OFF + E._lib.FS_STICKY_OFF
+        fs_sticky = ws.ctl_host[fs_off:fs_off + 4].view(torch.int32)[0].item() | \
+            ws.ctl_host[fs_off + E._lib.FS_STATE_BYTES:fs_off + E._lib.FS_STATE_BYTES + 4].view(torch.int32)[0].item()
+        if (int(sel32[11]) | int(sel32[16 + 11]) | int(fs_sticky)) != 0:
             # the sampled window of a fast order-statistic select missed (or its candidate buffer
             # overflowed): the thresholds are NaN.  Redo this tensor with the exhaustive select.
             if safe_select:
