@@ -408,6 +408,106 @@ SM_HD void col_ct_body(Exec& ex, int tile, int inst, const ColCtArgs a, const cf
   }
 }
 
+// ------------------------------------------------------------------ paired-column sweeps (pf: two adjacent columns per thread)
+// Same transform as col_ct_body, but every thread carries columns (c, c+1) through the butterflies as one
+// packed value: half the FP / load-store / index instructions per element, 8-byte global accesses, 16-byte
+// shared-memory accesses.  Lane mapping: 16 lanes x 2 columns = one 32-column tile row (128 B), two butterfly
+// slots per warp.  The pair (Ch, Ch+1) touches one zero-filled padding column, whose transform is zero again.
+SM_HD pf ldcg_pf(const float* p) {
+#if defined(__CUDA_ARCH__)
+  const float2 v = __ldcg(reinterpret_cast<const float2*>(p));
+  return pf_make(v.x, v.y);
+#else
+  return pf_make(p[0], p[1]);
+#endif
+}
+SM_HD void st_pf(float* p, pf v) {
+#if defined(__CUDA_ARCH__)
+  *reinterpret_cast<float2*>(p) = make_float2(pf_lo(v), pf_hi(v));
+#else
+  p[0] = pf_lo(v); p[1] = pf_hi(v);
+#endif
+}
+
+struct pf4 { pf re, im; };     // one shared-memory element: (re_c, re_c+1, im_c, im_c+1), 16 bytes
+struct ColSmemP {              // [idx][16 lane pairs]: a quarter warp covers all 32 banks, conflict free
+  pf4* buf; int lane;
+  SM_HD void load(int i, pf& re, pf& im) const { const pf4 v = buf[i * (SM_COL_TILE / 2) + lane]; re = v.re; im = v.im; }
+  SM_HD void store(int i, pf re, pf im) const { pf4 v; v.re = re; v.im = im; buf[i * (SM_COL_TILE / 2) + lane] = v; }
+};
+
+template <bool kInverse>
+struct ColCtSrcP {
+  const float* p0; const float* p1; size_t row0; size_t estride; bool valid; float thr;
+  SM_HD void load(int i, pf& a, pf& b) const {
+    a = pf_make(0.f, 0.f); b = a;
+    if (valid) {
+      const size_t off = row0 + (size_t)i * estride;
+      a = ldcg_pf(p0 + off); b = ldcg_pf(p1 + off);
+      if (kInverse) {                                      // p1 is the real plane in the inverse: cull on load
+        float b0 = pf_lo(b), b1 = pf_hi(b);
+        if (b0 < thr && -b0 < thr) b0 = 0.f;
+        if (b1 < thr && -b1 < thr) b1 = 0.f;
+        b = pf_make(b0, b1);
+      }
+    }
+  }
+};
+template <bool kBigTw>
+struct ColCtDstP {
+  float* p0; float* p1; size_t row0; size_t estride; bool valid; const cf* twR; int inst; float scale; bool write_p1;
+  SM_HD void store(int k, pf a, pf b) const {
+    if (kBigTw) { if (inst != 0) { const cf w = twR[(size_t)inst * k]; cmul(a, b, w.x, w.y); } }
+    if (!valid) return;
+    const size_t off = row0 + (size_t)k * estride;
+    st_pf(p0 + off, mulc(a, scale));
+    if (write_p1) st_pf(p1 + off, mulc(b, scale));
+  }
+};
+
+// one CTA (NW warps = 2*NW butterfly slots) = one instance x 32 columns, L = R1*R2
+template <int R1, int R2, int NW, bool kInverse, bool kBigTw, class Exec>
+SM_HD void col_ct_body_p(Exec& ex, int tile, int inst, const ColCtArgs a, const cf* twR, pf4* smem) {
+  constexpr int L = R1 * R2;
+  constexpr int NS = 2 * NW;
+  const int col0 = tile * SM_COL_TILE;
+  SM_FOR_THREADS(ex, tid) {
+    const int lane = tid & 15, slot = tid >> 4;
+    const int c = col0 + 2 * lane;
+    const bool valid = (c <= a.Ch);
+    const size_t row0 = (size_t)inst * a.inst_mul * a.P + c;
+    const size_t estride = (size_t)a.elem_mul * a.P;
+    const float thr = (kInverse && a.thr_ptr) ? *a.thr_ptr : 0.f;
+    const float scale = a.scale_ptr ? *a.scale_ptr : a.scale;
+    float* const p0 = (a.sel != nullptr && *a.sel != 0) ? a.p0_alt : a.p0;
+    ColCtSrcP<kInverse> gsrc{p0, a.p1, row0, estride, valid, thr};
+    ColCtDstP<kBigTw> gdst{p0, a.p1, row0, estride, valid, twR, inst, scale, kInverse ? true : (a.write_p1_fwd != 0)};
+    if constexpr (R2 == 1) {
+      for (int b = slot; b < 1; b += NS) stockham_bfly<R1, true, pf>(b, L, 1, a.tw_mul, twR, gsrc, gdst);
+    } else {
+      ColSmemP sout{smem, lane};
+#pragma unroll
+      for (int b = slot; b < R2; b += NS) stockham_bfly<R1, false, pf>(b, L, 1, a.tw_mul, twR, gsrc, sout);
+    }
+  }
+  if constexpr (R2 > 1) {
+    ex.sync();
+    SM_FOR_THREADS(ex, tid) {
+      const int lane = tid & 15, slot = tid >> 4;
+      const int c = col0 + 2 * lane;
+      const bool valid = (c <= a.Ch);
+      const size_t row0 = (size_t)inst * a.inst_mul * a.P + c;
+      const size_t estride = (size_t)a.elem_mul * a.P;
+      const float scale = a.scale_ptr ? *a.scale_ptr : a.scale;
+      float* const p0 = (a.sel != nullptr && *a.sel != 0) ? a.p0_alt : a.p0;
+      ColCtDstP<kBigTw> gdst{p0, a.p1, row0, estride, valid, twR, inst, scale, kInverse ? true : (a.write_p1_fwd != 0)};
+      ColSmemP sin{smem, lane};
+#pragma unroll
+      for (int b = slot; b < R1; b += NS) stockham_bfly<R2, true, pf>(b, L, R1, a.tw_mul, twR, sin, gdst);
+    }
+  }
+}
+
 }  // namespace smfft
 
 namespace smfft {

@@ -109,26 +109,70 @@ SM_HD void static_for(F&& f) {
   }
 }
 
+// ---------------------------------------------------------------------------------
+// value types of the butterflies: float, or pf = two independent fp32 lanes that go through
+// identical arithmetic (two adjacent columns of a column sweep).  On sm_100a a pf lives in an
+// aligned register pair and every operation is ONE packed instruction (FADD2 / FMUL2 / FFMA2,
+// PTX add/sub/mul/fma.rn.f32x2): the FFT kernels are instruction-issue bound (profiles/r01), and
+// packing halves the FP, load/store and index instructions per element.  Each lane rounds exactly
+// like the scalar operation, so a pf butterfly is bit-identical to two float butterflies.
+// ---------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+struct pf { unsigned long long v; };
+SM_HD pf pf_make(float a, float b) { pf r; asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(a), "f"(b)); return r; }
+SM_HD float pf_lo(pf x) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(x.v)); return a; }
+SM_HD float pf_hi(pf x) { float a, b; asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(x.v)); return b; }
+SM_HD pf operator+(pf a, pf b) { pf r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+SM_HD pf operator-(pf a, pf b) { pf r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+SM_HD pf operator*(pf a, pf b) { pf r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
+SM_HD pf pf_fma(pf a, pf b, pf c) { pf r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v)); return r; }
+#else
+struct pf { float a, b; };
+SM_HD pf pf_make(float a, float b) { pf r; r.a = a; r.b = b; return r; }
+SM_HD float pf_lo(pf x) { return x.a; }
+SM_HD float pf_hi(pf x) { return x.b; }
+SM_HD pf operator+(pf x, pf y) { return pf_make(x.a + y.a, x.b + y.b); }
+SM_HD pf operator-(pf x, pf y) { return pf_make(x.a - y.a, x.b - y.b); }
+SM_HD pf operator*(pf x, pf y) { return pf_make(x.a * y.a, x.b * y.b); }
+SM_HD pf pf_fma(pf x, pf y, pf z) { return pf_make(fmaf(x.a, y.a, z.a), fmaf(x.b, y.b, z.b)); }
+#endif
+SM_HD pf pf_bcast(float c) { return pf_make(c, c); }
+SM_HD pf& operator+=(pf& a, pf b) { a = a + b; return a; }
+
+// scalar-coefficient helpers, overloaded for both value types
+SM_HD float mulc(float x, float c) { return x * c; }
+SM_HD float fmac(float c, float x, float acc) { return acc + c * x; }        // contracted to one FFMA by nvcc
+SM_HD float zero_of(float) { return 0.f; }
+SM_HD pf mulc(pf x, float c) { return x * pf_bcast(c); }
+SM_HD pf fmac(float c, pf x, pf acc) { return pf_fma(pf_bcast(c), x, acc); }
+SM_HD pf zero_of(pf) { return pf_make(0.f, 0.f); }
+
 // y = x * W_N^K, W_N = exp(-2*pi*i/N), K and N compile-time.
-template <int K, int N>
-SM_HD void twmul(float xr, float xi, float& yr, float& yi) {
+template <int K, int N, class T>
+SM_HD void twmul(T xr, T xi, T& yr, T& yi) {
   constexpr int k = ((K % N) + N) % N;
   if constexpr (k == 0) { yr = xr; yi = xi; }
-  else if constexpr (4 * k == N) { yr = xi; yi = -xr; }          // -i
-  else if constexpr (2 * k == N) { yr = -xr; yi = -xi; }         // -1
-  else if constexpr (4 * k == 3 * N) { yr = -xi; yi = xr; }      // +i
+  else if constexpr (4 * k == N) { yr = xi; yi = zero_of(xr) - xr; }          // -i
+  else if constexpr (2 * k == N) { yr = zero_of(xr) - xr; yi = zero_of(xi) - xi; }         // -1
+  else if constexpr (4 * k == 3 * N) { yr = zero_of(xi) - xi; yi = xr; }      // +i
   else {
     constexpr float c = float(c_cos2pi(k, N));
     constexpr float s = float(c_sin2pi(k, N));
     // (xr + i xi)(c - i s)
-    yr = xr * c + xi * s;
-    yi = xi * c - xr * s;
+    yr = fmac(s, xi, mulc(xr, c));
+    yi = fmac(-s, xr, mulc(xi, c));
   }
 }
 
 SM_HD void cmul(float& xr, float& xi, float wr, float wi) {
   float tr = xr * wr - xi * wi;
   float ti = xr * wi + xi * wr;
+  xr = tr; xi = ti;
+}
+SM_HD void cmul(pf& xr, pf& xi, float wr, float wi) {       // one twiddle for both lanes
+  const pf pwr = pf_bcast(wr), pwi = pf_bcast(wi);
+  const pf tr = pf_fma(xr, pwr, zero_of(xr) - xi * pwi);
+  const pf ti = pf_fma(xr, pwi, xi * pwr);
   xr = tr; xi = ti;
 }
 
@@ -138,23 +182,23 @@ SM_HD void cmul(float& xr, float& xi, float wr, float wi) {
 template <int N> struct Dft;
 
 template <> struct Dft<1> {
-  static SM_HD void run(float (&)[1], float (&)[1]) {}
+  template <class T> static SM_HD void run(T (&)[1], T (&)[1]) {}
 };
 
 template <> struct Dft<2> {
-  static SM_HD void run(float (&re)[2], float (&im)[2]) {
-    float ar = re[0], ai = im[0], br = re[1], bi = im[1];
+  template <class T> static SM_HD void run(T (&re)[2], T (&im)[2]) {
+    T ar = re[0], ai = im[0], br = re[1], bi = im[1];
     re[0] = ar + br; im[0] = ai + bi;
     re[1] = ar - br; im[1] = ai - bi;
   }
 };
 
 template <> struct Dft<4> {
-  static SM_HD void run(float (&re)[4], float (&im)[4]) {
-    float t0r = re[0] + re[2], t0i = im[0] + im[2];
-    float t1r = re[0] - re[2], t1i = im[0] - im[2];
-    float t2r = re[1] + re[3], t2i = im[1] + im[3];
-    float t3r = re[1] - re[3], t3i = im[1] - im[3];
+  template <class T> static SM_HD void run(T (&re)[4], T (&im)[4]) {
+    T t0r = re[0] + re[2], t0i = im[0] + im[2];
+    T t1r = re[0] - re[2], t1i = im[0] - im[2];
+    T t2r = re[1] + re[3], t2i = im[1] + im[3];
+    T t3r = re[1] - re[3], t3i = im[1] - im[3];
     re[0] = t0r + t2r; im[0] = t0i + t2i;
     re[2] = t0r - t2r; im[2] = t0i - t2i;
     // X1 = t1 - i*t3 ; X3 = t1 + i*t3
@@ -165,26 +209,26 @@ template <> struct Dft<4> {
 
 // odd prime length, symmetric (real cos/sin) formulation: (P-1)^2 FMAs.
 template <int P> struct DftPrime {
-  static SM_HD void run(float (&re)[P], float (&im)[P]) {
+  template <class T> static SM_HD void run(T (&re)[P], T (&im)[P]) {
     constexpr int H = (P - 1) / 2;
-    float sr[H], si[H], dr[H], di[H];
+    T sr[H], si[H], dr[H], di[H];
     static_for<0, H>([&](auto j_) {
       constexpr int j = decltype(j_)::value;
       sr[j] = re[j + 1] + re[P - 1 - j]; si[j] = im[j + 1] + im[P - 1 - j];
       dr[j] = re[j + 1] - re[P - 1 - j]; di[j] = im[j + 1] - im[P - 1 - j];
     });
-    const float r0 = re[0], i0 = im[0];
-    float sumr = r0, sumi = i0;
-    static_for<0, H>([&](auto j_) { constexpr int j = decltype(j_)::value; sumr += sr[j]; sumi += si[j]; });
+    const T r0 = re[0], i0 = im[0];
+    T sumr = r0, sumi = i0;
+    static_for<0, H>([&](auto j_) { constexpr int j = decltype(j_)::value; sumr = sumr + sr[j]; sumi = sumi + si[j]; });
     static_for<1, H + 1>([&](auto k_) {
       constexpr int k = decltype(k_)::value;
-      float ar = r0, ai = i0, br = 0.f, bi = 0.f;
+      T ar = r0, ai = i0, br = zero_of(r0), bi = zero_of(r0);
       static_for<0, H>([&](auto j_) {
         constexpr int j = decltype(j_)::value;
         constexpr float c = float(c_cos2pi((j + 1) * k, P));
         constexpr float s = float(c_sin2pi((j + 1) * k, P));
-        ar += c * sr[j]; ai += c * si[j];
-        br += s * dr[j]; bi += s * di[j];
+        ar = fmac(c, sr[j], ar); ai = fmac(c, si[j], ai);
+        br = fmac(s, dr[j], br); bi = fmac(s, di[j], bi);
       });
       // X[k] = a - i*b ; X[P-k] = a + i*b   with a=(ar,ai), b=(br,bi)
       re[k] = ar + bi; im[k] = ai - br;
@@ -202,11 +246,11 @@ template <> struct Dft<13> : DftPrime<13> {};
 // composite length A*B, one Cooley-Tukey level in registers.
 // input index n = B*a + b, output index k = ka + A*kb.
 template <int A, int B> struct DftCT {
-  static SM_HD void run(float (&re)[A * B], float (&im)[A * B]) {
-    float tr[A * B], ti[A * B];
+  template <class T> static SM_HD void run(T (&re)[A * B], T (&im)[A * B]) {
+    T tr[A * B], ti[A * B];
     static_for<0, B>([&](auto b_) {
       constexpr int b = decltype(b_)::value;
-      float xr[A], xi[A];
+      T xr[A], xi[A];
       static_for<0, A>([&](auto a_) { constexpr int a = decltype(a_)::value; xr[a] = re[B * a + b]; xi[a] = im[B * a + b]; });
       Dft<A>::run(xr, xi);
       static_for<0, A>([&](auto k_) {
@@ -216,7 +260,7 @@ template <int A, int B> struct DftCT {
     });
     static_for<0, A>([&](auto k_) {
       constexpr int k = decltype(k_)::value;
-      float zr[B], zi[B];
+      T zr[B], zi[B];
       static_for<0, B>([&](auto b_) { constexpr int b = decltype(b_)::value; zr[b] = tr[k * B + b]; zi[b] = ti[k * B + b]; });
       Dft<B>::run(zr, zi);
       static_for<0, B>([&](auto q_) { constexpr int q = decltype(q_)::value; re[k + A * q] = zr[q]; im[k + A * q] = zi[q]; });
@@ -236,9 +280,9 @@ template <> struct Dft<16> : DftCT<4, 4> {};
 //   The twiddle table is W_M with M = N*tw_mul (so W_N^e = tab[e*tw_mul]).
 //   In the last stage (s*r == N) p is always 0 and the twiddles vanish (kLast).
 // ---------------------------------------------------------------------------------
-template <int r, bool kLast, class Src, class Dst>
+template <int r, bool kLast, class T = float, class Src, class Dst>
 SM_HD void stockham_bfly(int b, int N, int s, int tw_mul, const cf* tw, const Src& src, const Dst& dst) {
-  float re[r], im[r];
+  T re[r], im[r];
   const int Nr = N / r;
   static_for<0, r>([&](auto j_) {
     constexpr int j = decltype(j_)::value;
@@ -259,7 +303,7 @@ SM_HD void stockham_bfly(int b, int N, int s, int tw_mul, const cf* tw, const Sr
     static_for<1, r>([&](auto k_) {
       constexpr int k = decltype(k_)::value;
       const cf w = ldg_cf(tw + tstep * k);
-      float xr = re[k], xi = im[k];
+      T xr = re[k], xi = im[k];
       cmul(xr, xi, w.x, w.y);
       dst.store(obase + k * s, xr, xi);
     });

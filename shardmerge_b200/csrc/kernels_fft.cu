@@ -71,6 +71,13 @@ __global__ void __launch_bounds__(NW * 32, (R1 >= 11 || R2 >= 11) ? 3 : 4) k_col
   col_ct_body<R1, R2, NW, kInverse, kBigTw>(ex, (int)blockIdx.x, (int)blockIdx.y, a, twR, reinterpret_cast<cf*>(g_dyn_smem));
 }
 
+// paired-column variant (two adjacent columns per thread, packed f32x2 arithmetic)
+template <int R1, int R2, int NW, bool kInverse, bool kBigTw>
+__global__ void __launch_bounds__(NW * 32) k_col_p(const __grid_constant__ ColCtArgs a, const cf* __restrict__ twR) {
+  DeviceExec ex;
+  col_ct_body_p<R1, R2, NW, kInverse, kBigTw>(ex, (int)blockIdx.x, (int)blockIdx.y, a, twR, reinterpret_cast<pf4*>(g_dyn_smem));
+}
+
 // ---- both column sweeps of a four-step transform in ONE launch, the second one fed from L2 ----------------
 // A separate launch per sweep streams the whole spectrum through DRAM twice (16N bytes per transform).  Here the
 // CTAs of both sweeps share one 1-D grid, ordered so that the second-sweep CTAs of column tile t are dispatched
@@ -440,6 +447,43 @@ static int launch_col_ct_pair(bool inverse, bool big_tw, dim3 grid, const ColCtA
   return 0;
 }
 
+template <int R1, int R2, int NW>
+static int launch_col_p(bool inverse, bool big_tw, dim3 grid, const ColCtArgs& a, const cf* twR, cudaStream_t st) {
+  static bool done[4] = {false, false, false, false};
+  const int smem = (R2 > 1) ? R1 * R2 * SM_COL_TILE * 8 : 0;
+  cudaError_t e;
+#define SM_COLP_CASE(INV, BIG, IDX)                                                       \
+  e = opt_in(k_col_p<R1, R2, NW, INV, BIG>, &done[IDX]);                                  \
+  if (e != cudaSuccess) { sm_set_error("opt_in: %s", cudaGetErrorString(e)); return -100; } \
+  k_col_p<R1, R2, NW, INV, BIG><<<grid, NW * 32, smem, st>>>(a, twR);
+  if (!inverse && big_tw) { SM_COLP_CASE(false, true, 0) }
+  else if (!inverse) { SM_COLP_CASE(false, false, 1) }
+  else if (big_tw) { SM_COLP_CASE(true, true, 2) }
+  else { SM_COLP_CASE(true, false, 3) }
+#undef SM_COLP_CASE
+  SM_LAUNCH_CHECK();
+  return 0;
+}
+
+static bool use_col_pairs() {       // SM_COL_PAIRS=0: one column per thread (k_col_ct), for A-B timing
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SM_COL_PAIRS"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
+
+static int try_col_p(int n_rad, const int* rad, bool inverse, bool big_tw, dim3 grid, const ColCtArgs& a,
+                     const cf* twR, cudaStream_t st) {
+  if (n_rad != 2 || !use_col_pairs()) return 1;
+  const int r1 = rad[0], r2 = rad[1];
+  if (r1 == 8 && r2 == 8) return launch_col_p<8, 8, 4>(inverse, big_tw, grid, a, twR, st);
+  if (r1 == 16 && r2 == 8) return launch_col_p<16, 8, 4>(inverse, big_tw, grid, a, twR, st);
+  if (r1 == 16 && r2 == 16) return launch_col_p<16, 16, 8>(inverse, big_tw, grid, a, twR, st);
+  if (r1 == 7 && r2 == 16) return launch_col_p<7, 16, 4>(inverse, big_tw, grid, a, twR, st);
+  if (r1 == 11 && r2 == 8) return launch_col_p<11, 8, 4>(inverse, big_tw, grid, a, twR, st);
+  if (r1 == 8 && r2 == 4) return launch_col_p<8, 4, 2>(inverse, big_tw, grid, a, twR, st);
+  return 1;
+}
+
 // returns 1 if no specialised kernel exists for this factorization
 static int try_col_ct(int n_rad, const int* rad, bool inverse, bool big_tw, dim3 grid, const ColCtArgs& a,
                       const cf* twR, cudaStream_t st) {
@@ -635,7 +679,9 @@ static int launch_col(const SmPlan& p, const void* tables, int sweep, int invers
     c.P = p.P; c.Ch = p.Ch; c.inst_mul = ca.inst_mul; c.elem_mul = ca.elem_mul; c.tw_mul = ca.tw_mul;
     c.thr_ptr = cull_thr; c.scale_ptr = use_scale ? scale_dev : nullptr;
     c.scale = use_scale ? scale_host : 1.0f; c.write_p1_fwd = write_im;
-    const int rc = try_col_ct(ca.n_rad, ca.rad, inverse != 0, ca.big_tw != 0, dim3(ntiles, n_inst), c, tabR(p, tables), st);
+    int rc = try_col_p(ca.n_rad, ca.rad, inverse != 0, ca.big_tw != 0, dim3(ntiles, n_inst), c, tabR(p, tables), st);
+    if (rc <= 0) return rc;
+    rc = try_col_ct(ca.n_rad, ca.rad, inverse != 0, ca.big_tw != 0, dim3(ntiles, n_inst), c, tabR(p, tables), st);
     if (rc <= 0) return rc;
   }
   const int threads = (sweep == 0) ? p.thrA : p.thrB;

@@ -35,3 +35,19 @@ t0 = int(st[:, 0].min())
 for k in range(6):
     col = st[:, k]; col = col[col > 0]
     if len(col): print(f"stamp {k}: min {int(col.min()) - t0:7d} ns  max {int(col.max()) - t0:7d} ns  (n={len(col)})")
+hc = ws.sel_ws[al: al + kBins * 8].view(torch.int64).cpu()
+scnt = ws.sel_ws[al + kBins * 8 + kBins * 24: al + kBins * 8 + kBins * 24 + kBins * 4].view(torch.int32).cpu()
+print("bucket entries total", int((hc & 0xffffffff).sum()), "max", int((hc & 0xffffffff).max()), "keys", int((hc >> 32).sum()), "bcap", bcap)
+print("side entries total", int(scnt.sum()), "max", int(scnt.max()), "scap", scap)
+h = ws.ctl.cpu()
+o = 512
+import struct
+print("state lo hi shift status", struct.unpack_from("<QQIIII", bytes(h[o:o+32].tolist())))
+d1 = (st[:, 1] - st[:, 0]).float(); d2 = (st[:, 2] - st[:, 1]).float()
+import numpy as np
+for nm, d in (("loop", d1), ("flush", d2)):
+    q = np.percentile(d.numpy(), [0, 10, 50, 90, 99, 100])
+    print(nm, "percentiles ns", [int(v) for v in q])
+tot = (st[:, 2] - st[:, 0])
+idx = torch.argsort(tot, descending=True)[:12]
+print("slowest CTAs (block, smid, loop ns, flush ns):", [(int(i), int(st[i, 6]), int(d1[i]), int(d2[i])) for i in idx])
