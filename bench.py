@@ -319,8 +319,15 @@ def main():
     col_launch = sum(summ[t]["launches"] for t in ("col_fwd", "col_inv") if t in summ)
     achieved = col_bytes / (col_ms / 1000.0) / 1e9 if col_ms else None
     kernel_ms_total = sum(v["ms"] or 0.0 for v in summ.values())
-    roofline = dict(bound="hbm", kernel="k_col (column FFT sweeps, forward+inverse)", achieved=achieved, peak=peak,
-                    unit="GB/s", frac=(achieved / peak if achieved else None), traffic=None, peak_source=peak_src,
+    traffic, traffic_note = None, None
+    tpath = ROOT / "profiles" / "r01_traffic.json"
+    if tpath.exists():                                            # dram__bytes_read + dram__bytes_write of one captured launch
+        tj = json.loads(tpath.read_text())
+        traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+        traffic_note = dict(launch=tj["kernel"], algorithmic_bytes_of_that_launch=tj["algorithmic_bytes"], source=tj["source"])
+    roofline = dict(bound="hbm", kernel="k_col_p / k_col_ct (column FFT sweeps, forward+inverse)", achieved=achieved, peak=peak,
+                    unit="GB/s", frac=(achieved / peak if achieved else None), traffic=traffic, traffic_note=traffic_note,
+                    peak_source=peak_src,
                     bytes_per_launch=(col_bytes / col_launch if col_launch else None),
                     share_of_kernel_time=(col_ms / kernel_ms_total if kernel_ms_total else None),
                     measured="CUDA events around every kernel class during a serial (one stream) pass of the same steps "
@@ -406,9 +413,9 @@ def main():
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         shape = (a["KV"], a["H"])
-        r, dt = cpu_port_rate(shape, M, 1, repeats=2)
+        r, dt = cpu_port_rate(shape, M, 1, repeats=5)
         cpu_baseline = dict(value=r, unit="params/s", cores=1, kind="port",
-                            sample=f"2 x k_proj {shape[0]}x{shape[1]} through oracle/oracle_np.merge_layer "
+                            sample=f"5 x k_proj {shape[0]}x{shape[1]} through oracle/oracle_np.merge_layer "
                                    f"(numpy, single thread), {dt:.1f} s")
 
     if rank == 0:

@@ -71,7 +71,8 @@ __global__ void __launch_bounds__(NW * 32, (R1 >= 11 || R2 >= 11) ? 3 : 4) k_col
   col_ct_body<R1, R2, NW, kInverse, kBigTw>(ex, (int)blockIdx.x, (int)blockIdx.y, a, twR, reinterpret_cast<cf*>(g_dyn_smem));
 }
 
-// paired-column variant (two adjacent columns per thread, packed f32x2 arithmetic)
+// paired-column variant (two adjacent columns per thread, packed f32x2 arithmetic); capping registers for a 7th
+// resident CTA was measured slower (spills), so the compiler's own allocation (<= 80 registers) stands
 template <int R1, int R2, int NW, bool kInverse, bool kBigTw>
 __global__ void __launch_bounds__(NW * 32) k_col_p(const __grid_constant__ ColCtArgs a, const cf* __restrict__ twR) {
   DeviceExec ex;

@@ -534,6 +534,29 @@ def test_deferred_checks_pipeline(E):
         assert int(u.max()) <= 1 and float((u == 0).mean()) >= 0.9999
 
 
+def test_lanes_do_not_change_results(E):
+    """Consecutive tensors spread over several streams (FourierMerge.lanes) give bit-identical outputs to the
+    single-stream schedule: same kernels, same order per tensor, separate workspaces."""
+    shapes = [(1024, 2048), (512, 1024), (1024, 2048), (1, 4096), (2048, 1024), (1024, 2048)]
+    results = {}
+    for lanes in (1, 3):
+        fm = _merger()
+        fm.lanes = lanes
+        outs = []
+        for i, (R, C) in enumerate(shapes):
+            sh = (R, C) if R > 1 else (C,)
+            g = torch.Generator(device=DEV).manual_seed(900 + i)
+            base = (0.02 * torch.randn(sh, generator=g, device=DEV)).to(torch.bfloat16)
+            fts = [(base.float() + s * torch.randn(sh, generator=g, device=DEV)).to(torch.bfloat16) for s in (0.002, 0.0026)]
+            srcs = [E.make_source(base, ft, weight=a, name=f"m{k}") for k, (ft, a) in enumerate(zip(fts, (0.3, 0.5)))]
+            outs.append(fm.merge_sources(srcs, base, torch.device(DEV), layer_name=f"model.layers.{i}.x", defer=True))
+        fm.resolve_all()
+        torch.cuda.synchronize()
+        results[lanes] = [bits(o) for o in outs]
+    for a, b in zip(results[1], results[3]):
+        assert np.array_equal(a, b)
+
+
 def test_shape_mismatch_is_refused(E):
     fm = _merger()
     base = torch.zeros((64, 128), dtype=torch.bfloat16, device=DEV)
