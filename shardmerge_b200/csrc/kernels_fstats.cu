@@ -6,24 +6,38 @@
 // statistic of |Re R| (:138-148).  kernels_stats.cu does each of these as its own pass (that is
 // the step-by-step API, 25 launches, 16N bytes); here they are folded into TWO streaming passes:
 //
-//   k_fs_sample<0>   64 K random keys of the full (mirrored) spectra; the last CTA to finish turns
+//   k_fs_sample<0>   256 K random keys of the full (mirrored) spectra; the last CTA to finish turns
 //                    them into a key window [lo, hi] that brackets the cutoff statistic with ~6 sigma
-//                    of sampling noise, and into the bin width of a 2048-bin histogram over it
-//   k_fs_pass<0>     ONE pass over Re X0, Re X1 (4N bytes): keys below the window are counted, the
-//                    ~1 % inside it are appended to per-bin buckets; SLERP sums are accumulated for
-//                    every element whose mask the window already decides, the few with
-//                    lo <= |re1| <= hi go to per-bin side buckets (+ per-bin partial sums).
-//                    The last CTA finds the bin of the statistic, resolves the exact key inside that
-//                    one bucket, closes the sums and computes dot / cos / sin / ||rel||.
+//                    of sampling noise (<= 2^22 key bit patterns wide, else the status says so)
+//   k_fs_pass<0>     ONE pass over Re X0, Re X1 (4N bytes).  Keys below the window are counted in
+//                    registers.  The ~1 % inside it are histogrammed with fire-and-forget global
+//                    reductions at two resolutions: `fine` has one bin per key BIT PATTERN of the
+//                    window (2 M distinct addresses: no contention), `coarse` 2048 bins over it, kept
+//                    per CTA in shared memory and added to the global copy once at the end (coalesced).
+//                    SLERP sums are accumulated in registers for every element whose mask the window
+//                    already decides; the few with lo <= |re1| <= hi and equal signs are appended to a
+//                    per-CTA side list.  The last CTA picks the coarse bin of the statistic, then the
+//                    exact key from that bin's <= 2048 fine counters.
+//   k_fs_close       (cutoff pass only) all CTAs: add the side-list entries with |re1| >= key to the
+//                    sums; the last CTA computes dot / cos / sin / ||rel||.
 //   k_fs_sample<1>   the same sampling for |blend(re0, re1)| (the blend is cheap to evaluate at a
 //                    sample position) -> window for the cull statistic
-//   k_fs_pass<1>     the blend itself (read 4N, write 2N) with the count / bucket step folded into its
-//                    epilogue; the last CTA produces the exact cull threshold.
+//   k_fs_pass<1>     the blend itself (read 4N, write 2N) with the count / histogram step folded into
+//                    its epilogue; the last CTA produces the exact cull threshold.
+//
+// No thread waits on a returning global atomic or a block barrier inside the streaming loop, and no two
+// CTAs reduce into the same cache line while streaming.  (The first version staged candidates in shared
+// memory and flushed them under __syncthreads: barrier stalls were its largest stall reason and it moved
+// 0.9 TB/s, profiles/r01_ncu_full_fs_pass_raw.csv.  A second one reduced straight into a global coarse
+// histogram and per-bin partial sums: 64 + 384 contended cache lines made it 2x slower still.)
+// Columns 1..Ch-1 all carry Hermitian multiplicity 2, so the interior of a row is processed
+// unweighted and doubled at the end; the two edge column groups of each row (column 0, column Ch and
+// the zero padding behind it) take a generic per-element path.
 //
 // Exactness: the thresholds are the bit patterns of actual elements at the exact rank (Hermitian
 // multiplicities included), as in kernels_stats.cu; the masks therefore reproduce the reference's.
-// A window that misses, is too wide, or overflows a bucket (degenerate distributions) sets status
-// bits and the thresholds become NaN; the caller re-runs the tensor on the step-by-step path.
+// A window that misses, is too wide, or overflows a side bucket (degenerate distributions) sets
+// status bits and the thresholds become NaN; the caller re-runs the tensor on the step-by-step path.
 // Only tensors with more than 2^20 elements come here (sm_fstats_supported); smaller ones are launch
 // bound and use the step-by-step kernels.
 #include <cstddef>
@@ -32,15 +46,19 @@
 
 namespace {
 
-constexpr int kBins = 2048;
-constexpr unsigned int kNS = 1u << 16;
+constexpr int kBins = 2048;                    // coarse bins over the window
+constexpr int kMaxLists = 4096;                // side lists (one per CTA of the streaming pass)
+constexpr unsigned int kFineLog = 22;          // the window spans at most 2^22 key bit patterns
+constexpr unsigned int kFineMax = 1u << kFineLog;
+constexpr unsigned int kNS = 1u << 18;         // samples
+constexpr int kSampleThreads = 1024, kSamplePer = 4;
 
 struct FsState {                     // SM_FS_STATE_BYTES device bytes
   unsigned long long rank;           // rank of the statistic in the full key multiset
   unsigned long long below;          // keys below the window
   unsigned int lo, hi;               // window [lo, hi] (key bit patterns)
-  unsigned int shift;                // bucket = (key - lo) >> shift
-  unsigned int status;               // bit0 window missed, bit1 bucket overflow, bit2 window too wide   (SM_FS_STATUS_OFF)
+  unsigned int shift;                // coarse bin = (key - lo) >> shift
+  unsigned int status;               // bit0 window missed, bit1 side bucket overflow, bit2 window too wide   (SM_FS_STATUS_OFF)
   unsigned int ticket;
   unsigned int key;
   float value;
@@ -53,14 +71,19 @@ static_assert(sizeof(FsState) == SM_FS_STATE_BYTES, "FsState layout");
 static_assert(offsetof(FsState, status) == SM_FS_STATUS_OFF, "FsState status offset");
 static_assert(offsetof(FsState, sticky) == SM_FS_STICKY_OFF, "FsState sticky offset");
 
+constexpr int kSampleShift = 18;                         // sample histogram digit: key bits [30:18] (exponent + 5 mantissa bits)
+constexpr int kSampleBins = 1 << (31 - kSampleShift);    // 8192
+
 struct FsWs {                        // carved out of the caller's workspace
-  unsigned long long* hc;            // [kBins]  hi 32 bits: keys (with multiplicity), lo 32 bits: bucket entries
-  unsigned int* scnt;                // [kBins]  side bucket entries
-  double* hs;                        // [kBins][3] per-bin partial SLERP sums of the side entries
-  unsigned int* shist;               // [kSampleBins] sample histogram (zeroed by a memset node before k_fs_sample)
-  unsigned int* bkt;                 // [kBins][bcap]  key | (multiplicity - 1) << 31
-  float4* sbkt;                      // [kBins][scap]  (re0, re1, multiplicity, -)
-  unsigned int bcap, scap;
+  // one contiguous block, zeroed by a memset node before k_fs_sample:
+  unsigned int* shist;               // [kSampleBins] sample histogram
+  unsigned int* coarse;              // [kBins]  keys (with multiplicity) per coarse bin
+  unsigned int* scnt;                // [kMaxLists]  entries in the side list of pass CTA i
+  unsigned int* fine;                // [kFineMax] keys (with multiplicity) per bit pattern of the window
+  size_t zero_bytes;                 // size of that block
+  // not zeroed (guarded by scnt):
+  float2* sbkt;                      // [n_lists][scap]  (|re0| with "multiplicity 1" in the sign bit, |re1|)
+  unsigned int scap, n_lists;
   unsigned long long* dbg;           // development: per-CTA phase timestamps (NULL in production)
 };
 
@@ -138,7 +161,6 @@ __device__ void block_pick(const Load& load, int nbins, unsigned long long rank,
 }
 
 struct LoadSmem32 { const unsigned int* h; __device__ unsigned long long operator()(int b) const { return h[b]; } };
-struct LoadGlobalHi { const unsigned long long* h; __device__ unsigned long long operator()(int b) const { return __ldcg(h + b) >> 32; } };
 
 __device__ __forceinline__ double block_sum_d(double v, double* sh /* >= 32 */) {
 #pragma unroll
@@ -196,20 +218,16 @@ struct FsCommon {
   const float* thr_cut; const float* scal4; float t_sum;  // MODE 1 only
 };
 
-constexpr int kSampleShift = 18;                         // sample histogram digit: key bits [30:18] (exponent + 5 mantissa bits)
-constexpr int kSampleBins = 1 << (31 - kSampleShift);    // 8192
-
-struct LoadGlobal32 { const unsigned int* h; __device__ unsigned long long operator()(int b) const { return __ldcg(h + b); } };
-
-// 64 K random keys of the full (mirrored) spectrum are histogrammed by their top 14 key bits with global
-// reductions (spread over the L2 slices, no single-SM bottleneck); the last CTA to finish copies the 8 K bins to
-// shared memory (all loads in flight at once: single-CTA epilogues must not chain L2 round trips), finds the bins
-// holding the sample ranks k_lo / k_hi and takes their outer edges as the key window: at most one bin (3 % of the
-// key value) wider per side than the exact sample statistics would give.
+// 256 K random keys of the full (mirrored) spectrum are histogrammed by their top 13 key bits -- per CTA in
+// shared memory first (same-address global reductions serialise in L2), then one global reduction per CTA and
+// non-empty bin; the last CTA to finish copies the 8 K bins to shared memory (all loads in flight at once:
+// single-CTA epilogues must not chain L2 round trips), finds the bins holding the sample ranks k_lo / k_hi and
+// takes their outer edges as the key window: at most one bin (3 % of the key value) wider per side than the
+// exact sample statistics would give.
 template <int MODE>
-__global__ void __launch_bounds__(1024) k_fs_sample(const __grid_constant__ SmPlan pl, const __grid_constant__ FsCommon c,
-                                                    FsState* st, const __grid_constant__ FsWs ws, unsigned long long rank,
-                                                    long long k_lo, long long k_hi) {
+__global__ void __launch_bounds__(kSampleThreads) k_fs_sample(const __grid_constant__ SmPlan pl, const __grid_constant__ FsCommon c,
+                                                              FsState* st, const __grid_constant__ FsWs ws, unsigned long long rank,
+                                                              long long k_lo, long long k_hi) {
   __shared__ Pick out_a, out_b;
   __shared__ unsigned int s_h[kSampleBins];
   const unsigned int ns = kNS;
@@ -220,34 +238,38 @@ __global__ void __launch_bounds__(1024) k_fs_sample(const __grid_constant__ SmPl
   const float* re1 = sw ? c.reX : c.reY;
   BlendScal bs{};
   if (MODE == 1) { bs.thr = *c.thr_cut; bs.dot = c.scal4[0]; bs.ct = c.scal4[1]; bs.sn = c.scal4[2]; bs.rn = c.scal4[3]; bs.t_sum = c.t_sum; }
-  const unsigned int i = blockIdx.x * blockDim.x + threadIdx.x;
   FS_STAMP(0);
 #pragma unroll
-  for (int j = 0; j < kSampleBins / 1024; ++j) s_h[threadIdx.x + 1024 * j] = 0u;
+  for (int j = 0; j < kSampleBins / kSampleThreads; ++j) s_h[threadIdx.x + kSampleThreads * j] = 0u;
   __syncthreads();
-  // this kernel also zeroes the bucket counters / per-bin sums of the pass that follows
-  for (unsigned int z = i; z < (unsigned int)kBins; z += gridDim.x * blockDim.x) {
-    ws.hc[z] = 0ull; ws.scnt[z] = 0u; ws.hs[3 * z] = 0.0; ws.hs[3 * z + 1] = 0.0; ws.hs[3 * z + 2] = 0.0;
-  }
-  if (i < ns) {
-    unsigned long long j = __umul64hi(mix64(i + (MODE ? 0x51ed27ull : 0ull)), total);
-    const float* pp = re0;
-    if (MODE == 0 && j >= per_plane) { j -= per_plane; pp = re1; }
-    const unsigned int row = (unsigned int)(j / (unsigned long long)pl.C);
-    unsigned int col = (unsigned int)(j - (unsigned long long)row * pl.C);
-    if (col > (unsigned int)pl.Ch) col = pl.C - col;
-    const size_t off = (size_t)row * pl.P + col;
-    const unsigned int key = (MODE == 0) ? absbits(pp[off]) : absbits(blend1(re0[off], re1[off], bs));
-    // CTA-local histogram first: the populated bins are few, and same-address reductions serialise in L2
-    // (measured: 64 K direct global REDs took 12-17 us; one RED per CTA and non-empty bin takes < 1 us)
-    atomicAdd(&s_h[key >> kSampleShift], 1u);
+  {
+    float va[kSamplePer], vb[kSamplePer];                // all gathers of a thread in flight together
+#pragma unroll
+    for (int q = 0; q < kSamplePer; ++q) {
+      const unsigned int i = (blockIdx.x * kSamplePer + q) * kSampleThreads + threadIdx.x;
+      unsigned long long j = __umul64hi(mix64(i + (MODE ? 0x51ed27ull : 0ull)), total);
+      const float* pp = re0;
+      if (MODE == 0 && j >= per_plane) { j -= per_plane; pp = re1; }
+      const unsigned int row = (unsigned int)(j / (unsigned long long)pl.C);
+      unsigned int col = (unsigned int)(j - (unsigned long long)row * pl.C);
+      if (col > (unsigned int)pl.Ch) col = pl.C - col;
+      const size_t off = (size_t)row * pl.P + col;
+      if (MODE == 0) { va[q] = pp[off]; vb[q] = 0.f; }
+      else { va[q] = re0[off]; vb[q] = re1[off]; }
+    }
+#pragma unroll
+    for (int q = 0; q < kSamplePer; ++q) {
+      const unsigned int i = (blockIdx.x * kSamplePer + q) * kSampleThreads + threadIdx.x;
+      const unsigned int key = (MODE == 0) ? absbits(va[q]) : absbits(blend1(va[q], vb[q], bs));
+      if (i < ns) atomicAdd(&s_h[key >> kSampleShift], 1u);
+    }
   }
   __syncthreads();
   FS_STAMP(1);
 #pragma unroll
-  for (int j = 0; j < kSampleBins / 1024; ++j) {
-    const unsigned int v = s_h[threadIdx.x + 1024 * j];
-    if (v) atomicAdd(ws.shist + threadIdx.x + 1024 * j, v);
+  for (int j = 0; j < kSampleBins / kSampleThreads; ++j) {
+    const unsigned int v = s_h[threadIdx.x + kSampleThreads * j];
+    if (v) atomicAdd(ws.shist + threadIdx.x + kSampleThreads * j, v);
   }
   FS_STAMP(2);
   const bool last = fs_last_block(st);
@@ -255,15 +277,15 @@ __global__ void __launch_bounds__(1024) k_fs_sample(const __grid_constant__ SmPl
   if (!last) return;
   const bool want_a = (k_lo >= 0 && k_lo < (long long)ns), want_b = (k_hi >= 0 && k_hi < (long long)ns);
   {
-    unsigned int v[kSampleBins / 1024];
+    unsigned int v[kSampleBins / kSampleThreads];
 #pragma unroll
-    for (int j = 0; j < kSampleBins / 1024; ++j) v[j] = __ldcg(ws.shist + threadIdx.x + 1024 * j);
+    for (int j = 0; j < kSampleBins / kSampleThreads; ++j) v[j] = __ldcg(ws.shist + threadIdx.x + kSampleThreads * j);
 #pragma unroll
-    for (int j = 0; j < kSampleBins / 1024; ++j) s_h[threadIdx.x + 1024 * j] = v[j];
+    for (int j = 0; j < kSampleBins / kSampleThreads; ++j) s_h[threadIdx.x + kSampleThreads * j] = v[j];
   }
   __syncthreads();
-  block_pick<1024>(LoadSmem32{s_h}, kSampleBins, want_a ? (unsigned long long)k_lo : 0ull, &out_a);
-  block_pick<1024>(LoadSmem32{s_h}, kSampleBins, want_b ? (unsigned long long)k_hi : 0ull, &out_b);
+  block_pick<kSampleThreads>(LoadSmem32{s_h}, kSampleBins, want_a ? (unsigned long long)k_lo : 0ull, &out_a);
+  block_pick<kSampleThreads>(LoadSmem32{s_h}, kSampleBins, want_b ? (unsigned long long)k_hi : 0ull, &out_b);
   const int bin_a = out_a.bin, bin_b = out_b.bin;
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -272,9 +294,9 @@ __global__ void __launch_bounds__(1024) k_fs_sample(const __grid_constant__ SmPl
     if (hi > 0x7f800000u) hi = 0x7f800000u;             // NaN keys stay above every window
     unsigned int status = 0u;
     const unsigned long long width = hi >= lo ? (unsigned long long)hi - lo + 1ull : 0ull;
-    if (width == 0ull) status |= 4u;
     unsigned int l2 = 0;
     while ((1ull << l2) < width) ++l2;
+    if (width == 0ull || l2 > kFineLog) status |= 4u;    // the fine histogram has one counter per bit pattern
     st->rank = rank; st->below = 0ull; st->lo = lo; st->hi = hi;
     st->shift = l2 > 11 ? l2 - 11 : 0;
     st->status = status; st->key = 0u; st->value = 0.f; st->bstar = 0u;
@@ -287,132 +309,181 @@ __global__ void __launch_bounds__(1024) k_fs_sample(const __grid_constant__ SmPl
 // ---------------------------------------------------------------------------------------------
 // the streaming pass
 // ---------------------------------------------------------------------------------------------
-constexpr int kCandStage = 2048, kCandFlush = 1024;   // staged per CTA; flushed (uniformly) once half full
-constexpr int kSideStage = 512, kSideFlush = 256;
+// Straight-line fast path + per-warp deferral.  A float4 item is handled completely by branch-free code when it
+// is an interior column group (every key has multiplicity 2), no product a_i * b_i is zero / NaN (the sign of
+// the product then decides torch.sign(a) == torch.sign(b)) and none of its 8 keys lies inside the window.  Any
+// other item (~10 % of them) is appended -- operands and all -- to a queue private to the warp in shared
+// memory; whenever the queue holds 32 entries the warp drains it with ALL lanes busy, one entry per lane, through
+// the generic per-element code (weights, exact signs, histogram reductions, side list).  The first two versions
+// branched per key inside the loop: with 32 lanes x 8 keys some lane takes every branch, so the rare code ran
+// at 1/32 efficiency and made up half of the executed instructions (88 per element pair; now ~25).
+constexpr int kQCap = 64;            // entries per warp queue: < 32 left after a drain, <= 32 pushed per item
 
 struct PassCtx {
   float lo_f, hi_f;                  // the window as floats: for non-NaN keys, float order == bit-pattern order
-  unsigned int lo, span, shift, bcap, scap;
-  unsigned long long* hc; unsigned int* bkt;
-  unsigned int* scnt; float4* sbkt; double* hs;
+  unsigned int lo, shift, scap;
+  unsigned int* fine;
+  float2* slist;                     // this CTA's side list
+  unsigned int* status;
+  float* out;                        // MODE 1
+  int Ch;
 };
 
-// one key of multiplicity w: count it below the window, or stage it for its bucket (a shared-memory atomic; the
-// global bucket append -- a returning L2 atomic -- is batched in fs_flush so that no warp stalls on it per key)
-// CTA staging of the pass kernel, at namespace scope so that the out-of-line push helpers need no pointer arguments
-__shared__ unsigned int g_fs_hist[kBins];               // streaming phase: staged candidates; last CTA: bucket histogram
-__shared__ float4 g_fs_side[kSideStage];
-__shared__ unsigned int g_fs_ncand, g_fs_nside;
-static_assert(kCandStage <= kBins, "candidate staging aliases the histogram");
+// the out-of-line drain reads its parameters from shared memory (no pointer arguments, nothing forced into local memory)
+__shared__ PassCtx g_fs_ctx;
+__shared__ BlendScal g_fs_bs;
+__shared__ unsigned int g_fs_coarse[kBins];             // streaming phase: this CTA's coarse histogram; last CTA: scratch
+__shared__ unsigned int g_fs_nside;
+__shared__ float4 g_fs_qa[SM_EW_THREADS / 32][kQCap], g_fs_qb[SM_EW_THREADS / 32][kQCap];
+__shared__ uint2 g_fs_qm[SM_EW_THREADS / 32][kQCap];    // x: element offset of the item, y: first column | generic << 31
 
-__device__ __noinline__ void fs_push_cand(unsigned int e) {
-  const unsigned int pos = atomicAdd(&g_fs_ncand, 1u);
-  if (pos < (unsigned int)kCandStage) g_fs_hist[pos] = e;
-}
-__device__ __noinline__ void fs_push_side(float a, float b, float wf) {
-  const unsigned int pos = atomicAdd(&g_fs_nside, 1u);
-  if (pos < (unsigned int)kSideStage) g_fs_side[pos] = make_float4(a, b, wf, 0.f);
-}
-// torch.sign(a) == torch.sign(b) (sign(+-0) = sign(NaN) = 0).  A non-zero product decides it at once; the exact
-// comparison only runs for zeros, NaNs and products that underflow (a rarely taken, warp-coherent branch).
-__device__ __forceinline__ bool same_sign(float a, float b) {
-  const float p = a * b;
-  bool same = p > 0.f;
-  if (!(p > 0.f) && !(p < 0.f)) same = (sgn(a) == sgn(b));
-  return same;
+// the three-way blend, predicated (functions.py:134-136, one rounding per torch op; same arithmetic as blend1 / k_blend)
+__device__ __forceinline__ float fs_blend(const BlendScal& bs, float a, float b, bool same) {
+  const float rel = __fsub_rn(b, __fmul_rn(a, bs.dot));
+  const float o_slerp = __fadd_rn(__fmul_rn(a, bs.ct), __fmul_rn(__fdiv_rn(rel, bs.rn), bs.sn));
+  const float o_sum = __fadd_rn(a, __fmul_rn(bs.t_sum, b));
+  const float o_big = (fabsf(a) > fabsf(b)) ? a : b;
+  return same ? ((fabsf(b) < bs.thr) ? o_sum : o_slerp) : o_big;
 }
 
-// one element pair (MODE 0: statistics, MODE 1: blend), multiplicity w (0 for the zero-filled padding columns).
-// The common work is predicated / select based -- the three masks split a warp roughly 46 / 4 / 50 %, so branching
-// on them would run every side for every warp anyway -- and only the rare events (a key or an element inside the
-// window) branch, out of line.  Window tests are float compares on |v| (free abs modifier); NaN keys compare
-// false everywhere, i.e. they sit above the window like their bit patterns do.
+// NaN-propagating minimum (fminf would drop a NaN operand)
+__device__ __forceinline__ float fmin_nan(float x, float y) { float r; asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(x), "f"(y)); return r; }
+
+// true if no product a_i * b_i of the item is zero (incl. underflow) or NaN
+__device__ __forceinline__ bool fs_item_plain(const float4& a, const float4& b) {
+  const float m = fmin_nan(fmin_nan(fabsf(a.x * b.x), fabsf(a.y * b.y)), fmin_nan(fabsf(a.z * b.z), fabsf(a.w * b.w)));
+  return m > 0.f;                  // false for NaN
+}
+
+struct Acc { unsigned int below; float p00, p11, p01; bool anyw; };
+
+// interior element pair of a plain item, multiplicity 2 (the caller doubles counts and sums at the end).  Window tests
+// are float compares on |v| (free abs modifier); NaN keys compare false everywhere, i.e. they sit above the window like
+// their bit patterns do.  A key inside the window only raises a flag (the item is then queued as well).
 template <int MODE>
-__device__ __forceinline__ float fs_elem(const PassCtx& x, const BlendScal& bs, float a, float b, unsigned int w,
-                                         unsigned int& below, float& p00, float& p11, float& p01) {
-  const bool same = same_sign(a, b);
+__device__ __forceinline__ float fs_elem(const PassCtx& x, const BlendScal& bs, float a, float b, Acc& c) {
+  const bool same = a * b > 0.f;
   if (MODE == 0) {
-    below += (fabsf(a) < x.lo_f ? w : 0u) + (fabsf(b) < x.lo_f ? w : 0u);
-    if (fabsf(a) >= x.lo_f && fabsf(a) <= x.hi_f && w) fs_push_cand(absbits(a) | ((w - 1u) << 31));
-    const bool b_in_window = fabsf(b) >= x.lo_f && fabsf(b) <= x.hi_f && w;
-    if (b_in_window) fs_push_cand(absbits(b) | ((w - 1u) << 31));
-    const float wf = (float)w;
-    if (same && !(fabsf(b) <= x.hi_f)) {                 // |re1| >= thr for every thr in the window (NaN: never < thr)
-      p00 = fmaf(wf * a, a, p00); p11 = fmaf(wf * b, b, p11); p01 = fmaf(wf * a, b, p01);
-    }
-    if (same && b_in_window) fs_push_side(a, b, wf);                // undecided until the exact threshold is known
+    const float fa = fabsf(a), fb = fabsf(b);
+    const bool la = fa < x.lo_f, lb = fb < x.lo_f;
+    c.below += (la ? 1u : 0u) + (lb ? 1u : 0u);
+    c.anyw |= (!la && fa <= x.hi_f) | (!lb && fb <= x.hi_f);
+    // |re1| >= thr for every thr in the window (NaN: never < thr) -> the element is in the SLERP sums; masked operands
+    // instead of a branch (2 selects + 3 FMAs)
+    const bool in = same && !(fb <= x.hi_f);
+    const float ma = in ? a : 0.f, mb = in ? b : 0.f;
+    c.p00 = fmaf(ma, ma, c.p00); c.p11 = fmaf(mb, mb, c.p11); c.p01 = fmaf(ma, mb, c.p01);
     return 0.f;
   } else {
-    // functions.py:134-136, one rounding per torch op (same arithmetic as blend1 / k_blend)
-    const float rel = __fsub_rn(b, __fmul_rn(a, bs.dot));
-    const float o_slerp = __fadd_rn(__fmul_rn(a, bs.ct), __fmul_rn(__fdiv_rn(rel, bs.rn), bs.sn));
-    const float o_sum = __fadd_rn(a, __fmul_rn(bs.t_sum, b));
-    const float o_big = (fabsf(a) > fabsf(b)) ? a : b;
-    const float o = same ? ((fabsf(b) < bs.thr) ? o_sum : o_slerp) : o_big;
-    below += fabsf(o) < x.lo_f ? w : 0u;
-    if (fabsf(o) >= x.lo_f && fabsf(o) <= x.hi_f && w) fs_push_cand(absbits(o) | ((w - 1u) << 31));
+    const float o = fs_blend(bs, a, b, same);
+    const float fo = fabsf(o);
+    const bool lo_ = fo < x.lo_f;
+    c.below += lo_ ? 1u : 0u;
+    c.anyw |= (!lo_ && fo <= x.hi_f);
     return o;
   }
 }
 
-// all threads of the CTA: append the staged entries to their global buckets; returns the overflow flag
+// one key inside the window, multiplicity w: a fire-and-forget global reduction into its own counter (the window spans
+// ~2 M counters, so two keys rarely meet) and a shared-memory one into the CTA's coarse histogram
+__device__ __forceinline__ void fs_red_key(const PassCtx& x, unsigned int key, unsigned int w) {
+  const unsigned int d = key - x.lo;
+  atomicAdd(x.fine + d, w);
+  atomicAdd(&g_fs_coarse[d >> x.shift], w);
+}
+
+// what the drain adds to the block totals (only touched out of line)
+struct DrainAcc { unsigned long long below; double s00, s11, s01; };
+
+// Drain the top `n` (<= 32) entries of this warp's queue, one entry per lane.  A queued item is either "generic"
+// (edge column group: multiplicity 1 at columns 0 and Ch, 2 inside, 0 for the zero padding behind Ch; or an item
+// with a zero / NaN product: exact sign comparison) -- then everything is done here -- or a plain interior item with
+// a key inside the window: the fast path has done the counts, sums and (MODE 1) the output, only the window work is left.
 template <int MODE>
-__device__ unsigned int fs_flush(const PassCtx& x) {
-  unsigned int* s_cand = g_fs_hist; float4* s_side = g_fs_side;
-  unsigned int ovf = 0u;
-  unsigned int nc = g_fs_ncand, nsd = (MODE == 0) ? g_fs_nside : 0u;
-  if (nc > (unsigned int)kCandStage) { nc = kCandStage; ovf = 2u; }
-  if (nsd > (unsigned int)kSideStage) { nsd = kSideStage; ovf = 2u; }
-  for (unsigned int i = threadIdx.x; i < nc; i += blockDim.x) {
-    const unsigned int e = s_cand[i], k = e & 0x7fffffffu, w = 1u + (e >> 31);
-    const unsigned int bin = (k - x.lo) >> x.shift;
-    const unsigned int pos = (unsigned int)atomicAdd(x.hc + bin, ((unsigned long long)w << 32) | 1ull);
-    if (pos < x.bcap) x.bkt[(size_t)bin * x.bcap + pos] = e; else ovf = 2u;
-  }
-  if (MODE == 0) {
-    for (unsigned int i = threadIdx.x; i < nsd; i += blockDim.x) {
-      const float4 e = s_side[i];
-      const unsigned int bin = (absbits(e.y) - x.lo) >> x.shift;
-      const unsigned int pos = atomicAdd(x.scnt + bin, 1u);
-      if (pos < x.scap) x.sbkt[(size_t)bin * x.scap + pos] = e; else ovf = 2u;
-      const double da = (double)e.x, db = (double)e.y, dw = (double)e.z;
-      atomicAdd(x.hs + 3 * bin, dw * da * da); atomicAdd(x.hs + 3 * bin + 1, dw * db * db);
-      atomicAdd(x.hs + 3 * bin + 2, dw * da * db);
+__device__ __noinline__ void fs_drain(int wid, int first, int n, DrainAcc& acc) {
+  const PassCtx& x = g_fs_ctx;
+  const BlendScal& bs = g_fs_bs;
+  const int lane = threadIdx.x & 31;
+  __syncwarp();
+  if (lane < n) {
+    const float4 av = g_fs_qa[wid][first + lane], bv = g_fs_qb[wid][first + lane];
+    const uint2 m = g_fs_qm[wid][first + lane];
+    const bool generic = (m.y >> 31) != 0u;
+    const int c0 = (int)(m.y & 0x7fffffffu);
+    const float a[4] = {av.x, av.y, av.z, av.w}, b[4] = {bv.x, bv.y, bv.z, bv.w};
+    float o[4];
+    unsigned int below = 0u;
+    double s00 = 0.0, s11 = 0.0, s01 = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int col = c0 + i;
+      const unsigned int w = col > x.Ch ? 0u : ((col == 0 || col == x.Ch) ? 1u : 2u);
+      const bool same = (sgn(a[i]) == sgn(b[i]));         // torch.sign(a) == torch.sign(b) (sign(+-0) = sign(NaN) = 0)
+      if (MODE == 0) {
+        const float fa = fabsf(a[i]), fb = fabsf(b[i]);
+        const bool wa = fa >= x.lo_f && fa <= x.hi_f, wb = fb >= x.lo_f && fb <= x.hi_f;
+        if (wa && w) fs_red_key(x, __float_as_uint(fa), w);
+        if (wb && w) {
+          fs_red_key(x, __float_as_uint(fb), w);
+          if (same) {                                     // in the SLERP sums or not: known once the exact threshold is (k_fs_close)
+            const unsigned int pos = atomicAdd(&g_fs_nside, 1u);
+            if (pos < x.scap) x.slist[pos] = make_float2(w == 1u ? -fa : fa, fb);
+            else atomicOr(x.status, 2u);
+          }
+        }
+        if (generic) {
+          below += (fa < x.lo_f ? w : 0u) + (fb < x.lo_f ? w : 0u);
+          if (same && !(fb <= x.hi_f) && w) {
+            const double da = (double)a[i], db = (double)b[i], dw = (double)w;
+            s00 += dw * da * da; s11 += dw * db * db; s01 += dw * da * db;
+          }
+        }
+      } else {
+        o[i] = fs_blend(bs, a[i], b[i], same);
+        const float fo = fabsf(o[i]);
+        if (fo >= x.lo_f && fo <= x.hi_f && w) fs_red_key(x, __float_as_uint(fo), w);
+        if (generic) below += fo < x.lo_f ? w : 0u;
+      }
     }
+    if (MODE == 1 && generic) *reinterpret_cast<float4*>(x.out + m.x) = make_float4(o[0], o[1], o[2], o[3]);
+    if (generic) { acc.below += below; acc.s00 += s00; acc.s11 += s11; acc.s01 += s01; }
   }
-  __syncthreads();
-  if (threadIdx.x == 0) { g_fs_ncand = 0u; g_fs_nside = 0u; }
-  __syncthreads();
-  return ovf;
+  __syncwarp();
 }
 
 template <int MODE>
 __global__ void __launch_bounds__(SM_EW_THREADS, 4) k_fs_pass(const __grid_constant__ SmPlan pl, const __grid_constant__ FsCommon c,
                                                            FsState* st, const __grid_constant__ FsWs ws, float* out,
-                                                           double t, float* thr_out, float* scal4, double* sums_out) {
+                                                           float* thr_out) {
   __shared__ unsigned long long s_below[SM_EW_THREADS / 32];
   __shared__ double s_red[32];
   __shared__ Pick pick;
   __shared__ unsigned long long s_rank;
   __shared__ int s_ok;
-  unsigned int* const s_hist = g_fs_hist;
-  if (threadIdx.x == 0) { g_fs_ncand = 0u; g_fs_nside = 0u; }
-  __syncthreads();
+  unsigned int* const s_hist = g_fs_coarse;
+  constexpr int NT = SM_EW_THREADS;
   FS_STAMP(0);
   const bool sw = (c.sel != nullptr && *c.sel != 0);
   const float* __restrict__ re0 = sw ? c.reY : c.reX;
   const float* __restrict__ re1 = sw ? c.reX : c.reY;
   PassCtx x;
-  x.lo = st->lo; x.span = st->hi - x.lo; x.shift = st->shift; x.bcap = ws.bcap; x.scap = ws.scap;
+  x.lo = st->lo; x.shift = st->shift; x.scap = ws.scap;
   x.lo_f = __uint_as_float(x.lo); x.hi_f = __uint_as_float(st->hi);       // hi <= +inf (k_fs_sample)
-  x.hc = ws.hc; x.bkt = ws.bkt; x.scnt = ws.scnt; x.sbkt = ws.sbkt; x.hs = ws.hs;
+  x.fine = ws.fine; x.slist = ws.sbkt + (size_t)blockIdx.x * ws.scap;
+  x.status = &st->status; x.out = out; x.Ch = pl.Ch;
   const bool dead = st->status != 0u;
   BlendScal bs{};
   if (MODE == 1) { bs.thr = *c.thr_cut; bs.dot = c.scal4[0]; bs.ct = c.scal4[1]; bs.sn = c.scal4[2]; bs.rn = c.scal4[3]; bs.t_sum = c.t_sum; }
+  if (threadIdx.x == 0) { g_fs_ctx = x; g_fs_bs = bs; g_fs_nside = 0u; }
+#pragma unroll
+  for (int j = 0; j < kBins / NT; ++j) g_fs_coarse[threadIdx.x + NT * j] = 0u;
+  __syncthreads();
   const int Ch = pl.Ch;
-  unsigned int below32 = 0u;
-  unsigned int ovf = 0u;
-  double d00 = 0.0, d11 = 0.0, d01 = 0.0;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  unsigned int below_in = 0u;                            // keys below the window, fast path (unweighted)
+  double d00 = 0.0, d11 = 0.0, d01 = 0.0;                // SLERP sums, fast path (unweighted)
+  DrainAcc da{0ull, 0.0, 0.0, 0.0};                      // generic items (weighted)
+  int qn = 0;                                            // entries in this warp's queue (warp-uniform)
   // Work items are float4 column groups, numbered row-major over rows x G groups (G covers columns 0..Ch); the grid
   // strides over them so every thread gets the same share (no idle column blocks, no tail wave), two items in flight.
   const unsigned int G = (unsigned int)(Ch + 4) / 4u;
@@ -420,69 +491,76 @@ __global__ void __launch_bounds__(SM_EW_THREADS, 4) k_fs_pass(const __grid_const
   const unsigned int stride = gridDim.x * blockDim.x;
   const unsigned int step_row = stride / G, step_g = stride - step_row * G;
   if (!dead) {
-    int it = 0;
     unsigned int idx = blockIdx.x * blockDim.x + threadIdx.x;
     unsigned int row = idx / G, g = idx - row * G;
-    for (unsigned int base = blockIdx.x * blockDim.x; base < total; base += 2u * stride, ++it) {   // uniform trip count
+    for (unsigned int wbase = idx - lane; wbase < total; wbase += 2u * stride, idx += 2u * stride) {   // warp-uniform trip count
       // second item of this iteration: one grid stride further
       unsigned int row1 = row + step_row, g1 = g + step_g;
       if (g1 >= G) { g1 -= G; ++row1; }
-      const int n_item = idx < total ? (idx + stride < total ? 2 : 1) : 0;
-      if (n_item > 0) {
-        const size_t off[2] = {(size_t)row * pl.P + 4u * g, n_item == 2 ? (size_t)row1 * pl.P + 4u * g1 : (size_t)row * pl.P + 4u * g};
-        float4 a4[2], b4[2];                             // both items in flight before the first is consumed
-        a4[0] = *reinterpret_cast<const float4*>(re0 + off[0]); b4[0] = *reinterpret_cast<const float4*>(re1 + off[0]);
-        a4[1] = *reinterpret_cast<const float4*>(re0 + off[1]); b4[1] = *reinterpret_cast<const float4*>(re1 + off[1]);
-#pragma unroll 1
-        for (int r = 0; r < n_item; ++r) {               // rolled: one copy of the element code keeps the loop in the I-cache
-          const float4 av = r == 0 ? a4[0] : a4[1], bv = r == 0 ? b4[0] : b4[1];
-          const int c0 = 4 * (int)(r == 0 ? g : g1);
-          const float a[4] = {av.x, av.y, av.z, av.w}, b[4] = {bv.x, bv.y, bv.z, bv.w};
-          float p00 = 0.f, p11 = 0.f, p01 = 0.f;         // fp32 over one float4, fp64 across
-          float o[4];
+      const bool v0 = idx < total, v1 = idx + stride < total;
+      const size_t off0 = v0 ? (size_t)row * pl.P + 4u * g : 0;
+      const size_t off1 = v1 ? (size_t)row1 * pl.P + 4u * g1 : off0;
+      float4 a0, b0, a1, b1;                             // both items in flight before the first is consumed
+      a0 = *reinterpret_cast<const float4*>(re0 + off0); b0 = *reinterpret_cast<const float4*>(re1 + off0);
+      a1 = *reinterpret_cast<const float4*>(re0 + off1); b1 = *reinterpret_cast<const float4*>(re1 + off1);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            // multiplicity: 1 at columns 0 and Ch, 2 inside, 0 for the padding (zero-filled by the plane allocator and
-            // never written by any kernel, so padding elements contribute nothing)
-            const int col = c0 + i;
-            const unsigned int w = col > Ch ? 0u : ((col == 0 || col == Ch) ? 1u : 2u);
-            o[i] = fs_elem<MODE>(x, bs, a[i], b[i], w, below32, p00, p11, p01);
+      for (int r = 0; r < 2; ++r) {
+        const float4 av = r == 0 ? a0 : a1, bv = r == 0 ? b0 : b1;
+        const bool valid = r == 0 ? v0 : v1;
+        const unsigned int gg = r == 0 ? g : g1;
+        const size_t off = r == 0 ? off0 : off1;
+        const bool generic = (gg == 0u) || (gg == G - 1u) || !fs_item_plain(av, bv);
+        Acc ac{0u, 0.f, 0.f, 0.f, false};                // fp32 over one float4, fp64 across
+        float4 o;
+        o.x = fs_elem<MODE>(x, bs, av.x, bv.x, ac); o.y = fs_elem<MODE>(x, bs, av.y, bv.y, ac);
+        o.z = fs_elem<MODE>(x, bs, av.z, bv.z, ac); o.w = fs_elem<MODE>(x, bs, av.w, bv.w, ac);
+        const bool fast = valid && !generic;
+        if (fast) {
+          below_in += ac.below;
+          if (MODE == 0) { d00 += (double)ac.p00; d11 += (double)ac.p11; d01 += (double)ac.p01; }
+          else *reinterpret_cast<float4*>(out + off) = o;
+        }
+        const bool want = valid && (generic || ac.anyw);
+        const unsigned int m = __ballot_sync(0xffffffffu, want);
+        if (m) {                                         // warp-uniform
+          if (want) {
+            const int slot = qn + __popc(m & ((1u << lane) - 1u));
+            g_fs_qa[wid][slot] = av; g_fs_qb[wid][slot] = bv;
+            g_fs_qm[wid][slot] = make_uint2((unsigned int)off, 4u * gg | (generic ? 0x80000000u : 0u));
           }
-          if (MODE == 0) { d00 += (double)p00; d11 += (double)p11; d01 += (double)p01; }
-          else *reinterpret_cast<float4*>(out + (r == 0 ? off[0] : off[1])) = make_float4(o[0], o[1], o[2], o[3]);
+          qn += __popc(m);
+          if (qn >= 32) { qn -= 32; fs_drain<MODE>(wid, qn, 32, da); }
         }
       }
       // advance this thread by two grid strides
-      idx += 2u * stride;
       row = row1 + step_row; g = g1 + step_g;
       if (g >= G) { g -= G; ++row; }
-      if ((it & 7) == 7) {                               // every 8 iterations: flush the staging if it is half full
-        __syncthreads();
-        if (g_fs_ncand >= (unsigned int)kCandFlush || g_fs_nside >= (unsigned int)kSideFlush)
-          ovf |= fs_flush<MODE>(x);
-        else __syncthreads();                            // nobody appends before everybody has read the counters
-      }
     }
-    __syncthreads();
+    if (qn > 0) fs_drain<MODE>(wid, 0, qn, da);
     FS_STAMP(1);
-    ovf |= fs_flush<MODE>(x);
-    FS_STAMP(2);
   }
-  unsigned long long below = below32;
-  if (ovf) atomicOr(&st->status, ovf);
   {
+    unsigned long long below = 2ull * below_in + da.below;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xffffffffu, below, o);
     if ((threadIdx.x & 31) == 0) s_below[threadIdx.x >> 5] = below;
-    __syncthreads();
+    __syncthreads();                                     // also: every shared-memory reduction of the loop has landed
     if (threadIdx.x == 0) {
       unsigned long long bsum = 0ull;
-      for (int i = 0; i < SM_EW_THREADS / 32; ++i) bsum += s_below[i];
+      for (int i = 0; i < NT / 32; ++i) bsum += s_below[i];
       if (bsum) atomicAdd(&st->below, bsum);
+      if (MODE == 0) ws.scnt[blockIdx.x] = g_fs_nside < ws.scap ? g_fs_nside : ws.scap;
+    }
+    // this CTA's coarse histogram -> the global one: one coalesced reduction per warp and 32 bins
+#pragma unroll
+    for (int j = 0; j < kBins / NT; ++j) {
+      const unsigned int v = g_fs_coarse[threadIdx.x + NT * j];
+      if (v) atomicAdd(ws.coarse + threadIdx.x + NT * j, v);
     }
   }
   if (MODE == 0) {
-    const double r0 = block_sum_d(d00, s_red), r1 = block_sum_d(d11, s_red), r2 = block_sum_d(d01, s_red);
+    const double r0 = block_sum_d(2.0 * d00 + da.s00, s_red), r1 = block_sum_d(2.0 * d11 + da.s11, s_red),
+                 r2 = block_sum_d(2.0 * d01 + da.s01, s_red);
     if (threadIdx.x == 0 && (r0 != 0.0 || r1 != 0.0 || r2 != 0.0)) {
       atomicAdd(&st->s_in[0], r0); atomicAdd(&st->s_in[1], r1); atomicAdd(&st->s_in[2], r2);
     }
@@ -492,8 +570,7 @@ __global__ void __launch_bounds__(SM_EW_THREADS, 4) k_fs_pass(const __grid_const
   FS_STAMP(4);
   if (!last_cta) return;
 
-  // ---- last CTA: bin of the statistic -> exact key inside that bucket -> (MODE 0) close the sums
-  constexpr int NT = SM_EW_THREADS;
+  // ---- last CTA: coarse bin of the statistic -> exact key from that bin's fine counters
   if (threadIdx.x == 0) {
     const unsigned long long r = st->rank, bl = *((volatile unsigned long long*)&st->below);
     unsigned int status = *((volatile unsigned int*)&st->status);
@@ -506,12 +583,12 @@ __global__ void __launch_bounds__(SM_EW_THREADS, 4) k_fs_pass(const __grid_const
   unsigned int key = 0u;
   int bstar = -1;
   if (ok) {
-    {  // key counts per bucket -> shared memory, every load in flight at once
-      unsigned long long v[kBins / NT];
+    {  // key counts per coarse bin -> shared memory, every load in flight at once
+      unsigned int v[kBins / NT];
 #pragma unroll
-      for (int j = 0; j < kBins / NT; ++j) v[j] = __ldcg(ws.hc + threadIdx.x + NT * j);
+      for (int j = 0; j < kBins / NT; ++j) v[j] = __ldcg(ws.coarse + threadIdx.x + NT * j);
 #pragma unroll
-      for (int j = 0; j < kBins / NT; ++j) s_hist[threadIdx.x + NT * j] = (unsigned int)(v[j] >> 32);
+      for (int j = 0; j < kBins / NT; ++j) s_hist[threadIdx.x + NT * j] = v[j];
     }
     __syncthreads();
     block_pick<NT>(LoadSmem32{s_hist}, kBins, s_rank, &pick);
@@ -519,56 +596,25 @@ __global__ void __launch_bounds__(SM_EW_THREADS, 4) k_fs_pass(const __grid_const
     if (bstar < 0) ok = false;                            // rank beyond the window: the sample window missed
   }
   if (ok) {
-    // descend inside the bucket: 2048-bin shared histograms until one bin is one key (one level when the
-    // window spans <= 2^22 bit patterns, the usual case)
-    unsigned long long rin = pick.rank_in_bin;
-    unsigned int n_b = (unsigned int)__ldcg(ws.hc + bstar);
-    if (n_b > x.bcap) n_b = x.bcap;                       // overflow is already flagged in status
-    unsigned int cur_lo = x.lo + ((unsigned int)bstar << x.shift), wlog = x.shift;
-    while (true) {
-      const unsigned int sh2 = wlog > 11 ? wlog - 11 : 0;
-      for (int b = threadIdx.x; b < kBins; b += NT) s_hist[b] = 0u;
-      __syncthreads();
-      for (unsigned int i = threadIdx.x; i < n_b; i += NT) {
-        const unsigned int e = __ldcg(ws.bkt + (size_t)bstar * x.bcap + i);
-        const unsigned int d = (e & 0x7fffffffu) - cur_lo;              // unsigned wrap: keys below cur_lo fall out
-        if ((d >> wlog) == 0u) atomicAdd(&s_hist[d >> sh2], 1u + (e >> 31));
-      }
-      __syncthreads();
-      block_pick<NT>(LoadSmem32{s_hist}, kBins, rin, &pick);
-      if (pick.bin < 0) { ok = false; break; }
-      cur_lo += (unsigned int)pick.bin << sh2;
-      rin = pick.rank_in_bin;
-      if (sh2 == 0u) { key = cur_lo; break; }
-      wlog = sh2;
-    }
-  }
-  if (MODE == 0 && ok) {
-    // side entries: bins above the statistic's bin are "in" (per-bin partial sums); inside the bin decide per entry
-    double acc[3] = {0.0, 0.0, 0.0};
+    // the bin covers 2^shift <= 2048 bit patterns, one fine counter each
+    const unsigned long long rin = pick.rank_in_bin;
+    const unsigned int nf = 1u << x.shift;
+    const unsigned int f0 = (unsigned int)bstar << x.shift;
+    __syncthreads();
     {
-      double h[kBins / NT][3];
+      unsigned int v[kBins / NT];
 #pragma unroll
       for (int j = 0; j < kBins / NT; ++j) {
-        const int b = threadIdx.x + NT * j;
-#pragma unroll
-        for (int q = 0; q < 3; ++q) h[j][q] = (b > bstar) ? __ldcg(ws.hs + 3 * b + q) : 0.0;
+        const unsigned int i = threadIdx.x + NT * j;
+        v[j] = i < nf ? __ldcg(ws.fine + f0 + i) : 0u;
       }
 #pragma unroll
-      for (int j = 0; j < kBins / NT; ++j) { acc[0] += h[j][0]; acc[1] += h[j][1]; acc[2] += h[j][2]; }
+      for (int j = 0; j < kBins / NT; ++j) s_hist[threadIdx.x + NT * j] = v[j];
     }
-    unsigned int ns_b = __ldcg(ws.scnt + bstar);
-    if (ns_b > x.scap) ns_b = x.scap;
-    for (unsigned int i = threadIdx.x; i < ns_b; i += NT) {
-      const float4 e = __ldcg(ws.sbkt + (size_t)bstar * x.scap + i);
-      const double a = (double)e.x, b = (double)e.y, w = (double)e.z;
-      if (absbits(e.y) >= key) { acc[0] += w * a * a; acc[1] += w * b * b; acc[2] += w * a * b; }
-      // entries below the key were added to the bin's partial sums but bins <= bstar are not summed above
-    }
-    for (int j = 0; j < 3; ++j) {
-      const double r = block_sum_d(acc[j], s_red);
-      if (threadIdx.x == 0) st->s_in[j] = *((volatile double*)&st->s_in[j]) + r;
-    }
+    __syncthreads();
+    block_pick<NT>(LoadSmem32{s_hist}, kBins, rin, &pick);
+    if (pick.bin < 0) ok = false;
+    else key = x.lo + f0 + (unsigned int)pick.bin;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -577,27 +623,58 @@ __global__ void __launch_bounds__(SM_EW_THREADS, 4) k_fs_pass(const __grid_const
     st->ticket = 0u;
     if (st->status != 0u) {
       st->value = __uint_as_float(0x7fc00000u);
-      if (thr_out) *thr_out = st->value;
     } else {
       st->key = key; st->value = __uint_as_float(key); st->bstar = (unsigned int)bstar;
-      if (thr_out) *thr_out = st->value;
-      if (MODE == 0) {
-        double s[3] = {st->s_in[0], st->s_in[1], st->s_in[2]};
-        if (sums_out) { sums_out[0] = s[0]; sums_out[1] = s[1]; sums_out[2] = s[2]; }
-        if (scal4) fs_scalars(s, t, scal4);
-      }
     }
+    if (thr_out) *thr_out = st->value;
   }
   FS_STAMP(5);
 }
 
+// cutoff pass, second half: the side-list entries with |re1| >= key join the SLERP sums; the last CTA turns the sums
+// into the scalars of slerp().
+__global__ void __launch_bounds__(SM_EW_THREADS) k_fs_close(FsState* st, const __grid_constant__ FsWs ws, double t, float* scal4,
+                                                            double* sums_out) {
+  __shared__ double s_red[32];
+  const bool ok = st->status == 0u;
+  const unsigned int key = st->key;
+  double acc[3] = {0.0, 0.0, 0.0};
+  if (ok) {
+    for (unsigned int l = blockIdx.x; l < ws.n_lists; l += gridDim.x) {
+      const unsigned int n = __ldcg(ws.scnt + l);
+      const float2* lst = ws.sbkt + (size_t)l * ws.scap;
+      for (unsigned int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float2 e = __ldcg(lst + i);
+        if (__float_as_uint(e.y) >= key) {
+          const double a = (double)fabsf(e.x), b = (double)e.y, w = (__float_as_uint(e.x) >> 31) ? 1.0 : 2.0;
+          acc[0] += w * a * a; acc[1] += w * b * b; acc[2] += w * a * b;
+        }
+      }
+    }
+  }
+  for (int j = 0; j < 3; ++j) {
+    const double r = block_sum_d(acc[j], s_red);
+    if (threadIdx.x == 0 && r != 0.0) atomicAdd(&st->s_in[j], r);
+  }
+  if (!fs_last_block(st)) return;
+  if (threadIdx.x == 0) {
+    st->ticket = 0u;
+    if (ok) {
+      double s[3] = {*((volatile double*)&st->s_in[0]), *((volatile double*)&st->s_in[1]), *((volatile double*)&st->s_in[2])};
+      if (sums_out) { sums_out[0] = s[0]; sums_out[1] = s[1]; sums_out[2] = s[2]; }
+      if (scal4) fs_scalars(s, t, scal4);
+    }
+  }
+}
+
 inline dim3 fs_grid(const SmPlan& p) {
   int dev = 0, sms = 148;
-  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
   const long long items = (long long)p.R * ((p.Ch + 4) / 4);
   long long ctas = (long long)sms * 4;                   // one resident wave at 4 CTAs of 256 threads per SM (launch bounds)
   const long long need = (items + 2 * SM_EW_THREADS - 1) / (2 * SM_EW_THREADS);
   if (ctas > need) ctas = need;
+  if (ctas > kMaxLists) ctas = kMaxLists;
   if (ctas < 1) ctas = 1;
   return dim3((unsigned int)ctas, 1);
 }
@@ -609,16 +686,12 @@ void fs_sample_ranks(unsigned long long rank, unsigned long long total, long lon
   *k_lo = (long long)floor(ks - delta); *k_hi = (long long)ceil(ks + delta);
 }
 
-// bucket capacities: the window holds ~frac of the keys, spread over >= half of the 2048 buckets; x4 headroom.
-// Sized for the widest window any rank can need (p = 0.5).
-double fs_max_frac() { return 2.0 * (6.0 * sqrt((double)kNS * 0.25) + 16.0) / (double)kNS; }
-unsigned int fs_bcap(const SmPlan& p) {
-  const double entries = fs_max_frac() * (double)p.R * (double)(p.Ch + 1) * 2.0;      // two planes, one entry per stored bin
-  return (unsigned int)(entries / 1024.0 * 4.0) + 64u;
-}
-unsigned int fs_scap(const SmPlan& p) {
+// side list capacity per CTA: the window holds ~frac of the keys of one plane (widest window any rank can need,
+// p = 0.5, plus the two sample-histogram bins of slack), the CTAs share them evenly; x4 headroom.
+double fs_max_frac() { return 2.0 * (6.0 * sqrt((double)kNS * 0.25) + 16.0) / (double)kNS + 0.02; }
+unsigned int fs_scap(const SmPlan& p, unsigned int n_lists) {
   const double entries = fs_max_frac() * (double)p.R * (double)(p.Ch + 1);
-  return (unsigned int)(entries / 1024.0 * 4.0) + 64u;
+  return (unsigned int)(entries / (double)n_lists * 4.0) + 256u;
 }
 
 }  // namespace
@@ -630,13 +703,17 @@ extern "C" int sm_fstats_supported(const sm_plan* plan) {
   return (n > (1ull << 20) && 2ull * n < 0xfffffff0ull) ? 1 : 0;
 }
 
+static size_t fs_zero_bytes() {
+  return (size_t)kSampleBins * 4 + (size_t)kBins * 4 + (size_t)kMaxLists * 4 + (size_t)kFineMax * 4;
+}
+
 extern "C" size_t sm_fstats_ws_bytes(const sm_plan* plan) {
   const SmPlan& p = plan->p;
   if (!sm_fstats_supported(plan)) return 256;
-  size_t b = (size_t)kBins * (8 + 24 + 4) + (size_t)(1 << 13) * 4;
-  b += (size_t)kBins * fs_scap(p) * 16;
-  b += (size_t)kBins * fs_bcap(p) * 4;
-  return b + 512 + 65536;        // + development timestamps (SM_FS_STAMPS)
+  const unsigned int n_lists = fs_grid(p).x;
+  size_t b = fs_zero_bytes();
+  b += (size_t)n_lists * fs_scap(p, n_lists) * 8;
+  return b + 512 + 65536;        // + alignment, development timestamps (SM_FS_STAMPS)
 }
 
 static int fs_carve(const sm_plan* plan, void* wsp, size_t ws_bytes, FsWs* w) {
@@ -645,18 +722,21 @@ static int fs_carve(const sm_plan* plan, void* wsp, size_t ws_bytes, FsWs* w) {
   if (ws_bytes < sm_fstats_ws_bytes(plan)) { sm_set_error("fstats: workspace too small"); return -3; }
   char* b = reinterpret_cast<char*>(wsp);
   b = reinterpret_cast<char*>(((uintptr_t)b + 63) / 64 * 64);
-  w->hc = reinterpret_cast<unsigned long long*>(b); b += (size_t)kBins * 8;
-  w->hs = reinterpret_cast<double*>(b); b += (size_t)kBins * 3 * 8;
-  w->scnt = reinterpret_cast<unsigned int*>(b); b += (size_t)kBins * 4;
-  w->shist = reinterpret_cast<unsigned int*>(b); b += (size_t)(1 << 13) * 4;
-  w->bcap = fs_bcap(p); w->scap = fs_scap(p);
-  w->sbkt = reinterpret_cast<float4*>(b); b += (size_t)kBins * w->scap * 16;
-  w->bkt = reinterpret_cast<unsigned int*>(b);
-  b += (size_t)kBins * w->bcap * 4;
+  char* const z0 = b;
+  w->shist = reinterpret_cast<unsigned int*>(b); b += (size_t)kSampleBins * 4;
+  w->coarse = reinterpret_cast<unsigned int*>(b); b += (size_t)kBins * 4;
+  w->scnt = reinterpret_cast<unsigned int*>(b); b += (size_t)kMaxLists * 4;
+  w->fine = reinterpret_cast<unsigned int*>(b); b += (size_t)kFineMax * 4;
+  w->zero_bytes = (size_t)(b - z0);
+  w->n_lists = fs_grid(p).x;
+  w->scap = fs_scap(p, w->n_lists);
+  w->sbkt = reinterpret_cast<float2*>(b); b += (size_t)w->n_lists * w->scap * 8;
   b = reinterpret_cast<char*>(((uintptr_t)b + 63) / 64 * 64);
   w->dbg = getenv("SM_FS_STAMPS") ? reinterpret_cast<unsigned long long*>(b) : nullptr;   // development only
   return 0;
 }
+
+static inline int fs_sample_grid() { return (int)((kNS + kSampleThreads * kSamplePer - 1) / (kSampleThreads * kSamplePer)); }
 
 // Cutoff statistic + SLERP sums + scalars in one streaming pass (see the header of this file).
 extern "C" int sm_fstats_cutoff(const sm_plan* plan, const float* reX, const float* reY, const int* sel, uint64_t rank,
@@ -673,11 +753,14 @@ extern "C" int sm_fstats_cutoff(const sm_plan* plan, const float* reX, const flo
   FsCommon c{reX, reY, sel, nullptr, nullptr, 1.f};
   long long k_lo = 0, k_hi = 0;
   fs_sample_ranks(rank, total, &k_lo, &k_hi);
-  SM_CUDA_CHECK(cudaMemsetAsync(w.shist, 0, (size_t)kSampleBins * 4, s));
-  k_fs_sample<0><<<(int)(kNS / 1024), 1024, 0, s>>>(p, c, st, w, rank, k_lo, k_hi);
+  SM_CUDA_CHECK(cudaMemsetAsync(w.shist, 0, w.zero_bytes, s));
+  k_fs_sample<0><<<fs_sample_grid(), kSampleThreads, 0, s>>>(p, c, st, w, rank, k_lo, k_hi);
   SM_LAUNCH_CHECK();
   if (getenv("SM_FS_ONLY_SAMPLE")) return 0;
-  k_fs_pass<0><<<fs_grid(p), SM_EW_THREADS, 0, s>>>(p, c, st, w, nullptr, t, thr_cut_out, scal4_out, sums3_out);
+  k_fs_pass<0><<<w.n_lists, SM_EW_THREADS, 0, s>>>(p, c, st, w, nullptr, thr_cut_out);
+  SM_LAUNCH_CHECK();
+  const unsigned int close_grid = w.n_lists < 148u ? w.n_lists : 148u;
+  k_fs_close<<<close_grid, SM_EW_THREADS, 0, s>>>(st, w, t, scal4_out, sums3_out);
   SM_LAUNCH_CHECK();
   return 0;
 }
@@ -697,10 +780,10 @@ extern "C" int sm_fstats_blend_cull(const sm_plan* plan, const float* reX, const
   FsCommon c{reX, reY, sel, thr_cut, scal4, t_sum};
   long long k_lo = 0, k_hi = 0;
   fs_sample_ranks(rank, total, &k_lo, &k_hi);
-  SM_CUDA_CHECK(cudaMemsetAsync(w.shist, 0, (size_t)kSampleBins * 4, s));
-  k_fs_sample<1><<<(int)(kNS / 1024), 1024, 0, s>>>(p, c, st, w, rank, k_lo, k_hi);
+  SM_CUDA_CHECK(cudaMemsetAsync(w.shist, 0, w.zero_bytes, s));
+  k_fs_sample<1><<<fs_sample_grid(), kSampleThreads, 0, s>>>(p, c, st, w, rank, k_lo, k_hi);
   SM_LAUNCH_CHECK();
-  k_fs_pass<1><<<fs_grid(p), SM_EW_THREADS, 0, s>>>(p, c, st, w, out_re, 0.0, thr_cull_out, nullptr, nullptr);
+  k_fs_pass<1><<<w.n_lists, SM_EW_THREADS, 0, s>>>(p, c, st, w, out_re, thr_cull_out);
   SM_LAUNCH_CHECK();
   return 0;
 }
