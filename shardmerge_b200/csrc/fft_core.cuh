@@ -351,9 +351,9 @@ SM_HD void quad_twiddles(const cf* quad, int b, float (&wr)[r], float (&wi)[r]) 
 }
 
 // non-last first stage: s == 1, so q == 0, p == b, outputs go to r*b + k
-template <int r, class Src, class Dst>
+template <int r, class V = float, class Src, class Dst>
 SM_HD void stockham_bfly_first(int b, int N, const cf* quad, const Src& src, const Dst& dst) {
-  float re[r], im[r];
+  V re[r], im[r];
   const int Nr = N / r;
   static_for<0, r>([&](auto j_) {
     constexpr int j = decltype(j_)::value;
@@ -366,7 +366,7 @@ SM_HD void stockham_bfly_first(int b, int N, const cf* quad, const Src& src, con
   dst.store(obase, re[0], im[0]);
   static_for<1, r>([&](auto k_) {
     constexpr int k = decltype(k_)::value;
-    float xr = re[k], xi = im[k];
+    V xr = re[k], xi = im[k];
     cmul(xr, xi, wr[k], wi[k]);
     dst.store(obase + k, xr, xi);
   });

@@ -4,6 +4,7 @@
 // The arithmetic lives in fft_bodies.cuh (host/device); this file supplies the device
 // execution policy, the launch geometry and the reductions that need CUDA intrinsics.
 #include <cstdarg>
+#include <cstdlib>
 #include <mutex>
 #include "fft_bodies.cuh"
 #include "sm_internal.h"
@@ -293,6 +294,182 @@ __global__ void __launch_bounds__(T) k_row_inv_tma(int R, int C, int P, const __
   }
 }
 
+// ---- paired-row forward pass: two adjacent rows per CTA, carried through the butterflies as the two lanes of
+// packed f32x2 values (FADD2 / FMUL2 / FFMA2) ------------------------------------------------------------------
+// k_row_fwd_tma is instruction-issue bound (63 % issue slots, 97 instructions per complex point,
+// profiles/r01_ncu_full_rows_tma_raw.csv).  Here every FP, shared-memory and index instruction serves two rows,
+// and the untangle is fused into the last stage: thread t owns the last-stage butterflies t and s - t, whose
+// outputs are each other's mirror images (n <-> Ch - n), so the Hermitian half spectrum is formed in registers
+// (one shared-memory write and two reads per point less, one barrier less, each mirror pair computed once).
+// One work buffer: stage 1 fills it, stage 2 runs in place (a barrier between its loads and its stores), stage 3
+// only reads it.  Shapes: Ch = R1*R2*R3 with Ch / R3 == 2 * T (C = 4096: 16 x 16 x 8, T = 128).  Each lane rounds
+// exactly like the scalar kernel up to the untangle, which takes W^(Ch-n) = -conj(W^n) from the same table entry.
+struct RowSmem2 {               // [phys(i)] of (re_row0, re_row1, im_row0, im_row1); 1-in-16 padding like RowSmem
+  ulonglong2* buf;
+  __device__ __forceinline__ static int phys(int i) { return i + (i >> 4); }
+#if defined(__CUDA_ARCH__)      // pf is a 64-bit register pair on the device only
+  __device__ __forceinline__ void load(int i, pf& re, pf& im) const { const ulonglong2 v = buf[phys(i)]; re.v = v.x; im.v = v.y; }
+  __device__ __forceinline__ void store(int i, pf re, pf im) const { buf[phys(i)] = make_ulonglong2(re.v, im.v); }
+#else
+  void load(int, pf&, pf&) const {}
+  void store(int, pf, pf) const {}
+#endif
+};
+
+struct RowDeltaStaged2 {        // stage-1 source: staging = [base row0 | base row1 | ft row0 | ft row1], bf16
+  const uint32_t* b32; const uint32_t* f32; int half; pf* acc;       // half = words per row
+  __device__ __forceinline__ void load(int i, pf& re, pf& im) const {
+    const uint32_t b0 = b32[i], b1 = b32[half + i], f0 = f32[i], f1 = f32[half + i];
+    re = pf_make(bf16_bits_to_f32(f0 & 0xffffu), bf16_bits_to_f32(f1 & 0xffffu)) -
+         pf_make(bf16_bits_to_f32(b0 & 0xffffu), bf16_bits_to_f32(b1 & 0xffffu));
+    im = pf_make(bits_f32(f0 & 0xffff0000u), bits_f32(f1 & 0xffff0000u)) -
+         pf_make(bits_f32(b0 & 0xffff0000u), bits_f32(b1 & 0xffff0000u));
+    *acc = pf_fma(re, re, pf_fma(im, im, *acc));
+  }
+};
+
+// X[n] and X[Ch - n] of both rows from Z[n] = (ar, ai) and Z[Ch - n] = (br, bi); w = W_C^n
+__device__ __forceinline__ void untangle_pair2(pf ar, pf ai, pf br, pf bi, cf w, float* re0, float* im0, int P, int n, int m) {
+  const pf h = pf_bcast(0.5f);
+  const pf er = h * (ar + br), ei = h * (ai - bi), pr = h * (ai + bi), qi = zero_of(ar) - h * (ar - br);
+  const pf wx = pf_bcast(w.x), wy = pf_bcast(w.y);
+  const pf tr = pf_fma(pr, wx, zero_of(ar) - qi * wy);       // pr * w.x - qi * w.y
+  const pf ti = pf_fma(pr, wy, qi * wx);                      // pr * w.y + qi * w.x
+  const pf xr = er + tr, xi = ei + ti;
+  re0[n] = pf_lo(xr); re0[P + n] = pf_hi(xr); im0[n] = pf_lo(xi); im0[P + n] = pf_hi(xi);
+  if (m != n) {
+    const pf yr = er - tr, yi = ti - ei;
+    re0[m] = pf_lo(yr); re0[P + m] = pf_hi(yr); im0[m] = pf_lo(yi); im0[P + m] = pf_hi(yi);
+  }
+}
+
+template <int R1, int R2, int R3, int T>
+__global__ void __launch_bounds__(T, 3) k_row2_fwd(int R, int C, int P, const __grid_constant__ RowFwdArgs a,
+                                                const cf* __restrict__ twC, const cf* __restrict__ twQ,
+                                                double* __restrict__ sumsq, int work_bytes) {
+  constexpr int CH = R1 * R2 * R3;
+  constexpr int S3 = CH / R3;                       // stride (and butterfly count) of the last stage
+  static_assert(CH / R1 == T && CH / R2 == T && S3 == 2 * T, "k_row2_fwd: one butterfly per thread in stages 1-2, two in stage 3");
+  __shared__ uint64_t full;
+  __shared__ double wsum[16];
+  RowSmem2 sm{reinterpret_cast<ulonglong2*>(g_dyn_smem)};
+  char* stage = reinterpret_cast<char*>(g_dyn_smem) + work_bytes;
+  const int tid = threadIdx.x;
+  const int npairs = R >> 1;
+  if (tid == 0) { mbar_init(&full, 1); mbar_fence_init(); }
+  __syncthreads();
+  auto prefetch = [&](int pair) {                   // both rows of a pair are contiguous: one bulk copy per tensor
+    if (tid == 0 && pair < npairs) {
+      mbar_expect_tx(&full, 8u * (uint32_t)C);
+      bulk_g2s(stage, a.base + (size_t)pair * 2 * C, 4u * (uint32_t)C, &full);
+      bulk_g2s(stage + 4 * (size_t)C, a.ft + (size_t)pair * 2 * C, 4u * (uint32_t)C, &full);
+    }
+  };
+  prefetch((int)blockIdx.x);
+  uint32_t phase = 0;
+  double accd = 0.0;
+  // every twiddle of this thread is the same for all row pairs; the loads are issued ahead of the barrier / wait that
+  // precedes their use, so their latency is never exposed (the kernel is latency bound: 3 CTAs of 4 warps per SM)
+  const int p2 = tid / R1, q2 = tid - p2 * R1;
+  const int obase2 = q2 + R1 * R2 * p2, tstep2 = R1 * p2 * 2;
+  const int bA = tid, bB = tid == 0 ? S3 / 2 : S3 - tid;
+  for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+    pf accp = pf_make(0.f, 0.f);
+    {  // stage 1: delta + radix R1 (s = 1), first-stage quad twiddles (formed while the bulk copy lands)
+      float wr[R1], wi[R1];
+      quad_twiddles<R1>(twQ, tid, wr, wi);
+      mbar_wait(&full, phase); phase ^= 1u;
+      RowDeltaStaged2 src{reinterpret_cast<const uint32_t*>(stage), reinterpret_cast<const uint32_t*>(stage + 4 * (size_t)C), C / 2, &accp};
+      pf re[R1], im[R1];
+      constexpr int Nr = CH / R1;
+#pragma unroll
+      for (int j = 0; j < R1; ++j) src.load(tid + j * Nr, re[j], im[j]);
+      Dft<R1>::run(re, im);
+      sm.store(R1 * tid, re[0], im[0]);
+#pragma unroll
+      for (int k = 1; k < R1; ++k) {
+        pf xr = re[k], xi = im[k];
+        cmul(xr, xi, wr[k], wi[k]);
+        sm.store(R1 * tid + k, xr, xi);
+      }
+    }
+    __syncthreads();
+    prefetch(pair + (int)gridDim.x);                // the staging buffer is free again
+    {  // stage 2: radix R2, s = R1, in place
+      cf w[R2];
+#pragma unroll
+      for (int k = 1; k < R2; ++k) w[k] = ldg_cf(twC + tstep2 * k);
+      pf re[R2], im[R2];
+      constexpr int Nr = CH / R2;
+#pragma unroll
+      for (int j = 0; j < R2; ++j) sm.load(tid + j * Nr, re[j], im[j]);
+      __syncthreads();
+      Dft<R2>::run(re, im);
+      sm.store(obase2, re[0], im[0]);
+#pragma unroll
+      for (int k = 1; k < R2; ++k) {
+        pf xr = re[k], xi = im[k];
+        cmul(xr, xi, w[k].x, w[k].y);
+        sm.store(obase2 + k * R1, xr, xi);
+      }
+    }
+    __syncthreads();
+    {  // stage 3 (last, no twiddles) on the butterflies t and S3 - t (thread 0: 0 and S3 / 2) + untangle
+      cf w[R3];
+#pragma unroll
+      for (int k = 0; k < R3; ++k) w[k] = ldg_cf(twC + (tid != 0 ? bA + S3 * k : (k <= R3 / 2 ? S3 * k : S3 / 2 + S3 * (k - R3 / 2 - 1))));
+      pf ar[R3], ai[R3], br[R3], bi[R3];
+#pragma unroll
+      for (int j = 0; j < R3; ++j) { sm.load(bA + j * S3, ar[j], ai[j]); sm.load(bB + j * S3, br[j], bi[j]); }
+      __syncthreads();                              // the buffer has been read: the next pair's stage 1 may overwrite it
+      Dft<R3>::run(ar, ai);
+      Dft<R3>::run(br, bi);
+      float* re0 = a.re + (size_t)pair * 2 * P;
+      float* im0 = a.im + (size_t)pair * 2 * P;
+      if (tid != 0) {
+#pragma unroll
+        for (int k = 0; k < R3; ++k) {              // n = t + S3*k  <->  Ch - n = (S3 - t) + S3*(R3-1-k)
+          const int n = bA + S3 * k;
+          untangle_pair2(ar[k], ai[k], br[R3 - 1 - k], bi[R3 - 1 - k], w[k], re0, im0, P, n, CH - n);
+        }
+      } else {
+        // butterfly 0: n = S3*k <-> S3*(R3-k); n = 0 pairs with itself and also yields the Nyquist bin Ch
+        {
+          const pf h = ar[0], g = ai[0];
+          const pf x0 = h + g, xn = h - g;
+          re0[0] = pf_lo(x0); re0[P] = pf_hi(x0); im0[0] = 0.f; im0[P] = 0.f;
+          re0[CH] = pf_lo(xn); re0[P + CH] = pf_hi(xn); im0[CH] = 0.f; im0[P + CH] = 0.f;
+        }
+#pragma unroll
+        for (int k = 1; k <= R3 / 2; ++k) {         // w[k] = W^(S3*k)
+          const int n = S3 * k;
+          untangle_pair2(ar[k], ai[k], ar[R3 - k], ai[R3 - k], w[k], re0, im0, P, n, CH - n);
+        }
+        // butterfly S3/2: n = S3/2 + S3*k <-> S3/2 + S3*(R3-1-k); w[R3/2 + 1 + k] = W^(S3/2 + S3*k)
+#pragma unroll
+        for (int k = 0; k < R3 / 2 - 1; ++k) {
+          const int n = S3 / 2 + S3 * k;
+          untangle_pair2(br[k], bi[k], br[R3 - 1 - k], bi[R3 - 1 - k], w[R3 / 2 + 1 + k], re0, im0, P, n, CH - n);
+        }
+        {                                           // the last pair of that butterfly has no slot left in w[]
+          const int k = R3 / 2 - 1, n = S3 / 2 + S3 * k;
+          untangle_pair2(br[k], bi[k], br[R3 - 1 - k], bi[R3 - 1 - k], ldg_cf(twC + n), re0, im0, P, n, CH - n);
+        }
+      }
+    }
+    accd += (double)pf_lo(accp) + (double)pf_hi(accp);   // fp32 over one thread's share of one row, fp64 across
+  }
+  double acc = warp_sum(accd);
+  const int lane = tid & 31, wid = tid >> 5;
+  if (lane == 0) wsum[wid] = acc;
+  __syncthreads();
+  if (wid == 0) {
+    double v = lane < (T + 31) / 32 ? wsum[lane] : 0.0;
+    v = warp_sum(v);
+    if (lane == 0) atomicAdd(sumsq, v);
+  }
+}
+
 // scale a 1-D spectrum (no column sweep exists to fold the normalisation into)
 __global__ void k_scale_row(float* re, float* im, int n, const float* scale_dev, float scale_host, int write_im) {
   const float s = scale_dev ? *scale_dev : scale_host;
@@ -573,12 +750,46 @@ static int try_col2_ct(const int* p_rad, int p_n, const int* q_rad, int q_n, boo
   return 1;
 }
 
+static bool use_row_pairs() {       // SM_ROW_PAIRS=0: one row per CTA iteration (k_row_fwd_tma), for A-B timing
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SM_ROW_PAIRS"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
+
+// paired-row forward pass (k_row2_fwd); returns 1 if this shape / mode has none
+template <int R1, int R2, int R3, int R4, int T, bool kPad>
+static int try_row2_fwd(const SmPlan& p, const RowFwdArgs& fa, const cf* twC, const cf* twQ, double* sumsq, cudaStream_t st) {
+  if constexpr (R4 == 1 && kPad && (R1 * R2 * R3) / R3 == 2 * T && (R1 * R2 * R3) / R1 == T && (R1 * R2 * R3) / R2 == T) {
+    constexpr int CH = R1 * R2 * R3;
+    if (!use_row_pairs() || fa.mode != 0 || (p.R & 1) || p.R < 2 || p.C % 8 != 0) return 1;
+    static bool done = false;
+    static int occ = 0;
+    const int work_bytes = ((CH + (CH >> 4) + 1) * 16 + 127) / 128 * 128;
+    const int smem = work_bytes + 8 * p.C;
+    if (smem > 227 * 1024 - 256) return 1;
+    cudaError_t e = opt_in(k_row2_fwd<R1, R2, R3, T>, &done);
+    if (e == cudaSuccess && occ == 0) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_row2_fwd<R1, R2, R3, T>, T, smem);
+    if (e != cudaSuccess) { sm_set_error("row2 setup: %s", cudaGetErrorString(e)); return -100; }
+    int grid = num_sms() * (occ > 0 ? occ : 1);
+    if (grid > p.R / 2) grid = p.R / 2;
+    k_row2_fwd<R1, R2, R3, T><<<grid, T, smem, st>>>(p.R, p.C, p.P, fa, twC, twQ, sumsq, work_bytes);
+    SM_LAUNCH_CHECK();
+    return 0;
+  } else {
+    return 1;
+  }
+}
+
 template <int R1, int R2, int R3, int R4, int T, bool kPad>
 static int launch_row_ct(bool inverse, const SmPlan& p, const RowFwdArgs* fa, const RowInvArgs* ia, const cf* twC,
                          const cf* twQ, double* sumsq, cudaStream_t st) {
   static bool done[4] = {false, false, false, false};
   static int occ[2] = {0, 0};
   constexpr int CH = R1 * R2 * R3 * R4;
+  if (!inverse && use_tma()) {
+    const int rc = try_row2_fwd<R1, R2, R3, R4, T, kPad>(p, *fa, twC, twQ, sumsq, st);
+    if (rc <= 0) return rc;
+  }
   constexpr int nst = (R2 > 1) + (R3 > 1) + (R4 > 1) + 1;
   constexpr int bufstride = kPad ? (CH + (CH >> 4) + 1) : CH;
   cudaError_t e;
@@ -599,7 +810,13 @@ static int launch_row_ct(bool inverse, const SmPlan& p, const RowFwdArgs* fa, co
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], k_row_inv_tma<R1, R2, R3, R4, T, kPad>, T, smem);
     }
     if (e != cudaSuccess) { sm_set_error("row tma setup: %s", cudaGetErrorString(e)); return -100; }
-    int grid = num_sms() * (occ[which] > 0 ? occ[which] : 1);
+    int per_sm = occ[which] > 0 ? occ[which] : 1;
+    {                               // SM_ROW_OCC=n caps the resident row CTAs per SM (leaves room for another lane's kernels)
+      static int cap = -1;
+      if (cap < 0) { const char* e = getenv("SM_ROW_OCC"); cap = e ? atoi(e) : 0; }
+      if (cap > 0 && per_sm > cap) per_sm = cap;
+    }
+    int grid = num_sms() * per_sm;
     if (grid > p.R) grid = p.R;
     if (!inverse) k_row_fwd_tma<R1, R2, R3, R4, T, kPad><<<grid, T, smem, st>>>(p.R, p.C, p.P, *fa, twC, twQ, sumsq, work_bytes);
     else k_row_inv_tma<R1, R2, R3, R4, T, kPad><<<grid, T, smem, st>>>(p.R, p.C, p.P, *ia, twC, twQ, work_bytes);

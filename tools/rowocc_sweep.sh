@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+for o in 4 3 2; do for l in 1 3; do
+  SM_ROW_OCC=$o SHARDMERGE_LANES=$l timeout 600 python bench.py --layers 4 --steps 3 --warmup 3 --no-cpu-baseline --no-e2e 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('rowocc $o lanes $l value %.2f G ms %.2f'%(d['value']/1e9,d['ms_per_step']))"
+done; done
