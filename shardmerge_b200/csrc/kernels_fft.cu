@@ -470,6 +470,151 @@ __global__ void __launch_bounds__(T, 3) k_row2_fwd(int R, int C, int P, const __
   }
 }
 
+// ---- paired-row inverse pass: the mirror image of k_row2_fwd ------------------------------------------------------
+// Two adjacent spectrum rows per CTA as f32x2 lanes: tangle (from the staged re / im rows) + radix R1 with quad
+// twiddles -> in-place radix R2 -> radix R3 straight into the epilogue (x 1/N, NaN -> 0 / Inf count, x target_norm,
+// + base, NaN -> 0 / Inf count, bf16 RNE).  Only the spectrum is staged by bulk copies; the bf16 base words of a
+// thread's outputs are plain loads issued before the last stage's shared-memory reads (their latency is covered by
+// the stage), which keeps the CTA at 68 KB of shared memory: 3 CTAs per SM.  Same arithmetic per lane as
+// k_row_inv_tma.  No cull on load here (2-D tensors cull in the first inverse column sweep).
+struct RowTangleStaged2 {
+  const float* re; const float* im; int P; int Ch;
+  __device__ __forceinline__ void load(int k, cf w, pf& ore, pf& oim) const {
+    pf xr = pf_make(re[k], re[P + k]), xi = pf_make(im[k], im[P + k]);
+    pf mr = pf_make(re[Ch - k], re[P + Ch - k]), mi = pf_make(im[Ch - k], im[P + Ch - k]);
+    if (k == 0) { xi = pf_make(0.f, 0.f); mi = xi; }    // .real semantics: bins 0 and Ch are real
+    const pf Ar = xr + mr, Ai = xi - mi, Br = xr - mr, Bi = xi + mi;
+    const pf wx = pf_bcast(w.x), wy = pf_bcast(w.y);
+    const pf br = pf_fma(Br, wx, Bi * wy);              // B * conj(w)
+    const pf bi = pf_fma(Bi, wx, zero_of(Br) - Br * wy);
+    const pf zr = Ar - bi, zi = Ai + br;
+    ore = zi; oim = zr;                                 // handed to the forward engine swapped
+  }
+};
+
+__device__ __forceinline__ float epi_fix(float v, unsigned int* flags, int which) {
+  return not_finite(v) ? sm_fix_nonfinite(v, flags, which) : v;
+}
+
+// element j of the pair: (a, b) = swapped engine output -> x[2j] = b / N, x[2j+1] = a / N for both rows
+__device__ __forceinline__ void epilogue_store2(const RowInvArgs& a, float scale, uint32_t bb0, uint32_t bb1, uint32_t* out0,
+                                                uint32_t* out1, float* of0, float* of1, int j, pf va, pf vb) {
+  const pf n = pf_bcast(a.inv_n);
+  pf x0 = vb * n, x1 = va * n;
+  float x00 = pf_lo(x0), x01 = pf_hi(x0), x10 = pf_lo(x1), x11 = pf_hi(x1);   // xRC: element R of the pair, row C
+  if (a.check_ifft) { x00 = epi_fix(x00, a.flags, 0); x01 = epi_fix(x01, a.flags, 0); x10 = epi_fix(x10, a.flags, 0); x11 = epi_fix(x11, a.flags, 0); }
+  x00 *= scale; x01 *= scale; x10 *= scale; x11 *= scale;
+  if (a.out_mode == 0) {
+    x00 = bf16_bits_to_f32(bb0 & 0xffffu) + x00; x10 = bits_f32(bb0 & 0xffff0000u) + x10;
+    x01 = bf16_bits_to_f32(bb1 & 0xffffu) + x01; x11 = bits_f32(bb1 & 0xffff0000u) + x11;
+    x00 = epi_fix(x00, a.flags, 2); x10 = epi_fix(x10, a.flags, 2); x01 = epi_fix(x01, a.flags, 2); x11 = epi_fix(x11, a.flags, 2);
+    out0[j] = pack_bf16x2_rne(x00, x10);
+    out1[j] = pack_bf16x2_rne(x01, x11);
+  } else {
+    reinterpret_cast<float2*>(of0)[j] = make_float2(x00, x10);
+    reinterpret_cast<float2*>(of1)[j] = make_float2(x01, x11);
+  }
+}
+
+template <int R1, int R2, int R3, int T>
+__global__ void __launch_bounds__(T, 3) k_row2_inv(int R, int C, int P, const __grid_constant__ RowInvArgs a,
+                                                   const cf* __restrict__ twC, const cf* __restrict__ twQ, int work_bytes) {
+  constexpr int CH = R1 * R2 * R3;
+  constexpr int S3 = CH / R3;
+  static_assert(CH / R1 == T && CH / R2 == T && S3 == 2 * T, "k_row2_inv: one butterfly per thread in stages 1-2, two in stage 3");
+  __shared__ uint64_t full;
+  RowSmem2 sm{reinterpret_cast<ulonglong2*>(g_dyn_smem)};
+  char* st_re = reinterpret_cast<char*>(g_dyn_smem) + work_bytes;
+  char* st_im = st_re + 8 * (size_t)P;
+  const int tid = threadIdx.x;
+  const int npairs = R >> 1;
+  if (tid == 0) { mbar_init(&full, 1); mbar_fence_init(); }
+  __syncthreads();
+  const float* im_plane = (a.sel != nullptr && *a.sel != 0) ? a.im_alt : a.im;
+  auto prefetch = [&](int pair) {                   // both rows of a pair are contiguous in each plane
+    if (tid == 0 && pair < npairs) {
+      mbar_expect_tx(&full, 16u * (uint32_t)P);
+      bulk_g2s(st_re, a.re + (size_t)pair * 2 * P, 8u * (uint32_t)P, &full);
+      bulk_g2s(st_im, im_plane + (size_t)pair * 2 * P, 8u * (uint32_t)P, &full);
+    }
+  };
+  prefetch((int)blockIdx.x);
+  const float scale = a.scale_ptr ? *a.scale_ptr : a.scale_host;
+  uint32_t phase = 0;
+  const int p2 = tid / R1, q2 = tid - p2 * R1;
+  const int obase2 = q2 + R1 * R2 * p2, tstep2 = R1 * p2 * 2;
+  for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+    {  // stage 1: tangle + radix R1 (s = 1), first-stage quad twiddles; all twiddles fetched while the bulk copy lands
+      float wr[R1], wi[R1];
+      quad_twiddles<R1>(twQ, tid, wr, wi);
+      constexpr int Nr = CH / R1;
+      cf wt[R1];
+#pragma unroll
+      for (int j = 0; j < R1; ++j) wt[j] = ldg_cf(twC + tid + j * Nr);
+      mbar_wait(&full, phase); phase ^= 1u;
+      RowTangleStaged2 src{reinterpret_cast<const float*>(st_re), reinterpret_cast<const float*>(st_im), P, CH};
+      pf re[R1], im[R1];
+#pragma unroll
+      for (int j = 0; j < R1; ++j) src.load(tid + j * Nr, wt[j], re[j], im[j]);
+      Dft<R1>::run(re, im);
+      sm.store(R1 * tid, re[0], im[0]);
+#pragma unroll
+      for (int k = 1; k < R1; ++k) {
+        pf xr = re[k], xi = im[k];
+        cmul(xr, xi, wr[k], wi[k]);
+        sm.store(R1 * tid + k, xr, xi);
+      }
+    }
+    __syncthreads();
+    prefetch(pair + (int)gridDim.x);                // the staging buffers are free again
+    {  // stage 2: radix R2, s = R1, in place
+      cf w[R2];
+#pragma unroll
+      for (int k = 1; k < R2; ++k) w[k] = ldg_cf(twC + tstep2 * k);
+      pf re[R2], im[R2];
+      constexpr int Nr = CH / R2;
+#pragma unroll
+      for (int j = 0; j < R2; ++j) sm.load(tid + j * Nr, re[j], im[j]);
+      __syncthreads();
+      Dft<R2>::run(re, im);
+      sm.store(obase2, re[0], im[0]);
+#pragma unroll
+      for (int k = 1; k < R2; ++k) {
+        pf xr = re[k], xi = im[k];
+        cmul(xr, xi, w[k].x, w[k].y);
+        sm.store(obase2 + k * R1, xr, xi);
+      }
+    }
+    __syncthreads();
+    {  // stage 3 (last): butterflies t and t + T, outputs straight into the epilogue
+      const size_t row0 = (size_t)pair * 2;
+      const uint32_t* base0 = reinterpret_cast<const uint32_t*>(a.base + row0 * C);
+      const uint32_t* base1 = base0 + C / 2;
+      uint32_t* out0 = a.out_mode == 0 ? reinterpret_cast<uint32_t*>(a.out_bf16 + row0 * C) : nullptr;
+      uint32_t* out1 = out0 + C / 2;
+      float* of0 = a.out_mode != 0 ? a.out_f32 + row0 * C : nullptr;
+      float* of1 = of0 + C;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int b = tid + h * T;
+        uint32_t bb0[R3], bb1[R3];
+#pragma unroll
+        for (int k = 0; k < R3; ++k) {
+          bb0[k] = a.out_mode == 0 ? ldg_u32(base0 + b + k * S3) : 0u;
+          bb1[k] = a.out_mode == 0 ? ldg_u32(base1 + b + k * S3) : 0u;
+        }
+        pf re[R3], im[R3];
+#pragma unroll
+        for (int j = 0; j < R3; ++j) sm.load(b + j * S3, re[j], im[j]);
+        if (h == 1) __syncthreads();                // the buffer has been read: the next pair's stage 1 may overwrite it
+        Dft<R3>::run(re, im);
+#pragma unroll
+        for (int k = 0; k < R3; ++k) epilogue_store2(a, scale, bb0[k], bb1[k], out0, out1, of0, of1, b + k * S3, re[k], im[k]);
+      }
+    }
+  }
+}
+
 // scale a 1-D spectrum (no column sweep exists to fold the normalisation into)
 __global__ void k_scale_row(float* re, float* im, int n, const float* scale_dev, float scale_host, int write_im) {
   const float s = scale_dev ? *scale_dev : scale_host;
@@ -780,6 +925,30 @@ static int try_row2_fwd(const SmPlan& p, const RowFwdArgs& fa, const cf* twC, co
   }
 }
 
+// paired-row inverse pass (k_row2_inv); returns 1 if this shape / mode has none
+template <int R1, int R2, int R3, int R4, int T, bool kPad>
+static int try_row2_inv(const SmPlan& p, const RowInvArgs& ia, const cf* twC, const cf* twQ, cudaStream_t st) {
+  if constexpr (R4 == 1 && kPad && (R1 * R2 * R3) / R3 == 2 * T && (R1 * R2 * R3) / R1 == T && (R1 * R2 * R3) / R2 == T) {
+    constexpr int CH = R1 * R2 * R3;
+    if (!use_row_pairs() || ia.cull_thr != nullptr || (p.R & 1) || p.R < 2 || p.C % 8 != 0 || p.P % 4 != 0) return 1;
+    static bool done = false;
+    static int occ = 0;
+    const int work_bytes = ((CH + (CH >> 4) + 1) * 16 + 127) / 128 * 128;
+    const int smem = work_bytes + 16 * p.P;
+    if (smem > 227 * 1024 - 256) return 1;
+    cudaError_t e = opt_in(k_row2_inv<R1, R2, R3, T>, &done);
+    if (e == cudaSuccess && occ == 0) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_row2_inv<R1, R2, R3, T>, T, smem);
+    if (e != cudaSuccess) { sm_set_error("row2 inv setup: %s", cudaGetErrorString(e)); return -100; }
+    int grid = num_sms() * (occ > 0 ? occ : 1);
+    if (grid > p.R / 2) grid = p.R / 2;
+    k_row2_inv<R1, R2, R3, T><<<grid, T, smem, st>>>(p.R, p.C, p.P, ia, twC, twQ, work_bytes);
+    SM_LAUNCH_CHECK();
+    return 0;
+  } else {
+    return 1;
+  }
+}
+
 template <int R1, int R2, int R3, int R4, int T, bool kPad>
 static int launch_row_ct(bool inverse, const SmPlan& p, const RowFwdArgs* fa, const RowInvArgs* ia, const cf* twC,
                          const cf* twQ, double* sumsq, cudaStream_t st) {
@@ -788,6 +957,10 @@ static int launch_row_ct(bool inverse, const SmPlan& p, const RowFwdArgs* fa, co
   constexpr int CH = R1 * R2 * R3 * R4;
   if (!inverse && use_tma()) {
     const int rc = try_row2_fwd<R1, R2, R3, R4, T, kPad>(p, *fa, twC, twQ, sumsq, st);
+    if (rc <= 0) return rc;
+  }
+  if (inverse && use_tma()) {
+    const int rc = try_row2_inv<R1, R2, R3, R4, T, kPad>(p, *ia, twC, twQ, st);
     if (rc <= 0) return rc;
   }
   constexpr int nst = (R2 > 1) + (R3 > 1) + (R4 > 1) + 1;

@@ -10,7 +10,7 @@ h=[i for i,r in enumerate(rows) if r and r[0]=="ID"][0]
 hdr=rows[h]; ki=hdr.index("Kernel Name"); vi=hdr.index("Metric Value"); gi=hdr.index("Grid Size")
 seq=[(r[ki].split("(")[0][-40:], float(r[vi].replace(",","")), r[gi]) for r in rows[h+1:] if len(r)>vi]
 # last iteration only: find last k_prepare
-idx=[i for i,s in enumerate(seq) if "k_row_fwd" in s[0]]
+idx=[i for i,s in enumerate(seq) if "k_row_fwd" in s[0] or "k_row2_fwd" in s[0]]
 start=idx[-2] if len(idx)>=2 else 0
 tot=0
 for s in seq[start:]:
