@@ -403,9 +403,31 @@ def main():
             t = torch.tensor([ems], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ems = float(t.item())
+        # what plain pinned copies achieve on this box, both directions at once (the e2e path moves 6 B in and 2 B out
+        # per merged parameter, so it is bounded by the host link, not by the kernels)
+        pin_in = torch.empty(1 << 29, dtype=torch.uint8).pin_memory(); dev_in = torch.empty(1 << 29, dtype=torch.uint8, device=dev)
+        pin_out = torch.empty(1 << 28, dtype=torch.uint8).pin_memory(); dev_out = torch.empty(1 << 28, dtype=torch.uint8, device=dev)
+        s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+        torch.cuda.synchronize(dev)
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        s_in.wait_event(p0); s_out.wait_event(p0)
+        with torch.cuda.stream(s_in):
+            for _ in range(2):
+                dev_in.copy_(pin_in, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            for _ in range(2):
+                pin_out.copy_(dev_out, non_blocking=True)
+        torch.cuda.current_stream(dev).wait_stream(s_in); torch.cuda.current_stream(dev).wait_stream(s_out)
+        p1.record(); torch.cuda.synchronize(dev)
+        link_ms = p0.elapsed_time(p1)
+        link = dict(h2d_gbs=2 * (1 << 29) / link_ms / 1e6, d2h_gbs=2 * (1 << 28) / link_ms / 1e6,
+                    note="1 GiB in + 0.5 GiB out, pinned, concurrent (the 3:1 ratio of the merge)")
+        del pin_in, dev_in, pin_out, dev_out
         e2e_params = sum(numel(host["synth/base"][n].shape) for n in names)
         e2e = dict(value=world * e2e_params * args.steps / (ems / 1000.0), unit="params/s",
-                   h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, layers=Le,
+                   h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, layers=Le, host_link_probe=link,
+                   h2d_gbs_achieved=world * h2d * args.steps / (ems / 1000.0) / 1e9 / world,
                    api="MergeTensorsBase._process_layers (FourierMerge._merge_layer + writer.add_tensor per tensor) on "
                        "pinned host tensors: H2D of base + finetunes and D2H of the merged tensor inside the timed region")
 

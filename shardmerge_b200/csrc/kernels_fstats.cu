@@ -334,8 +334,23 @@ __shared__ PassCtx g_fs_ctx;
 __shared__ BlendScal g_fs_bs;
 __shared__ unsigned int g_fs_coarse[kBins];             // streaming phase: this CTA's coarse histogram; last CTA: scratch
 __shared__ unsigned int g_fs_nside;
-__shared__ float4 g_fs_qa[SM_EW_THREADS / 32][kQCap], g_fs_qb[SM_EW_THREADS / 32][kQCap];
-__shared__ uint2 g_fs_qm[SM_EW_THREADS / 32][kQCap];    // x: element offset of the item, y: first column | generic << 31
+// one CTA of 1024 threads per SM: a quarter of the CTAs means a quarter of the end-of-kernel reductions into the
+// same 64 cache lines of the global coarse histogram (they serialise in L2: 3.5 us with 592 CTAs, measured)
+constexpr int kPassThreads = 512, kPassCtasPerSm = 2, kPassWarps = kPassThreads / 32;
+// the warp queues live in dynamic shared memory (80 KB): [kPassWarps][kQCap] of float4 a, float4 b, uint2 meta
+extern __shared__ __align__(16) unsigned char g_fs_dyn[];
+__device__ __forceinline__ float4* fs_qa(int wid) { return reinterpret_cast<float4*>(g_fs_dyn) + wid * kQCap; }
+__device__ __forceinline__ float4* fs_qb(int wid) { return reinterpret_cast<float4*>(g_fs_dyn) + (kPassWarps + wid) * kQCap; }
+__device__ __forceinline__ uint2* fs_qm(int wid) {      // x: element offset of the item, y: first column | generic << 31
+  return reinterpret_cast<uint2*>(g_fs_dyn + (size_t)2 * kPassWarps * kQCap * sizeof(float4)) + wid * kQCap;
+}
+constexpr size_t kPassDynSmem = (size_t)kPassWarps * kQCap * (2 * sizeof(float4) + sizeof(uint2));
+// work distribution: every CTA (= SM) owns an equal contiguous share of the items; inside it a warp takes chunks
+// of kChunkIters x 64 consecutive float4 items, the first by its own number, further ones from a shared-memory
+// counter (fetched one chunk ahead), so all warps of an SM finish together.  With a static split over 4 CTAs per
+// SM the slowest CTA finished 40 % after the fastest (phase timestamps, tools/fs_stamps.py).
+constexpr unsigned int kChunkIters = 2, kChunkItems = kChunkIters * 64;
+__shared__ unsigned int g_fs_chunk;
 
 // the three-way blend, predicated (functions.py:134-136, one rounding per torch op; same arithmetic as blend1 / k_blend)
 __device__ __forceinline__ float fs_blend(const BlendScal& bs, float a, float b, bool same) {
@@ -406,8 +421,8 @@ __device__ __noinline__ void fs_drain(int wid, int first, int n, DrainAcc& acc) 
   const int lane = threadIdx.x & 31;
   __syncwarp();
   if (lane < n) {
-    const float4 av = g_fs_qa[wid][first + lane], bv = g_fs_qb[wid][first + lane];
-    const uint2 m = g_fs_qm[wid][first + lane];
+    const float4 av = fs_qa(wid)[first + lane], bv = fs_qb(wid)[first + lane];
+    const uint2 m = fs_qm(wid)[first + lane];
     const bool generic = (m.y >> 31) != 0u;
     const int c0 = (int)(m.y & 0x7fffffffu);
     const float a[4] = {av.x, av.y, av.z, av.w}, b[4] = {bv.x, bv.y, bv.z, bv.w};
@@ -452,16 +467,16 @@ __device__ __noinline__ void fs_drain(int wid, int first, int n, DrainAcc& acc) 
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(SM_EW_THREADS, 4) k_fs_pass(const __grid_constant__ SmPlan pl, const __grid_constant__ FsCommon c,
-                                                           FsState* st, const __grid_constant__ FsWs ws, float* out,
-                                                           float* thr_out) {
-  __shared__ unsigned long long s_below[SM_EW_THREADS / 32];
+__global__ void __launch_bounds__(kPassThreads, kPassCtasPerSm) k_fs_pass(const __grid_constant__ SmPlan pl, const __grid_constant__ FsCommon c,
+                                                            FsState* st, const __grid_constant__ FsWs ws, float* out,
+                                                            float* thr_out) {
+  __shared__ unsigned long long s_below[kPassWarps];
   __shared__ double s_red[32];
   __shared__ Pick pick;
   __shared__ unsigned long long s_rank;
   __shared__ int s_ok;
   unsigned int* const s_hist = g_fs_coarse;
-  constexpr int NT = SM_EW_THREADS;
+  constexpr int NT = kPassThreads;
   FS_STAMP(0);
   const bool sw = (c.sel != nullptr && *c.sel != 0);
   const float* __restrict__ re0 = sw ? c.reY : c.reX;
@@ -474,7 +489,7 @@ __global__ void __launch_bounds__(SM_EW_THREADS, 4) k_fs_pass(const __grid_const
   const bool dead = st->status != 0u;
   BlendScal bs{};
   if (MODE == 1) { bs.thr = *c.thr_cut; bs.dot = c.scal4[0]; bs.ct = c.scal4[1]; bs.sn = c.scal4[2]; bs.rn = c.scal4[3]; bs.t_sum = c.t_sum; }
-  if (threadIdx.x == 0) { g_fs_ctx = x; g_fs_bs = bs; g_fs_nside = 0u; }
+  if (threadIdx.x == 0) { g_fs_ctx = x; g_fs_bs = bs; g_fs_nside = 0u; g_fs_chunk = 0u; }
 #pragma unroll
   for (int j = 0; j < kBins / NT; ++j) g_fs_coarse[threadIdx.x + NT * j] = 0u;
   __syncthreads();
@@ -484,57 +499,64 @@ __global__ void __launch_bounds__(SM_EW_THREADS, 4) k_fs_pass(const __grid_const
   double d00 = 0.0, d11 = 0.0, d01 = 0.0;                // SLERP sums, fast path (unweighted)
   DrainAcc da{0ull, 0.0, 0.0, 0.0};                      // generic items (weighted)
   int qn = 0;                                            // entries in this warp's queue (warp-uniform)
-  // Work items are float4 column groups, numbered row-major over rows x G groups (G covers columns 0..Ch); the grid
-  // strides over them so every thread gets the same share (no idle column blocks, no tail wave), two items in flight.
+  float4* const qa = fs_qa(wid); float4* const qb = fs_qb(wid); uint2* const qm = fs_qm(wid);
+  // Work items are float4 column groups, numbered row-major over rows x G groups (G covers columns 0..Ch).
   const unsigned int G = (unsigned int)(Ch + 4) / 4u;
   const unsigned int total = (unsigned int)pl.R * G;
-  const unsigned int stride = gridDim.x * blockDim.x;
-  const unsigned int step_row = stride / G, step_g = stride - step_row * G;
+  const unsigned int nchunks = (total + kChunkItems - 1u) / kChunkItems;
+  const unsigned int cpb = (nchunks + gridDim.x - 1u) / gridDim.x;               // chunks per CTA
+  const unsigned int c0 = blockIdx.x * cpb, c_end = min(c0 + cpb, nchunks);
   if (!dead) {
-    unsigned int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    unsigned int row = idx / G, g = idx - row * G;
-    for (unsigned int wbase = idx - lane; wbase < total; wbase += 2u * stride, idx += 2u * stride) {   // warp-uniform trip count
-      // second item of this iteration: one grid stride further
-      unsigned int row1 = row + step_row, g1 = g + step_g;
-      if (g1 >= G) { g1 -= G; ++row1; }
-      const bool v0 = idx < total, v1 = idx + stride < total;
-      const size_t off0 = v0 ? (size_t)row * pl.P + 4u * g : 0;
-      const size_t off1 = v1 ? (size_t)row1 * pl.P + 4u * g1 : off0;
-      float4 a0, b0, a1, b1;                             // both items in flight before the first is consumed
-      a0 = *reinterpret_cast<const float4*>(re0 + off0); b0 = *reinterpret_cast<const float4*>(re1 + off0);
-      a1 = *reinterpret_cast<const float4*>(re0 + off1); b1 = *reinterpret_cast<const float4*>(re1 + off1);
+    unsigned int chunk = c0 + wid, next = 0u;
+    while (chunk < c_end) {                              // warp-uniform
+      if (lane == 0) next = c0 + kPassWarps + atomicAdd(&g_fs_chunk, 1u);        // consumed after this chunk
+      unsigned int idx = chunk * kChunkItems + lane;
+      unsigned int row = idx / G, g = idx - row * G;
+#pragma unroll 1
+      for (unsigned int it = 0; it < kChunkIters; ++it, idx += 64u) {
+        // two items per iteration: this lane's and the one 32 further (a warp reads 1 KB contiguous per plane)
+        unsigned int row1 = row, g1 = g + 32u;
+        while (g1 >= G) { g1 -= G; ++row1; }
+        const bool v0 = idx < total, v1 = idx + 32u < total;
+        const size_t off0 = v0 ? (size_t)row * pl.P + 4u * g : 0;
+        const size_t off1 = v1 ? (size_t)row1 * pl.P + 4u * g1 : off0;
+        float4 a0, b0, a1, b1;                           // both items in flight before the first is consumed
+        a0 = *reinterpret_cast<const float4*>(re0 + off0); b0 = *reinterpret_cast<const float4*>(re1 + off0);
+        a1 = *reinterpret_cast<const float4*>(re0 + off1); b1 = *reinterpret_cast<const float4*>(re1 + off1);
 #pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        const float4 av = r == 0 ? a0 : a1, bv = r == 0 ? b0 : b1;
-        const bool valid = r == 0 ? v0 : v1;
-        const unsigned int gg = r == 0 ? g : g1;
-        const size_t off = r == 0 ? off0 : off1;
-        const bool generic = (gg == 0u) || (gg == G - 1u) || !fs_item_plain(av, bv);
-        Acc ac{0u, 0.f, 0.f, 0.f, false};                // fp32 over one float4, fp64 across
-        float4 o;
-        o.x = fs_elem<MODE>(x, bs, av.x, bv.x, ac); o.y = fs_elem<MODE>(x, bs, av.y, bv.y, ac);
-        o.z = fs_elem<MODE>(x, bs, av.z, bv.z, ac); o.w = fs_elem<MODE>(x, bs, av.w, bv.w, ac);
-        const bool fast = valid && !generic;
-        if (fast) {
-          below_in += ac.below;
-          if (MODE == 0) { d00 += (double)ac.p00; d11 += (double)ac.p11; d01 += (double)ac.p01; }
-          else *reinterpret_cast<float4*>(out + off) = o;
-        }
-        const bool want = valid && (generic || ac.anyw);
-        const unsigned int m = __ballot_sync(0xffffffffu, want);
-        if (m) {                                         // warp-uniform
-          if (want) {
-            const int slot = qn + __popc(m & ((1u << lane) - 1u));
-            g_fs_qa[wid][slot] = av; g_fs_qb[wid][slot] = bv;
-            g_fs_qm[wid][slot] = make_uint2((unsigned int)off, 4u * gg | (generic ? 0x80000000u : 0u));
+        for (int r = 0; r < 2; ++r) {
+          const float4 av = r == 0 ? a0 : a1, bv = r == 0 ? b0 : b1;
+          const bool valid = r == 0 ? v0 : v1;
+          const unsigned int gg = r == 0 ? g : g1;
+          const size_t off = r == 0 ? off0 : off1;
+          const bool generic = (gg == 0u) || (gg == G - 1u) || !fs_item_plain(av, bv);
+          Acc ac{0u, 0.f, 0.f, 0.f, false};              // fp32 over one float4, fp64 across
+          float4 o;
+          o.x = fs_elem<MODE>(x, bs, av.x, bv.x, ac); o.y = fs_elem<MODE>(x, bs, av.y, bv.y, ac);
+          o.z = fs_elem<MODE>(x, bs, av.z, bv.z, ac); o.w = fs_elem<MODE>(x, bs, av.w, bv.w, ac);
+          const bool fast = valid && !generic;
+          if (fast) {
+            below_in += ac.below;
+            if (MODE == 0) { d00 += (double)ac.p00; d11 += (double)ac.p11; d01 += (double)ac.p01; }
+            else *reinterpret_cast<float4*>(out + off) = o;
           }
-          qn += __popc(m);
-          if (qn >= 32) { qn -= 32; fs_drain<MODE>(wid, qn, 32, da); }
+          const bool want = valid && (generic || ac.anyw);
+          const unsigned int m = __ballot_sync(0xffffffffu, want);
+          if (m) {                                       // warp-uniform
+            if (want) {
+              const int slot = qn + __popc(m & ((1u << lane) - 1u));
+              qa[slot] = av; qb[slot] = bv;
+              qm[slot] = make_uint2((unsigned int)off, 4u * gg | (generic ? 0x80000000u : 0u));
+            }
+            qn += __popc(m);
+            if (qn >= 32) { qn -= 32; fs_drain<MODE>(wid, qn, 32, da); }
+          }
         }
+        // advance by 64 items
+        row = row1; g = g1 + 32u;
+        while (g >= G) { g -= G; ++row; }
       }
-      // advance this thread by two grid strides
-      row = row1 + step_row; g = g1 + step_g;
-      if (g >= G) { g -= G; ++row; }
+      chunk = __shfl_sync(0xffffffffu, next, 0);
     }
     if (qn > 0) fs_drain<MODE>(wid, 0, qn, da);
     FS_STAMP(1);
@@ -547,7 +569,7 @@ __global__ void __launch_bounds__(SM_EW_THREADS, 4) k_fs_pass(const __grid_const
     __syncthreads();                                     // also: every shared-memory reduction of the loop has landed
     if (threadIdx.x == 0) {
       unsigned long long bsum = 0ull;
-      for (int i = 0; i < NT / 32; ++i) bsum += s_below[i];
+      for (int i = 0; i < kPassWarps; ++i) bsum += s_below[i];
       if (bsum) atomicAdd(&st->below, bsum);
       if (MODE == 0) ws.scnt[blockIdx.x] = g_fs_nside < ws.scap ? g_fs_nside : ws.scap;
     }
@@ -671,8 +693,8 @@ inline dim3 fs_grid(const SmPlan& p) {
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
   const long long items = (long long)p.R * ((p.Ch + 4) / 4);
-  long long ctas = (long long)sms * 4;                   // one resident wave at 4 CTAs of 256 threads per SM (launch bounds)
-  const long long need = (items + 2 * SM_EW_THREADS - 1) / (2 * SM_EW_THREADS);
+  long long ctas = (long long)sms * kPassCtasPerSm;      // one resident wave
+  const long long need = (items + 2 * kPassThreads - 1) / (2 * kPassThreads);
   if (ctas > need) ctas = need;
   if (ctas > kMaxLists) ctas = kMaxLists;
   if (ctas < 1) ctas = 1;
@@ -736,6 +758,16 @@ static int fs_carve(const sm_plan* plan, void* wsp, size_t ws_bytes, FsWs* w) {
   return 0;
 }
 
+static int fs_pass_attr() {          // opt in to the 80 KB of dynamic shared memory of k_fs_pass, once
+  static int rc = 1;
+  if (rc == 1) {
+    cudaError_t e = cudaFuncSetAttribute((const void*)k_fs_pass<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPassDynSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)k_fs_pass<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPassDynSmem);
+    if (e != cudaSuccess) { sm_set_error("fstats: shared-memory opt-in failed: %s", cudaGetErrorString(e)); rc = -100; } else rc = 0;
+  }
+  return rc;
+}
+
 static inline int fs_sample_grid() { return (int)((kNS + kSampleThreads * kSamplePer - 1) / (kSampleThreads * kSamplePer)); }
 
 // Cutoff statistic + SLERP sums + scalars in one streaming pass (see the header of this file).
@@ -757,7 +789,8 @@ extern "C" int sm_fstats_cutoff(const sm_plan* plan, const float* reX, const flo
   k_fs_sample<0><<<fs_sample_grid(), kSampleThreads, 0, s>>>(p, c, st, w, rank, k_lo, k_hi);
   SM_LAUNCH_CHECK();
   if (getenv("SM_FS_ONLY_SAMPLE")) return 0;
-  k_fs_pass<0><<<w.n_lists, SM_EW_THREADS, 0, s>>>(p, c, st, w, nullptr, thr_cut_out);
+  if ((rc = fs_pass_attr())) return rc;
+  k_fs_pass<0><<<w.n_lists, kPassThreads, kPassDynSmem, s>>>(p, c, st, w, nullptr, thr_cut_out);
   SM_LAUNCH_CHECK();
   const unsigned int close_grid = w.n_lists < 148u ? w.n_lists : 148u;
   k_fs_close<<<close_grid, SM_EW_THREADS, 0, s>>>(st, w, t, scal4_out, sums3_out);
@@ -783,7 +816,8 @@ extern "C" int sm_fstats_blend_cull(const sm_plan* plan, const float* reX, const
   SM_CUDA_CHECK(cudaMemsetAsync(w.shist, 0, w.zero_bytes, s));
   k_fs_sample<1><<<fs_sample_grid(), kSampleThreads, 0, s>>>(p, c, st, w, rank, k_lo, k_hi);
   SM_LAUNCH_CHECK();
-  k_fs_pass<1><<<w.n_lists, SM_EW_THREADS, 0, s>>>(p, c, st, w, out_re, thr_cull_out);
+  if ((rc = fs_pass_attr())) return rc;
+  k_fs_pass<1><<<w.n_lists, kPassThreads, kPassDynSmem, s>>>(p, c, st, w, out_re, thr_cull_out);
   SM_LAUNCH_CHECK();
   return 0;
 }

@@ -119,7 +119,7 @@ extern "C" int sm_pair_merge_slerp_async(const sm_plan* plan, const void* tables
   const uint64_t rank_cull = (uint64_t)(N * a->cull_pct);
   if (fused_stats && a->cutoff_pct > 0) {
     // cutoff statistic + SLERP sums + scalars: one pass over Re X, Re Y (kernels_fstats.cu)
-    Scope s(st, SM_CLS_SELECT2, 4.0 * N, 2);
+    Scope s(st, SM_CLS_SELECT2, 4.0 * N, 3);
     if ((rc = sm_fstats_cutoff(plan, a->re[0], a->re[1], swap, rank_cut, a->t, fs0, a->sel_ws, a->sel_ws_bytes,
                                flt + SM_F_THR_CUT, flt + SM_F_DOT, dbl + 2, st))) return rc;
   } else {

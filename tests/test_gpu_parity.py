@@ -437,9 +437,10 @@ def test_pair_merge_vs_oracle_mid_size(E, shape, seed):
     assert absd.max() <= 2.0 ** -7 * np.abs(O.bf16_to_f32(oo)).max() + 1e-4   # never more than one bf16 ulp of the largest value
 
 
-@pytest.mark.parametrize("shape", [(4096, 4096), (14336, 4096), (4096, 14336), (1024, 4096)])
+@pytest.mark.parametrize("shape", [(4096, 4096), (14336, 4096), (4096, 14336), (1024, 4096),
+                                   (8192, 8192), (1024, 8192), (28672, 8192), (8192, 28672)])
 def test_full_size_properties(E, shape):
-    """Llama-3.1-8B shapes, size-independent properties: FFT round trip, Parseval, linearity, exact
+    """Llama-3.1-8B and 70B shapes, size-independent properties: FFT round trip, Parseval, linearity, exact
     rank of the order statistic (by counting), bf16 output finite."""
     R, C = shape
     g = torch.Generator(device=DEV).manual_seed(R + 3 * C)
