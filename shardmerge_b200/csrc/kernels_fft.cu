@@ -470,6 +470,160 @@ __global__ void __launch_bounds__(T, 3) k_row2_fwd(int R, int C, int P, const __
   }
 }
 
+// ---- paired-row forward pass, four stages (C = 14336: Ch = 7 x 16 x 8 x 8, T = 448) --------------------------------
+// Same idea as k_row2_fwd for rows whose packed pair no longer leaves room for a staging buffer: the work buffer alone
+// is Ch x 16 B = 112 KB (one CTA per SM).  Stage 1 therefore reads the bf16 rows straight from global memory -- 28
+// independent 4-byte loads per butterfly, ~50 KB in flight per SM -- and one thread asks the copy engine to pull the
+// NEXT pair's rows into L2 (cp.async.bulk.prefetch.L2) so those loads are L2 hits issued behind this pair's compute.
+// Stages 2 and 3 run in place, stage 4 forms the half spectrum in registers (butterflies t and S - t).  The one-row
+// kernel k_row_fwd_tma<7,16,8,8,448> executes 2.3x the instructions per element (profiles/r01_ncu_full_rows7_*).
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
+
+struct RowSmem2Flat {            // no padding: the radix-7 first stage (stride 7) and the later strides are conflict free
+  ulonglong2* buf;
+#if defined(__CUDA_ARCH__)
+  __device__ __forceinline__ void load(int i, pf& re, pf& im) const { const ulonglong2 v = buf[i]; re.v = v.x; im.v = v.y; }
+  __device__ __forceinline__ void store(int i, pf re, pf im) const { buf[i] = make_ulonglong2(re.v, im.v); }
+#else
+  void load(int, pf&, pf&) const {}
+  void store(int, pf, pf) const {}
+#endif
+};
+
+struct RowDeltaGlobal2 {         // stage-1 source: bf16 words of both rows straight from global memory
+  const uint32_t* b32; const uint32_t* f32; int half; pf* acc;       // half = words per row
+  __device__ __forceinline__ void load(int i, pf& re, pf& im) const {
+    const uint32_t b0 = ldg_u32(b32 + i), b1 = ldg_u32(b32 + half + i), f0 = ldg_u32(f32 + i), f1 = ldg_u32(f32 + half + i);
+    re = pf_make(bf16_bits_to_f32(f0 & 0xffffu), bf16_bits_to_f32(f1 & 0xffffu)) -
+         pf_make(bf16_bits_to_f32(b0 & 0xffffu), bf16_bits_to_f32(b1 & 0xffffu));
+    im = pf_make(bits_f32(f0 & 0xffff0000u), bits_f32(f1 & 0xffff0000u)) -
+         pf_make(bits_f32(b0 & 0xffff0000u), bits_f32(b1 & 0xffff0000u));
+    *acc = pf_fma(re, re, pf_fma(im, im, *acc));
+  }
+};
+
+template <int R1, int R2, int R3, int R4, int T>
+__global__ void __launch_bounds__(T, 1) k_row2_fwd4(int R, int C, int P, const __grid_constant__ RowFwdArgs a,
+                                                    const cf* __restrict__ twC, const cf* __restrict__ twQ,
+                                                    double* __restrict__ sumsq) {
+  constexpr int CH = R1 * R2 * R3 * R4;
+  constexpr int NB1 = CH / R1, NB2 = CH / R2, NB3 = CH / R3, S4 = CH / R4;
+  constexpr int s2 = R1, s3 = R1 * R2;
+  static_assert(NB2 == T && NB3 == 2 * T && S4 == 2 * T, "k_row2_fwd4: 1 / 2 / 2 butterflies per thread in stages 2 / 3 / 4");
+  __shared__ double wsum[16];
+  RowSmem2Flat sm{reinterpret_cast<ulonglong2*>(g_dyn_smem)};
+  const int tid = threadIdx.x;
+  const int npairs = R >> 1;
+  double accd = 0.0;
+  if (tid == 0 && (int)blockIdx.x < npairs) {
+    bulk_prefetch_l2(a.base + (size_t)blockIdx.x * 2 * C, 4u * (uint32_t)C);
+    bulk_prefetch_l2(a.ft + (size_t)blockIdx.x * 2 * C, 4u * (uint32_t)C);
+  }
+  for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+    pf accp = pf_make(0.f, 0.f);
+    {  // stage 1: delta + radix R1 (s = 1) on the butterflies t, t + T, ... ; first-stage quad twiddles
+      RowDeltaGlobal2 src{reinterpret_cast<const uint32_t*>(a.base + (size_t)pair * 2 * C),
+                          reinterpret_cast<const uint32_t*>(a.ft + (size_t)pair * 2 * C), C / 2, &accp};
+#pragma unroll 1
+      for (int b = tid; b < NB1; b += T) stockham_bfly_first<R1, pf>(b, CH, twQ, src, sm);
+    }
+    __syncthreads();
+    if (tid == 0 && pair + (int)gridDim.x < npairs) {   // next pair's rows -> L2 while this pair is transformed
+      bulk_prefetch_l2(a.base + (size_t)(pair + gridDim.x) * 2 * C, 4u * (uint32_t)C);
+      bulk_prefetch_l2(a.ft + (size_t)(pair + gridDim.x) * 2 * C, 4u * (uint32_t)C);
+    }
+    {  // stage 2: radix R2, s = R1, in place, one butterfly per thread
+      pf re[R2], im[R2];
+#pragma unroll
+      for (int j = 0; j < R2; ++j) sm.load(tid + j * NB2, re[j], im[j]);
+      __syncthreads();
+      Dft<R2>::run(re, im);
+      const int p = tid / s2, q = tid - p * s2;
+      const int obase = q + s2 * R2 * p, tstep = s2 * p * 2;
+      sm.store(obase, re[0], im[0]);
+#pragma unroll
+      for (int k = 1; k < R2; ++k) {
+        const cf w = ldg_cf(twC + tstep * k);
+        pf xr = re[k], xi = im[k];
+        cmul(xr, xi, w.x, w.y);
+        sm.store(obase + k * s2, xr, xi);
+      }
+    }
+    __syncthreads();
+    {  // stage 3: radix R3, s = R1*R2, in place, butterflies t and t + T
+      pf re[2][R3], im[2][R3];
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int j = 0; j < R3; ++j) sm.load(tid + h * T + j * NB3, re[h][j], im[h][j]);
+      __syncthreads();
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        Dft<R3>::run(re[h], im[h]);
+        const int b = tid + h * T;
+        const int p = b / s3, q = b - p * s3;
+        const int obase = q + s3 * R3 * p, tstep = s3 * p * 2;
+        sm.store(obase, re[h][0], im[h][0]);
+#pragma unroll
+        for (int k = 1; k < R3; ++k) {
+          const cf w = ldg_cf(twC + tstep * k);
+          pf xr = re[h][k], xi = im[h][k];
+          cmul(xr, xi, w.x, w.y);
+          sm.store(obase + k * s3, xr, xi);
+        }
+      }
+    }
+    __syncthreads();
+    {  // stage 4 (last, no twiddles) on the butterflies t and S4 - t (thread 0: 0 and S4 / 2) + untangle
+      const int bA = tid, bB = tid == 0 ? S4 / 2 : S4 - tid;
+      pf ar[R4], ai[R4], br[R4], bi[R4];
+#pragma unroll
+      for (int j = 0; j < R4; ++j) { sm.load(bA + j * S4, ar[j], ai[j]); sm.load(bB + j * S4, br[j], bi[j]); }
+      __syncthreads();                              // the buffer has been read: the next pair's stage 1 may overwrite it
+      Dft<R4>::run(ar, ai);
+      Dft<R4>::run(br, bi);
+      float* re0 = a.re + (size_t)pair * 2 * P;
+      float* im0 = a.im + (size_t)pair * 2 * P;
+      if (tid != 0) {
+#pragma unroll
+        for (int k = 0; k < R4; ++k) {              // n = t + S4*k  <->  Ch - n = (S4 - t) + S4*(R4-1-k)
+          const int n = bA + S4 * k;
+          untangle_pair2(ar[k], ai[k], br[R4 - 1 - k], bi[R4 - 1 - k], ldg_cf(twC + n), re0, im0, P, n, CH - n);
+        }
+      } else {
+        {
+          const pf h = ar[0], g = ai[0];
+          const pf x0 = h + g, xn = h - g;
+          re0[0] = pf_lo(x0); re0[P] = pf_hi(x0); im0[0] = 0.f; im0[P] = 0.f;
+          re0[CH] = pf_lo(xn); re0[P + CH] = pf_hi(xn); im0[CH] = 0.f; im0[P + CH] = 0.f;
+        }
+#pragma unroll
+        for (int k = 1; k <= R4 / 2; ++k) {
+          const int n = S4 * k;
+          untangle_pair2(ar[k], ai[k], ar[R4 - k], ai[R4 - k], ldg_cf(twC + n), re0, im0, P, n, CH - n);
+        }
+#pragma unroll
+        for (int k = 0; k < R4 / 2; ++k) {
+          const int n = S4 / 2 + S4 * k;
+          untangle_pair2(br[k], bi[k], br[R4 - 1 - k], bi[R4 - 1 - k], ldg_cf(twC + n), re0, im0, P, n, CH - n);
+        }
+      }
+    }
+    accd += (double)pf_lo(accp) + (double)pf_hi(accp);
+  }
+  double acc = warp_sum(accd);
+  const int lane = tid & 31, wid = tid >> 5;
+  if (lane == 0) wsum[wid] = acc;
+  __syncthreads();
+  if (wid == 0) {
+    double v = lane < (T + 31) / 32 ? wsum[lane] : 0.0;
+    v = warp_sum(v);
+    if (lane == 0) atomicAdd(sumsq, v);
+  }
+}
+
 // ---- paired-row inverse pass: the mirror image of k_row2_fwd ------------------------------------------------------
 // Two adjacent spectrum rows per CTA as f32x2 lanes: tangle (from the staged re / im rows) + radix R1 with quad
 // twiddles -> in-place radix R2 -> radix R3 straight into the epilogue (x 1/N, NaN -> 0 / Inf count, x target_norm,
@@ -614,6 +768,129 @@ __global__ void __launch_bounds__(T, 3) k_row2_inv(int R, int C, int P, const __
     }
   }
 }
+
+// ---- paired-row inverse pass, four stages (C = 14336): the mirror image of k_row2_fwd4 ------------------------------
+// No staging (the work buffer fills the SM): the tangle reads the two spectrum rows straight from global memory, the
+// next pair's rows are pulled into L2 by the copy engine in the meantime; stages 2-3 in place; the last stage feeds the
+// epilogue with the bf16 base words loaded ahead of its shared-memory reads.
+struct RowTangleGlobal2 {
+  const float* re; const float* im; const cf* twC; int P; int Ch;
+  __device__ __forceinline__ void load(int k, pf& ore, pf& oim) const {
+    pf xr = pf_make(ldg_f32(re + k), ldg_f32(re + P + k)), xi = pf_make(ldg_f32(im + k), ldg_f32(im + P + k));
+    pf mr = pf_make(ldg_f32(re + Ch - k), ldg_f32(re + P + Ch - k)), mi = pf_make(ldg_f32(im + Ch - k), ldg_f32(im + P + Ch - k));
+    const cf w = ldg_cf(twC + k);
+    if (k == 0) { xi = pf_make(0.f, 0.f); mi = xi; }    // .real semantics: bins 0 and Ch are real
+    const pf Ar = xr + mr, Ai = xi - mi, Br = xr - mr, Bi = xi + mi;
+    const pf wx = pf_bcast(w.x), wy = pf_bcast(w.y);
+    const pf br = pf_fma(Br, wx, Bi * wy);              // B * conj(w)
+    const pf bi = pf_fma(Bi, wx, zero_of(Br) - Br * wy);
+    const pf zr = Ar - bi, zi = Ai + br;
+    ore = zi; oim = zr;                                 // handed to the forward engine swapped
+  }
+};
+
+template <int R1, int R2, int R3, int R4, int T>
+__global__ void __launch_bounds__(T, 1) k_row2_inv4(int R, int C, int P, const __grid_constant__ RowInvArgs a,
+                                                    const cf* __restrict__ twC, const cf* __restrict__ twQ) {
+  constexpr int CH = R1 * R2 * R3 * R4;
+  constexpr int NB1 = CH / R1, NB2 = CH / R2, NB3 = CH / R3, S4 = CH / R4;
+  constexpr int s2 = R1, s3 = R1 * R2;
+  static_assert(NB2 == T && NB3 == 2 * T && S4 == 2 * T, "k_row2_inv4: 1 / 2 / 2 butterflies per thread in stages 2 / 3 / 4");
+  RowSmem2Flat sm{reinterpret_cast<ulonglong2*>(g_dyn_smem)};
+  const int tid = threadIdx.x;
+  const int npairs = R >> 1;
+  const float* im_plane = (a.sel != nullptr && *a.sel != 0) ? a.im_alt : a.im;
+  const float scale = a.scale_ptr ? *a.scale_ptr : a.scale_host;
+  auto prefetch = [&](int pair) {
+    if (tid == 0 && pair < npairs) {
+      bulk_prefetch_l2(a.re + (size_t)pair * 2 * P, 8u * (uint32_t)P);
+      bulk_prefetch_l2(im_plane + (size_t)pair * 2 * P, 8u * (uint32_t)P);
+      if (a.out_mode == 0) bulk_prefetch_l2(a.base + (size_t)pair * 2 * C, 4u * (uint32_t)C);
+    }
+  };
+  prefetch((int)blockIdx.x);
+  for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
+    {  // stage 1: tangle + radix R1 (s = 1) on the butterflies t, t + T, ...
+      RowTangleGlobal2 src{a.re + (size_t)pair * 2 * P, im_plane + (size_t)pair * 2 * P, twC, P, CH};
+#pragma unroll 1
+      for (int b = tid; b < NB1; b += T) stockham_bfly_first<R1, pf>(b, CH, twQ, src, sm);
+    }
+    __syncthreads();
+    prefetch(pair + (int)gridDim.x);
+    {  // stage 2: radix R2, s = R1, in place, one butterfly per thread
+      pf re[R2], im[R2];
+#pragma unroll
+      for (int j = 0; j < R2; ++j) sm.load(tid + j * NB2, re[j], im[j]);
+      __syncthreads();
+      Dft<R2>::run(re, im);
+      const int p = tid / s2, q = tid - p * s2;
+      const int obase = q + s2 * R2 * p, tstep = s2 * p * 2;
+      sm.store(obase, re[0], im[0]);
+#pragma unroll
+      for (int k = 1; k < R2; ++k) {
+        const cf w = ldg_cf(twC + tstep * k);
+        pf xr = re[k], xi = im[k];
+        cmul(xr, xi, w.x, w.y);
+        sm.store(obase + k * s2, xr, xi);
+      }
+    }
+    __syncthreads();
+    {  // stage 3: radix R3, s = R1*R2, in place, butterflies t and t + T
+      pf re[2][R3], im[2][R3];
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int j = 0; j < R3; ++j) sm.load(tid + h * T + j * NB3, re[h][j], im[h][j]);
+      __syncthreads();
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        Dft<R3>::run(re[h], im[h]);
+        const int b = tid + h * T;
+        const int p = b / s3, q = b - p * s3;
+        const int obase = q + s3 * R3 * p, tstep = s3 * p * 2;
+        sm.store(obase, re[h][0], im[h][0]);
+#pragma unroll
+        for (int k = 1; k < R3; ++k) {
+          const cf w = ldg_cf(twC + tstep * k);
+          pf xr = re[h][k], xi = im[h][k];
+          cmul(xr, xi, w.x, w.y);
+          sm.store(obase + k * s3, xr, xi);
+        }
+      }
+    }
+    __syncthreads();
+    {  // stage 4 (last): butterflies t and t + T, outputs straight into the epilogue
+      const size_t row0 = (size_t)pair * 2;
+      const uint32_t* base0 = reinterpret_cast<const uint32_t*>(a.base + row0 * C);
+      const uint32_t* base1 = base0 + C / 2;
+      uint32_t* out0 = a.out_mode == 0 ? reinterpret_cast<uint32_t*>(a.out_bf16 + row0 * C) : nullptr;
+      uint32_t* out1 = out0 + C / 2;
+      float* of0 = a.out_mode != 0 ? a.out_f32 + row0 * C : nullptr;
+      float* of1 = of0 + C;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int b = tid + h * T;
+        uint32_t bb0[R4], bb1[R4];
+#pragma unroll
+        for (int k = 0; k < R4; ++k) {
+          bb0[k] = a.out_mode == 0 ? ldg_u32(base0 + b + k * S4) : 0u;
+          bb1[k] = a.out_mode == 0 ? ldg_u32(base1 + b + k * S4) : 0u;
+        }
+        pf re[R4], im[R4];
+#pragma unroll
+        for (int j = 0; j < R4; ++j) sm.load(b + j * S4, re[j], im[j]);
+        if (h == 1) __syncthreads();                // the buffer has been read: the next pair's stage 1 may overwrite it
+        Dft<R4>::run(re, im);
+#pragma unroll
+        for (int k = 0; k < R4; ++k) epilogue_store2(a, scale, bb0[k], bb1[k], out0, out1, of0, of1, b + k * S4, re[k], im[k]);
+      }
+    }
+  }
+}
+
+// paired-row four-stage inverse pass (k_row2_inv4); returns 1 if this shape / mode has none
+template <int R1, int R2, int R3, int R4, int T>
+static int try_row2_inv4(const SmPlan& p, const RowInvArgs& ia, const cf* twC, const cf* twQ, cudaStream_t st);
 
 // scale a 1-D spectrum (no column sweep exists to fold the normalisation into)
 __global__ void k_scale_row(float* re, float* im, int n, const float* scale_dev, float scale_host, int write_im) {
@@ -925,6 +1202,47 @@ static int try_row2_fwd(const SmPlan& p, const RowFwdArgs& fa, const cf* twC, co
   }
 }
 
+// paired-row four-stage forward pass (k_row2_fwd4); returns 1 if this shape / mode has none
+template <int R1, int R2, int R3, int R4, int T>
+static int try_row2_fwd4(const SmPlan& p, const RowFwdArgs& fa, const cf* twC, const cf* twQ, double* sumsq, cudaStream_t st) {
+  if constexpr (R4 > 1 && (R1 * R2 * R3 * R4) / R2 == T && (R1 * R2 * R3 * R4) / R3 == 2 * T && (R1 * R2 * R3 * R4) / R4 == 2 * T) {
+    constexpr int CH = R1 * R2 * R3 * R4;
+    if (!use_row_pairs() || fa.mode != 0 || (p.R & 1) || p.R < 2 || p.C % 8 != 0) return 1;
+    static bool done = false;
+    const int smem = CH * 16;
+    if (smem > 227 * 1024 - 256) return 1;
+    cudaError_t e = opt_in(k_row2_fwd4<R1, R2, R3, R4, T>, &done);
+    if (e != cudaSuccess) { sm_set_error("row2 fwd4 setup: %s", cudaGetErrorString(e)); return -100; }
+    int grid = num_sms();
+    if (grid > p.R / 2) grid = p.R / 2;
+    k_row2_fwd4<R1, R2, R3, R4, T><<<grid, T, smem, st>>>(p.R, p.C, p.P, fa, twC, twQ, sumsq);
+    SM_LAUNCH_CHECK();
+    return 0;
+  } else {
+    return 1;
+  }
+}
+
+template <int R1, int R2, int R3, int R4, int T>
+static int try_row2_inv4(const SmPlan& p, const RowInvArgs& ia, const cf* twC, const cf* twQ, cudaStream_t st) {
+  if constexpr (R4 > 1 && (R1 * R2 * R3 * R4) / R2 == T && (R1 * R2 * R3 * R4) / R3 == 2 * T && (R1 * R2 * R3 * R4) / R4 == 2 * T) {
+    constexpr int CH = R1 * R2 * R3 * R4;
+    if (!use_row_pairs() || ia.cull_thr != nullptr || (p.R & 1) || p.R < 2 || p.C % 8 != 0 || p.P % 4 != 0) return 1;
+    static bool done = false;
+    const int smem = CH * 16;
+    if (smem > 227 * 1024 - 256) return 1;
+    cudaError_t e = opt_in(k_row2_inv4<R1, R2, R3, R4, T>, &done);
+    if (e != cudaSuccess) { sm_set_error("row2 inv4 setup: %s", cudaGetErrorString(e)); return -100; }
+    int grid = num_sms();
+    if (grid > p.R / 2) grid = p.R / 2;
+    k_row2_inv4<R1, R2, R3, R4, T><<<grid, T, smem, st>>>(p.R, p.C, p.P, ia, twC, twQ);
+    SM_LAUNCH_CHECK();
+    return 0;
+  } else {
+    return 1;
+  }
+}
+
 // paired-row inverse pass (k_row2_inv); returns 1 if this shape / mode has none
 template <int R1, int R2, int R3, int R4, int T, bool kPad>
 static int try_row2_inv(const SmPlan& p, const RowInvArgs& ia, const cf* twC, const cf* twQ, cudaStream_t st) {
@@ -956,11 +1274,15 @@ static int launch_row_ct(bool inverse, const SmPlan& p, const RowFwdArgs* fa, co
   static int occ[2] = {0, 0};
   constexpr int CH = R1 * R2 * R3 * R4;
   if (!inverse && use_tma()) {
-    const int rc = try_row2_fwd<R1, R2, R3, R4, T, kPad>(p, *fa, twC, twQ, sumsq, st);
+    int rc = try_row2_fwd<R1, R2, R3, R4, T, kPad>(p, *fa, twC, twQ, sumsq, st);
+    if (rc <= 0) return rc;
+    rc = try_row2_fwd4<R1, R2, R3, R4, T>(p, *fa, twC, twQ, sumsq, st);
     if (rc <= 0) return rc;
   }
   if (inverse && use_tma()) {
-    const int rc = try_row2_inv<R1, R2, R3, R4, T, kPad>(p, *ia, twC, twQ, st);
+    int rc = try_row2_inv<R1, R2, R3, R4, T, kPad>(p, *ia, twC, twQ, st);
+    if (rc <= 0) return rc;
+    rc = try_row2_inv4<R1, R2, R3, R4, T>(p, *ia, twC, twQ, st);
     if (rc <= 0) return rc;
   }
   constexpr int nst = (R2 > 1) + (R3 > 1) + (R4 > 1) + 1;
