@@ -51,7 +51,7 @@ constexpr int kMaxLists = 4096;                // side lists (one per CTA of the
 constexpr unsigned int kFineLog = 22;          // the window spans at most 2^22 key bit patterns
 constexpr unsigned int kFineMax = 1u << kFineLog;
 constexpr unsigned int kNS = 1u << 18;         // samples
-constexpr int kSampleThreads = 1024, kSamplePer = 4;
+constexpr int kSampleThreads = 1024, kSamplePer = 1;
 
 struct FsState {                     // SM_FS_STATE_BYTES device bytes
   unsigned long long rank;           // rank of the statistic in the full key multiset
@@ -75,7 +75,7 @@ constexpr int kSampleShift = 18;                         // sample histogram dig
 constexpr int kSampleBins = 1 << (31 - kSampleShift);    // 8192
 
 struct FsWs {                        // carved out of the caller's workspace
-  // one contiguous block, zeroed by a memset node before k_fs_sample:
+  // one contiguous block; the caller hands it over zero-filled once, afterwards k_fs_sample keeps it so:
   unsigned int* shist;               // [kSampleBins] sample histogram
   unsigned int* coarse;              // [kBins]  keys (with multiplicity) per coarse bin
   unsigned int* scnt;                // [kMaxLists]  entries in the side list of pass CTA i
@@ -241,6 +241,13 @@ __global__ void __launch_bounds__(kSampleThreads) k_fs_sample(const __grid_const
   FS_STAMP(0);
 #pragma unroll
   for (int j = 0; j < kSampleBins / kSampleThreads; ++j) s_h[threadIdx.x + kSampleThreads * j] = 0u;
+  {  // this kernel also clears the histograms of the pass that follows (fire-and-forget stores, done long before it starts):
+     // no memset node in the chain.  The sample histogram itself is left clean by the last CTA below.
+    uint4* const z = reinterpret_cast<uint4*>(ws.coarse);          // [coarse | scnt | fine] is one contiguous block
+    const size_t n16 = ((size_t)kBins + kMaxLists + kFineMax) / 4;
+    const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) z[i] = zero;
+  }
   __syncthreads();
   {
     float va[kSamplePer], vb[kSamplePer];                // all gathers of a thread in flight together
@@ -282,6 +289,8 @@ __global__ void __launch_bounds__(kSampleThreads) k_fs_sample(const __grid_const
     for (int j = 0; j < kSampleBins / kSampleThreads; ++j) v[j] = __ldcg(ws.shist + threadIdx.x + kSampleThreads * j);
 #pragma unroll
     for (int j = 0; j < kSampleBins / kSampleThreads; ++j) s_h[threadIdx.x + kSampleThreads * j] = v[j];
+#pragma unroll
+    for (int j = 0; j < kSampleBins / kSampleThreads; ++j) ws.shist[threadIdx.x + kSampleThreads * j] = 0u;   // clean for the next call
   }
   __syncthreads();
   block_pick<kSampleThreads>(LoadSmem32{s_h}, kSampleBins, want_a ? (unsigned long long)k_lo : 0ull, &out_a);
@@ -742,7 +751,9 @@ static int fs_carve(const sm_plan* plan, void* wsp, size_t ws_bytes, FsWs* w) {
   const SmPlan& p = plan->p;
   if (!sm_fstats_supported(plan)) { sm_set_error("fstats: tensor too small / too large for the fused statistics"); return -2; }
   if (ws_bytes < sm_fstats_ws_bytes(plan)) { sm_set_error("fstats: workspace too small"); return -3; }
-  char* b = reinterpret_cast<char*>(wsp);
+  // the LAST sm_fstats_ws_bytes() of the caller's buffer: its histograms persist (zero) from call to call, and a
+  // caller that shares one buffer with sm_select_kth_abs (which uses the front) must not have them overwritten
+  char* b = reinterpret_cast<char*>(wsp) + (ws_bytes - sm_fstats_ws_bytes(plan));
   b = reinterpret_cast<char*>(((uintptr_t)b + 63) / 64 * 64);
   char* const z0 = b;
   w->shist = reinterpret_cast<unsigned int*>(b); b += (size_t)kSampleBins * 4;
@@ -785,7 +796,6 @@ extern "C" int sm_fstats_cutoff(const sm_plan* plan, const float* reX, const flo
   FsCommon c{reX, reY, sel, nullptr, nullptr, 1.f};
   long long k_lo = 0, k_hi = 0;
   fs_sample_ranks(rank, total, &k_lo, &k_hi);
-  SM_CUDA_CHECK(cudaMemsetAsync(w.shist, 0, w.zero_bytes, s));
   k_fs_sample<0><<<fs_sample_grid(), kSampleThreads, 0, s>>>(p, c, st, w, rank, k_lo, k_hi);
   SM_LAUNCH_CHECK();
   if (getenv("SM_FS_ONLY_SAMPLE")) return 0;
@@ -813,7 +823,6 @@ extern "C" int sm_fstats_blend_cull(const sm_plan* plan, const float* reX, const
   FsCommon c{reX, reY, sel, thr_cut, scal4, t_sum};
   long long k_lo = 0, k_hi = 0;
   fs_sample_ranks(rank, total, &k_lo, &k_hi);
-  SM_CUDA_CHECK(cudaMemsetAsync(w.shist, 0, w.zero_bytes, s));
   k_fs_sample<1><<<fs_sample_grid(), kSampleThreads, 0, s>>>(p, c, st, w, rank, k_lo, k_hi);
   SM_LAUNCH_CHECK();
   if ((rc = fs_pass_attr())) return rc;

@@ -163,9 +163,11 @@ class Workspace:
         self.sel = self.ctl[_OFF_SEL:_OFF_SEL + 128]
         self.safe_select = safe_select
         mode = 1 if safe_select else 0
-        nbytes = max(plan.lib.sm_select_ws_bytes(plan.handle, 2, mode), plan.lib.sm_select_ws_bytes(plan.handle, 1, mode),
-                     plan.lib.sm_fstats_ws_bytes(plan.handle))
-        self.sel_ws = torch.zeros(nbytes, dtype=torch.uint8, device=dev)   # sm_fstats_* wants it zero-filled once
+        # select scratch in front, the fused statistics' persistent histograms behind it (sm_fstats_* uses the LAST
+        # sm_fstats_ws_bytes of the buffer and wants them zero-filled once)
+        nbytes = max(plan.lib.sm_select_ws_bytes(plan.handle, 2, mode), plan.lib.sm_select_ws_bytes(plan.handle, 1, mode))
+        nbytes = (nbytes + 255) // 256 * 256 + plan.lib.sm_fstats_ws_bytes(plan.handle)
+        self.sel_ws = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
         # pinned landing zone for the scalar block
         self.ctl_host = torch.empty(_CTL_BYTES, dtype=torch.uint8).pin_memory()
 
