@@ -481,11 +481,15 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, uint32_t 
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
 }
 
-struct RowSmem2Flat {            // no padding: the radix-7 first stage (stride 7) and the later strides are conflict free
+// kPad = false: no padding (an odd first radix -- stride 7 -- and the later strides are conflict free as they are);
+// kPad = true: one 16-byte element of padding per 8 (power-of-two radices: a quarter warp then covers all banks)
+template <bool kPad>
+struct RowSmem2X {
   ulonglong2* buf;
+  __device__ __forceinline__ static int phys(int i) { return kPad ? i + (i >> 3) : i; }
 #if defined(__CUDA_ARCH__)
-  __device__ __forceinline__ void load(int i, pf& re, pf& im) const { const ulonglong2 v = buf[i]; re.v = v.x; im.v = v.y; }
-  __device__ __forceinline__ void store(int i, pf re, pf im) const { buf[i] = make_ulonglong2(re.v, im.v); }
+  __device__ __forceinline__ void load(int i, pf& re, pf& im) const { const ulonglong2 v = buf[phys(i)]; re.v = v.x; im.v = v.y; }
+  __device__ __forceinline__ void store(int i, pf re, pf im) const { buf[phys(i)] = make_ulonglong2(re.v, im.v); }
 #else
   void load(int, pf&, pf&) const {}
   void store(int, pf, pf) const {}
@@ -504,16 +508,17 @@ struct RowDeltaGlobal2 {         // stage-1 source: bf16 words of both rows stra
   }
 };
 
-template <int R1, int R2, int R3, int R4, int T>
-__global__ void __launch_bounds__(T, 1) k_row2_fwd4(int R, int C, int P, const __grid_constant__ RowFwdArgs a,
+template <int R1, int R2, int R3, int R4, int T, bool kPad, int kCtas>
+__global__ void __launch_bounds__(T, kCtas) k_row2_fwd4(int R, int C, int P, const __grid_constant__ RowFwdArgs a,
                                                     const cf* __restrict__ twC, const cf* __restrict__ twQ,
                                                     double* __restrict__ sumsq) {
   constexpr int CH = R1 * R2 * R3 * R4;
   constexpr int NB1 = CH / R1, NB2 = CH / R2, NB3 = CH / R3, S4 = CH / R4;
   constexpr int s2 = R1, s3 = R1 * R2;
-  static_assert(NB2 == T && NB3 == 2 * T && S4 == 2 * T, "k_row2_fwd4: 1 / 2 / 2 butterflies per thread in stages 2 / 3 / 4");
+  constexpr int H2 = NB2 / T;
+  static_assert(NB2 == H2 * T && H2 >= 1 && H2 <= 2 && NB3 == 2 * T && S4 == 2 * T, "k_row2_fwd4: 1-2 / 2 / 2 butterflies per thread in stages 2 / 3 / 4");
   __shared__ double wsum[16];
-  RowSmem2Flat sm{reinterpret_cast<ulonglong2*>(g_dyn_smem)};
+  RowSmem2X<kPad> sm{reinterpret_cast<ulonglong2*>(g_dyn_smem)};
   const int tid = threadIdx.x;
   const int npairs = R >> 1;
   double accd = 0.0;
@@ -534,21 +539,27 @@ __global__ void __launch_bounds__(T, 1) k_row2_fwd4(int R, int C, int P, const _
       bulk_prefetch_l2(a.base + (size_t)(pair + gridDim.x) * 2 * C, 4u * (uint32_t)C);
       bulk_prefetch_l2(a.ft + (size_t)(pair + gridDim.x) * 2 * C, 4u * (uint32_t)C);
     }
-    {  // stage 2: radix R2, s = R1, in place, one butterfly per thread
-      pf re[R2], im[R2];
+    {  // stage 2: radix R2, s = R1, in place, butterflies t (and t + T)
+      pf re[H2][R2], im[H2][R2];
 #pragma unroll
-      for (int j = 0; j < R2; ++j) sm.load(tid + j * NB2, re[j], im[j]);
+      for (int h = 0; h < H2; ++h)
+#pragma unroll
+        for (int j = 0; j < R2; ++j) sm.load(tid + h * T + j * NB2, re[h][j], im[h][j]);
       __syncthreads();
-      Dft<R2>::run(re, im);
-      const int p = tid / s2, q = tid - p * s2;
-      const int obase = q + s2 * R2 * p, tstep = s2 * p * 2;
-      sm.store(obase, re[0], im[0]);
 #pragma unroll
-      for (int k = 1; k < R2; ++k) {
-        const cf w = ldg_cf(twC + tstep * k);
-        pf xr = re[k], xi = im[k];
-        cmul(xr, xi, w.x, w.y);
-        sm.store(obase + k * s2, xr, xi);
+      for (int h = 0; h < H2; ++h) {
+        Dft<R2>::run(re[h], im[h]);
+        const int b = tid + h * T;
+        const int p = b / s2, q = b - p * s2;
+        const int obase = q + s2 * R2 * p, tstep = s2 * p * 2;
+        sm.store(obase, re[h][0], im[h][0]);
+#pragma unroll
+        for (int k = 1; k < R2; ++k) {
+          const cf w = ldg_cf(twC + tstep * k);
+          pf xr = re[h][k], xi = im[h][k];
+          cmul(xr, xi, w.x, w.y);
+          sm.store(obase + k * s2, xr, xi);
+        }
       }
     }
     __syncthreads();
@@ -789,14 +800,15 @@ struct RowTangleGlobal2 {
   }
 };
 
-template <int R1, int R2, int R3, int R4, int T>
-__global__ void __launch_bounds__(T, 1) k_row2_inv4(int R, int C, int P, const __grid_constant__ RowInvArgs a,
+template <int R1, int R2, int R3, int R4, int T, bool kPad, int kCtas>
+__global__ void __launch_bounds__(T, kCtas) k_row2_inv4(int R, int C, int P, const __grid_constant__ RowInvArgs a,
                                                     const cf* __restrict__ twC, const cf* __restrict__ twQ) {
   constexpr int CH = R1 * R2 * R3 * R4;
   constexpr int NB1 = CH / R1, NB2 = CH / R2, NB3 = CH / R3, S4 = CH / R4;
   constexpr int s2 = R1, s3 = R1 * R2;
-  static_assert(NB2 == T && NB3 == 2 * T && S4 == 2 * T, "k_row2_inv4: 1 / 2 / 2 butterflies per thread in stages 2 / 3 / 4");
-  RowSmem2Flat sm{reinterpret_cast<ulonglong2*>(g_dyn_smem)};
+  constexpr int H2 = NB2 / T;
+  static_assert(NB2 == H2 * T && H2 >= 1 && H2 <= 2 && NB3 == 2 * T && S4 == 2 * T, "k_row2_inv4: 1-2 / 2 / 2 butterflies per thread in stages 2 / 3 / 4");
+  RowSmem2X<kPad> sm{reinterpret_cast<ulonglong2*>(g_dyn_smem)};
   const int tid = threadIdx.x;
   const int npairs = R >> 1;
   const float* im_plane = (a.sel != nullptr && *a.sel != 0) ? a.im_alt : a.im;
@@ -817,21 +829,27 @@ __global__ void __launch_bounds__(T, 1) k_row2_inv4(int R, int C, int P, const _
     }
     __syncthreads();
     prefetch(pair + (int)gridDim.x);
-    {  // stage 2: radix R2, s = R1, in place, one butterfly per thread
-      pf re[R2], im[R2];
+    {  // stage 2: radix R2, s = R1, in place, butterflies t (and t + T)
+      pf re[H2][R2], im[H2][R2];
 #pragma unroll
-      for (int j = 0; j < R2; ++j) sm.load(tid + j * NB2, re[j], im[j]);
+      for (int h = 0; h < H2; ++h)
+#pragma unroll
+        for (int j = 0; j < R2; ++j) sm.load(tid + h * T + j * NB2, re[h][j], im[h][j]);
       __syncthreads();
-      Dft<R2>::run(re, im);
-      const int p = tid / s2, q = tid - p * s2;
-      const int obase = q + s2 * R2 * p, tstep = s2 * p * 2;
-      sm.store(obase, re[0], im[0]);
 #pragma unroll
-      for (int k = 1; k < R2; ++k) {
-        const cf w = ldg_cf(twC + tstep * k);
-        pf xr = re[k], xi = im[k];
-        cmul(xr, xi, w.x, w.y);
-        sm.store(obase + k * s2, xr, xi);
+      for (int h = 0; h < H2; ++h) {
+        Dft<R2>::run(re[h], im[h]);
+        const int b = tid + h * T;
+        const int p = b / s2, q = b - p * s2;
+        const int obase = q + s2 * R2 * p, tstep = s2 * p * 2;
+        sm.store(obase, re[h][0], im[h][0]);
+#pragma unroll
+        for (int k = 1; k < R2; ++k) {
+          const cf w = ldg_cf(twC + tstep * k);
+          pf xr = re[h][k], xi = im[h][k];
+          cmul(xr, xi, w.x, w.y);
+          sm.store(obase + k * s2, xr, xi);
+        }
       }
     }
     __syncthreads();
@@ -887,10 +905,6 @@ __global__ void __launch_bounds__(T, 1) k_row2_inv4(int R, int C, int P, const _
     }
   }
 }
-
-// paired-row four-stage inverse pass (k_row2_inv4); returns 1 if this shape / mode has none
-template <int R1, int R2, int R3, int R4, int T>
-static int try_row2_inv4(const SmPlan& p, const RowInvArgs& ia, const cf* twC, const cf* twQ, cudaStream_t st);
 
 // scale a 1-D spectrum (no column sweep exists to fold the normalisation into)
 __global__ void k_scale_row(float* re, float* im, int n, const float* scale_dev, float scale_host, int write_im) {
@@ -1202,45 +1216,52 @@ static int try_row2_fwd(const SmPlan& p, const RowFwdArgs& fa, const cf* twC, co
   }
 }
 
-// paired-row four-stage forward pass (k_row2_fwd4); returns 1 if this shape / mode has none
-template <int R1, int R2, int R3, int R4, int T>
-static int try_row2_fwd4(const SmPlan& p, const RowFwdArgs& fa, const cf* twC, const cf* twQ, double* sumsq, cudaStream_t st) {
-  if constexpr (R4 > 1 && (R1 * R2 * R3 * R4) / R2 == T && (R1 * R2 * R3 * R4) / R3 == 2 * T && (R1 * R2 * R3 * R4) / R4 == 2 * T) {
-    constexpr int CH = R1 * R2 * R3 * R4;
-    if (!use_row_pairs() || fa.mode != 0 || (p.R & 1) || p.R < 2 || p.C % 8 != 0) return 1;
-    static bool done = false;
-    const int smem = CH * 16;
-    if (smem > 227 * 1024 - 256) return 1;
-    cudaError_t e = opt_in(k_row2_fwd4<R1, R2, R3, R4, T>, &done);
-    if (e != cudaSuccess) { sm_set_error("row2 fwd4 setup: %s", cudaGetErrorString(e)); return -100; }
-    int grid = num_sms();
-    if (grid > p.R / 2) grid = p.R / 2;
-    k_row2_fwd4<R1, R2, R3, R4, T><<<grid, T, smem, st>>>(p.R, p.C, p.P, fa, twC, twQ, sumsq);
-    SM_LAUNCH_CHECK();
-    return 0;
-  } else {
-    return 1;
-  }
+// paired-row four-stage passes (k_row2_fwd4 / k_row2_inv4) with their own factorization Ch = R1*R2*R3*R4 (it need not be
+// the plan's: the twiddle tables do not depend on it and the quad table covers first radices down to 8);
+// return 1 if this mode has none
+template <int R1, int R2, int R3, int R4, int T, bool kPad, int kCtas>
+static int launch_row2_fwd4(const SmPlan& p, const RowFwdArgs& fa, const cf* twC, const cf* twQ, double* sumsq, cudaStream_t st) {
+  constexpr int CH = R1 * R2 * R3 * R4;
+  if (!use_row_pairs() || fa.mode != 0 || (p.R & 1) || p.R < 2 || p.C % 8 != 0 || p.Ch != CH) return 1;
+  static bool done = false;
+  const int smem = (kPad ? CH + (CH >> 3) + 1 : CH) * 16;
+  if (smem > 227 * 1024 - 256) return 1;
+  cudaError_t e = opt_in(k_row2_fwd4<R1, R2, R3, R4, T, kPad, kCtas>, &done);
+  if (e != cudaSuccess) { sm_set_error("row2 fwd4 setup: %s", cudaGetErrorString(e)); return -100; }
+  int grid = num_sms() * kCtas;
+  if (grid > p.R / 2) grid = p.R / 2;
+  k_row2_fwd4<R1, R2, R3, R4, T, kPad, kCtas><<<grid, T, smem, st>>>(p.R, p.C, p.P, fa, twC, twQ, sumsq);
+  SM_LAUNCH_CHECK();
+  return 0;
 }
 
-template <int R1, int R2, int R3, int R4, int T>
+template <int R1, int R2, int R3, int R4, int T, bool kPad, int kCtas>
+static int launch_row2_inv4(const SmPlan& p, const RowInvArgs& ia, const cf* twC, const cf* twQ, cudaStream_t st) {
+  constexpr int CH = R1 * R2 * R3 * R4;
+  if (!use_row_pairs() || ia.cull_thr != nullptr || (p.R & 1) || p.R < 2 || p.C % 8 != 0 || p.P % 4 != 0 || p.Ch != CH) return 1;
+  static bool done = false;
+  const int smem = (kPad ? CH + (CH >> 3) + 1 : CH) * 16;
+  if (smem > 227 * 1024 - 256) return 1;
+  cudaError_t e = opt_in(k_row2_inv4<R1, R2, R3, R4, T, kPad, kCtas>, &done);
+  if (e != cudaSuccess) { sm_set_error("row2 inv4 setup: %s", cudaGetErrorString(e)); return -100; }
+  int grid = num_sms() * kCtas;
+  if (grid > p.R / 2) grid = p.R / 2;
+  k_row2_inv4<R1, R2, R3, R4, T, kPad, kCtas><<<grid, T, smem, st>>>(p.R, p.C, p.P, ia, twC, twQ);
+  SM_LAUNCH_CHECK();
+  return 0;
+}
+
+// which four-stage paired kernel serves the plan's row length: C = 14336 as 7 x 16 x 8 x 8 (one CTA of 448 threads per
+// SM), C = 8192 as 8 x 8 x 8 x 8 (two CTAs of 256 threads, padded buffer) whatever the plan's own radices are
+static int try_row2_fwd4(const SmPlan& p, const RowFwdArgs& fa, const cf* twC, const cf* twQ, double* sumsq, cudaStream_t st) {
+  if (p.Ch == 7168) return launch_row2_fwd4<7, 16, 8, 8, 448, false, 1>(p, fa, twC, twQ, sumsq, st);
+  if (p.Ch == 4096) return launch_row2_fwd4<8, 8, 8, 8, 256, true, 2>(p, fa, twC, twQ, sumsq, st);
+  return 1;
+}
 static int try_row2_inv4(const SmPlan& p, const RowInvArgs& ia, const cf* twC, const cf* twQ, cudaStream_t st) {
-  if constexpr (R4 > 1 && (R1 * R2 * R3 * R4) / R2 == T && (R1 * R2 * R3 * R4) / R3 == 2 * T && (R1 * R2 * R3 * R4) / R4 == 2 * T) {
-    constexpr int CH = R1 * R2 * R3 * R4;
-    if (!use_row_pairs() || ia.cull_thr != nullptr || (p.R & 1) || p.R < 2 || p.C % 8 != 0 || p.P % 4 != 0) return 1;
-    static bool done = false;
-    const int smem = CH * 16;
-    if (smem > 227 * 1024 - 256) return 1;
-    cudaError_t e = opt_in(k_row2_inv4<R1, R2, R3, R4, T>, &done);
-    if (e != cudaSuccess) { sm_set_error("row2 inv4 setup: %s", cudaGetErrorString(e)); return -100; }
-    int grid = num_sms();
-    if (grid > p.R / 2) grid = p.R / 2;
-    k_row2_inv4<R1, R2, R3, R4, T><<<grid, T, smem, st>>>(p.R, p.C, p.P, ia, twC, twQ);
-    SM_LAUNCH_CHECK();
-    return 0;
-  } else {
-    return 1;
-  }
+  if (p.Ch == 7168) return launch_row2_inv4<7, 16, 8, 8, 448, false, 1>(p, ia, twC, twQ, st);
+  if (p.Ch == 4096) return launch_row2_inv4<8, 8, 8, 8, 256, true, 2>(p, ia, twC, twQ, st);
+  return 1;
 }
 
 // paired-row inverse pass (k_row2_inv); returns 1 if this shape / mode has none
@@ -1276,13 +1297,13 @@ static int launch_row_ct(bool inverse, const SmPlan& p, const RowFwdArgs* fa, co
   if (!inverse && use_tma()) {
     int rc = try_row2_fwd<R1, R2, R3, R4, T, kPad>(p, *fa, twC, twQ, sumsq, st);
     if (rc <= 0) return rc;
-    rc = try_row2_fwd4<R1, R2, R3, R4, T>(p, *fa, twC, twQ, sumsq, st);
+    rc = try_row2_fwd4(p, *fa, twC, twQ, sumsq, st);
     if (rc <= 0) return rc;
   }
   if (inverse && use_tma()) {
     int rc = try_row2_inv<R1, R2, R3, R4, T, kPad>(p, *ia, twC, twQ, st);
     if (rc <= 0) return rc;
-    rc = try_row2_inv4<R1, R2, R3, R4, T>(p, *ia, twC, twQ, st);
+    rc = try_row2_inv4(p, *ia, twC, twQ, st);
     if (rc <= 0) return rc;
   }
   constexpr int nst = (R2 > 1) + (R3 > 1) + (R4 > 1) + 1;

@@ -34,7 +34,11 @@ void sm_set_error(const char* fmt, ...);
 // of float2; the quad table (fft_core.cuh: first-stage twiddles) starts 32-byte aligned.
 static inline size_t sm_tab_off_R(const SmPlan& p) { return (size_t)p.C * 8; }
 static inline size_t sm_tab_off_Q(const SmPlan& p) { return (((size_t)p.C + (size_t)p.R) * 8 + 31) / 32 * 32; }
-static inline int sm_quad_count(const SmPlan& p) { return p.n_row > 1 ? p.Ch / p.row_rad[0] : 0; }
+static inline int sm_quad_count(const SmPlan& p) {     // entries b < Ch / r for the smallest first radix r any row kernel uses
+  if (p.n_row <= 1) return 0;
+  const int n = p.Ch / p.row_rad[0], n8 = (p.Ch % 8 == 0) ? p.Ch / 8 : 0;
+  return n > n8 ? n : n8;
+}
 // after the quads: 2 x ntiles u32 tile counters of the fused two-sweep column kernel (zero between launches)
 static inline int sm_col_tiles(const SmPlan& p) { return (p.Ch + 1 + SM_COL_TILE - 1) / SM_COL_TILE; }
 static inline size_t sm_tab_off_K(const SmPlan& p) { return (sm_tab_off_Q(p) + 32 * (size_t)sm_quad_count(p) + 63) / 64 * 64; }

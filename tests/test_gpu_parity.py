@@ -394,7 +394,8 @@ def test_golden_tensor_cases(E, golden_dir):
         assert rel_l2(X, d["fft0"]) < 2e-6
 
 
-@pytest.mark.parametrize("shape,seed", [((1024, 4096), 21), ((2048, 1024), 22), ((1, 8192), 23)])
+@pytest.mark.parametrize("shape,seed", [((1024, 4096), 21), ((2048, 1024), 22), ((1, 8192), 23), ((512, 8192), 24),
+                                        ((256, 14336), 25)])
 def test_pair_merge_vs_oracle_mid_size(E, shape, seed):
     """Synthetic Llama-like tensors at sizes the oracle finishes in seconds."""
     R, C = shape
