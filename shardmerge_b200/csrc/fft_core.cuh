@@ -330,10 +330,11 @@ SM_HD void ldg_quad(const cf* quad, int b, cf (&q)[4]) {
 
 SM_CX int c_top_bit(int k) { int t = 1; while (2 * t <= k) t *= 2; return t; }
 
+// qmul: the table was built for a transform qmul times longer (W_N = W_{qmul N}^qmul): read entry qmul * b
 template <int r>
-SM_HD void quad_twiddles(const cf* quad, int b, float (&wr)[r], float (&wi)[r]) {
+SM_HD void quad_twiddles(const cf* quad, int b, float (&wr)[r], float (&wi)[r], int qmul = 1) {
   cf q[4];
-  ldg_quad(quad, b, q);
+  ldg_quad(quad, b * qmul, q);
   wr[0] = 1.f; wi[0] = 0.f;
   if constexpr (r > 1) { wr[1] = q[0].x; wi[1] = q[0].y; }
   if constexpr (r > 2) { wr[2] = q[1].x; wi[2] = q[1].y; }
@@ -352,7 +353,7 @@ SM_HD void quad_twiddles(const cf* quad, int b, float (&wr)[r], float (&wi)[r]) 
 
 // non-last first stage: s == 1, so q == 0, p == b, outputs go to r*b + k
 template <int r, class V = float, class Src, class Dst>
-SM_HD void stockham_bfly_first(int b, int N, const cf* quad, const Src& src, const Dst& dst) {
+SM_HD void stockham_bfly_first(int b, int N, const cf* quad, const Src& src, const Dst& dst, int qmul = 1) {
   V re[r], im[r];
   const int Nr = N / r;
   static_for<0, r>([&](auto j_) {
@@ -360,7 +361,7 @@ SM_HD void stockham_bfly_first(int b, int N, const cf* quad, const Src& src, con
     src.load(b + j * Nr, re[j], im[j]);
   });
   float wr[r], wi[r];
-  quad_twiddles<r>(quad, b, wr, wi);
+  quad_twiddles<r>(quad, b, wr, wi, qmul);
   Dft<r>::run(re, im);
   const int obase = r * b;
   dst.store(obase, re[0], im[0]);

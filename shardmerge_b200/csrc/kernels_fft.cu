@@ -635,6 +635,159 @@ __global__ void __launch_bounds__(T, kCtas) k_row2_fwd4(int R, int C, int P, con
   }
 }
 
+// ---- longest rows (C = 28672, Ch = 14336): ONE row per CTA, the f32x2 lanes carry its even / odd halves ----------------
+// Two such rows do not fit one SM (2 x 14336 x 16 B).  Instead the packed length-Ch transform of one row is split by
+// decimation in time, Z[k] = E[k] + W_Ch^k O[k], Z[k + Ch/2] = E[k] - W_Ch^k O[k]: E and O are two independent
+// transforms of length Ch/2 = 7 x 16 x 8 x 8 over the even / odd complex elements, i.e. exactly the two lanes of the
+// four-stage paired engine (one 8-byte load per tensor feeds both).  The last stage then holds E, O at n and at
+// Ch/2 - n, which is all the radix-2 combine plus the untangle of the four bins n, n + Ch/2, Ch/2 - n, Ch - n need.
+// The one-row scalar kernel k_row_fwd_ct<7,16,16,8,512> moves 2.0 TB/s on these rows (no room for a staging buffer).
+struct RowDeltaGlobalEO {        // stage-1 source: complex elements 2i (lane 0) and 2i + 1 (lane 1) of one row
+  const uint2* b64; const uint2* f64; pf* acc;
+  __device__ __forceinline__ void load(int i, pf& re, pf& im) const {
+    const uint2 b = __ldg(b64 + i), f = __ldg(f64 + i);
+    re = pf_make(bf16_bits_to_f32(f.x & 0xffffu), bf16_bits_to_f32(f.y & 0xffffu)) -
+         pf_make(bf16_bits_to_f32(b.x & 0xffffu), bf16_bits_to_f32(b.y & 0xffffu));
+    im = pf_make(bits_f32(f.x & 0xffff0000u), bits_f32(f.y & 0xffff0000u)) -
+         pf_make(bits_f32(b.x & 0xffff0000u), bits_f32(b.y & 0xffff0000u));
+    *acc = pf_fma(re, re, pf_fma(im, im, *acc));
+  }
+};
+
+// X[n] and X[m] (m = full length - n) of one row from Z[n] = (ar, ai) and Z[m] = (br, bi); w = W_C^n
+__device__ __forceinline__ void untangle_pair1(float ar, float ai, float br, float bi, cf w, float* re0, float* im0, int n, int m) {
+  const float er = 0.5f * (ar + br), ei = 0.5f * (ai - bi), pr = 0.5f * (ai + bi), qi = -0.5f * (ar - br);
+  const float tr = pr * w.x - qi * w.y, ti = pr * w.y + qi * w.x;
+  re0[n] = er + tr; im0[n] = ei + ti;
+  if (m != n) { re0[m] = er - tr; im0[m] = ti - ei; }
+}
+
+// the four bins n, n + H, H - n, 2H - n (H = Ch/2) from (E, O)[n] = lanes of (xr, xi) and (E, O)[H - n] = lanes of (yr, yi)
+__device__ __forceinline__ void combine_untangle4(pf xr, pf xi, pf yr, pf yi, const cf* __restrict__ twC, float* re0, float* im0,
+                                                  int n, int H) {
+  const int m = H - n;                               // 0 < n < H
+  const cf wn = ldg_cf(twC + 2 * n), wm = ldg_cf(twC + 2 * m);        // W_Ch^n, W_Ch^m (the table is W_C, C = 2 Ch)
+  float onr = pf_hi(xr), oni = pf_hi(xi), omr = pf_hi(yr), omi = pf_hi(yi);
+  cmul(onr, oni, wn.x, wn.y);
+  cmul(omr, omi, wm.x, wm.y);
+  const float enr = pf_lo(xr), eni = pf_lo(xi), emr = pf_lo(yr), emi = pf_lo(yi);
+  // Z[n] = E + wO, Z[n + H] = E - wO; same at m
+  untangle_pair1(enr + onr, eni + oni, emr - omr, emi - omi, ldg_cf(twC + n), re0, im0, n, 2 * H - n);      // (n, Ch - n = H + m)
+  if (m != n) untangle_pair1(enr - onr, eni - oni, emr + omr, emi + omi, ldg_cf(twC + n + H), re0, im0, n + H, m);   // (n + H, m)
+}
+
+template <int R1, int R2, int R3, int R4, int T>
+__global__ void __launch_bounds__(T, 1) k_row1_fwd_eo(int R, int C, int P, const __grid_constant__ RowFwdArgs a,
+                                                      const cf* __restrict__ twC, const cf* __restrict__ twQ2,
+                                                      double* __restrict__ sumsq) {
+  constexpr int CH = R1 * R2 * R3 * R4;             // length of the even / odd transforms = Ch / 2
+  constexpr int NB1 = CH / R1, NB2 = CH / R2, NB3 = CH / R3, S4 = CH / R4;
+  constexpr int s2 = R1, s3 = R1 * R2;
+  static_assert(NB2 == T && NB3 == 2 * T && S4 == 2 * T, "k_row1_fwd_eo: 1 / 2 / 2 butterflies per thread in stages 2 / 3 / 4");
+  __shared__ double wsum[16];
+  RowSmem2X<false> sm{reinterpret_cast<ulonglong2*>(g_dyn_smem)};
+  const int tid = threadIdx.x;
+  double accd = 0.0;
+  if (tid == 0 && (int)blockIdx.x < R) {
+    bulk_prefetch_l2(a.base + (size_t)blockIdx.x * C, 2u * (uint32_t)C);
+    bulk_prefetch_l2(a.ft + (size_t)blockIdx.x * C, 2u * (uint32_t)C);
+  }
+  for (int row = blockIdx.x; row < R; row += gridDim.x) {
+    pf accp = pf_make(0.f, 0.f);
+    {  // stage 1: delta + radix R1 (s = 1); the sub-transforms have twiddles W_CH = W_C^4: twiddle tables are read at stride 4
+      RowDeltaGlobalEO src{reinterpret_cast<const uint2*>(a.base + (size_t)row * C), reinterpret_cast<const uint2*>(a.ft + (size_t)row * C), &accp};
+#pragma unroll 1
+      for (int b = tid; b < NB1; b += T) stockham_bfly_first<R1, pf>(b, CH, twQ2, src, sm, 2);
+    }
+    __syncthreads();
+    if (tid == 0 && row + (int)gridDim.x < R) {
+      bulk_prefetch_l2(a.base + (size_t)(row + gridDim.x) * C, 2u * (uint32_t)C);
+      bulk_prefetch_l2(a.ft + (size_t)(row + gridDim.x) * C, 2u * (uint32_t)C);
+    }
+    {  // stage 2: radix R2, s = R1, in place, one butterfly per thread
+      pf re[R2], im[R2];
+#pragma unroll
+      for (int j = 0; j < R2; ++j) sm.load(tid + j * NB2, re[j], im[j]);
+      __syncthreads();
+      Dft<R2>::run(re, im);
+      const int p = tid / s2, q = tid - p * s2;
+      const int obase = q + s2 * R2 * p, tstep = s2 * p * 4;
+      sm.store(obase, re[0], im[0]);
+#pragma unroll
+      for (int k = 1; k < R2; ++k) {
+        const cf w = ldg_cf(twC + tstep * k);
+        pf xr = re[k], xi = im[k];
+        cmul(xr, xi, w.x, w.y);
+        sm.store(obase + k * s2, xr, xi);
+      }
+    }
+    __syncthreads();
+    {  // stage 3: radix R3, s = R1*R2, in place, butterflies t and t + T
+      pf re[2][R3], im[2][R3];
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int j = 0; j < R3; ++j) sm.load(tid + h * T + j * NB3, re[h][j], im[h][j]);
+      __syncthreads();
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        Dft<R3>::run(re[h], im[h]);
+        const int b = tid + h * T;
+        const int p = b / s3, q = b - p * s3;
+        const int obase = q + s3 * R3 * p, tstep = s3 * p * 4;
+        sm.store(obase, re[h][0], im[h][0]);
+#pragma unroll
+        for (int k = 1; k < R3; ++k) {
+          const cf w = ldg_cf(twC + tstep * k);
+          pf xr = re[h][k], xi = im[h][k];
+          cmul(xr, xi, w.x, w.y);
+          sm.store(obase + k * s3, xr, xi);
+        }
+      }
+    }
+    __syncthreads();
+    {  // stage 4 (last) on the butterflies t and S4 - t (thread 0: 0 and S4 / 2), then combine + untangle
+      const int bA = tid, bB = tid == 0 ? S4 / 2 : S4 - tid;
+      pf ar[R4], ai[R4], br[R4], bi[R4];
+#pragma unroll
+      for (int j = 0; j < R4; ++j) { sm.load(bA + j * S4, ar[j], ai[j]); sm.load(bB + j * S4, br[j], bi[j]); }
+      __syncthreads();                              // the buffer has been read: the next row's stage 1 may overwrite it
+      Dft<R4>::run(ar, ai);
+      Dft<R4>::run(br, bi);
+      float* re0 = a.re + (size_t)row * P;
+      float* im0 = a.im + (size_t)row * P;
+      if (tid != 0) {
+#pragma unroll
+        for (int k = 0; k < R4; ++k)                // n = t + S4*k  <->  CH - n = (S4 - t) + S4*(R4-1-k)
+          combine_untangle4(ar[k], ai[k], br[R4 - 1 - k], bi[R4 - 1 - k], twC, re0, im0, bA + S4 * k, CH);
+      } else {
+        {  // n = 0: Z[0] = E0 + O0 -> X[0], X[Ch]; Z[CH] = E0 - O0 pairs with itself -> X[CH]
+          const float e0r = pf_lo(ar[0]), e0i = pf_lo(ai[0]), o0r = pf_hi(ar[0]), o0i = pf_hi(ai[0]);
+          const float zr = e0r + o0r, zi = e0i + o0i;
+          re0[0] = zr + zi; im0[0] = 0.f; re0[2 * CH] = zr - zi; im0[2 * CH] = 0.f;
+          untangle_pair1(e0r - o0r, e0i - o0i, e0r - o0r, e0i - o0i, ldg_cf(twC + CH), re0, im0, CH, CH);
+        }
+#pragma unroll
+        for (int k = 1; k <= R4 / 2; ++k)           // butterfly 0: n = S4*k <-> S4*(R4-k)
+          combine_untangle4(ar[k], ai[k], ar[R4 - k], ai[R4 - k], twC, re0, im0, S4 * k, CH);
+#pragma unroll
+        for (int k = 0; k < R4 / 2; ++k)            // butterfly S4/2: n = S4/2 + S4*k <-> S4/2 + S4*(R4-1-k)
+          combine_untangle4(br[k], bi[k], br[R4 - 1 - k], bi[R4 - 1 - k], twC, re0, im0, S4 / 2 + S4 * k, CH);
+      }
+    }
+    accd += (double)pf_lo(accp) + (double)pf_hi(accp);
+  }
+  double acc = warp_sum(accd);
+  const int lane = tid & 31, wid = tid >> 5;
+  if (lane == 0) wsum[wid] = acc;
+  __syncthreads();
+  if (wid == 0) {
+    double v = lane < (T + 31) / 32 ? wsum[lane] : 0.0;
+    v = warp_sum(v);
+    if (lane == 0) atomicAdd(sumsq, v);
+  }
+}
+
 // ---- paired-row inverse pass: the mirror image of k_row2_fwd ------------------------------------------------------
 // Two adjacent spectrum rows per CTA as f32x2 lanes: tangle (from the staged re / im rows) + radix R1 with quad
 // twiddles -> in-place radix R2 -> radix R3 straight into the epilogue (x 1/N, NaN -> 0 / Inf count, x target_norm,
@@ -901,6 +1054,139 @@ __global__ void __launch_bounds__(T, kCtas) k_row2_inv4(int R, int C, int P, con
         Dft<R4>::run(re, im);
 #pragma unroll
         for (int k = 0; k < R4; ++k) epilogue_store2(a, scale, bb0[k], bb1[k], out0, out1, of0, of1, b + k * S4, re[k], im[k]);
+      }
+    }
+  }
+}
+
+// ---- longest rows, inverse: the mirror image of k_row1_fwd_eo -------------------------------------------------------------
+// Decimation in frequency on the input of the length-Ch engine: u[2m] = FFT_{Ch/2}(U[n] + U[n + Ch/2])[m] and
+// u[2m+1] = FFT_{Ch/2}((U[n] - U[n + Ch/2]) W_Ch^n)[m] are the two lanes; lane 0 / lane 1 of output m are the complex
+// elements 2m / 2m+1 of the row, i.e. four consecutive real outputs: one 8-byte bf16 store (and base load) per m.
+struct RowTangleGlobalEO {
+  const float* re; const float* im; const cf* twC; int H;                // H = Ch / 2
+  __device__ __forceinline__ void tangle(int k, float& ore, float& oim) const {     // RowTangleSrc::load without the cull
+    float xr = ldg_f32(re + k), xi = ldg_f32(im + k), mr = ldg_f32(re + 2 * H - k), mi = ldg_f32(im + 2 * H - k);
+    if (k == 0) { xi = 0.f; mi = 0.f; }
+    const float Ar = xr + mr, Ai = xi - mi, Br = xr - mr, Bi = xi + mi;
+    const cf w = ldg_cf(twC + k);
+    const float br = Br * w.x + Bi * w.y, bi = Bi * w.x - Br * w.y;
+    ore = Ai + br; oim = Ar - bi;
+  }
+  __device__ __forceinline__ void load(int n, pf& ore, pf& oim) const {
+    float u1r, u1i, u2r, u2i;
+    tangle(n, u1r, u1i);
+    tangle(n + H, u2r, u2i);
+    float dr = u1r - u2r, di = u1i - u2i;
+    const cf w = ldg_cf(twC + 2 * n);                                     // W_Ch^n
+    cmul(dr, di, w.x, w.y);
+    ore = pf_make(u1r + u2r, dr); oim = pf_make(u1i + u2i, di);
+  }
+};
+
+// output m of the even / odd engine: lane 0 -> x[4m], x[4m+1]; lane 1 -> x[4m+2], x[4m+3]
+__device__ __forceinline__ void epilogue_store_eo(const RowInvArgs& a, float scale, uint2 bb, uint2* out64, float4* of, int m, pf va, pf vb) {
+  const pf n = pf_bcast(a.inv_n);
+  const pf x0 = vb * n, x1 = va * n;
+  float x00 = pf_lo(x0), x01 = pf_hi(x0), x10 = pf_lo(x1), x11 = pf_hi(x1);   // xEL: element E of the complex pair, lane L
+  if (a.check_ifft) { x00 = epi_fix(x00, a.flags, 0); x01 = epi_fix(x01, a.flags, 0); x10 = epi_fix(x10, a.flags, 0); x11 = epi_fix(x11, a.flags, 0); }
+  x00 *= scale; x01 *= scale; x10 *= scale; x11 *= scale;
+  if (a.out_mode == 0) {
+    x00 = bf16_bits_to_f32(bb.x & 0xffffu) + x00; x10 = bits_f32(bb.x & 0xffff0000u) + x10;
+    x01 = bf16_bits_to_f32(bb.y & 0xffffu) + x01; x11 = bits_f32(bb.y & 0xffff0000u) + x11;
+    x00 = epi_fix(x00, a.flags, 2); x10 = epi_fix(x10, a.flags, 2); x01 = epi_fix(x01, a.flags, 2); x11 = epi_fix(x11, a.flags, 2);
+    out64[m] = make_uint2(pack_bf16x2_rne(x00, x10), pack_bf16x2_rne(x01, x11));
+  } else {
+    of[m] = make_float4(x00, x10, x01, x11);
+  }
+}
+
+template <int R1, int R2, int R3, int R4, int T>
+__global__ void __launch_bounds__(T, 1) k_row1_inv_eo(int R, int C, int P, const __grid_constant__ RowInvArgs a,
+                                                      const cf* __restrict__ twC, const cf* __restrict__ twQ2) {
+  constexpr int CH = R1 * R2 * R3 * R4;             // length of the two lane transforms = Ch / 2
+  constexpr int NB1 = CH / R1, NB2 = CH / R2, NB3 = CH / R3, S4 = CH / R4;
+  constexpr int s2 = R1, s3 = R1 * R2;
+  static_assert(NB2 == T && NB3 == 2 * T && S4 == 2 * T, "k_row1_inv_eo: 1 / 2 / 2 butterflies per thread in stages 2 / 3 / 4");
+  RowSmem2X<false> sm{reinterpret_cast<ulonglong2*>(g_dyn_smem)};
+  const int tid = threadIdx.x;
+  const float* im_plane = (a.sel != nullptr && *a.sel != 0) ? a.im_alt : a.im;
+  const float scale = a.scale_ptr ? *a.scale_ptr : a.scale_host;
+  auto prefetch = [&](int row) {
+    if (tid == 0 && row < R) {
+      bulk_prefetch_l2(a.re + (size_t)row * P, 4u * (uint32_t)P);
+      bulk_prefetch_l2(im_plane + (size_t)row * P, 4u * (uint32_t)P);
+      if (a.out_mode == 0) bulk_prefetch_l2(a.base + (size_t)row * C, 2u * (uint32_t)C);
+    }
+  };
+  prefetch((int)blockIdx.x);
+  for (int row = blockIdx.x; row < R; row += gridDim.x) {
+    {  // stage 1: tangle + even / odd split + radix R1 (s = 1)
+      RowTangleGlobalEO src{a.re + (size_t)row * P, im_plane + (size_t)row * P, twC, CH};
+#pragma unroll 1
+      for (int b = tid; b < NB1; b += T) stockham_bfly_first<R1, pf>(b, CH, twQ2, src, sm, 2);
+    }
+    __syncthreads();
+    prefetch(row + (int)gridDim.x);
+    {  // stage 2: radix R2, s = R1, in place, one butterfly per thread
+      pf re[R2], im[R2];
+#pragma unroll
+      for (int j = 0; j < R2; ++j) sm.load(tid + j * NB2, re[j], im[j]);
+      __syncthreads();
+      Dft<R2>::run(re, im);
+      const int p = tid / s2, q = tid - p * s2;
+      const int obase = q + s2 * R2 * p, tstep = s2 * p * 4;
+      sm.store(obase, re[0], im[0]);
+#pragma unroll
+      for (int k = 1; k < R2; ++k) {
+        const cf w = ldg_cf(twC + tstep * k);
+        pf xr = re[k], xi = im[k];
+        cmul(xr, xi, w.x, w.y);
+        sm.store(obase + k * s2, xr, xi);
+      }
+    }
+    __syncthreads();
+    {  // stage 3: radix R3, s = R1*R2, in place, butterflies t and t + T
+      pf re[2][R3], im[2][R3];
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int j = 0; j < R3; ++j) sm.load(tid + h * T + j * NB3, re[h][j], im[h][j]);
+      __syncthreads();
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        Dft<R3>::run(re[h], im[h]);
+        const int b = tid + h * T;
+        const int p = b / s3, q = b - p * s3;
+        const int obase = q + s3 * R3 * p, tstep = s3 * p * 4;
+        sm.store(obase, re[h][0], im[h][0]);
+#pragma unroll
+        for (int k = 1; k < R3; ++k) {
+          const cf w = ldg_cf(twC + tstep * k);
+          pf xr = re[h][k], xi = im[h][k];
+          cmul(xr, xi, w.x, w.y);
+          sm.store(obase + k * s3, xr, xi);
+        }
+      }
+    }
+    __syncthreads();
+    {  // stage 4 (last): butterflies t and t + T, outputs straight into the epilogue
+      const uint2* base64 = reinterpret_cast<const uint2*>(a.base + (size_t)row * C);
+      uint2* out64 = a.out_mode == 0 ? reinterpret_cast<uint2*>(a.out_bf16 + (size_t)row * C) : nullptr;
+      float4* of = a.out_mode != 0 ? reinterpret_cast<float4*>(a.out_f32 + (size_t)row * C) : nullptr;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int b = tid + h * T;
+        uint2 bb[R4];
+#pragma unroll
+        for (int k = 0; k < R4; ++k) bb[k] = a.out_mode == 0 ? __ldg(base64 + b + k * S4) : make_uint2(0u, 0u);
+        pf re[R4], im[R4];
+#pragma unroll
+        for (int j = 0; j < R4; ++j) sm.load(b + j * S4, re[j], im[j]);
+        if (h == 1) __syncthreads();                // the buffer has been read: the next row's stage 1 may overwrite it
+        Dft<R4>::run(re, im);
+#pragma unroll
+        for (int k = 0; k < R4; ++k) epilogue_store_eo(a, scale, bb[k], out64, of, b + k * S4, re[k], im[k]);
       }
     }
   }
@@ -1253,12 +1539,45 @@ static int launch_row2_inv4(const SmPlan& p, const RowInvArgs& ia, const cf* twC
 
 // which four-stage paired kernel serves the plan's row length: C = 14336 as 7 x 16 x 8 x 8 (one CTA of 448 threads per
 // SM), C = 8192 as 8 x 8 x 8 x 8 (two CTAs of 256 threads, padded buffer) whatever the plan's own radices are
+// one row per CTA, lanes = even / odd halves (k_row1_fwd_eo): Ch = 2 * R1*R2*R3*R4
+template <int R1, int R2, int R3, int R4, int T>
+static int launch_row1_fwd_eo(const SmPlan& p, const RowFwdArgs& fa, const cf* twC, const cf* twQ, double* sumsq, cudaStream_t st) {
+  constexpr int CH = R1 * R2 * R3 * R4;
+  if (!use_row_pairs() || fa.mode != 0 || p.R < 1 || p.C % 8 != 0 || p.Ch != 2 * CH) return 1;
+  static bool done = false;
+  const int smem = CH * 16;
+  cudaError_t e = opt_in(k_row1_fwd_eo<R1, R2, R3, R4, T>, &done);
+  if (e != cudaSuccess) { sm_set_error("row1 fwd eo setup: %s", cudaGetErrorString(e)); return -100; }
+  int grid = num_sms();
+  if (grid > p.R) grid = p.R;
+  k_row1_fwd_eo<R1, R2, R3, R4, T><<<grid, T, smem, st>>>(p.R, p.C, p.P, fa, twC, twQ, sumsq);
+  SM_LAUNCH_CHECK();
+  return 0;
+}
+
 static int try_row2_fwd4(const SmPlan& p, const RowFwdArgs& fa, const cf* twC, const cf* twQ, double* sumsq, cudaStream_t st) {
+  if (p.Ch == 14336) return launch_row1_fwd_eo<7, 16, 8, 8, 448>(p, fa, twC, twQ, sumsq, st);
   if (p.Ch == 7168) return launch_row2_fwd4<7, 16, 8, 8, 448, false, 1>(p, fa, twC, twQ, sumsq, st);
   if (p.Ch == 4096) return launch_row2_fwd4<8, 8, 8, 8, 256, true, 2>(p, fa, twC, twQ, sumsq, st);
   return 1;
 }
+template <int R1, int R2, int R3, int R4, int T>
+static int launch_row1_inv_eo(const SmPlan& p, const RowInvArgs& ia, const cf* twC, const cf* twQ, cudaStream_t st) {
+  constexpr int CH = R1 * R2 * R3 * R4;
+  if (!use_row_pairs() || ia.cull_thr != nullptr || p.R < 1 || p.C % 8 != 0 || p.Ch != 2 * CH) return 1;
+  static bool done = false;
+  const int smem = CH * 16;
+  cudaError_t e = opt_in(k_row1_inv_eo<R1, R2, R3, R4, T>, &done);
+  if (e != cudaSuccess) { sm_set_error("row1 inv eo setup: %s", cudaGetErrorString(e)); return -100; }
+  int grid = num_sms();
+  if (grid > p.R) grid = p.R;
+  k_row1_inv_eo<R1, R2, R3, R4, T><<<grid, T, smem, st>>>(p.R, p.C, p.P, ia, twC, twQ);
+  SM_LAUNCH_CHECK();
+  return 0;
+}
+
 static int try_row2_inv4(const SmPlan& p, const RowInvArgs& ia, const cf* twC, const cf* twQ, cudaStream_t st) {
+  if (p.Ch == 14336) return launch_row1_inv_eo<7, 16, 8, 8, 448>(p, ia, twC, twQ, st);
   if (p.Ch == 7168) return launch_row2_inv4<7, 16, 8, 8, 448, false, 1>(p, ia, twC, twQ, st);
   if (p.Ch == 4096) return launch_row2_inv4<8, 8, 8, 8, 256, true, 2>(p, ia, twC, twQ, st);
   return 1;

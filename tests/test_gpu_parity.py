@@ -395,7 +395,7 @@ def test_golden_tensor_cases(E, golden_dir):
 
 
 @pytest.mark.parametrize("shape,seed", [((1024, 4096), 21), ((2048, 1024), 22), ((1, 8192), 23), ((512, 8192), 24),
-                                        ((256, 14336), 25)])
+                                        ((256, 14336), 25), ((128, 28672), 26)])
 def test_pair_merge_vs_oracle_mid_size(E, shape, seed):
     """Synthetic Llama-like tensors at sizes the oracle finishes in seconds."""
     R, C = shape
