@@ -676,14 +676,15 @@ __device__ __forceinline__ void combine_untangle4(pf xr, pf xi, pf yr, pf yi, co
   if (m != n) untangle_pair1(enr - onr, eni - oni, emr + omr, emi + omi, ldg_cf(twC + n + H), re0, im0, n + H, m);   // (n + H, m)
 }
 
-template <int R1, int R2, int R3, int R4, int T>
-__global__ void __launch_bounds__(T, 1) k_row1_fwd_eo(int R, int C, int P, const __grid_constant__ RowFwdArgs a,
+template <int R1, int R2, int R3, int R4, int T, int kCtas>
+__global__ void __launch_bounds__(T, kCtas) k_row1_fwd_eo(int R, int C, int P, const __grid_constant__ RowFwdArgs a,
                                                       const cf* __restrict__ twC, const cf* __restrict__ twQ2,
                                                       double* __restrict__ sumsq) {
   constexpr int CH = R1 * R2 * R3 * R4;             // length of the even / odd transforms = Ch / 2
   constexpr int NB1 = CH / R1, NB2 = CH / R2, NB3 = CH / R3, S4 = CH / R4;
   constexpr int s2 = R1, s3 = R1 * R2;
-  static_assert(NB2 == T && NB3 == 2 * T && S4 == 2 * T, "k_row1_fwd_eo: 1 / 2 / 2 butterflies per thread in stages 2 / 3 / 4");
+  constexpr int H2 = NB2 / T;
+  static_assert(NB2 == H2 * T && H2 >= 1 && H2 <= 2 && NB3 == 2 * T && S4 == 2 * T, "k_row1_fwd_eo: 1-2 / 2 / 2 butterflies per thread in stages 2 / 3 / 4");
   __shared__ double wsum[16];
   RowSmem2X<false> sm{reinterpret_cast<ulonglong2*>(g_dyn_smem)};
   const int tid = threadIdx.x;
@@ -704,21 +705,27 @@ __global__ void __launch_bounds__(T, 1) k_row1_fwd_eo(int R, int C, int P, const
       bulk_prefetch_l2(a.base + (size_t)(row + gridDim.x) * C, 2u * (uint32_t)C);
       bulk_prefetch_l2(a.ft + (size_t)(row + gridDim.x) * C, 2u * (uint32_t)C);
     }
-    {  // stage 2: radix R2, s = R1, in place, one butterfly per thread
-      pf re[R2], im[R2];
+    {  // stage 2: radix R2, s = R1, in place, butterflies t (and t + T)
+      pf re[H2][R2], im[H2][R2];
 #pragma unroll
-      for (int j = 0; j < R2; ++j) sm.load(tid + j * NB2, re[j], im[j]);
+      for (int h = 0; h < H2; ++h)
+#pragma unroll
+        for (int j = 0; j < R2; ++j) sm.load(tid + h * T + j * NB2, re[h][j], im[h][j]);
       __syncthreads();
-      Dft<R2>::run(re, im);
-      const int p = tid / s2, q = tid - p * s2;
-      const int obase = q + s2 * R2 * p, tstep = s2 * p * 4;
-      sm.store(obase, re[0], im[0]);
 #pragma unroll
-      for (int k = 1; k < R2; ++k) {
-        const cf w = ldg_cf(twC + tstep * k);
-        pf xr = re[k], xi = im[k];
-        cmul(xr, xi, w.x, w.y);
-        sm.store(obase + k * s2, xr, xi);
+      for (int h = 0; h < H2; ++h) {
+        Dft<R2>::run(re[h], im[h]);
+        const int b = tid + h * T;
+        const int p = b / s2, q = b - p * s2;
+        const int obase = q + s2 * R2 * p, tstep = s2 * p * 4;
+        sm.store(obase, re[h][0], im[h][0]);
+#pragma unroll
+        for (int k = 1; k < R2; ++k) {
+          const cf w = ldg_cf(twC + tstep * k);
+          pf xr = re[h][k], xi = im[h][k];
+          cmul(xr, xi, w.x, w.y);
+          sm.store(obase + k * s2, xr, xi);
+        }
       }
     }
     __syncthreads();
@@ -1101,13 +1108,14 @@ __device__ __forceinline__ void epilogue_store_eo(const RowInvArgs& a, float sca
   }
 }
 
-template <int R1, int R2, int R3, int R4, int T>
-__global__ void __launch_bounds__(T, 1) k_row1_inv_eo(int R, int C, int P, const __grid_constant__ RowInvArgs a,
+template <int R1, int R2, int R3, int R4, int T, int kCtas>
+__global__ void __launch_bounds__(T, kCtas) k_row1_inv_eo(int R, int C, int P, const __grid_constant__ RowInvArgs a,
                                                       const cf* __restrict__ twC, const cf* __restrict__ twQ2) {
   constexpr int CH = R1 * R2 * R3 * R4;             // length of the two lane transforms = Ch / 2
   constexpr int NB1 = CH / R1, NB2 = CH / R2, NB3 = CH / R3, S4 = CH / R4;
   constexpr int s2 = R1, s3 = R1 * R2;
-  static_assert(NB2 == T && NB3 == 2 * T && S4 == 2 * T, "k_row1_inv_eo: 1 / 2 / 2 butterflies per thread in stages 2 / 3 / 4");
+  constexpr int H2 = NB2 / T;
+  static_assert(NB2 == H2 * T && H2 >= 1 && H2 <= 2 && NB3 == 2 * T && S4 == 2 * T, "k_row1_inv_eo: 1-2 / 2 / 2 butterflies per thread in stages 2 / 3 / 4");
   RowSmem2X<false> sm{reinterpret_cast<ulonglong2*>(g_dyn_smem)};
   const int tid = threadIdx.x;
   const float* im_plane = (a.sel != nullptr && *a.sel != 0) ? a.im_alt : a.im;
@@ -1128,21 +1136,27 @@ __global__ void __launch_bounds__(T, 1) k_row1_inv_eo(int R, int C, int P, const
     }
     __syncthreads();
     prefetch(row + (int)gridDim.x);
-    {  // stage 2: radix R2, s = R1, in place, one butterfly per thread
-      pf re[R2], im[R2];
+    {  // stage 2: radix R2, s = R1, in place, butterflies t (and t + T)
+      pf re[H2][R2], im[H2][R2];
 #pragma unroll
-      for (int j = 0; j < R2; ++j) sm.load(tid + j * NB2, re[j], im[j]);
+      for (int h = 0; h < H2; ++h)
+#pragma unroll
+        for (int j = 0; j < R2; ++j) sm.load(tid + h * T + j * NB2, re[h][j], im[h][j]);
       __syncthreads();
-      Dft<R2>::run(re, im);
-      const int p = tid / s2, q = tid - p * s2;
-      const int obase = q + s2 * R2 * p, tstep = s2 * p * 4;
-      sm.store(obase, re[0], im[0]);
 #pragma unroll
-      for (int k = 1; k < R2; ++k) {
-        const cf w = ldg_cf(twC + tstep * k);
-        pf xr = re[k], xi = im[k];
-        cmul(xr, xi, w.x, w.y);
-        sm.store(obase + k * s2, xr, xi);
+      for (int h = 0; h < H2; ++h) {
+        Dft<R2>::run(re[h], im[h]);
+        const int b = tid + h * T;
+        const int p = b / s2, q = b - p * s2;
+        const int obase = q + s2 * R2 * p, tstep = s2 * p * 4;
+        sm.store(obase, re[h][0], im[h][0]);
+#pragma unroll
+        for (int k = 1; k < R2; ++k) {
+          const cf w = ldg_cf(twC + tstep * k);
+          pf xr = re[h][k], xi = im[h][k];
+          cmul(xr, xi, w.x, w.y);
+          sm.store(obase + k * s2, xr, xi);
+        }
       }
     }
     __syncthreads();
@@ -1539,45 +1553,53 @@ static int launch_row2_inv4(const SmPlan& p, const RowInvArgs& ia, const cf* twC
 
 // which four-stage paired kernel serves the plan's row length: C = 14336 as 7 x 16 x 8 x 8 (one CTA of 448 threads per
 // SM), C = 8192 as 8 x 8 x 8 x 8 (two CTAs of 256 threads, padded buffer) whatever the plan's own radices are
+static bool use_row_eo() {          // SM_ROW_EO=0: C = 14336 rows as row pairs (k_row2_*4) instead of even / odd halves, for A-B timing
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SM_ROW_EO"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
+
 // one row per CTA, lanes = even / odd halves (k_row1_fwd_eo): Ch = 2 * R1*R2*R3*R4
-template <int R1, int R2, int R3, int R4, int T>
+template <int R1, int R2, int R3, int R4, int T, int kCtas>
 static int launch_row1_fwd_eo(const SmPlan& p, const RowFwdArgs& fa, const cf* twC, const cf* twQ, double* sumsq, cudaStream_t st) {
   constexpr int CH = R1 * R2 * R3 * R4;
   if (!use_row_pairs() || fa.mode != 0 || p.R < 1 || p.C % 8 != 0 || p.Ch != 2 * CH) return 1;
   static bool done = false;
   const int smem = CH * 16;
-  cudaError_t e = opt_in(k_row1_fwd_eo<R1, R2, R3, R4, T>, &done);
+  cudaError_t e = opt_in(k_row1_fwd_eo<R1, R2, R3, R4, T, kCtas>, &done);
   if (e != cudaSuccess) { sm_set_error("row1 fwd eo setup: %s", cudaGetErrorString(e)); return -100; }
-  int grid = num_sms();
+  int grid = num_sms() * kCtas;
   if (grid > p.R) grid = p.R;
-  k_row1_fwd_eo<R1, R2, R3, R4, T><<<grid, T, smem, st>>>(p.R, p.C, p.P, fa, twC, twQ, sumsq);
+  k_row1_fwd_eo<R1, R2, R3, R4, T, kCtas><<<grid, T, smem, st>>>(p.R, p.C, p.P, fa, twC, twQ, sumsq);
   SM_LAUNCH_CHECK();
   return 0;
 }
 
 static int try_row2_fwd4(const SmPlan& p, const RowFwdArgs& fa, const cf* twC, const cf* twQ, double* sumsq, cudaStream_t st) {
-  if (p.Ch == 14336) return launch_row1_fwd_eo<7, 16, 8, 8, 448>(p, fa, twC, twQ, sumsq, st);
+  if (p.Ch == 14336) return launch_row1_fwd_eo<7, 16, 8, 8, 448, 1>(p, fa, twC, twQ, sumsq, st);
+  if (p.Ch == 7168 && use_row_eo()) return launch_row1_fwd_eo<7, 8, 8, 8, 224, 2>(p, fa, twC, twQ, sumsq, st);
   if (p.Ch == 7168) return launch_row2_fwd4<7, 16, 8, 8, 448, false, 1>(p, fa, twC, twQ, sumsq, st);
   if (p.Ch == 4096) return launch_row2_fwd4<8, 8, 8, 8, 256, true, 2>(p, fa, twC, twQ, sumsq, st);
   return 1;
 }
-template <int R1, int R2, int R3, int R4, int T>
+template <int R1, int R2, int R3, int R4, int T, int kCtas>
 static int launch_row1_inv_eo(const SmPlan& p, const RowInvArgs& ia, const cf* twC, const cf* twQ, cudaStream_t st) {
   constexpr int CH = R1 * R2 * R3 * R4;
   if (!use_row_pairs() || ia.cull_thr != nullptr || p.R < 1 || p.C % 8 != 0 || p.Ch != 2 * CH) return 1;
   static bool done = false;
   const int smem = CH * 16;
-  cudaError_t e = opt_in(k_row1_inv_eo<R1, R2, R3, R4, T>, &done);
+  cudaError_t e = opt_in(k_row1_inv_eo<R1, R2, R3, R4, T, kCtas>, &done);
   if (e != cudaSuccess) { sm_set_error("row1 inv eo setup: %s", cudaGetErrorString(e)); return -100; }
-  int grid = num_sms();
+  int grid = num_sms() * kCtas;
   if (grid > p.R) grid = p.R;
-  k_row1_inv_eo<R1, R2, R3, R4, T><<<grid, T, smem, st>>>(p.R, p.C, p.P, ia, twC, twQ);
+  k_row1_inv_eo<R1, R2, R3, R4, T, kCtas><<<grid, T, smem, st>>>(p.R, p.C, p.P, ia, twC, twQ);
   SM_LAUNCH_CHECK();
   return 0;
 }
 
 static int try_row2_inv4(const SmPlan& p, const RowInvArgs& ia, const cf* twC, const cf* twQ, cudaStream_t st) {
-  if (p.Ch == 14336) return launch_row1_inv_eo<7, 16, 8, 8, 448>(p, ia, twC, twQ, st);
+  if (p.Ch == 14336) return launch_row1_inv_eo<7, 16, 8, 8, 448, 1>(p, ia, twC, twQ, st);
+  if (p.Ch == 7168 && use_row_eo()) return launch_row1_inv_eo<7, 8, 8, 8, 224, 2>(p, ia, twC, twQ, st);
   if (p.Ch == 7168) return launch_row2_inv4<7, 16, 8, 8, 448, false, 1>(p, ia, twC, twQ, st);
   if (p.Ch == 4096) return launch_row2_inv4<8, 8, 8, 8, 256, true, 2>(p, ia, twC, twQ, st);
   return 1;
