@@ -104,6 +104,36 @@ def test_forward_bf16_delta(E):
     assert abs(float(dbl[E.D_SUMSQ0]) / float((delta ** 2).sum()) - 1) < 5e-7
 
 
+@pytest.mark.parametrize("shape", [(2, 4096), (6, 4096), (5, 4096), (2, 8192), (6, 8192), (7, 8192), (2, 14336), (3, 14336),
+                                   (2, 28672), (5, 28672), (130, 4096), (150, 14336)])
+def test_paired_row_kernels_edge_row_counts(E, shape):
+    """Every family of the packed-f32x2 row kernels (row pairs at C = 4096 / 8192, even / odd halves at C = 14336 /
+    28672) at the smallest and at odd row counts (odd R falls back to the one-row kernels where pairs are needed):
+    bf16 delta -> spectrum vs numpy, sum of squares, and back through the bf16 epilogue (x scale, + base, RNE)."""
+    R, C = shape
+    g = torch.Generator(device=DEV).manual_seed(R * 31 + C)
+    base = (0.02 * torch.randn((R, C), generator=g, device=DEV)).to(torch.bfloat16)
+    ft = (base.float() + 0.002 * torch.randn((R, C), generator=g, device=DEV)).to(torch.bfloat16)
+    ws = E.get_workspace(R, C, DEV)
+    ws.ctl.zero_()
+    E.fwd_rows(ws, 0, E.Source(base=base, ft=ft), E.D_SUMSQ0)
+    E.fwd_cols(ws, 0, scale=1.0)
+    delta = (ft.float() - base.float()).double().cpu().numpy()
+    assert rel_l2(planes_to_numpy(ws, 0), np.fft.rfft2(delta)) < 1e-6
+    dbl, _, _, _ = ws.read_ctl()
+    assert abs(float(dbl[E.D_SUMSQ0]) / float((delta ** 2).sum()) - 1) < 5e-7
+    E.inv_cols(ws, ws.re[0], ws.im[0], cull=False)
+    out = torch.empty((R, C), dtype=torch.bfloat16, device=DEV)
+    E.inv_rows(ws, ws.re[0], ws.im[0], False, 0.37, base, out, check_ifft=True)     # 0.5 would put half the results on exact bf16 ties
+    want = (base.float() + 0.37 * (ft.float() - base.float())).to(torch.bfloat16)
+    u = bf16_ulp_distance(bits(out), bits(want))
+    # (an ulp distance > 1 only happens next to zero, where base + 0.37 delta cancels and the ulp is tiny)
+    assert float((u <= 1).mean()) >= 0.9999 and float((u == 0).mean()) >= 0.995, (float((u <= 1).mean()), float((u == 0).mean()))
+    assert float((out.float() - want.float()).abs().max()) <= 2.0 ** -8 * float(want.float().abs().max())
+    _, _, flags, _ = ws.read_ctl()
+    assert [int(v) for v in flags[:4]] == [0, 0, 0, 0]
+
+
 def _expanded_sorted(planes, R, C):
     w = half_weights(R, C)
     keys = np.concatenate([np.repeat(np.abs(p).ravel(), w.ravel()) for p in planes])
