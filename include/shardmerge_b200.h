@@ -244,6 +244,14 @@ int sm_profile_enable(int on);
  * accumulated since the last collect (host arrays of n_classes entries). */
 int sm_profile_collect(double* ms, double* bytes, int* launches, int n_classes);
 
+/* ---- element-wise strategies (next to the spectral path: the reference's other MergeTensorsBase subclasses) ----------
+ * mode 0: AdditionMerge._merge_layer (shard/merge/addition.py:44-83): out = sum_k (ft_k - base), every op rounded to
+ *         bf16 like the reference's in-dtype arithmetic; the base is NOT added back.
+ * mode 1: TaskAdditionMerge._merge_layer (shard/merge/taskaddition.py:44-83): deltas whose sign differs from the
+ *         majority sign are zeroed, the rest summed (fp32 accumulation in model order, one rounding).
+ * bf16 in / out, n elements, `fts` = HOST array of n_models (<= 8) device pointers; all 16-byte aligned. */
+int sm_elem_merge_bf16(int mode, size_t n, const void* base, const void* const* fts, int n_models, void* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -278,3 +278,39 @@ def merge_layer(base_out_bf16, models, target_norm_offset=1e-10, cull_start_pct=
     if info is not None:
         info.update(branches=branches, target_norm=target_norm, norms=[float(x) for x in norms])
     return f32_to_bf16(result)                                               # :276
+
+
+# --------------------------------------------------------------------------- element-wise strategies
+def _bf16_round(x: np.ndarray) -> np.ndarray:
+    """fp32 values rounded to bf16 and widened again (one bf16 rounding, as after every torch bf16 op)."""
+    return bf16_to_f32(f32_to_bf16(np.asarray(x, dtype=np.float32)))
+
+
+def addition_merge(base_bf16: np.ndarray, fts_bf16) -> np.ndarray:
+    """AdditionMerge._merge_layer (shard/merge/addition.py:44-83): out = 0; out += (ft - base) per model, every
+    operation in the tensors' own dtype (bf16: computed in fp32, rounded to bf16 after each op).  The summed
+    delta is returned -- the base is NOT added back.  uint16 bit patterns in, uint16 out."""
+    with np.errstate(invalid="ignore", over="ignore"):
+        b = bf16_to_f32(base_bf16)
+        out = np.zeros(b.shape, dtype=np.float32)
+        for ft in fts_bf16:
+            delta = _bf16_round(bf16_to_f32(ft) - b)               # :72
+            out = _bf16_round(out + delta)                         # :73
+    return f32_to_bf16(out)
+
+
+def taskaddition_merge(base_bf16: np.ndarray, fts_bf16) -> np.ndarray:
+    """TaskAdditionMerge._merge_layer (shard/merge/taskaddition.py:44-83): bf16 deltas, majority sign over the models
+    (sign of the sum of signs), deltas whose sign differs from it zeroed, the rest summed (torch.sum over bf16
+    accumulates in fp32 in model order and rounds once)."""
+    with np.errstate(invalid="ignore", over="ignore"):
+        b = bf16_to_f32(base_bf16)
+        d = np.stack([_bf16_round(bf16_to_f32(ft) - b) for ft in fts_bf16], axis=0)      # :68
+        sgn = np.sign(d)                                            # :71   (NaN stays NaN)
+        w = np.sign(sgn.sum(axis=0, dtype=np.float32))             # :73
+        mask = (sgn == w[None]).astype(np.float32)                 # :75   (NaN == NaN is False)
+        masked = _bf16_round(d * mask)                             # :76
+        acc = np.zeros(b.shape, dtype=np.float32)
+        for k in range(masked.shape[0]):                           # :78
+            acc = acc + masked[k]
+    return f32_to_bf16(acc)

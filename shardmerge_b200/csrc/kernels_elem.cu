@@ -1,0 +1,150 @@
+// kernels_elem.cu -- the element-wise strategies of the reference as single streaming kernels.
+//
+//   mode 0  AdditionMerge._merge_layer      (shard/merge/addition.py:44-83):  out = 0; out += (ft_k - base) for every model
+//   mode 1  TaskAdditionMerge._merge_layer  (shard/merge/taskaddition.py:44-83): deltas whose sign differs from the
+//           majority sign (sign of the sum of signs) are zeroed, the rest summed
+//
+// The reference does every step in the tensors' own dtype; for bf16 that is "compute in fp32, round to bf16 after each
+// torch op", and torch.sum over bf16 accumulates in fp32 in model order and rounds once.  The kernels reproduce exactly
+// that rounding sequence, so the results are bit-identical to the reference's (tests/golden/elem_*.npz), NaN payloads
+// aside.  HBM-bound: (M + 1) reads and one write of 2 bytes per element; 8 elements (16 bytes per tensor) per thread.
+#include <cuda_bf16.h>
+#include "sm_internal.h"
+
+namespace {
+
+constexpr int kMaxModels = 8;
+struct ElemArgs { const uint4* base; const uint4* ft[kMaxModels]; uint4* out; int M; size_t n8; size_t n; };
+
+__device__ __forceinline__ float bf16_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+// one bf16 rounding (RNE), widened again: what every torch bf16 op leaves behind
+__device__ __forceinline__ float bf16r(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+// torch.sign for floats: NaN stays NaN
+__device__ __forceinline__ float sgnf(float x) { return x > 0.f ? 1.f : (x < 0.f ? -1.f : (x == x ? 0.f : x)); }
+
+__device__ __forceinline__ void unpack8(const uint4 v, float (&f)[8]) {
+  f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+  f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// M is a compile-time constant: all M + 1 16-byte loads of a thread are issued before the first is consumed, and the
+// sign-agreement mode keeps the raw words in registers instead of reading the finetunes twice
+template <int MODE, int M>
+__device__ __forceinline__ void merge8(const uint4 (&raw)[M], const float (&b)[8], float (&o)[8]) {
+  if (MODE == 0) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = 0.f;
+#pragma unroll
+    for (int k = 0; k < M; ++k) {
+      float f[8];
+      unpack8(raw[k], f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = bf16r(o[e] + bf16r(f[e] - b[e]));      // addition.py:72-73
+    }
+  } else {
+    float ssum[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { ssum[e] = 0.f; o[e] = 0.f; }
+#pragma unroll
+    for (int k = 0; k < M; ++k) {                      // taskaddition.py:68-73: bf16 deltas, sum of their signs
+      float f[8];
+      unpack8(raw[k], f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) ssum[e] += sgnf(bf16r(f[e] - b[e]));
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) ssum[e] = sgnf(ssum[e]);
+#pragma unroll
+    for (int k = 0; k < M; ++k) {                      // :75-78: mask by the majority sign, fp32 sum in model order
+      float f[8];
+      unpack8(raw[k], f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float d = bf16r(f[e] - b[e]);
+        const float m = (sgnf(d) == ssum[e]) ? 1.f : 0.f;
+        o[e] += bf16r(d * m);
+      }
+    }
+  }
+}
+
+template <int MODE, int M>
+__global__ void __launch_bounds__(256) k_elem_merge(const __grid_constant__ ElemArgs a) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < a.n8; i += stride) {
+    uint4 raw[M];
+    const uint4 rb = __ldg(a.base + i);
+#pragma unroll
+    for (int k = 0; k < M; ++k) raw[k] = __ldg(a.ft[k] + i);
+    float b[8], o[8];
+    unpack8(rb, b);
+    merge8<MODE, M>(raw, b, o);
+    a.out[i] = make_uint4(pack2(o[0], o[1]), pack2(o[2], o[3]), pack2(o[4], o[5]), pack2(o[6], o[7]));
+  }
+  // tail (n not a multiple of 8): one element per thread of the first CTA
+  if (blockIdx.x == 0) {
+    const uint16_t* base16 = reinterpret_cast<const uint16_t*>(a.base);
+    uint16_t* out16 = reinterpret_cast<uint16_t*>(a.out);
+    for (size_t j = a.n8 * 8 + threadIdx.x; j < a.n; j += blockDim.x) {
+      const float b = __uint_as_float((uint32_t)base16[j] << 16);
+      float o = 0.f, ssum = 0.f;
+      if (MODE == 0) {
+        for (int k = 0; k < M; ++k) {
+          const float f = __uint_as_float((uint32_t)reinterpret_cast<const uint16_t*>(a.ft[k])[j] << 16);
+          o = bf16r(o + bf16r(f - b));
+        }
+      } else {
+        for (int k = 0; k < M; ++k) {
+          const float f = __uint_as_float((uint32_t)reinterpret_cast<const uint16_t*>(a.ft[k])[j] << 16);
+          ssum += sgnf(bf16r(f - b));
+        }
+        for (int k = 0; k < M; ++k) {
+          const float f = __uint_as_float((uint32_t)reinterpret_cast<const uint16_t*>(a.ft[k])[j] << 16);
+          const float d = bf16r(f - b);
+          o += bf16r(d * ((sgnf(d) == sgnf(ssum)) ? 1.f : 0.f));
+        }
+      }
+      __nv_bfloat16 h = __float2bfloat16_rn(o);
+      out16[j] = *reinterpret_cast<uint16_t*>(&h);
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int sm_elem_merge_bf16(int mode, size_t n, const void* base, const void* const* fts, int n_models, void* out,
+                                  void* stream) {
+  if (mode < 0 || mode > 1) { sm_set_error("elem_merge: unknown mode %d", mode); return -2; }
+  if (n_models < 1 || n_models > kMaxModels) { sm_set_error("elem_merge: 1..%d models, got %d", kMaxModels, n_models); return -2; }
+  ElemArgs a{};
+  a.base = reinterpret_cast<const uint4*>(base); a.out = reinterpret_cast<uint4*>(out); a.M = n_models;
+  a.n = n; a.n8 = n / 8;
+  bool aligned = ((uintptr_t)base % 16 == 0) && ((uintptr_t)out % 16 == 0);
+  for (int k = 0; k < n_models; ++k) { a.ft[k] = reinterpret_cast<const uint4*>(fts[k]); aligned = aligned && ((uintptr_t)fts[k] % 16 == 0); }
+  if (!aligned) { sm_set_error("elem_merge: tensors must be 16-byte aligned"); return -2; }
+  if (n == 0) return 0;
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
+  size_t need = (a.n8 + 255) / 256;
+  if (need < 1) need = 1;
+  const size_t cap = (size_t)sms * 16;                  // two resident waves of 8 CTAs per SM, grid-stride over the rest
+  const unsigned int grid = (unsigned int)(need < cap ? need : cap);
+  cudaStream_t st = (cudaStream_t)stream;
+#define SM_ELEM_CASE(MM)                                                 \
+  case MM:                                                               \
+    if (mode == 0) k_elem_merge<0, MM><<<grid, 256, 0, st>>>(a);         \
+    else k_elem_merge<1, MM><<<grid, 256, 0, st>>>(a);                   \
+    break;
+  switch (n_models) {
+    SM_ELEM_CASE(1) SM_ELEM_CASE(2) SM_ELEM_CASE(3) SM_ELEM_CASE(4)
+    SM_ELEM_CASE(5) SM_ELEM_CASE(6) SM_ELEM_CASE(7) SM_ELEM_CASE(8)
+  }
+#undef SM_ELEM_CASE
+  SM_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,2 +1,4 @@
 from .base import MergeTensorsBase  # noqa: F401
 from .fast_fourier import FourierMerge  # noqa: F401
+from .addition import AdditionMerge  # noqa: F401
+from .taskaddition import TaskAdditionMerge  # noqa: F401

@@ -135,3 +135,19 @@ def test_bf16_roundtrip():
     import torch
     tb = torch.from_numpy(x).to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16)
     assert np.array_equal(tb, b)
+
+
+def _nan_equal_bits(a, b):
+    fa, fb = O.bf16_to_f32(a), O.bf16_to_f32(b)
+    return (a == b) | ((fa != fa) & (fb != fb))
+
+
+@pytest.mark.parametrize("name", ["elem_addition_3x_64x128", "elem_addition_2x_special_32x64", "elem_taskaddition_3x_64x128",
+                                  "elem_taskaddition_4x_96x40", "elem_taskaddition_2x_special_32x64"])
+def test_elementwise_strategies_match_reference_bit_for_bit(golden_dir, name):
+    """AdditionMerge / TaskAdditionMerge (shard/merge/addition.py, taskaddition.py) run by the reference on CPU
+    (oracle/make_golden_elem.py): the numpy restatement reproduces every bf16 rounding, incl. zeros, inf, NaN."""
+    d = np.load(golden_dir / f"{name}.npz")
+    fts = [d[f"ft{k}"] for k in range(int(d["n"]))]
+    got = O.taskaddition_merge(d["base"], fts) if "taskaddition" in name else O.addition_merge(d["base"], fts)
+    assert _nan_equal_bits(got, d["out"]).all()
