@@ -820,6 +820,11 @@ struct RowTangleStaged2 {
 __device__ __forceinline__ float epi_fix(float v, unsigned int* flags, int which) {
   return not_finite(v) ? sm_fix_nonfinite(v, flags, which) : v;
 }
+// one test for four values: the NaN-propagating maximum of the magnitudes is NaN / Inf iff any of them is
+__device__ __forceinline__ float fmax_nan(float x, float y) { float r; asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(x), "f"(y)); return r; }
+__device__ __forceinline__ bool any_not_finite4(float a, float b, float c, float d) {
+  return not_finite(fmax_nan(fmax_nan(fabsf(a), fabsf(b)), fmax_nan(fabsf(c), fabsf(d))));
+}
 
 // element j of the pair: (a, b) = swapped engine output -> x[2j] = b / N, x[2j+1] = a / N for both rows
 __device__ __forceinline__ void epilogue_store2(const RowInvArgs& a, float scale, uint32_t bb0, uint32_t bb1, uint32_t* out0,
@@ -827,12 +832,16 @@ __device__ __forceinline__ void epilogue_store2(const RowInvArgs& a, float scale
   const pf n = pf_bcast(a.inv_n);
   pf x0 = vb * n, x1 = va * n;
   float x00 = pf_lo(x0), x01 = pf_hi(x0), x10 = pf_lo(x1), x11 = pf_hi(x1);   // xRC: element R of the pair, row C
-  if (a.check_ifft) { x00 = epi_fix(x00, a.flags, 0); x01 = epi_fix(x01, a.flags, 0); x10 = epi_fix(x10, a.flags, 0); x11 = epi_fix(x11, a.flags, 0); }
+  if (a.check_ifft && any_not_finite4(x00, x01, x10, x11)) {     // exceptional: one rarely taken branch for the four values
+    x00 = epi_fix(x00, a.flags, 0); x01 = epi_fix(x01, a.flags, 0); x10 = epi_fix(x10, a.flags, 0); x11 = epi_fix(x11, a.flags, 0);
+  }
   x00 *= scale; x01 *= scale; x10 *= scale; x11 *= scale;
   if (a.out_mode == 0) {
     x00 = bf16_bits_to_f32(bb0 & 0xffffu) + x00; x10 = bits_f32(bb0 & 0xffff0000u) + x10;
     x01 = bf16_bits_to_f32(bb1 & 0xffffu) + x01; x11 = bits_f32(bb1 & 0xffff0000u) + x11;
-    x00 = epi_fix(x00, a.flags, 2); x10 = epi_fix(x10, a.flags, 2); x01 = epi_fix(x01, a.flags, 2); x11 = epi_fix(x11, a.flags, 2);
+    if (any_not_finite4(x00, x01, x10, x11)) {
+      x00 = epi_fix(x00, a.flags, 2); x10 = epi_fix(x10, a.flags, 2); x01 = epi_fix(x01, a.flags, 2); x11 = epi_fix(x11, a.flags, 2);
+    }
     out0[j] = pack_bf16x2_rne(x00, x10);
     out1[j] = pack_bf16x2_rne(x01, x11);
   } else {
@@ -1096,12 +1105,16 @@ __device__ __forceinline__ void epilogue_store_eo(const RowInvArgs& a, float sca
   const pf n = pf_bcast(a.inv_n);
   const pf x0 = vb * n, x1 = va * n;
   float x00 = pf_lo(x0), x01 = pf_hi(x0), x10 = pf_lo(x1), x11 = pf_hi(x1);   // xEL: element E of the complex pair, lane L
-  if (a.check_ifft) { x00 = epi_fix(x00, a.flags, 0); x01 = epi_fix(x01, a.flags, 0); x10 = epi_fix(x10, a.flags, 0); x11 = epi_fix(x11, a.flags, 0); }
+  if (a.check_ifft && any_not_finite4(x00, x01, x10, x11)) {     // exceptional: one rarely taken branch for the four values
+    x00 = epi_fix(x00, a.flags, 0); x01 = epi_fix(x01, a.flags, 0); x10 = epi_fix(x10, a.flags, 0); x11 = epi_fix(x11, a.flags, 0);
+  }
   x00 *= scale; x01 *= scale; x10 *= scale; x11 *= scale;
   if (a.out_mode == 0) {
     x00 = bf16_bits_to_f32(bb.x & 0xffffu) + x00; x10 = bits_f32(bb.x & 0xffff0000u) + x10;
     x01 = bf16_bits_to_f32(bb.y & 0xffffu) + x01; x11 = bits_f32(bb.y & 0xffff0000u) + x11;
-    x00 = epi_fix(x00, a.flags, 2); x10 = epi_fix(x10, a.flags, 2); x01 = epi_fix(x01, a.flags, 2); x11 = epi_fix(x11, a.flags, 2);
+    if (any_not_finite4(x00, x01, x10, x11)) {
+      x00 = epi_fix(x00, a.flags, 2); x10 = epi_fix(x10, a.flags, 2); x01 = epi_fix(x01, a.flags, 2); x11 = epi_fix(x11, a.flags, 2);
+    }
     out64[m] = make_uint2(pack_bf16x2_rne(x00, x10), pack_bf16x2_rne(x01, x11));
   } else {
     of[m] = make_float4(x00, x10, x01, x11);

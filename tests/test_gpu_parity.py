@@ -338,20 +338,26 @@ def test_inverse_epilogue_bf16_within_1ulp(E, shape):
     assert [int(v) for v in flags] == [0, 0, 0, 0]
 
 
-def test_epilogue_nan_inf_policy(E):
-    R, C = 8, 64
+@pytest.mark.parametrize("shape", [(8, 64), (4, 4096), (4, 8192), (4, 14336), (3, 28672)])
+def test_epilogue_nan_inf_policy(E, shape):
+    """NaN -> 0 (counted), Inf kept (counted) after the base add (fast_fourier.py:270-274), in every epilogue variant
+    (one-row, row pairs, even / odd halves)."""
+    R, C = shape
     ws = E.get_workspace(R, C, DEV)
     ws.ctl.zero_()
     Z = np.zeros((R, C // 2 + 1), dtype=np.complex128)
     numpy_to_planes(ws, 0, Z)
     base = torch.zeros((R, C), dtype=torch.bfloat16, device=DEV)
     base[0, 0] = float("inf"); base[0, 1] = float("nan")
+    base[R - 1, C - 1] = float("nan"); base[R - 1, C - 2] = float("-inf"); base[1, 7] = float("nan")
     out = torch.empty((R, C), dtype=torch.bfloat16, device=DEV)
     E.inv_cols(ws, ws.re[0], ws.im[0], cull=False)
     E.inv_rows(ws, ws.re[0], ws.im[0], False, 1.0, base, out, check_ifft=True)
     _, _, flags, _ = ws.read_ctl()
-    assert int(flags[2]) == 1 and int(flags[3]) == 1 and int(flags[0]) == 0
+    assert int(flags[2]) == 3 and int(flags[3]) == 2 and int(flags[0]) == 0 and int(flags[1]) == 0
     assert out[0, 1].item() == 0.0 and torch.isinf(out[0, 0])
+    assert out[R - 1, C - 1].item() == 0.0 and out[R - 1, C - 2].item() == float("-inf") and out[1, 7].item() == 0.0
+    assert int(torch.count_nonzero(out.float() != 0)) == 2
 
 
 # ------------------------------------------------------------------------------------------
