@@ -343,7 +343,24 @@ __device__ __forceinline__ void untangle_pair2(pf ar, pf ai, pf br, pf bi, cf w,
   }
 }
 
-template <int R1, int R2, int R3, int T>
+// kEO: the two lanes are the even / odd halves of ONE row instead of two rows (see k_row1_fwd_eo below): C = 8192 then has
+// the staging and work-buffer footprint of a C = 4096 row pair and runs through this three-stage, bulk-copy fed kernel
+__device__ __forceinline__ void untangle_pair1(float ar, float ai, float br, float bi, cf w, float* re0, float* im0, int n, int m);
+__device__ __forceinline__ void combine_untangle4(pf xr, pf xi, pf yr, pf yi, const cf* __restrict__ twC, float* re0, float* im0,
+                                                  int n, int H);
+struct RowDeltaStagedEO {        // stage-1 source: complex elements 2i (lane 0) and 2i + 1 (lane 1) of one staged row
+  const uint2* b64; const uint2* f64; pf* acc;
+  __device__ __forceinline__ void load(int i, pf& re, pf& im) const {
+    const uint2 b = b64[i], f = f64[i];
+    re = pf_make(bf16_bits_to_f32(f.x & 0xffffu), bf16_bits_to_f32(f.y & 0xffffu)) -
+         pf_make(bf16_bits_to_f32(b.x & 0xffffu), bf16_bits_to_f32(b.y & 0xffffu));
+    im = pf_make(bits_f32(f.x & 0xffff0000u), bits_f32(f.y & 0xffff0000u)) -
+         pf_make(bits_f32(b.x & 0xffff0000u), bits_f32(b.y & 0xffff0000u));
+    *acc = pf_fma(re, re, pf_fma(im, im, *acc));
+  }
+};
+
+template <int R1, int R2, int R3, int T, bool kEO>
 __global__ void __launch_bounds__(T, 3) k_row2_fwd(int R, int C, int P, const __grid_constant__ RowFwdArgs a,
                                                 const cf* __restrict__ twC, const cf* __restrict__ twQ,
                                                 double* __restrict__ sumsq, int work_bytes) {
@@ -355,14 +372,17 @@ __global__ void __launch_bounds__(T, 3) k_row2_fwd(int R, int C, int P, const __
   RowSmem2 sm{reinterpret_cast<ulonglong2*>(g_dyn_smem)};
   char* stage = reinterpret_cast<char*>(g_dyn_smem) + work_bytes;
   const int tid = threadIdx.x;
-  const int npairs = R >> 1;
+  constexpr int kRows = kEO ? 1 : 2;                // rows per iteration
+  constexpr int kTw = kEO ? 4 : 2;                  // W_CH^e = twC[e * kTw]
+  const int npairs = kEO ? R : (R >> 1);
+  const uint32_t row_bytes = 2u * (uint32_t)C * kRows;    // bf16 bytes of one iteration's rows, per tensor
   if (tid == 0) { mbar_init(&full, 1); mbar_fence_init(); }
   __syncthreads();
-  auto prefetch = [&](int pair) {                   // both rows of a pair are contiguous: one bulk copy per tensor
+  auto prefetch = [&](int pair) {                   // the rows of an iteration are contiguous: one bulk copy per tensor
     if (tid == 0 && pair < npairs) {
-      mbar_expect_tx(&full, 8u * (uint32_t)C);
-      bulk_g2s(stage, a.base + (size_t)pair * 2 * C, 4u * (uint32_t)C, &full);
-      bulk_g2s(stage + 4 * (size_t)C, a.ft + (size_t)pair * 2 * C, 4u * (uint32_t)C, &full);
+      mbar_expect_tx(&full, 2u * row_bytes);
+      bulk_g2s(stage, a.base + (size_t)pair * kRows * C, row_bytes, &full);
+      bulk_g2s(stage + row_bytes, a.ft + (size_t)pair * kRows * C, row_bytes, &full);
     }
   };
   prefetch((int)blockIdx.x);
@@ -371,19 +391,25 @@ __global__ void __launch_bounds__(T, 3) k_row2_fwd(int R, int C, int P, const __
   // every twiddle of this thread is the same for all row pairs; the loads are issued ahead of the barrier / wait that
   // precedes their use, so their latency is never exposed (the kernel is latency bound: 3 CTAs of 4 warps per SM)
   const int p2 = tid / R1, q2 = tid - p2 * R1;
-  const int obase2 = q2 + R1 * R2 * p2, tstep2 = R1 * p2 * 2;
+  const int obase2 = q2 + R1 * R2 * p2, tstep2 = R1 * p2 * kTw;
   const int bA = tid, bB = tid == 0 ? S3 / 2 : S3 - tid;
   for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
     pf accp = pf_make(0.f, 0.f);
     {  // stage 1: delta + radix R1 (s = 1), first-stage quad twiddles (formed while the bulk copy lands)
       float wr[R1], wi[R1];
-      quad_twiddles<R1>(twQ, tid, wr, wi);
+      quad_twiddles<R1>(twQ, tid, wr, wi, kEO ? 2 : 1);
       mbar_wait(&full, phase); phase ^= 1u;
-      RowDeltaStaged2 src{reinterpret_cast<const uint32_t*>(stage), reinterpret_cast<const uint32_t*>(stage + 4 * (size_t)C), C / 2, &accp};
       pf re[R1], im[R1];
       constexpr int Nr = CH / R1;
+      if constexpr (kEO) {
+        RowDeltaStagedEO src{reinterpret_cast<const uint2*>(stage), reinterpret_cast<const uint2*>(stage + row_bytes), &accp};
 #pragma unroll
-      for (int j = 0; j < R1; ++j) src.load(tid + j * Nr, re[j], im[j]);
+        for (int j = 0; j < R1; ++j) src.load(tid + j * Nr, re[j], im[j]);
+      } else {
+        RowDeltaStaged2 src{reinterpret_cast<const uint32_t*>(stage), reinterpret_cast<const uint32_t*>(stage + row_bytes), C / 2, &accp};
+#pragma unroll
+        for (int j = 0; j < R1; ++j) src.load(tid + j * Nr, re[j], im[j]);
+      }
       Dft<R1>::run(re, im);
       sm.store(R1 * tid, re[0], im[0]);
 #pragma unroll
@@ -414,7 +440,31 @@ __global__ void __launch_bounds__(T, 3) k_row2_fwd(int R, int C, int P, const __
       }
     }
     __syncthreads();
-    {  // stage 3 (last, no twiddles) on the butterflies t and S3 - t (thread 0: 0 and S3 / 2) + untangle
+    if constexpr (kEO) {  // stage 3 on the butterflies t and S3 - t, then radix-2 combine + untangle (as in k_row1_fwd_eo)
+      pf ar[R3], ai[R3], br[R3], bi[R3];
+#pragma unroll
+      for (int j = 0; j < R3; ++j) { sm.load(bA + j * S3, ar[j], ai[j]); sm.load(bB + j * S3, br[j], bi[j]); }
+      __syncthreads();                              // the buffer has been read: the next row's stage 1 may overwrite it
+      Dft<R3>::run(ar, ai);
+      Dft<R3>::run(br, bi);
+      float* re0 = a.re + (size_t)pair * P;
+      float* im0 = a.im + (size_t)pair * P;
+      if (tid != 0) {
+#pragma unroll
+        for (int k = 0; k < R3; ++k) combine_untangle4(ar[k], ai[k], br[R3 - 1 - k], bi[R3 - 1 - k], twC, re0, im0, bA + S3 * k, CH);
+      } else {
+        {  // n = 0: Z[0] = E0 + O0 -> X[0], X[Ch]; Z[CH] = E0 - O0 pairs with itself -> X[CH]
+          const float e0r = pf_lo(ar[0]), e0i = pf_lo(ai[0]), o0r = pf_hi(ar[0]), o0i = pf_hi(ai[0]);
+          const float zr = e0r + o0r, zi = e0i + o0i;
+          re0[0] = zr + zi; im0[0] = 0.f; re0[2 * CH] = zr - zi; im0[2 * CH] = 0.f;
+          untangle_pair1(e0r - o0r, e0i - o0i, e0r - o0r, e0i - o0i, ldg_cf(twC + CH), re0, im0, CH, CH);
+        }
+#pragma unroll
+        for (int k = 1; k <= R3 / 2; ++k) combine_untangle4(ar[k], ai[k], ar[R3 - k], ai[R3 - k], twC, re0, im0, S3 * k, CH);
+#pragma unroll
+        for (int k = 0; k < R3 / 2; ++k) combine_untangle4(br[k], bi[k], br[R3 - 1 - k], bi[R3 - 1 - k], twC, re0, im0, S3 / 2 + S3 * k, CH);
+      }
+    } else {  // stage 3 (last, no twiddles) on the butterflies t and S3 - t (thread 0: 0 and S3 / 2) + untangle
       cf w[R3];
 #pragma unroll
       for (int k = 0; k < R3; ++k) w[k] = ldg_cf(twC + (tid != 0 ? bA + S3 * k : (k <= R3 / 2 ? S3 * k : S3 / 2 + S3 * (k - R3 / 2 - 1))));
@@ -850,46 +900,79 @@ __device__ __forceinline__ void epilogue_store2(const RowInvArgs& a, float scale
   }
 }
 
-template <int R1, int R2, int R3, int T>
+// kEO: the lanes are the even / odd halves of ONE row (decimation in frequency on the engine's input, see k_row1_inv_eo)
+__device__ __forceinline__ void epilogue_store_eo(const RowInvArgs& a, float scale, uint2 bb, uint2* out64, float4* of, int m, pf va, pf vb);
+struct RowTangleStagedEO {       // staged spectrum row (re, im), H = Ch / 2
+  const float* re; const float* im; const cf* twC; int H;
+  __device__ __forceinline__ void tangle(int k, float& ore, float& oim) const {
+    float xr = re[k], xi = im[k], mr = re[2 * H - k], mi = im[2 * H - k];
+    if (k == 0) { xi = 0.f; mi = 0.f; }
+    const float Ar = xr + mr, Ai = xi - mi, Br = xr - mr, Bi = xi + mi;
+    const cf w = ldg_cf(twC + k);
+    const float br = Br * w.x + Bi * w.y, bi = Bi * w.x - Br * w.y;
+    ore = Ai + br; oim = Ar - bi;
+  }
+  __device__ __forceinline__ void load(int n, pf& ore, pf& oim) const {
+    float u1r, u1i, u2r, u2i;
+    tangle(n, u1r, u1i);
+    tangle(n + H, u2r, u2i);
+    float dr = u1r - u2r, di = u1i - u2i;
+    const cf w = ldg_cf(twC + 2 * n);                                     // W_Ch^n
+    cmul(dr, di, w.x, w.y);
+    ore = pf_make(u1r + u2r, dr); oim = pf_make(u1i + u2i, di);
+  }
+};
+
+template <int R1, int R2, int R3, int T, bool kEO>
 __global__ void __launch_bounds__(T, 3) k_row2_inv(int R, int C, int P, const __grid_constant__ RowInvArgs a,
                                                    const cf* __restrict__ twC, const cf* __restrict__ twQ, int work_bytes) {
   constexpr int CH = R1 * R2 * R3;
   constexpr int S3 = CH / R3;
+  constexpr int kRows = kEO ? 1 : 2;
+  constexpr int kTw = kEO ? 4 : 2;
   static_assert(CH / R1 == T && CH / R2 == T && S3 == 2 * T, "k_row2_inv: one butterfly per thread in stages 1-2, two in stage 3");
   __shared__ uint64_t full;
   RowSmem2 sm{reinterpret_cast<ulonglong2*>(g_dyn_smem)};
   char* st_re = reinterpret_cast<char*>(g_dyn_smem) + work_bytes;
-  char* st_im = st_re + 8 * (size_t)P;
+  const uint32_t plane_bytes = 4u * (uint32_t)P * kRows;
+  char* st_im = st_re + plane_bytes;
   const int tid = threadIdx.x;
-  const int npairs = R >> 1;
+  const int npairs = kEO ? R : (R >> 1);
   if (tid == 0) { mbar_init(&full, 1); mbar_fence_init(); }
   __syncthreads();
   const float* im_plane = (a.sel != nullptr && *a.sel != 0) ? a.im_alt : a.im;
-  auto prefetch = [&](int pair) {                   // both rows of a pair are contiguous in each plane
+  auto prefetch = [&](int pair) {                   // the rows of an iteration are contiguous in each plane
     if (tid == 0 && pair < npairs) {
-      mbar_expect_tx(&full, 16u * (uint32_t)P);
-      bulk_g2s(st_re, a.re + (size_t)pair * 2 * P, 8u * (uint32_t)P, &full);
-      bulk_g2s(st_im, im_plane + (size_t)pair * 2 * P, 8u * (uint32_t)P, &full);
+      mbar_expect_tx(&full, 2u * plane_bytes);
+      bulk_g2s(st_re, a.re + (size_t)pair * kRows * P, plane_bytes, &full);
+      bulk_g2s(st_im, im_plane + (size_t)pair * kRows * P, plane_bytes, &full);
     }
   };
   prefetch((int)blockIdx.x);
   const float scale = a.scale_ptr ? *a.scale_ptr : a.scale_host;
   uint32_t phase = 0;
   const int p2 = tid / R1, q2 = tid - p2 * R1;
-  const int obase2 = q2 + R1 * R2 * p2, tstep2 = R1 * p2 * 2;
+  const int obase2 = q2 + R1 * R2 * p2, tstep2 = R1 * p2 * kTw;
   for (int pair = blockIdx.x; pair < npairs; pair += gridDim.x) {
     {  // stage 1: tangle + radix R1 (s = 1), first-stage quad twiddles; all twiddles fetched while the bulk copy lands
       float wr[R1], wi[R1];
-      quad_twiddles<R1>(twQ, tid, wr, wi);
+      quad_twiddles<R1>(twQ, tid, wr, wi, kEO ? 2 : 1);
       constexpr int Nr = CH / R1;
-      cf wt[R1];
-#pragma unroll
-      for (int j = 0; j < R1; ++j) wt[j] = ldg_cf(twC + tid + j * Nr);
-      mbar_wait(&full, phase); phase ^= 1u;
-      RowTangleStaged2 src{reinterpret_cast<const float*>(st_re), reinterpret_cast<const float*>(st_im), P, CH};
       pf re[R1], im[R1];
+      if constexpr (kEO) {
+        mbar_wait(&full, phase); phase ^= 1u;
+        RowTangleStagedEO src{reinterpret_cast<const float*>(st_re), reinterpret_cast<const float*>(st_im), twC, CH};
 #pragma unroll
-      for (int j = 0; j < R1; ++j) src.load(tid + j * Nr, wt[j], re[j], im[j]);
+        for (int j = 0; j < R1; ++j) src.load(tid + j * Nr, re[j], im[j]);
+      } else {
+        cf wt[R1];
+#pragma unroll
+        for (int j = 0; j < R1; ++j) wt[j] = ldg_cf(twC + tid + j * Nr);
+        mbar_wait(&full, phase); phase ^= 1u;
+        RowTangleStaged2 src{reinterpret_cast<const float*>(st_re), reinterpret_cast<const float*>(st_im), P, CH};
+#pragma unroll
+        for (int j = 0; j < R1; ++j) src.load(tid + j * Nr, wt[j], re[j], im[j]);
+      }
       Dft<R1>::run(re, im);
       sm.store(R1 * tid, re[0], im[0]);
 #pragma unroll
@@ -920,7 +1003,25 @@ __global__ void __launch_bounds__(T, 3) k_row2_inv(int R, int C, int P, const __
       }
     }
     __syncthreads();
-    {  // stage 3 (last): butterflies t and t + T, outputs straight into the epilogue
+    if constexpr (kEO) {  // stage 3 (last): lane 0 / 1 of output m are the complex elements 2m / 2m + 1 of the row
+      const uint2* base64 = reinterpret_cast<const uint2*>(a.base + (size_t)pair * C);
+      uint2* out64 = a.out_mode == 0 ? reinterpret_cast<uint2*>(a.out_bf16 + (size_t)pair * C) : nullptr;
+      float4* of = a.out_mode != 0 ? reinterpret_cast<float4*>(a.out_f32 + (size_t)pair * C) : nullptr;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int b = tid + h * T;
+        uint2 bb[R3];
+#pragma unroll
+        for (int k = 0; k < R3; ++k) bb[k] = a.out_mode == 0 ? __ldg(base64 + b + k * S3) : make_uint2(0u, 0u);
+        pf re[R3], im[R3];
+#pragma unroll
+        for (int j = 0; j < R3; ++j) sm.load(b + j * S3, re[j], im[j]);
+        if (h == 1) __syncthreads();                // the buffer has been read: the next row's stage 1 may overwrite it
+        Dft<R3>::run(re, im);
+#pragma unroll
+        for (int k = 0; k < R3; ++k) epilogue_store_eo(a, scale, bb[k], out64, of, b + k * S3, re[k], im[k]);
+      }
+    } else {  // stage 3 (last): butterflies t and t + T, outputs straight into the epilogue
       const size_t row0 = (size_t)pair * 2;
       const uint32_t* base0 = reinterpret_cast<const uint32_t*>(a.base + row0 * C);
       const uint32_t* base1 = base0 + C / 2;
@@ -1516,12 +1617,12 @@ static int try_row2_fwd(const SmPlan& p, const RowFwdArgs& fa, const cf* twC, co
     const int work_bytes = ((CH + (CH >> 4) + 1) * 16 + 127) / 128 * 128;
     const int smem = work_bytes + 8 * p.C;
     if (smem > 227 * 1024 - 256) return 1;
-    cudaError_t e = opt_in(k_row2_fwd<R1, R2, R3, T>, &done);
-    if (e == cudaSuccess && occ == 0) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_row2_fwd<R1, R2, R3, T>, T, smem);
+    cudaError_t e = opt_in(k_row2_fwd<R1, R2, R3, T, false>, &done);
+    if (e == cudaSuccess && occ == 0) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_row2_fwd<R1, R2, R3, T, false>, T, smem);
     if (e != cudaSuccess) { sm_set_error("row2 setup: %s", cudaGetErrorString(e)); return -100; }
     int grid = num_sms() * (occ > 0 ? occ : 1);
     if (grid > p.R / 2) grid = p.R / 2;
-    k_row2_fwd<R1, R2, R3, T><<<grid, T, smem, st>>>(p.R, p.C, p.P, fa, twC, twQ, sumsq, work_bytes);
+    k_row2_fwd<R1, R2, R3, T, false><<<grid, T, smem, st>>>(p.R, p.C, p.P, fa, twC, twQ, sumsq, work_bytes);
     SM_LAUNCH_CHECK();
     return 0;
   } else {
@@ -1588,7 +1689,27 @@ static int launch_row1_fwd_eo(const SmPlan& p, const RowFwdArgs& fa, const cf* t
   return 0;
 }
 
+// three-stage bulk-copy fed kernel with the lanes = even / odd halves of one row (k_row2_fwd<..., kEO = true>): Ch = 2 * R1*R2*R3
+template <int R1, int R2, int R3, int T>
+static int launch_row1_fwd_eo3(const SmPlan& p, const RowFwdArgs& fa, const cf* twC, const cf* twQ, double* sumsq, cudaStream_t st) {
+  constexpr int CH = R1 * R2 * R3;
+  if (!use_row_pairs() || fa.mode != 0 || p.R < 2 || p.C % 8 != 0 || p.Ch != 2 * CH) return 1;
+  static bool done = false;
+  static int occ = 0;
+  const int work_bytes = ((CH + (CH >> 4) + 1) * 16 + 127) / 128 * 128;
+  const int smem = work_bytes + 4 * p.C;
+  cudaError_t e = opt_in(k_row2_fwd<R1, R2, R3, T, true>, &done);
+  if (e == cudaSuccess && occ == 0) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_row2_fwd<R1, R2, R3, T, true>, T, smem);
+  if (e != cudaSuccess) { sm_set_error("row1 fwd eo3 setup: %s", cudaGetErrorString(e)); return -100; }
+  int grid = num_sms() * (occ > 0 ? occ : 1);
+  if (grid > p.R) grid = p.R;
+  k_row2_fwd<R1, R2, R3, T, true><<<grid, T, smem, st>>>(p.R, p.C, p.P, fa, twC, twQ, sumsq, work_bytes);
+  SM_LAUNCH_CHECK();
+  return 0;
+}
+
 static int try_row2_fwd4(const SmPlan& p, const RowFwdArgs& fa, const cf* twC, const cf* twQ, double* sumsq, cudaStream_t st) {
+  if (p.Ch == 4096 && use_row_eo()) return launch_row1_fwd_eo3<16, 16, 8, 128>(p, fa, twC, twQ, sumsq, st);
   if (p.Ch == 14336) return launch_row1_fwd_eo<7, 16, 8, 8, 448, 1>(p, fa, twC, twQ, sumsq, st);
   if (p.Ch == 7168 && use_row_eo()) return launch_row1_fwd_eo<7, 8, 8, 8, 224, 2>(p, fa, twC, twQ, sumsq, st);
   if (p.Ch == 7168) return launch_row2_fwd4<7, 16, 8, 8, 448, false, 1>(p, fa, twC, twQ, sumsq, st);
@@ -1610,7 +1731,26 @@ static int launch_row1_inv_eo(const SmPlan& p, const RowInvArgs& ia, const cf* t
   return 0;
 }
 
+template <int R1, int R2, int R3, int T>
+static int launch_row1_inv_eo3(const SmPlan& p, const RowInvArgs& ia, const cf* twC, const cf* twQ, cudaStream_t st) {
+  constexpr int CH = R1 * R2 * R3;
+  if (!use_row_pairs() || ia.cull_thr != nullptr || p.R < 2 || p.C % 8 != 0 || p.P % 4 != 0 || p.Ch != 2 * CH) return 1;
+  static bool done = false;
+  static int occ = 0;
+  const int work_bytes = ((CH + (CH >> 4) + 1) * 16 + 127) / 128 * 128;
+  const int smem = work_bytes + 8 * p.P;
+  cudaError_t e = opt_in(k_row2_inv<R1, R2, R3, T, true>, &done);
+  if (e == cudaSuccess && occ == 0) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_row2_inv<R1, R2, R3, T, true>, T, smem);
+  if (e != cudaSuccess) { sm_set_error("row1 inv eo3 setup: %s", cudaGetErrorString(e)); return -100; }
+  int grid = num_sms() * (occ > 0 ? occ : 1);
+  if (grid > p.R) grid = p.R;
+  k_row2_inv<R1, R2, R3, T, true><<<grid, T, smem, st>>>(p.R, p.C, p.P, ia, twC, twQ, work_bytes);
+  SM_LAUNCH_CHECK();
+  return 0;
+}
+
 static int try_row2_inv4(const SmPlan& p, const RowInvArgs& ia, const cf* twC, const cf* twQ, cudaStream_t st) {
+  if (p.Ch == 4096 && use_row_eo()) return launch_row1_inv_eo3<16, 16, 8, 128>(p, ia, twC, twQ, st);
   if (p.Ch == 14336) return launch_row1_inv_eo<7, 16, 8, 8, 448, 1>(p, ia, twC, twQ, st);
   if (p.Ch == 7168 && use_row_eo()) return launch_row1_inv_eo<7, 8, 8, 8, 224, 2>(p, ia, twC, twQ, st);
   if (p.Ch == 7168) return launch_row2_inv4<7, 16, 8, 8, 448, false, 1>(p, ia, twC, twQ, st);
@@ -1629,12 +1769,12 @@ static int try_row2_inv(const SmPlan& p, const RowInvArgs& ia, const cf* twC, co
     const int work_bytes = ((CH + (CH >> 4) + 1) * 16 + 127) / 128 * 128;
     const int smem = work_bytes + 16 * p.P;
     if (smem > 227 * 1024 - 256) return 1;
-    cudaError_t e = opt_in(k_row2_inv<R1, R2, R3, T>, &done);
-    if (e == cudaSuccess && occ == 0) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_row2_inv<R1, R2, R3, T>, T, smem);
+    cudaError_t e = opt_in(k_row2_inv<R1, R2, R3, T, false>, &done);
+    if (e == cudaSuccess && occ == 0) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_row2_inv<R1, R2, R3, T, false>, T, smem);
     if (e != cudaSuccess) { sm_set_error("row2 inv setup: %s", cudaGetErrorString(e)); return -100; }
     int grid = num_sms() * (occ > 0 ? occ : 1);
     if (grid > p.R / 2) grid = p.R / 2;
-    k_row2_inv<R1, R2, R3, T><<<grid, T, smem, st>>>(p.R, p.C, p.P, ia, twC, twQ, work_bytes);
+    k_row2_inv<R1, R2, R3, T, false><<<grid, T, smem, st>>>(p.R, p.C, p.P, ia, twC, twQ, work_bytes);
     SM_LAUNCH_CHECK();
     return 0;
   } else {
