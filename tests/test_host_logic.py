@@ -203,20 +203,29 @@ WORKER = textwrap.dedent("""
                       output_dir=sys.argv[2])
     m = CpuStandIn(cfg, index_manager=InMemoryIndex(models))
     mine = asyncio.run(schedule.merge_distributed(m, "cpu", dist.get_rank(), 2, barrier=dist.barrier))
-    print("RANK", dist.get_rank(), "SHARDS", ",".join(mine))
+    print("RANK", dist.get_rank(), "SHARDS", ",".join(mine), flush=True)
+    dist.barrier()                                # nobody tears the store down while the other rank still talks to it
     dist.destroy_process_group()
 """)
 
 
 def test_merge_distributed_world2_gloo(tmp_path):
     from safetensors import safe_open
-    port = 29500 + (os.getpid() % 2000)
+    import shutil
+    import socket
     script = tmp_path / "worker.py"
-    script.write_text(WORKER % dict(root=str(ROOT), port=port))
     out = tmp_path / "out"
-    procs = [subprocess.Popen([sys.executable, str(script), str(r), str(out)], stdout=subprocess.PIPE,
-                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
-    logs = [p.communicate(timeout=180)[0] for p in procs]
+    for attempt in range(3):                      # a rendezvous port can be taken between the probe and the bind: retry
+        with socket.socket() as sk:
+            sk.bind(("127.0.0.1", 0))
+            port = sk.getsockname()[1]
+        script.write_text(WORKER % dict(root=str(ROOT), port=port))
+        shutil.rmtree(out, ignore_errors=True)
+        procs = [subprocess.Popen([sys.executable, str(script), str(r), str(out)], stdout=subprocess.PIPE,
+                                  stderr=subprocess.STDOUT, text=True) for r in range(2)]
+        logs = [p.communicate(timeout=180)[0] for p in procs]
+        if all(p.returncode == 0 for p in procs):
+            break
     assert all(p.returncode == 0 for p in procs), logs
     owned = [set(l.split("SHARDS")[1].strip().split(",")) for l in logs]
     assert owned[0] and owned[1] and not (owned[0] & owned[1])
