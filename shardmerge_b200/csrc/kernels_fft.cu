@@ -1714,6 +1714,9 @@ static int try_row2_fwd4(const SmPlan& p, const RowFwdArgs& fa, const cf* twC, c
   if (p.Ch == 7168 && use_row_eo()) return launch_row1_fwd_eo<7, 8, 8, 8, 224, 2>(p, fa, twC, twQ, sumsq, st);
   if (p.Ch == 7168) return launch_row2_fwd4<7, 16, 8, 8, 448, false, 1>(p, fa, twC, twQ, sumsq, st);
   if (p.Ch == 4096) return launch_row2_fwd4<8, 8, 8, 8, 256, true, 2>(p, fa, twC, twQ, sumsq, st);
+  // TinyLlama shapes: C = 2048 as row pairs 8 x 8 x 4 x 4, C = 5632 as even / odd halves of 11 x 8 x 4 x 4
+  if (p.Ch == 1024) return launch_row2_fwd4<8, 8, 4, 4, 128, true, 4>(p, fa, twC, twQ, sumsq, st);
+  if (p.Ch == 2816) return launch_row1_fwd_eo<11, 8, 4, 4, 176, 2>(p, fa, twC, twQ, sumsq, st);
   return 1;
 }
 template <int R1, int R2, int R3, int R4, int T, int kCtas>
@@ -1755,6 +1758,8 @@ static int try_row2_inv4(const SmPlan& p, const RowInvArgs& ia, const cf* twC, c
   if (p.Ch == 7168 && use_row_eo()) return launch_row1_inv_eo<7, 8, 8, 8, 224, 2>(p, ia, twC, twQ, st);
   if (p.Ch == 7168) return launch_row2_inv4<7, 16, 8, 8, 448, false, 1>(p, ia, twC, twQ, st);
   if (p.Ch == 4096) return launch_row2_inv4<8, 8, 8, 8, 256, true, 2>(p, ia, twC, twQ, st);
+  if (p.Ch == 1024) return launch_row2_inv4<8, 8, 4, 4, 128, true, 4>(p, ia, twC, twQ, st);
+  if (p.Ch == 2816) return launch_row1_inv_eo<11, 8, 4, 4, 176, 2>(p, ia, twC, twQ, st);
   return 1;
 }
 

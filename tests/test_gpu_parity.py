@@ -105,7 +105,7 @@ def test_forward_bf16_delta(E):
 
 
 @pytest.mark.parametrize("shape", [(2, 4096), (6, 4096), (5, 4096), (2, 8192), (6, 8192), (7, 8192), (2, 14336), (3, 14336),
-                                   (2, 28672), (5, 28672), (130, 4096), (150, 14336)])
+                                   (2, 28672), (5, 28672), (130, 4096), (150, 14336), (2, 2048), (260, 2048), (3, 5632), (6, 5632), (200, 5632)])
 def test_paired_row_kernels_edge_row_counts(E, shape):
     """Every family of the packed-f32x2 row kernels (row pairs at C = 4096 / 8192, even / odd halves at C = 14336 /
     28672) at the smallest and at odd row counts (odd R falls back to the one-row kernels where pairs are needed):
@@ -338,7 +338,7 @@ def test_inverse_epilogue_bf16_within_1ulp(E, shape):
     assert [int(v) for v in flags] == [0, 0, 0, 0]
 
 
-@pytest.mark.parametrize("shape", [(8, 64), (4, 4096), (4, 8192), (4, 14336), (3, 28672)])
+@pytest.mark.parametrize("shape", [(8, 64), (4, 4096), (4, 8192), (4, 14336), (3, 28672), (4, 2048), (3, 5632)])
 def test_epilogue_nan_inf_policy(E, shape):
     """NaN -> 0 (counted), Inf kept (counted) after the base add (fast_fourier.py:270-274), in every epilogue variant
     (one-row, row pairs, even / odd halves)."""
