@@ -325,7 +325,7 @@ def main():
         tj = json.loads(tpath.read_text())
         traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
         traffic_note = dict(launch=tj["kernel"], algorithmic_bytes_of_that_launch=tj["algorithmic_bytes"], source=tj["source"])
-    roofline = dict(bound="hbm", kernel="k_col_p / k_col_ct (column FFT sweeps, forward+inverse)", achieved=achieved, peak=peak,
+    roofline = dict(bound="hbm", kernel="k_col_p3 / k_col_p (column FFT sweeps, forward+inverse)", achieved=achieved, peak=peak,
                     unit="GB/s", frac=(achieved / peak if achieved else None), traffic=traffic, traffic_note=traffic_note,
                     peak_source=peak_src,
                     bytes_per_launch=(col_bytes / col_launch if col_launch else None),

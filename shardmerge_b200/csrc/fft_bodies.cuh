@@ -508,6 +508,72 @@ SM_HD void col_ct_body_p(Exec& ex, int tile, int inst, const ColCtArgs a, const 
   }
 }
 
+// three register stages (radices <= 8) with the middle one in place: the two-stage sweeps of the long instances (L = 112 /
+// 128) need a radix-16 butterfly of packed values, 80 registers, 6 CTAs per SM; radices <= 8 need ~56 (the L = 64 sweeps
+// run at 6.0 TB/s with 9-10 CTAs per SM against 4.8 TB/s, profiles/r01).  L = R1*R2*R3, L / R1 <= 2 NW and L / R2 <= 2 NW.
+template <int R1, int R2, int R3, int NW, bool kInverse, bool kBigTw, class Exec>
+SM_HD void col_ct_body_p3(Exec& ex, int tile, int inst, const ColCtArgs a, const cf* twR, pf4* smem) {
+  constexpr int L = R1 * R2 * R3;
+  constexpr int NS = 2 * NW;
+  static_assert(L / R2 <= NS, "col_ct_body_p3: at most one middle-stage butterfly per slot (it runs in place)");
+  const int col0 = tile * SM_COL_TILE;
+  pf re2[R2], im2[R2];
+  SM_FOR_THREADS(ex, tid) {
+    const int lane = tid & 15, slot = tid >> 4;
+    const int c = col0 + 2 * lane;
+    const bool valid = (c <= a.Ch);
+    const size_t row0 = (size_t)inst * a.inst_mul * a.P + c;
+    const size_t estride = (size_t)a.elem_mul * a.P;
+    const float thr = (kInverse && a.thr_ptr) ? *a.thr_ptr : 0.f;
+    float* const p0 = (a.sel != nullptr && *a.sel != 0) ? a.p0_alt : a.p0;
+    ColCtSrcP<kInverse> gsrc{p0, a.p1, row0, estride, valid, thr};
+    ColSmemP sm{smem, lane};
+#pragma unroll
+    for (int b = slot; b < L / R1; b += NS) stockham_bfly<R1, false, pf>(b, L, 1, a.tw_mul, twR, gsrc, sm);
+  }
+  ex.sync();
+  SM_FOR_THREADS(ex, tid) {
+    const int lane = tid & 15, slot = tid >> 4;
+    ColSmemP sm{smem, lane};
+    if (slot < L / R2) {
+#pragma unroll
+      for (int j = 0; j < R2; ++j) sm.load(slot + j * (L / R2), re2[j], im2[j]);
+    }
+  }
+  ex.sync();
+  SM_FOR_THREADS(ex, tid) {
+    const int lane = tid & 15, slot = tid >> 4;
+    ColSmemP sm{smem, lane};
+    if (slot < L / R2) {
+      Dft<R2>::run(re2, im2);
+      const int p = slot / R1, q = slot - p * R1;
+      const int obase = q + R1 * R2 * p, tstep = R1 * p * a.tw_mul;
+      sm.store(obase, re2[0], im2[0]);
+#pragma unroll
+      for (int k = 1; k < R2; ++k) {
+        const cf w = ldg_cf(twR + tstep * k);
+        pf xr = re2[k], xi = im2[k];
+        cmul(xr, xi, w.x, w.y);
+        sm.store(obase + k * R1, xr, xi);
+      }
+    }
+  }
+  ex.sync();
+  SM_FOR_THREADS(ex, tid) {
+    const int lane = tid & 15, slot = tid >> 4;
+    const int c = col0 + 2 * lane;
+    const bool valid = (c <= a.Ch);
+    const size_t row0 = (size_t)inst * a.inst_mul * a.P + c;
+    const size_t estride = (size_t)a.elem_mul * a.P;
+    const float scale = a.scale_ptr ? *a.scale_ptr : a.scale;
+    float* const p0 = (a.sel != nullptr && *a.sel != 0) ? a.p0_alt : a.p0;
+    ColCtDstP<kBigTw> gdst{p0, a.p1, row0, estride, valid, twR, inst, scale, kInverse ? true : (a.write_p1_fwd != 0)};
+    ColSmemP sm{smem, lane};
+#pragma unroll
+    for (int b = slot; b < L / R3; b += NS) stockham_bfly<R3, true, pf>(b, L, R1 * R2, a.tw_mul, twR, sm, gdst);
+  }
+}
+
 }  // namespace smfft
 
 namespace smfft {

@@ -80,6 +80,12 @@ __global__ void __launch_bounds__(NW * 32) k_col_p(const __grid_constant__ ColCt
   col_ct_body_p<R1, R2, NW, kInverse, kBigTw>(ex, (int)blockIdx.x, (int)blockIdx.y, a, twR, reinterpret_cast<pf4*>(g_dyn_smem));
 }
 
+template <int R1, int R2, int R3, int NW, bool kInverse, bool kBigTw>
+__global__ void __launch_bounds__(NW * 32) k_col_p3(const __grid_constant__ ColCtArgs a, const cf* __restrict__ twR) {
+  DeviceExec ex;
+  col_ct_body_p3<R1, R2, R3, NW, kInverse, kBigTw>(ex, (int)blockIdx.x, (int)blockIdx.y, a, twR, reinterpret_cast<pf4*>(g_dyn_smem));
+}
+
 // ---- both column sweeps of a four-step transform in ONE launch, the second one fed from L2 ----------------
 // A separate launch per sweep streams the whole spectrum through DRAM twice (16N bytes per transform).  Here the
 // CTAs of both sweeps share one 1-D grid, ordered so that the second-sweep CTAs of column tile t are dispatched
@@ -1493,6 +1499,24 @@ static int launch_col_p(bool inverse, bool big_tw, dim3 grid, const ColCtArgs& a
   return 0;
 }
 
+template <int R1, int R2, int R3, int NW>
+static int launch_col_p3(bool inverse, bool big_tw, dim3 grid, const ColCtArgs& a, const cf* twR, cudaStream_t st) {
+  static bool done[4] = {false, false, false, false};
+  const int smem = R1 * R2 * R3 * SM_COL_TILE * 8;
+  cudaError_t e;
+#define SM_COLP3_CASE(INV, BIG, IDX)                                                      \
+  e = opt_in(k_col_p3<R1, R2, R3, NW, INV, BIG>, &done[IDX]);                             \
+  if (e != cudaSuccess) { sm_set_error("opt_in: %s", cudaGetErrorString(e)); return -100; } \
+  k_col_p3<R1, R2, R3, NW, INV, BIG><<<grid, NW * 32, smem, st>>>(a, twR);
+  if (!inverse && big_tw) { SM_COLP3_CASE(false, true, 0) }
+  else if (!inverse) { SM_COLP3_CASE(false, false, 1) }
+  else if (big_tw) { SM_COLP3_CASE(true, true, 2) }
+  else { SM_COLP3_CASE(true, false, 3) }
+#undef SM_COLP3_CASE
+  SM_LAUNCH_CHECK();
+  return 0;
+}
+
 static bool use_col_pairs() {       // SM_COL_PAIRS=0: one column per thread (k_col_ct), for A-B timing
   static int v = -1;
   if (v < 0) { const char* e = getenv("SM_COL_PAIRS"); v = (e && e[0] == '0') ? 0 : 1; }
@@ -1504,6 +1528,14 @@ static int try_col_p(int n_rad, const int* rad, bool inverse, bool big_tw, dim3 
   if (n_rad != 2 || !use_col_pairs()) return 1;
   const int r1 = rad[0], r2 = rad[1];
   if (r1 == 8 && r2 == 8) return launch_col_p<8, 8, 4>(inverse, big_tw, grid, a, twR, st);
+  // the long instances as three stages of radices <= 8 (~52 registers instead of 80: 32 resident warps per SM instead
+  // of 24; measured col_fwd -6 %, col_inv -4 %); a Stockham transform is natural order in / out whatever its radices,
+  // so the plan's (16, 8) / (7, 16) split may be re-factored (L = 256 as 8 x 8 x 4 with 512-thread CTAs measured 1 % slower
+  // than its two-stage kernel and is not used).  SM_COL3=0: the two-stage kernels (A-B timing).
+  static int col3 = -1;
+  if (col3 < 0) { const char* e = getenv("SM_COL3"); col3 = (e && e[0] == '0') ? 0 : 1; }
+  if (col3 && r1 == 16 && r2 == 8) return launch_col_p3<8, 8, 2, 8>(inverse, big_tw, grid, a, twR, st);
+  if (col3 && r1 == 7 && r2 == 16) return launch_col_p3<7, 8, 2, 8>(inverse, big_tw, grid, a, twR, st);
   if (r1 == 16 && r2 == 8) return launch_col_p<16, 8, 4>(inverse, big_tw, grid, a, twR, st);
   if (r1 == 16 && r2 == 16) return launch_col_p<16, 16, 8>(inverse, big_tw, grid, a, twR, st);
   if (r1 == 7 && r2 == 16) return launch_col_p<7, 16, 4>(inverse, big_tw, grid, a, twR, st);

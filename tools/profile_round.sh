@@ -4,14 +4,10 @@ mkdir -p gpurun_out
 python bench.py --layers 1 --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/bench_1layer.json 2> gpurun_out/bench_1layer.err || exit 1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/ncu_launches_bench_1layer.csv python bench.py --layers 1 --steps 1 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/ncu_bench.log 2>&1
 python tools/profile_one.py 14336 4096 2 > gpurun_out/plain_one.log 2>&1 || exit 1
-for spec in "k_row2_fwd:row2_fwd" "k_row2_inv:row2_inv" "k_fs_pass:fs_pass"; do
+for spec in "k_col_p3:col_p3" "k_row2_inv:row2_inv"; do
   re=${spec%%:*}; nm=${spec##*:}
   ncu --set full --clock-control none --import-source on -k regex:$re -s 1 -c 2 -o gpurun_out/ncu_full_$nm -f python tools/profile_one.py 14336 4096 2 > gpurun_out/ncu_full_$nm.log 2>&1
   ncu -i gpurun_out/ncu_full_$nm.ncu-rep --page raw --csv > gpurun_out/ncu_full_${nm}_raw.csv 2>/dev/null
   rm -f gpurun_out/ncu_full_$nm.ncu-rep          # gpurun_out/ is limited to 64 MiB; the CSV export is what profiles/ keeps
 done
-python tools/profile_one.py 4096 14336 2 > gpurun_out/plain_one2.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"k_row1_(fwd|inv)_eo" -s 1 -c 2 -o gpurun_out/ncu_full_rows7 -f python tools/profile_one.py 4096 14336 2 > gpurun_out/ncu_full_rows7.log 2>&1
-ncu -i gpurun_out/ncu_full_rows7.ncu-rep --page raw --csv > gpurun_out/ncu_full_rows7_raw.csv 2>/dev/null
-rm -f gpurun_out/ncu_full_rows7.ncu-rep
 ls -la gpurun_out/*.csv
