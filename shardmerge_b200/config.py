@@ -7,6 +7,7 @@ from dataclasses import dataclass, fields
 from pathlib import Path
 from typing import List
 
+import click
 import torch
 import yaml
 
@@ -85,8 +86,8 @@ class MergeConfig:
             raw = yaml.safe_load(fh)
         missing = [k for k in _REQUIRED if k not in raw]
         if missing:
-            raise ValueError(f"Missing required configuration fields: {', '.join(missing)}")
+            raise click.BadParameter(f"Missing required configuration fields: {', '.join(missing)}")   # shard/config.py:110-115
         if not isinstance(raw["finetune_merge"], list):
-            raise ValueError("finetune_merge must be a list of model entries")
+            raise click.BadParameter("finetune_merge must be a list of model URIs")                    # :118-121
         raw["finetune_merge"] = [MergeModel(**entry) for entry in raw["finetune_merge"]]
         return cls(**raw)

@@ -213,6 +213,9 @@ def get_workspace(R: int, C: int, device, n_spectra: int = 2, safe_select: bool 
     key = (dev.index, R, C, safe_select, lane)
     ws = _workspaces.get(key)
     if ws is None or ws.n_spectra < n_spectra:
+        if ws is not None:
+            # the planes being replaced may still be read by kernels enqueued on another stream
+            torch.cuda.synchronize(dev)
         ws = _workspaces[key] = Workspace(get_plan(R, C, dev), n_spectra, safe_select)
     return ws
 
@@ -453,20 +456,29 @@ def spectral_pair(ws: Workspace, slot0: int, slot1: int, *, scale0: float, scale
 # ------------------------------------------------------------------------------------------
 # fused, host-sync-free pair merge (csrc/pipeline.cu)
 # ------------------------------------------------------------------------------------------
-class _PinnedRing:
-    """Pinned landing slots for scalar blocks whose check is deferred."""
+class _PinnedPool:
+    """Pinned landing slots for scalar blocks whose check is deferred.  A slot is handed out by take() and comes
+    back through give() when its PendingPair has been resolved (or dropped); the pool grows by a chunk when every
+    slot is out, so any number of tensors can be in flight before resolve_all()."""
 
-    def __init__(self, slots: int = 1024):
-        self.buf = torch.empty((slots, _CTL_BYTES), dtype=torch.uint8).pin_memory()
-        self.slots, self.next = slots, 0
+    CHUNK = 256
+
+    def __init__(self):
+        self.chunks: list = []
+        self.free: list = []
 
     def take(self) -> torch.Tensor:
-        t = self.buf[self.next]
-        self.next = (self.next + 1) % self.slots
-        return t
+        if not self.free:
+            buf = torch.empty((self.CHUNK, _CTL_BYTES), dtype=torch.uint8).pin_memory()
+            self.chunks.append(buf)
+            self.free.extend(buf[i] for i in range(self.CHUNK))
+        return self.free.pop()
+
+    def give(self, slot: torch.Tensor):
+        self.free.append(slot)
 
 
-_ring: Optional[_PinnedRing] = None
+_ring: Optional[_PinnedPool] = None
 
 
 class PendingPair:
@@ -478,7 +490,19 @@ class PendingPair:
         self.redo = None
         self.info: dict = {}
 
+    def __del__(self):
+        # a handle dropped without resolve(): the copy may still be in flight, wait before the slot is reused
+        if self.host_ctl is not None and _ring is not None:
+            try:
+                self.event.synchronize()
+                _ring.give(self.host_ctl)
+            except Exception:
+                pass
+            self.host_ctl = None
+
     def resolve(self) -> dict:
+        if self.host_ctl is None:
+            return self.info
         self.event.synchronize()
         h = self.host_ctl
         dbl = h[0:64].view(torch.float64); flt = h[64:128].view(torch.float32)
@@ -491,6 +515,8 @@ class PendingPair:
                          swap=int(ints[0]), branch=_lib.BRANCH_NAMES.get(int(ints[1]), "?"),
                          select_sticky=st0 | st1, flags=[int(v) for v in flags],
                          thr_cut=float(flt[0]), thr_cull=float(flt[1]), dot=float(flt[2]))
+        _ring.give(h)
+        self.host_ctl = None
         return self.info
 
 
@@ -518,7 +544,7 @@ def pair_merge_async(ws: Workspace, s0: Source, s1: Source, base_out: torch.Tens
     _lib.check(lib.sm_pair_merge_slerp_async(pl.handle, pl.tables.data_ptr(), ctypes.byref(a), _stream(dev)),
                "sm_pair_merge_slerp_async")
     if _ring is None:
-        _ring = _PinnedRing()
+        _ring = _PinnedPool()
     host = _ring.take()
     host.copy_(ws.ctl, non_blocking=True)
     ev = torch.cuda.Event()

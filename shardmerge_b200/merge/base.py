@@ -68,9 +68,9 @@ class MergeTensorsBase(ABC):
                 raise ValueError(f"Model {m.model} architecture mismatch with base model {self.config.output_base_model}\n"
                                  f"Missing keys: {want - have}\nExtra keys: {have - want}")
 
-    def get_writer(self, layer_order: list) -> ModelWriter:
+    def get_writer(self, layer_order: list, **kwargs) -> ModelWriter:
         return ModelWriter(base_index=self.index_doc, output_path=self.config.output_path, layer_order=layer_order,
-                           output_astype=self.config.output_astype)
+                           output_astype=self.config.output_astype, **kwargs)
 
     async def merge(self, device: str):
         await self.initialize()
@@ -81,6 +81,9 @@ class MergeTensorsBase(ABC):
         try:
             for group in writer.shard_layers():
                 await self._process_layers(writer, [sl for sl in group if not sl.written], device)
+        except BaseException:
+            writer.flush_partial()       # keep what was merged: the next run resumes behind it (shard/writer.py:93-113)
+            raise
         finally:
             self.defer_checks = False
         writer.finalize()
@@ -95,29 +98,34 @@ class MergeTensorsBase(ABC):
     # drains between tensors.  depth 0 = the reference's strictly sequential behaviour.
     pipeline_depth = 0
 
-    def _settle(self, keep: int = 0):
-        """Make every result except the newest `keep` final (override where results are deferred)."""
+    def _finalize(self, tensor: torch.Tensor):
+        """Make `tensor` (a value `_merge_layer` returned) final before it is handed to the writer.  Strategies
+        whose `_merge_layer` only enqueues device work override this: they wait for that tensor's device-side
+        status, redo it on another path if the device asked for that, and raise what the reference would raise."""
 
     def prefetch_layer(self, shard_layer: ShardLayer, device: str):
         """Start the host-to-device copies of the tensors `_merge_layer(shard_layer)` will ask for (override per
         strategy; needs an index manager with `prefetch`, see shardmerge_b200/index.py)."""
 
+    prefetch_depth = 3           # tensors whose uploads may be in flight ahead of the one being merged
+
     async def _process_layers(self, writer: ModelWriter, shard_layers: List[ShardLayer], device: str):
         current = None
         in_flight = []
+        ahead = 0                # shard_layers[:ahead] have had their uploads started
         try:
             for i, current in enumerate(shard_layers):
-                if i == 0:
-                    self.prefetch_layer(current, device)
-                if i + 1 < len(shard_layers):
-                    self.prefetch_layer(shard_layers[i + 1], device)      # its upload overlaps this tensor's kernels
+                while ahead < len(shard_layers) and ahead <= i + self.prefetch_depth:
+                    self.prefetch_layer(shard_layers[ahead], device)       # uploads overlap the kernels of tensors i..
+                    ahead += 1
                 in_flight.append((current, await self._merge_layer(current, device)))
                 while len(in_flight) > self.pipeline_depth:
-                    self._settle(keep=len(in_flight) - 1)
                     done, tensor = in_flight.pop(0)
+                    self._finalize(tensor)
                     writer.add_tensor(done.layer_name, tensor)
-            self._settle(keep=0)
-            for done, tensor in in_flight:
+            while in_flight:
+                done, tensor = in_flight.pop(0)
+                self._finalize(tensor)
                 writer.add_tensor(done.layer_name, tensor)
         except Exception as exc:
             logger.error(f"Error processing {getattr(current, 'layer_name', '?')}: {exc}")

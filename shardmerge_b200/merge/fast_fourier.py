@@ -122,11 +122,17 @@ class FourierMerge(MergeTensorsBase):
             base_out = await fetch(self.config.output_base_model)
         return self.merge_sources(sources, base_out, dev, layer_name=name, defer=self.defer_checks)
 
-    def _settle(self, keep: int = 0):
-        n = max(len(self.pending) - keep, 0)
-        head, self.pending = self.pending[:n], self.pending[n:]
-        for pend in head:
-            self._resolve(pend)
+    def _finalize(self, tensor: torch.Tensor):
+        """Resolve the deferred check of `tensor` (and of every older deferred tensor): wait for its scalar block,
+        redo it step by step if the device chose another branch, raise on Inf.  Pass-through and step-path tensors
+        never enter `self.pending` and are final already.  The handle is found by identity, not by position:
+        `_process_layers` interleaves fused, pass-through and step-path tensors."""
+        for i, pend in enumerate(self.pending):
+            if pend.out is tensor:
+                head, self.pending = self.pending[: i + 1], self.pending[i + 1:]
+                for p in head:
+                    self._resolve(p)
+                return
 
     # -------------------------------------------------------------------------------------
     def merge_sources(self, sources: List[E.Source], base_out: torch.Tensor, dev, layer_name: str = "",
@@ -206,7 +212,9 @@ class FourierMerge(MergeTensorsBase):
             raise IndexError("list index out of range")      # what the reference does with no applicable model
         R, C = E.shape_rc(base_out)
         base_bf16 = base_out if base_out.dtype == torch.bfloat16 else None
-        ws = E.get_workspace(R, C, dev, n_spectra=max(2, len(sources)), safe_select=safe_select)
+        # its own workspace (lane "steps"): a redo or a 1 / 3+ model tensor runs on the caller's stream while fused
+        # chains of the same shape may still be in flight on the lane streams with the lane workspaces
+        ws = E.get_workspace(R, C, dev, n_spectra=max(2, len(sources)), safe_select=safe_select, lane="steps")
         ws.ctl.zero_()
         info = dict(branches=[], layer=layer_name)
         self.last_info = info

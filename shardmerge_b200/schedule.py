@@ -7,8 +7,8 @@ The reference merges tensors in one sequential loop on one device (shard/merge/b
 on the data path.
 
 Two granularities:
-  * tensor_partition  -- longest-processing-time-first over (tensor, numel): the balance bound
-                         for the compute (used by bench.py --workload llama70b, config 3/4).
+  * tensor_partition  -- longest-processing-time-first over (tensor, numel): what `bench.py --gpus N` uses to
+                         split ONE model's tensor list over the ranks (strong scaling, configs 3/4).
   * shard_partition   -- LPT over whole output shards: every rank owns complete safetensors files,
                          so the writer needs no cross-rank assembly (what merge_distributed uses).
 One process per GPU; torch.distributed is used only for rendezvous / barriers.
@@ -72,11 +72,25 @@ async def merge_distributed(merger, device: str, rank: int, world: int, barrier=
     numels = getattr(im, "tensor_numels", lambda m: {n: 1 for n in weight_map})(base)
     n_models = len(merger.config.finetune_merge)
     mine = set(shard_partition(weight_map, numels, world, n_models)[rank])
-    writer = merger.get_writer(layer_order)
-    for group in writer.shard_layers():
-        if not group or group[0].shard_name not in mine:
-            continue
-        await merger._process_layers(writer, [sl for sl in group if not sl.written], device)
+    # rank 0 alone creates the output directory's index copy (tmp file + rename); the others open it afterwards.
+    # Every rank scans and writes only its own shards, so no rank ever opens a file another one is writing.
+    if rank == 0:
+        writer = merger.get_writer(layer_order, only_shards=mine, write_index=True)
+    if barrier is not None:
+        barrier()
+    if rank != 0:
+        writer = merger.get_writer(layer_order, only_shards=mine, write_index=(barrier is None))
+    merger.defer_checks = getattr(merger, "pipeline_depth", 0) > 0
+    try:
+        for group in writer.shard_layers():
+            if not group or group[0].shard_name not in mine:
+                continue
+            await merger._process_layers(writer, [sl for sl in group if not sl.written], device)
+    except BaseException:
+        writer.flush_partial()
+        raise
+    finally:
+        merger.defer_checks = False
     writer.finalize(only_shards=mine)
     if barrier is not None:
         barrier()

@@ -6,23 +6,36 @@ with metadata {"format": "pt"} (:143), tensors cast to output_astype (:133); exi
 scanned at start and their tensors count as written (resume, :93-113); finalize() raises if a
 tensor is missing (:151-161).
 
-What changes is the I/O schedule: the reference re-reads and re-writes the
-whole shard for every tensor (:125-143, O(k^2) bytes per shard).  Here a shard's tensors are
-staged in pinned host buffers by asynchronous device-to-host copies on a side stream -- the
-merge of the next tensor overlaps the copy -- and each shard file is written exactly once, when
-its last tensor has arrived (or at finalize() for shards completed across a resumed run).
+What changes is the I/O schedule.  The reference re-reads and re-writes the
+whole shard for every tensor (:125-143, O(k^2) bytes per shard) and copies device -> host
+synchronously (:133).  Here
+
+  * a tensor is copied device -> pinned host memory asynchronously on a side stream
+    (`_stage`); the pinned buffers come from a pool (no cudaHostAlloc per tensor) and go back to
+    it when their shard is on disk;
+  * a shard is written exactly once, when its last tensor has arrived, by a worker thread
+    (`_ShardWriter`) so the file write overlaps the merge of the next shard.  The file is the
+    safetensors container (8-byte little-endian header length, JSON header, raw little-endian
+    tensor data) written straight from the pinned buffers, byte-identical to what
+    `safetensors.torch.save_file` produces for the same tensors, to a temporary name that is
+    renamed into place (a reader never sees a partial shard);
+  * `flush_partial()` writes the incomplete shards too (called when a merge aborts), so a
+    resumed run continues at tensor granularity like the reference's.
 """
 from __future__ import annotations
 
 import json
 import logging
+import os
+import queue
+import struct
+import threading
 from dataclasses import dataclass, field
 from pathlib import Path
-from typing import Dict, Generator, List, Set
+from typing import Dict, Generator, List, Optional, Set
 
 import torch
 from safetensors import safe_open
-from safetensors.torch import save_file
 
 from .constants import INPUT_LAYER, OUTPUT_LAYER
 
@@ -53,6 +66,102 @@ class ShardLayer:
         raise ValueError(f"Unknown layer name: {name}")
 
 
+# ------------------------------------------------------------------------------------------
+# safetensors container, written from host buffers without an intermediate copy
+# ------------------------------------------------------------------------------------------
+# dtype -> (safetensors name, rank in the format's dtype order: tensors are laid out by descending rank, then name)
+_ST_DTYPES = {
+    torch.bool: ("BOOL", 0), torch.uint8: ("U8", 1), torch.int8: ("I8", 2),
+    torch.float8_e5m2: ("F8_E5M2", 3), torch.float8_e4m3fn: ("F8_E4M3", 4),
+    torch.int16: ("I16", 5), torch.uint16: ("U16", 6), torch.float16: ("F16", 7), torch.bfloat16: ("BF16", 8),
+    torch.int32: ("I32", 9), torch.uint32: ("U32", 10), torch.float32: ("F32", 11), torch.float64: ("F64", 12),
+    torch.int64: ("I64", 13), torch.uint64: ("U64", 14),
+}
+
+
+def write_safetensors(path, tensors: Dict[str, torch.Tensor], metadata: Optional[Dict[str, str]] = None):
+    """Write `tensors` (contiguous CPU tensors) as one safetensors file.  Same bytes as
+    safetensors.torch.save_file(tensors, path, metadata) (tests/test_host_logic.py checks that), but the data goes
+    from the tensors' own (pinned) memory to the file: no per-tensor bytes() copy."""
+    items = []
+    for name, t in tensors.items():
+        if t.device.type != "cpu" or not t.is_contiguous():
+            raise ValueError(f"write_safetensors needs contiguous CPU tensors ({name})")
+        if t.dtype not in _ST_DTYPES:
+            raise ValueError(f"dtype {t.dtype} of {name} has no safetensors name")
+        items.append((name, t))
+    items.sort(key=lambda it: (-_ST_DTYPES[it[1].dtype][1], it[0]))
+    header = {}
+    if metadata is not None:
+        header["__metadata__"] = dict(metadata)
+    off = 0
+    for name, t in items:
+        n = t.numel() * t.element_size()
+        header[name] = {"dtype": _ST_DTYPES[t.dtype][0], "shape": list(t.shape), "data_offsets": [off, off + n]}
+        off += n
+    blob = json.dumps(header, separators=(",", ":"), ensure_ascii=False).encode("utf-8")
+    blob += b" " * (-len(blob) % 8)
+    with open(path, "wb") as fh:
+        fh.write(struct.pack("<Q", len(blob)))
+        fh.write(blob)
+        for _, t in items:
+            if t.numel():
+                fh.write(memoryview(t.reshape(-1).view(torch.uint8).numpy()))
+
+
+class _PinnedPool:
+    """Pinned host buffers by byte size; a merge touches a handful of distinct tensor sizes, so after the first
+    shard every `_stage` re-uses a buffer instead of calling cudaHostAlloc."""
+
+    def __init__(self):
+        self.free: Dict[int, list] = {}
+        self.lock = threading.Lock()
+
+    def take(self, nbytes: int) -> torch.Tensor:
+        with self.lock:
+            lst = self.free.get(nbytes)
+            if lst:
+                return lst.pop()
+        return torch.empty(max(nbytes, 1), dtype=torch.uint8).pin_memory()
+
+    def give(self, buf: torch.Tensor):
+        with self.lock:
+            self.free.setdefault(buf.numel(), []).append(buf)
+
+
+class _ShardWriter:
+    """One worker thread that turns (shard, staged tensors) jobs into files.  At most `depth` jobs wait in the queue, so
+    the pinned memory a merge holds is bounded by depth + 2 shards."""
+
+    def __init__(self, depth: int = 2):
+        self.jobs: "queue.Queue" = queue.Queue(maxsize=depth)
+        self.errors: list = []
+        self.thread = threading.Thread(target=self._run, name="shardmerge-writer", daemon=True)
+        self.thread.start()
+
+    def _run(self):
+        while True:
+            job = self.jobs.get()
+            try:
+                if job is None:
+                    return
+                job()
+            except Exception as exc:           # kept for finalize(): the reference logs and drops the shard
+                self.errors.append(exc)
+            finally:
+                self.jobs.task_done()
+
+    def submit(self, job):
+        self.jobs.put(job)
+
+    def drain(self):
+        self.jobs.join()
+
+    def close(self):
+        self.jobs.put(None)
+        self.thread.join()
+
+
 @dataclass
 class ModelWriter:
     base_index: dict
@@ -61,6 +170,9 @@ class ModelWriter:
     output_astype: torch.dtype
     written_shard_layers: Set[tuple] = field(default_factory=set)
     shard_to_tensors: Dict[str, Set[str]] = field(default_factory=dict)
+    only_shards: Optional[Set[str]] = None       # multi-GPU merge: the shards this process owns (schedule.py)
+    write_index: bool = True                     # multi-GPU merge: rank 0 writes the index copy, the others only read it
+    async_write: bool = True
 
     def __post_init__(self):
         self.output_path = Path(self.output_path)
@@ -70,21 +182,29 @@ class ModelWriter:
             logger.info(f"Index already exists: {self.index_path}")
             with open(self.index_path) as fh:
                 self.base_index = json.load(fh)
-        else:
-            with open(self.index_path, "w") as fh:
+        elif self.write_index:
+            tmp = self.index_path.with_name(self.index_path.name + f".tmp{os.getpid()}")
+            with open(tmp, "w") as fh:
                 json.dump(self.base_index, fh, indent=2)
+            os.replace(tmp, self.index_path)     # a concurrent reader sees the old state or the whole file
         self.shard_to_tensors = {}
         for tensor_name, shard_name in self.base_index["weight_map"].items():
             self.shard_to_tensors.setdefault(shard_name, set()).add(tensor_name)
         self._order_pos = {n: i for i, n in enumerate(self.layer_order)}
-        self._staged: Dict[str, Dict[str, torch.Tensor]] = {}      # shard -> {tensor: pinned host tensor}
+        self._staged: Dict[str, Dict[str, torch.Tensor]] = {}      # shard -> {tensor: host tensor (view of a pinned buffer)}
+        self._bufs: Dict[str, list] = {}                           # shard -> pinned buffers to give back
         self._events: Dict[str, list] = {}
         self._copy_stream = None
+        self._pool = _PinnedPool()
+        self._worker: Optional[_ShardWriter] = None
+        self._lock = threading.Lock()
         self._check_existing_shards()
 
     # ------------------------------------------------------------------ resume
     def _check_existing_shards(self):
         for shard_name, names in self.shard_to_tensors.items():
+            if self.only_shards is not None and shard_name not in self.only_shards:
+                continue                                   # another rank may be writing it right now
             path = self.output_path / shard_name
             if not path.exists():
                 continue
@@ -105,7 +225,9 @@ class ModelWriter:
             if self._copy_stream is None:
                 self._copy_stream = torch.cuda.Stream(device=t.device)
             src = t if t.dtype == self.output_astype else t.to(self.output_astype)
-            host = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
+            src = src.contiguous()
+            buf = self._pool.take(src.numel() * src.element_size())
+            host = buf[: src.numel() * src.element_size()].view(src.dtype).reshape(src.shape)
             produced = torch.cuda.current_stream(t.device).record_event()
             with torch.cuda.stream(self._copy_stream):
                 self._copy_stream.wait_event(produced)
@@ -113,16 +235,35 @@ class ModelWriter:
                 src.record_stream(self._copy_stream)
                 done = self._copy_stream.record_event()
             self._events.setdefault(shard_name, []).append(done)
+            self._bufs.setdefault(shard_name, []).append(buf)
         else:
-            host = t.clone().to(self.output_astype)
+            host = t.clone().to(self.output_astype).contiguous()
         self._staged.setdefault(shard_name, {})[layer_name] = host
 
     def _flush(self, shard_name: str):
-        staged = self._staged.get(shard_name)
+        staged = self._staged.pop(shard_name, None)
         if not staged:
             return
-        for ev in self._events.pop(shard_name, []):
-            ev.synchronize()
+        events = self._events.pop(shard_name, [])
+        bufs = self._bufs.pop(shard_name, [])
+
+        def job():
+            try:
+                for ev in events:
+                    ev.synchronize()
+                self._write_shard(shard_name, staged)
+            finally:
+                for b in bufs:
+                    self._pool.give(b)
+
+        if self.async_write:
+            if self._worker is None:
+                self._worker = _ShardWriter()
+            self._worker.submit(job)
+        else:
+            job()
+
+    def _write_shard(self, shard_name: str, staged: Dict[str, torch.Tensor]):
         path = self.output_path / shard_name
         tensors = dict(staged)
         if path.exists():                                   # resumed run: keep what an earlier run wrote
@@ -130,45 +271,67 @@ class ModelWriter:
                 for key in f.keys():
                     tensors.setdefault(key, f.get_tensor(key))
         ordered = {n: tensors[n] for n in sorted(tensors, key=lambda n: self._order_pos.get(n, 1 << 30))}
+        tmp = path.with_name(path.name + f".tmp{os.getpid()}")
         try:
-            save_file(ordered, str(path), metadata={"format": "pt"})
-            for name in staged:
-                self.written_shard_layers.add((shard_name, name))
+            write_safetensors(tmp, ordered, metadata={"format": "pt"})
+            os.replace(tmp, path)
+            with self._lock:
+                for name in staged:
+                    self.written_shard_layers.add((shard_name, name))
             logger.info(f"Wrote shard {shard_name} ({len(ordered)} tensors)")
-        except Exception as exc:                             # reference behaviour: log, drop the file
+        except Exception as exc:                             # reference behaviour: log, drop the file (:146-149)
             logger.error(f"Error saving shard {shard_name}: {exc}")
-            if path.exists():
-                path.unlink()
-        self._staged.pop(shard_name, None)
+            for p in (tmp, path):
+                if p.exists():
+                    p.unlink()
 
     # ------------------------------------------------------------------ reference API
     def add_tensor(self, layer_name: str, tensor: torch.Tensor):
         shard_name = self.base_index["weight_map"][layer_name]
-        if (shard_name, layer_name) in self.written_shard_layers:
-            logger.info(f"Skipping {layer_name} as it's already in written shard {shard_name}")
-            return
+        with self._lock:
+            if (shard_name, layer_name) in self.written_shard_layers:
+                logger.info(f"Skipping {layer_name} as it's already in written shard {shard_name}")
+                return
+            on_disk = {n for (s, n) in self.written_shard_layers if s == shard_name}
         self._stage(shard_name, layer_name, tensor)
-        have = {n for (s, n) in self.written_shard_layers if s == shard_name} | set(self._staged[shard_name])
-        if have >= self.shard_to_tensors[shard_name]:
+        if on_disk | set(self._staged[shard_name]) >= self.shard_to_tensors[shard_name]:
             self._flush(shard_name)
+
+    def wait(self):
+        """Block until every shard handed to the writer thread is on disk."""
+        if self._worker is not None:
+            self._worker.drain()
+
+    def flush_partial(self):
+        """Write every staged tensor now, complete shard or not (a merge that aborts calls this so that the next run
+        resumes after the last merged tensor, as with the reference's write-per-tensor)."""
+        for shard_name in list(self._staged):
+            self._flush(shard_name)
+        if self._worker is not None:
+            self._worker.drain()
 
     def finalize(self, only_shards=None):
         """Flush what is staged and verify completeness (shard/writer.py:151-161).  `only_shards`
         restricts the check to the shards this process owns (multi-GPU merge, schedule.py)."""
-        for shard_name in list(self._staged):
-            self._flush(shard_name)
+        self.flush_partial()
+        if self._worker is not None:
+            self._worker.close()
+            errors, self._worker = self._worker.errors, None
+            if errors:
+                raise errors[0]
+        only = only_shards if only_shards is not None else self.only_shards
         missing = [(s, n) for s, names in self.shard_to_tensors.items() for n in names
-                   if (only_shards is None or s in only_shards) and (s, n) not in self.written_shard_layers]
+                   if (only is None or s in only) and (s, n) not in self.written_shard_layers]
         if missing:
             logger.error(f"Failed to write all layers. Missing: {missing}")
             raise RuntimeError(f"Incomplete model output: missing {len(missing)} layers")
 
     def shard_layers(self) -> Generator[List[ShardLayer], None, None]:
         for shard_name in sorted(self.shard_to_tensors):
-            names = sorted(self.shard_to_tensors[shard_name], key=lambda n: self.layer_order.index(n))
+            names = sorted(self.shard_to_tensors[shard_name], key=lambda n: self._order_pos[n])
             group = []
             for n in names:
-                sl = ShardLayer(self.layer_order.index(n), shard_name, n, (shard_name, n) in self.written_shard_layers)
+                sl = ShardLayer(self._order_pos[n], shard_name, n, (shard_name, n) in self.written_shard_layers)
                 sl.layer_number                                # validates the name like the reference does
                 group.append(sl)
             yield group

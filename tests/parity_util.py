@@ -23,12 +23,39 @@ def flip_accounted(ours, ref, k=16):
     D = np.fft.fftn(d) if d.ndim > 1 else np.fft.fft(d)
     E = (np.abs(D) ** 2).ravel()
     tot = float(E.sum())
-    refE = float(np.sum(np.abs(np.fft.fftn(ref) if ref.ndim > 1 else np.fft.fft(ref)) ** 2))
+    refE = float(np.sum(ref ** 2)) * ref.size           # Parseval: sum |FFT(ref)|^2 without a second transform
     if tot == 0.0:
         return 0.0, 0.0, 0.0
     k = min(k, E.size)
     top = float(np.partition(E, E.size - k)[E.size - k:].sum())
     return float(np.sqrt(tot / refE)), float(np.sqrt(max(tot - top, 0.0) / refE)), top / tot
+
+
+def flipped_bins(ours, ref, tol=1e-5, kmax=64):
+    """How many bins of the difference spectrum have to be set aside before the residual relative L2 error is <= tol,
+    and which (row, column) frequencies they are: those are the mask / threshold decisions that went the other way.
+    -> dict(n=..., bins=[[row, col, share of the error energy], ...]); n = -1 if kmax bins do not suffice."""
+    ours = np.asarray(ours, dtype=np.float64); ref = np.asarray(ref, dtype=np.float64)
+    d = ours - ref
+    D = np.fft.fftn(d) if d.ndim > 1 else np.fft.fft(d)
+    E = (np.abs(D) ** 2)
+    tot = float(E.sum())
+    refE = float(np.sum(ref ** 2)) * ref.size           # Parseval: sum |FFT(ref)|^2
+    if tot == 0.0 or np.sqrt(tot / refE) <= tol:
+        return dict(n=0, bins=[])
+    flat = E.ravel()
+    k = min(kmax, flat.size)
+    idx = np.argpartition(flat, flat.size - k)[flat.size - k:]
+    idx = idx[np.argsort(-flat[idx])]
+    rest = tot
+    bins = []
+    for n, i in enumerate(idx, 1):
+        rest -= float(flat[i])
+        pos = np.unravel_index(int(i), E.shape)
+        bins.append([int(p) for p in pos] + [round(float(flat[i]) / tot, 6)])
+        if np.sqrt(max(rest, 0.0) / refE) <= tol:
+            return dict(n=n, bins=bins)
+    return dict(n=-1, bins=bins)
 
 
 def bf16_ulp_distance(a_bits, b_bits):

@@ -9,6 +9,7 @@ import sys
 import textwrap
 from pathlib import Path
 
+import click
 import numpy as np
 import pytest
 import torch
@@ -44,7 +45,7 @@ def test_config_yaml_roundtrip(tmp_path):
     cfg.update({"device": "cuda:1"}, cache_dir="x", bogus=1)
     assert cfg.device == "cuda:1" and cfg.cache_dir == "x" and not hasattr(cfg, "bogus")
     (tmp_path / "bad.yaml").write_text("output_dir: x\n")
-    with pytest.raises(ValueError):
+    with pytest.raises(click.BadParameter):
         MergeConfig.from_yaml(tmp_path / "bad.yaml")
     with pytest.raises(TypeError):
         MergeModel(model="a", base="b", unknown_key=1)
@@ -124,7 +125,8 @@ def test_writer_write_once_resume_finalize(tmp_path):
     for sl in first[1:]:
         w.add_tensor(sl.layer_name, idx.models["m"][sl.layer_name])
     path = tmp_path / "out" / first[0].shard_name
-    assert path.exists()
+    w.wait()                                               # the file is written by the writer thread
+    assert path.exists() and not list((tmp_path / "out").glob("*.tmp*"))
     with safe_open(path, framework="pt") as f:
         assert set(f.keys()) == {sl.layer_name for sl in first} and f.metadata() == {"format": "pt"}
         t = f.get_tensor(first[0].layer_name)
@@ -142,6 +144,87 @@ def test_writer_write_once_resume_finalize(tmp_path):
         for sl in g:
             w2.add_tensor(sl.layer_name, idx.models["m"][sl.layer_name])
     w2.finalize()
+
+
+def test_write_safetensors_matches_save_file(tmp_path):
+    """The writer's own container code must produce the bytes safetensors.torch.save_file produces."""
+    from safetensors.torch import save_file
+    from shardmerge_b200.writer import write_safetensors
+    g = torch.Generator().manual_seed(3)
+    t = {"model.layers.1.b": torch.randn(5, 7, generator=g).to(torch.bfloat16),
+         "model.layers.0.a": torch.randn(3, generator=g),
+         "model.norm.weight": torch.randn(4, 2, 3, generator=g).to(torch.float16),
+         "x.i64": torch.arange(5), "x.u8": torch.arange(7, dtype=torch.uint8), "x.scalar": torch.tensor(1.5),
+         "x.empty": torch.zeros((0, 4), dtype=torch.bfloat16), "x.bool": torch.tensor([True, False, True])}
+    for meta in ({"format": "pt"}, None):
+        save_file(t, str(tmp_path / "a.safetensors"), metadata=meta)
+        write_safetensors(tmp_path / "b.safetensors", t, metadata=meta)
+        assert (tmp_path / "a.safetensors").read_bytes() == (tmp_path / "b.safetensors").read_bytes()
+    with pytest.raises(ValueError):
+        write_safetensors(tmp_path / "c.safetensors", {"nc": torch.zeros(4, 4).t()[1:]})
+
+
+def test_writer_flush_partial_resumes_at_tensor_granularity(tmp_path):
+    """A merge that aborts mid-shard keeps the tensors it already produced (resume granularity)."""
+    from safetensors import safe_open
+    idx = InMemoryIndex({"m": _toy_model(0)})
+    asyncio.run(idx.add_model("m"))
+    order, doc = idx.get_layer_order("m"), idx.model_indexes["m"]
+    w = ModelWriter(base_index=doc, output_path=tmp_path / "out", layer_order=order, output_astype=torch.bfloat16)
+    group = next(g for g in w.shard_layers() if len(g) > 1)
+    w.add_tensor(group[0].layer_name, idx.models["m"][group[0].layer_name])
+    w.flush_partial()
+    with safe_open(tmp_path / "out" / group[0].shard_name, framework="pt") as f:
+        assert set(f.keys()) == {group[0].layer_name}
+    w2 = ModelWriter(base_index=doc, output_path=tmp_path / "out", layer_order=order, output_astype=torch.bfloat16)
+    g2 = next(g for g in w2.shard_layers() if g[0].shard_name == group[0].shard_name)
+    assert [sl.written for sl in g2] == [True] + [False] * (len(g2) - 1)
+    for sl in g2[1:]:
+        w2.add_tensor(sl.layer_name, idx.models["m"][sl.layer_name])
+    w2.wait()
+    with safe_open(tmp_path / "out" / group[0].shard_name, framework="pt") as f:
+        assert set(f.keys()) == {sl.layer_name for sl in g2}
+        assert torch.equal(f.get_tensor(group[0].layer_name), idx.models["m"][group[0].layer_name])
+
+
+def test_process_layers_finalizes_each_tensor_before_the_writer_sees_it():
+    """deferred results must be resolved by identity before writer.add_tensor, whatever mix of
+    deferred and immediate tensors is in flight (fused chain followed by pass-through tensors)."""
+    from shardmerge_b200.merge.base import MergeTensorsBase
+    log = []
+
+    class Deferred(MergeTensorsBase):
+        pipeline_depth = 1
+
+        def __init__(self):
+            self.pending = []
+
+        def get_readme(self):
+            return ""
+
+        async def _merge_layer(self, shard_layer, device):
+            t = torch.zeros(1)
+            if shard_layer.layer_name.startswith("model.layers."):     # "fused": result is final only after _finalize
+                self.pending.append(t)
+            return t
+
+        def _finalize(self, tensor):
+            for i, p in enumerate(self.pending):
+                if p is tensor:
+                    del self.pending[: i + 1]
+                    tensor += 1
+                    return
+
+    class Sink:
+        def add_tensor(self, name, tensor):
+            log.append((name, float(tensor)))
+
+    names = ["model.layers.0.a", "model.norm.weight", "lm_head.weight", "model.layers.1.a", "model.layers.1.b",
+             "model.embed_tokens.weight", "model.layers.2.a"]
+    m = Deferred()
+    asyncio.run(m._process_layers(Sink(), [ShardLayer(i, "s", n, False) for i, n in enumerate(names)], "cpu"))
+    assert [n for n, _ in log] == names
+    assert all(v == (1.0 if n.startswith("model.layers.") else 0.0) for n, v in log) and not m.pending
 
 
 def test_local_safetensors_index(tmp_path):

@@ -151,3 +151,37 @@ def test_elementwise_strategies_match_reference_bit_for_bit(golden_dir, name):
     fts = [d[f"ft{k}"] for k in range(int(d["n"]))]
     got = O.taskaddition_merge(d["base"], fts) if "taskaddition" in name else O.addition_merge(d["base"], fts)
     assert _nan_equal_bits(got, d["out"]).all()
+
+
+def test_oracle_vs_reference_cli_fixture(golden_dir):
+    """tests/golden/cli_tiny/ is what the reference CLI (`python -m shard merge`, device cpu) wrote for the files
+    oracle/make_golden_cli.py generates: the oracle's merge_layer on the same bits must give the same bf16 tensors up
+    to the flips of the discontinuous algorithm (small tensors: one flipped bin shows in ~1 % of the roundings)."""
+    import sys
+    import torch
+    from pathlib import Path
+    from safetensors import safe_open
+    from tests.parity_util import bf16_ulp_distance
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "oracle"))
+    import make_golden_cli as G
+    models = G.make_models()
+
+    def b(t):
+        return t.contiguous().view(torch.int16).numpy().view(np.uint16)
+
+    n = 0
+    for f in sorted((golden_dir / "cli_tiny").glob("*.safetensors")):
+        with safe_open(f, framework="pt") as sf:
+            for k in sf.keys():
+                ref = sf.get_tensor(k)
+                if not k.startswith("model.layers."):
+                    src = "synth/ft0" if "embed" in k else "synth/ft1"       # is_input / is_output pass-through
+                    assert torch.equal(ref, models[src][k]), k
+                    continue
+                base = b(models["synth/base"][k])
+                oo = O.merge_layer(base, [dict(base=base, ft=b(models[f"synth/ft{i}"][k]), alpha=a, name=f"m{i}")
+                                          for i, a in enumerate(G.ALPHAS)])
+                u = bf16_ulp_distance(oo.reshape(ref.shape), b(ref))
+                assert float((u <= 1).mean()) >= 0.98, (k, float((u <= 1).mean()))
+                n += 1
+    assert n == 18
