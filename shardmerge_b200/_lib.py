@@ -22,6 +22,7 @@ SIGNATURES = {
     "sm_plan_pitch": (_i, [_vp]),
     "sm_plan_row_freq": (_i, [_vp, _i]),
     "sm_plan_col_passes": (_i, [_vp]),
+    "sm_plan_col_launches": (_i, [_vp]),
     "sm_plan_describe": (_i, [_vp, C.c_char_p, _i]),
     "sm_plan_table_bytes": (_sz, [_vp]),
     "sm_plan_init_tables": (_i, [_vp, _vp, _vp]),

@@ -243,6 +243,8 @@ struct ColArgs {
   const float* cull_thr;       // nullable: |re| < thr -> 0 on load (first inverse sweep)
   const float* scale_ptr; float scale_host; int use_scale;   // outputs *= scale (last forward sweep)
   int write_im;                // 0: do not store the imaginary plane
+  const int* wsel; int wskip;  // nullable: forward, do not store the imaginary plane if (*wsel != 0) == (wskip != 0)
+  int tile0;                   // first column tile of this launch (column bands, kernels_fft.cu: col_band_tiles)
 };
 
 struct ColGlobalSrc {
@@ -276,7 +278,7 @@ template <class Exec>
 SM_HD void col_body(Exec& ex, const SmPlan& pl, int tile, int inst, const ColArgs& a, const cf* twR, cf* smem) {
   const int T = ex.nthreads(), nwarps = T / 32;
   const int L = a.L;
-  const int col0 = tile * SM_COL_TILE;
+  const int col0 = (tile + a.tile0) * SM_COL_TILE;
   int s = 1, cur = 0;
   for (int st = 0; st < a.n_rad; ++st) {
     const int r = a.rad[st], nb = L / r;
@@ -290,7 +292,8 @@ SM_HD void col_body(Exec& ex, const SmPlan& pl, int tile, int inst, const ColArg
       float* const imp = (a.sel != nullptr && *a.sel != 0) ? a.im_alt : a.im;
       ColGlobalSrc gsrc{a.re, imp, row0, estride, valid, a.swap, a.cull_thr ? *a.cull_thr : 0.f};
       ColGlobalDst gdst{a.re, imp, row0, estride, valid, a.swap, twR, a.big_tw ? inst : 0,
-                        a.use_scale ? (a.scale_ptr ? *a.scale_ptr : a.scale_host) : 1.0f, a.write_im};
+                        a.use_scale ? (a.scale_ptr ? *a.scale_ptr : a.scale_host) : 1.0f,
+                        (a.write_im != 0 && !(a.wsel != nullptr && (*a.wsel != 0) == (a.wskip != 0))) ? 1 : 0};
       ColSmem sin{smem + (size_t)(cur ^ 1) * L * SM_COL_TILE, lane};
       ColSmem sout{smem + (size_t)cur * L * SM_COL_TILE, lane};
       for (int b = wid; b < nb; b += nwarps) {
@@ -340,7 +343,11 @@ struct ColCtArgs {
   const float* scale_ptr;      // nullable: outputs *= *scale_ptr, else *= scale
   float scale;
   int write_p1_fwd;            // forward: 0 -> do not store the imaginary plane
+  const int* wsel; int wskip;  // nullable: forward, do not store the imaginary plane if (*wsel != 0) == (wskip != 0)
+                               // (the fused chain: the model that ends up in role v1 only contributes Re, functions.py:108-136)
+  int tile0;                   // first column tile of this launch (column bands)
 };
+#define SM_COL_WRITE_P1(a) ((a).write_p1_fwd != 0 && !((a).wsel != nullptr && (*(a).wsel != 0) == ((a).wskip != 0)))
 
 template <bool kInverse>
 struct ColCtSrc {
@@ -370,7 +377,7 @@ struct ColCtDst {
 template <int R1, int R2, int NW, bool kInverse, bool kBigTw, class Exec>
 SM_HD void col_ct_body(Exec& ex, int tile, int inst, const ColCtArgs a, const cf* twR, cf* smem) {
   constexpr int L = R1 * R2;
-  const int col0 = tile * SM_COL_TILE;
+  const int col0 = (tile + a.tile0) * SM_COL_TILE;
   SM_FOR_THREADS(ex, tid) {
     const int lane = tid & 31, wid = tid >> 5;
     const int c = col0 + lane;
@@ -381,7 +388,7 @@ SM_HD void col_ct_body(Exec& ex, int tile, int inst, const ColCtArgs a, const cf
     const float scale = a.scale_ptr ? *a.scale_ptr : a.scale;
     float* const p0 = (a.sel != nullptr && *a.sel != 0) ? a.p0_alt : a.p0;
     ColCtSrc<kInverse> gsrc{p0, a.p1, row0, estride, valid, thr};
-    ColCtDst<kBigTw> gdst{p0, a.p1, row0, estride, valid, twR, inst, scale, kInverse ? true : (a.write_p1_fwd != 0)};
+    ColCtDst<kBigTw> gdst{p0, a.p1, row0, estride, valid, twR, inst, scale, kInverse ? true : SM_COL_WRITE_P1(a)};
     if constexpr (R2 == 1) {
       for (int b = wid; b < 1; b += NW) stockham_bfly<R1, true>(b, L, 1, a.tw_mul, twR, gsrc, gdst);
     } else {
@@ -400,7 +407,7 @@ SM_HD void col_ct_body(Exec& ex, int tile, int inst, const ColCtArgs a, const cf
       const size_t estride = (size_t)a.elem_mul * a.P;
       const float scale = a.scale_ptr ? *a.scale_ptr : a.scale;
       float* const p0 = (a.sel != nullptr && *a.sel != 0) ? a.p0_alt : a.p0;
-      ColCtDst<kBigTw> gdst{p0, a.p1, row0, estride, valid, twR, inst, scale, kInverse ? true : (a.write_p1_fwd != 0)};
+      ColCtDst<kBigTw> gdst{p0, a.p1, row0, estride, valid, twR, inst, scale, kInverse ? true : SM_COL_WRITE_P1(a)};
       ColSmem sin{smem, lane};
 #pragma unroll
       for (int b = wid; b < R1; b += NW) stockham_bfly<R2, true>(b, L, R1, a.tw_mul, twR, sin, gdst);
@@ -470,7 +477,7 @@ template <int R1, int R2, int NW, bool kInverse, bool kBigTw, class Exec>
 SM_HD void col_ct_body_p(Exec& ex, int tile, int inst, const ColCtArgs a, const cf* twR, pf4* smem) {
   constexpr int L = R1 * R2;
   constexpr int NS = 2 * NW;
-  const int col0 = tile * SM_COL_TILE;
+  const int col0 = (tile + a.tile0) * SM_COL_TILE;
   SM_FOR_THREADS(ex, tid) {
     const int lane = tid & 15, slot = tid >> 4;
     const int c = col0 + 2 * lane;
@@ -481,7 +488,7 @@ SM_HD void col_ct_body_p(Exec& ex, int tile, int inst, const ColCtArgs a, const 
     const float scale = a.scale_ptr ? *a.scale_ptr : a.scale;
     float* const p0 = (a.sel != nullptr && *a.sel != 0) ? a.p0_alt : a.p0;
     ColCtSrcP<kInverse> gsrc{p0, a.p1, row0, estride, valid, thr};
-    ColCtDstP<kBigTw> gdst{p0, a.p1, row0, estride, valid, twR, inst, scale, kInverse ? true : (a.write_p1_fwd != 0)};
+    ColCtDstP<kBigTw> gdst{p0, a.p1, row0, estride, valid, twR, inst, scale, kInverse ? true : SM_COL_WRITE_P1(a)};
     if constexpr (R2 == 1) {
       for (int b = slot; b < 1; b += NS) stockham_bfly<R1, true, pf>(b, L, 1, a.tw_mul, twR, gsrc, gdst);
     } else {
@@ -500,7 +507,7 @@ SM_HD void col_ct_body_p(Exec& ex, int tile, int inst, const ColCtArgs a, const 
       const size_t estride = (size_t)a.elem_mul * a.P;
       const float scale = a.scale_ptr ? *a.scale_ptr : a.scale;
       float* const p0 = (a.sel != nullptr && *a.sel != 0) ? a.p0_alt : a.p0;
-      ColCtDstP<kBigTw> gdst{p0, a.p1, row0, estride, valid, twR, inst, scale, kInverse ? true : (a.write_p1_fwd != 0)};
+      ColCtDstP<kBigTw> gdst{p0, a.p1, row0, estride, valid, twR, inst, scale, kInverse ? true : SM_COL_WRITE_P1(a)};
       ColSmemP sin{smem, lane};
 #pragma unroll
       for (int b = slot; b < R1; b += NS) stockham_bfly<R2, true, pf>(b, L, R1, a.tw_mul, twR, sin, gdst);
@@ -516,7 +523,7 @@ SM_HD void col_ct_body_p3(Exec& ex, int tile, int inst, const ColCtArgs a, const
   constexpr int L = R1 * R2 * R3;
   constexpr int NS = 2 * NW;
   static_assert(L / R2 <= NS, "col_ct_body_p3: at most one middle-stage butterfly per slot (it runs in place)");
-  const int col0 = tile * SM_COL_TILE;
+  const int col0 = (tile + a.tile0) * SM_COL_TILE;
   pf re2[R2], im2[R2];
   SM_FOR_THREADS(ex, tid) {
     const int lane = tid & 15, slot = tid >> 4;
@@ -567,7 +574,7 @@ SM_HD void col_ct_body_p3(Exec& ex, int tile, int inst, const ColCtArgs a, const
     const size_t estride = (size_t)a.elem_mul * a.P;
     const float scale = a.scale_ptr ? *a.scale_ptr : a.scale;
     float* const p0 = (a.sel != nullptr && *a.sel != 0) ? a.p0_alt : a.p0;
-    ColCtDstP<kBigTw> gdst{p0, a.p1, row0, estride, valid, twR, inst, scale, kInverse ? true : (a.write_p1_fwd != 0)};
+    ColCtDstP<kBigTw> gdst{p0, a.p1, row0, estride, valid, twR, inst, scale, kInverse ? true : SM_COL_WRITE_P1(a)};
     ColSmemP sm{smem, lane};
 #pragma unroll
     for (int b = slot; b < L / R3; b += NS) stockham_bfly<R3, true, pf>(b, L, R1 * R2, a.tw_mul, twR, sm, gdst);

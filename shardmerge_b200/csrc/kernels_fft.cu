@@ -1362,6 +1362,7 @@ __global__ void k_inv_norm(const double* sumsq, float* out) {
 }
 
 // ------------------------------------------------------------------ host side
+static int col_band_tiles(const SmPlan& p);
 static std::once_flag g_attr_once;
 static int g_attr_rc = 0;
 static int ensure_attrs() {
@@ -1398,6 +1399,13 @@ extern "C" sm_plan* sm_plan_create(int R, int C) {
 extern "C" void sm_plan_destroy(sm_plan* plan) { delete plan; }
 extern "C" int sm_plan_pitch(const sm_plan* plan) { return plan->p.P; }
 extern "C" int sm_plan_col_passes(const sm_plan* plan) { return plan->p.col_passes; }
+extern "C" int sm_plan_col_launches(const sm_plan* plan) {     // kernel launches of ONE column transform (bands x sweeps)
+  const SmPlan& p = plan->p;
+  if (p.col_passes == 0) return 1;
+  if (p.col_passes == 1) return 1;
+  const int ntiles = sm_col_tiles(p), band = col_band_tiles(p);
+  return 2 * ((ntiles + band - 1) / band);
+}
 extern "C" int sm_plan_row_freq(const sm_plan* plan, int stored) { return sm_row_freq(&plan->p, stored); }
 extern "C" size_t sm_plan_table_bytes(const sm_plan* plan) {
   return sm_tab_bytes(plan->p);
@@ -1928,22 +1936,23 @@ extern "C" int sm_fwd_rows_f32(const sm_plan* plan, const void* tables, const fl
 
 static int launch_col(const SmPlan& p, const void* tables, int sweep, int inverse, float* re, float* im,
                       const float* cull_thr, const float* scale_dev, float scale_host, int use_scale,
-                      int write_im, cudaStream_t st, float* im_alt = nullptr, const int* sel = nullptr) {
+                      int write_im, cudaStream_t st, float* im_alt = nullptr, const int* sel = nullptr,
+                      const int* wsel = nullptr, int wskip = 0, int tile0 = 0, int band_tiles = 0) {
   if (ensure_attrs()) return -100;
   ColArgs ca{};
   int n_inst = 0;
   sm_col_args(p, sweep, inverse, &ca, &n_inst);
   ca.re = re; ca.im = im; ca.cull_thr = cull_thr; ca.im_alt = im_alt; ca.sel = sel;
   ca.scale_ptr = scale_dev; ca.scale_host = scale_host; ca.use_scale = use_scale;
-  ca.write_im = write_im;
-  const int ntiles = (p.Ch + 1 + SM_COL_TILE - 1) / SM_COL_TILE;
+  ca.write_im = write_im; ca.wsel = wsel; ca.wskip = wskip; ca.tile0 = tile0;
+  const int ntiles = band_tiles > 0 ? band_tiles : (p.Ch + 1 + SM_COL_TILE - 1) / SM_COL_TILE;
   {
     ColCtArgs c{};
     c.p0 = inverse ? im : re; c.p1 = inverse ? re : im;
     c.p0_alt = inverse ? im_alt : nullptr; c.sel = inverse ? sel : nullptr;
     c.P = p.P; c.Ch = p.Ch; c.inst_mul = ca.inst_mul; c.elem_mul = ca.elem_mul; c.tw_mul = ca.tw_mul;
     c.thr_ptr = cull_thr; c.scale_ptr = use_scale ? scale_dev : nullptr;
-    c.scale = use_scale ? scale_host : 1.0f; c.write_p1_fwd = write_im;
+    c.scale = use_scale ? scale_host : 1.0f; c.write_p1_fwd = write_im; c.wsel = wsel; c.wskip = wskip; c.tile0 = tile0;
     int rc = try_col_p(ca.n_rad, ca.rad, inverse != 0, ca.big_tw != 0, dim3(ntiles, n_inst), c, tabR(p, tables), st);
     if (rc <= 0) return rc;
     rc = try_col_ct(ca.n_rad, ca.rad, inverse != 0, ca.big_tw != 0, dim3(ntiles, n_inst), c, tabR(p, tables), st);
@@ -1954,6 +1963,24 @@ static int launch_col(const SmPlan& p, const void* tables, int sweep, int invers
   k_col<<<dim3(ntiles, n_inst), threads, smem, st>>>(p, ca, tabR(p, tables));
   SM_LAUNCH_CHECK();
   return 0;
+}
+
+// Column bands: the two sweeps of a four-step column transform run band by band over the column tiles, sweep A of a
+// band immediately followed by sweep B of the same band, so that the second sweep finds the band (R x 32 x tiles x 8 B)
+// in the 126 MB L2 instead of streaming the whole spectrum through DRAM a second time (a spectrum is 0.07 - 1.9 GB).
+// SM_COL_BAND_MB sets the band size; 0 = one launch per sweep, which is the DEFAULT: measured on the Llama-8B-shaped bench
+// (profiles/r02_band_sweep.log) bands of 16 / 32 / 64 MB take 9.1 / 7.1 / 5.9 ms per 4 layers for the forward sweeps against
+// 5.1 ms unbanded -- the sweeps are latency bound, and the per-launch ramp-up / tail of 5 - 15 small launches costs more than
+// the L2 hits save.  Kept as an A-B switch.
+static int col_band_tiles(const SmPlan& p) {
+  static int mb = -1;
+  if (mb < 0) { const char* e = getenv("SM_COL_BAND_MB"); mb = e ? atoi(e) : 0; if (mb < 0) mb = 0; }
+  const int ntiles = sm_col_tiles(p);
+  if (mb == 0) return ntiles;
+  const double tile_bytes = (double)p.R * SM_COL_TILE * 8.0;
+  int t = (int)((double)mb * 1048576.0 / tile_bytes);
+  if (t < 1) t = 1;
+  return t < ntiles ? t : ntiles;
 }
 
 // both sweeps of a two-sweep plan in one launch (k_col2_ct); returns 1 if this plan has no fused kernel
@@ -1988,6 +2015,11 @@ static int launch_col2_pair(const SmPlan& p, const void* tables, int inverse, fl
 
 extern "C" int sm_fwd_cols(const sm_plan* plan, const void* tables, float* re, float* im,
                            const float* scale_dev, float scale_host, int write_im, void* stream) {
+  return sm_fwd_cols_sel(plan, tables, re, im, scale_dev, scale_host, write_im, nullptr, 0, stream);
+}
+
+int sm_fwd_cols_sel(const sm_plan* plan, const void* tables, float* re, float* im, const float* scale_dev, float scale_host,
+                    int write_im, const int* wsel, int wskip, void* stream) {
   const SmPlan& p = plan->p;
   cudaStream_t st = (cudaStream_t)stream;
   {
@@ -1999,11 +2031,16 @@ extern "C" int sm_fwd_cols(const sm_plan* plan, const void* tables, float* re, f
     SM_LAUNCH_CHECK();
     return 0;
   }
-  for (int sweep = 0; sweep < p.col_passes; ++sweep) {
-    const bool lastsweep = (sweep == p.col_passes - 1);
-    int rc = launch_col(p, tables, sweep, 0, re, im, nullptr, scale_dev, scale_host, lastsweep ? 1 : 0,
-                        lastsweep ? write_im : 1, st);
-    if (rc) return rc;
+  const int ntiles = sm_col_tiles(p);
+  const int band = p.col_passes == 2 ? col_band_tiles(p) : ntiles;
+  for (int t0 = 0; t0 < ntiles; t0 += band) {
+    const int nt = ntiles - t0 < band ? ntiles - t0 : band;
+    for (int sweep = 0; sweep < p.col_passes; ++sweep) {
+      const bool lastsweep = (sweep == p.col_passes - 1);
+      int rc = launch_col(p, tables, sweep, 0, re, im, nullptr, scale_dev, scale_host, lastsweep ? 1 : 0,
+                          lastsweep ? write_im : 1, st, nullptr, nullptr, lastsweep ? wsel : nullptr, wskip, t0, nt);
+      if (rc) return rc;
+    }
   }
   return 0;
 }
@@ -2021,11 +2058,16 @@ int sm_inv_cols_sel(const sm_plan* plan, const void* tables, float* re, float* i
     const int rc = launch_col2_pair(p, tables, 1, re, im, cull_thr, nullptr, 1.f, 1, (cudaStream_t)stream, im_alt, sel);
     if (rc <= 0) return rc;
   }
-  for (int i = 0; i < p.col_passes; ++i) {
-    const int sweep = p.col_passes - 1 - i;   // undo sweep B first, then sweep A
-    int rc = launch_col(p, tables, sweep, 1, re, im, i == 0 ? cull_thr : nullptr, nullptr, 1.f, 0, 1,
-                        (cudaStream_t)stream, im_alt, sel);
-    if (rc) return rc;
+  const int ntiles = sm_col_tiles(p);
+  const int band = p.col_passes == 2 ? col_band_tiles(p) : ntiles;
+  for (int t0 = 0; t0 < ntiles; t0 += band) {
+    const int nt = ntiles - t0 < band ? ntiles - t0 : band;
+    for (int i = 0; i < p.col_passes; ++i) {
+      const int sweep = p.col_passes - 1 - i;   // undo sweep B first, then sweep A
+      int rc = launch_col(p, tables, sweep, 1, re, im, i == 0 ? cull_thr : nullptr, nullptr, 1.f, 0, 1,
+                          (cudaStream_t)stream, im_alt, sel, nullptr, 0, t0, nt);
+      if (rc) return rc;
+    }
   }
   return 0;
 }

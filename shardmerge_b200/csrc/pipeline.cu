@@ -93,6 +93,7 @@ extern "C" int sm_pair_merge_slerp_async(const sm_plan* plan, const void* tables
   void* sel0 = ctl + SM_CTL_SEL;
   void* sel1 = ctl + SM_CTL_SEL + SM_SELECT_STATE_BYTES;
   const int sweeps = p.col_passes;
+  const int col_launches = sm_plan_col_launches(plan);
   int rc;
   SM_CUDA_CHECK(cudaMemsetAsync(ctl, 0, SM_CTL_BYTES, st));
   {
@@ -106,9 +107,11 @@ extern "C" int sm_pair_merge_slerp_async(const sm_plan* plan, const void* tables
     SM_LAUNCH_CHECK();
   }
   {
-    Scope s(st, SM_CLS_COL_FWD, 16.0 * N * (sweeps > 0 ? sweeps : 1), 2 * (sweeps > 0 ? sweeps : 1));
-    if ((rc = sm_fwd_cols(plan, tables, a->re[0], a->im[0], flt + SM_F_SCALE_X, 1.f, 1, st))) return rc;
-    if ((rc = sm_fwd_cols(plan, tables, a->re[1], a->im[1], flt + SM_F_SCALE_Y, 1.f, 1, st))) return rc;
+    Scope s(st, SM_CLS_COL_FWD, 16.0 * N * (sweeps > 0 ? sweeps : 1) - 2.0 * N, 2 * col_launches);
+    // only the model in role v0 (the larger norm, `swap` picks it) contributes its imaginary plane: the other one's
+    // last sweep does not store it (2N bytes less)
+    if ((rc = sm_fwd_cols_sel(plan, tables, a->re[0], a->im[0], flt + SM_F_SCALE_X, 1.f, 1, swap, 1, st))) return rc;
+    if ((rc = sm_fwd_cols_sel(plan, tables, a->re[1], a->im[1], flt + SM_F_SCALE_Y, 1.f, 1, swap, 0, st))) return rc;
   }
   void* fs0 = ctl + SM_CTL_FS;
   void* fs1 = ctl + SM_CTL_FS + SM_FS_STATE_BYTES;
@@ -152,7 +155,7 @@ extern "C" int sm_pair_merge_slerp_async(const sm_plan* plan, const void* tables
     }
   }
   if (sweeps > 0) {
-    Scope s(st, SM_CLS_COL_INV, 8.0 * N * sweeps, sweeps);
+    Scope s(st, SM_CLS_COL_INV, 8.0 * N * sweeps, col_launches);
     if ((rc = sm_inv_cols_sel(plan, tables, a->re[2], a->im[0], a->im[1], swap, cull ? flt + SM_F_THR_CULL : nullptr, st)))
       return rc;
   }

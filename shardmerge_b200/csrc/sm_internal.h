@@ -54,6 +54,9 @@ int sm_slerp_reduce_sel(const sm_plan* plan, const float* reX, const float* reY,
                         const float* thr_cut, double* sums3, void* stream);
 int sm_blend_sel(const sm_plan* plan, int mode, int agreement, const float* reX, const float* reY, const int* sel,
                  const float* thr_cut, const float* scal4, float t_sum, float* out_re, void* stream);
+// forward column sweeps that skip the imaginary plane's final store when (*wsel != 0) == (wskip != 0)
+int sm_fwd_cols_sel(const sm_plan* plan, const void* tables, float* re, float* im, const float* scale_dev, float scale_host,
+                    int write_im, const int* wsel, int wskip, void* stream);
 int sm_inv_cols_sel(const sm_plan* plan, const void* tables, float* re, float* im, float* im_alt, const int* sel,
                     const float* cull_thr, void* stream);
 int sm_inv_rows_bf16_sel(const sm_plan* plan, const void* tables, const float* re, const float* im,

@@ -296,7 +296,7 @@ def fwd_cols(ws: Workspace, slot: int, scale: float = 1.0, scale_slot: Optional[
     N = pl.R * pl.C
     sweeps = max(1, pl.lib.sm_plan_col_passes(pl.handle))
     nbytes = 8 * N * sweeps - (0 if write_im else 2 * N)
-    rc = _run("col_fwd", sweeps, nbytes, pl.device, lambda: lib.sm_fwd_cols(
+    rc = _run("col_fwd", pl.lib.sm_plan_col_launches(pl.handle), nbytes, pl.device, lambda: lib.sm_fwd_cols(
         pl.handle, pl.tables.data_ptr(), ws.re[slot].data_ptr(), ws.im[slot].data_ptr(),
         None if scale_slot is None else ws.fptr(scale_slot), float(scale), 1 if write_im else 0, _stream(pl.device)))
     _lib.check(rc, "sm_fwd_cols")
@@ -357,7 +357,7 @@ def inv_cols(ws: Workspace, re: torch.Tensor, im: torch.Tensor, cull: bool):
     sweeps = pl.lib.sm_plan_col_passes(pl.handle)
     if sweeps == 0:
         return
-    _lib.check(_run("col_inv", sweeps, 8 * pl.R * pl.C * sweeps, pl.device, lambda: lib.sm_inv_cols(
+    _lib.check(_run("col_inv", pl.lib.sm_plan_col_launches(pl.handle), 8 * pl.R * pl.C * sweeps, pl.device, lambda: lib.sm_inv_cols(
         pl.handle, pl.tables.data_ptr(), re.data_ptr(), im.data_ptr(),
         ws.fptr(F_THR_CULL) if cull else None, _stream(pl.device))), "sm_inv_cols")
 
@@ -539,7 +539,8 @@ def pair_merge_async(ws: Workspace, s0: Source, s1: Source, base_out: torch.Tens
     sweeps = lib.sm_plan_col_passes(pl.handle)
     if PROFILER is not None:
         fs = lib.sm_fstats_supported(pl.handle) and not ws.safe_select
-        PROFILER.launches += 2 + 1 + 2 * max(sweeps, 1) + ((2 + 2) if fs else (11 + 2 + 1 + 11)) + sweeps + 1
+        cl = lib.sm_plan_col_launches(pl.handle)          # launches of one column transform (column bands x sweeps)
+        PROFILER.launches += 2 + 1 + 2 * cl + ((2 + 2) if fs else (11 + 2 + 1 + 11)) + (cl if sweeps else 0) + 1
         PROFILER.fused_calls += 1
     _lib.check(lib.sm_pair_merge_slerp_async(pl.handle, pl.tables.data_ptr(), ctypes.byref(a), _stream(dev)),
                "sm_pair_merge_slerp_async")

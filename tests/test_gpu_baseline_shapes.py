@@ -229,7 +229,9 @@ def test_golden_taps_through_cuda_blend(E, golden_dir):
         ar = F.arithmetic_fft_components(torch.from_numpy(d["fft0"]), torch.from_numpy(d["fft1"]), 1.0, True, DEV,
                                          do_imag=False).numpy()
         oa = O.arithmetic_fft_components(d["fft0"], d["fft1"], 1.0, True, do_imag=False)
-        assert np.array_equal(ar.real[half], np.asarray(oa).real[half].astype(np.float32)), f
+        # (the C ABI packs a full spectrum into the Hermitian half with the projection (X[k] + conj X[-k]) / 2, so the
+        # reference's not-quite-Hermitian MKL spectra come out within rounding, not bit for bit)
+        assert rel_l2(ar.real[half], np.asarray(oa).real[half]) < 1e-6, f
         ta = F.task_arithmetic_fft2(torch.from_numpy(d["v0"]), torch.from_numpy(d["v1"]), 1.0, DEV, agreement=True).numpy()
         to = O.task_arithmetic_fft2(d["v0"], d["v1"], 1.0, agreement=True)
         assert flip_accounted(ta, np.asarray(to), k=8)[1] < 1e-5, f
