@@ -12,16 +12,20 @@ bf16) -> merged bf16 tensor, through FourierMerge.merge_sources (t
 reference and are not part of the timed work.
 
   value : whole-job merged params/s with inputs resident in HBM (device-timed, CUDA events,
-          max over ranks).  N > 1: every rank merges its own copy of the workload (tensors are
-          independent, no collective on the data path) -> weak scaling.
-  e2e   : same metric through FourierMerge._merge_layer with HOST (pinned) tensors: per tensor
-          the H2D copies of base + finetunes and the D2H copy of the result are inside the
-          timed region.
-  roofline : dominant kernel class (column FFT sweeps, k_col): algorithmic bytes / CUDA-event
-          time of its launches inside the timed region vs MEASURED_PEAKS.json hbm_gbs.
-  cpu_baseline : oracle/oracle_np.py (numpy port of the reference algorithm) timed on this
-          box's host cores on a bounded sample of the same workload.
-  --impl reference : the same port with all host threads (one tensor per thread), as its own arm.
+          max over ranks).  N > 1: ONE model's tensor list is split over the ranks by
+          shardmerge_b200.schedule.tensor_partition (longest-processing-time-first, whole tensors,
+          no collective on the data path) -> strong scaling.
+  e2e   : same metric through MergeTensorsBase._process_layers = FourierMerge._merge_layer +
+          ModelWriter.add_tensor per tensor, on HOST (pinned) tensors: the H2D copies of base +
+          finetunes, the D2H copy of every result into the writer's pinned staging and the
+          safetensors shard files (tmpfs) are inside the timed region.
+  roofline : dominant kernel class (column FFT sweeps): SURVEY 8(d) algorithmic bytes (8N per
+          column transform, three transforms per pair) / CUDA-event time of its launches vs
+          MEASURED_PEAKS.json hbm_gbs; `per_sweep` keeps the bytes the two sweeps really move.
+  cpu_baseline / --impl reference : the REFERENCE ITSELF (oracle/_ref, a git-ignored copy of the
+          reference's Python package: FourierMerge._merge_layer(device="cpu"),
+          shard/merge/fast_fourier.py:103-276) on this box's host cores with all torch threads, on
+          a bounded sample of the same workload; the numpy port only if oracle/_ref is absent.
 """
 from __future__ import annotations
 
@@ -162,26 +166,58 @@ def cpu_port_rate(shape, n_ft, threads, repeats=1):
     return threads * repeats * numel(shape) / dt, dt
 
 
+def cpu_reference_rate(shapes, n_ft, repeats=1):
+    """The unmodified reference's FourierMerge._merge_layer(device="cpu") (oracle/ref_runner.py) on one tensor per
+    shape in `shapes` -> (params/s, seconds, threads, kind, per-shape seconds).  Falls back to the numpy port."""
+    from oracle import ref_runner as RR
+    if not RR.available():
+        r, dt = cpu_port_rate(shapes[0], n_ft, 1, repeats=repeats)
+        return r, dt, 1, "port", {f"{shapes[0][0]}x{shapes[0][1]}": dt}
+    import torch
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    jobs = []
+    for i, shape in enumerate(shapes):
+        base, fts = synth_tensor(torch, shape, 7000 + i, n_ft, "cpu")
+        jobs.append((shape, base, fts))
+    per = {}
+    t0 = time.perf_counter()
+    for _ in range(repeats):
+        for shape, base, fts in jobs:
+            t1 = time.perf_counter()
+            RR.merge_layer(base, fts, list(ALPHAS[:n_ft]), device="cpu")
+            per[f"{shape[0]}x{shape[1]}"] = round(time.perf_counter() - t1, 2)
+    dt = time.perf_counter() - t0
+    return repeats * sum(numel(sh) for sh in shapes) / dt, dt, threads, "reference", per
+
+
+def reference_sample_shapes(a):
+    """one k_proj-shaped and one q_proj-shaped tensor: ~15 s of the reference on 8 host cores at Llama-8B shapes."""
+    return [(a["KV"], a["H"]), (a["H"], a["H"])]
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     a = ARCH[args.workload]
-    shape = (a["KV"], a["H"])
-    threads = max(1, min(os.cpu_count() or 1, 64))      # one tensor per host thread (numpy's FFT / sort are single-threaded)
+    shapes = reference_sample_shapes(a)
     for _ in range(min(args.warmup, 1)):
-        cpu_port_rate(shape, args.finetunes, threads)
-    rates, secs = [], []
+        cpu_reference_rate(shapes[:1], args.finetunes)
+    params, secs, per = 0, 0.0, {}
     for _ in range(args.steps):
-        r, dt = cpu_port_rate(shape, args.finetunes, threads)
-        rates.append(r); secs.append(dt)
-    value = sum(threads * numel(shape) for _ in secs) / sum(secs)
-    sample = f"{threads} x k_proj {shape[0]}x{shape[1]} per step (one tensor per host thread), numpy port of the reference"
+        r, dt, threads, kind, per = cpu_reference_rate(shapes, args.finetunes)
+        params += sum(numel(sh) for sh in shapes); secs += dt
+    value = params / secs
+    what = ("the reference's FourierMerge._merge_layer(device='cpu') (oracle/_ref)" if kind == "reference"
+            else "numpy port of the reference (oracle/_ref absent)")
+    sample = (f"per step one tensor each of {' and '.join(f'{s[0]}x{s[1]}' for s in shapes)} through {what}, "
+              f"torch threads = {threads}; seconds per tensor {per}; at most one warm-up step")
     line = dict(impl="reference", metric="merged_params_per_sec", value=value, unit="params/s", n_gpus=args.gpus,
-                steps=args.steps, warmup=args.warmup, ms_per_step=1000 * sum(secs) / len(secs), higher_is_better=True,
-                scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                steps=args.steps, warmup=min(args.warmup, 1), ms_per_step=1000 * secs / args.steps, higher_is_better=True,
+                scaling="strong", vs_baseline=None, dtype="f32", data="synthetic",
                 config=dict(workload=workload_name(args.workload, args.finetunes), sample=sample),
-                cpu_baseline=dict(value=value, unit="params/s", cores=threads, kind="port", sample=sample),
+                cpu_baseline=dict(value=value, unit="params/s", cores=threads, kind=kind, sample=sample),
                 e2e=dict(value=value, unit="params/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0)
     print(json.dumps(line))
@@ -195,9 +231,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="llama8b", choices=sorted(ARCH))
-    ap.add_argument("--layers", type=int, default=0, help="layers resident per rank (0 = as many as fit, up to L)")
+    ap.add_argument("--layers", type=int, default=0, help="layers of the model (0 = all L, or as many as fit on the ranks together)")
     ap.add_argument("--finetunes", type=int, default=2)
-    ap.add_argument("--e2e-layers", type=int, default=2)
+    ap.add_argument("--e2e-layers", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profile-json", default="", help="write the per-kernel-class summary here")
@@ -220,10 +256,11 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     from shardmerge_b200 import engine as E
+    from shardmerge_b200 import schedule
     from shardmerge_b200.config import MergeConfig, MergeModel
     from shardmerge_b200.index import InMemoryIndex
     from shardmerge_b200.merge.fast_fourier import FourierMerge
-    from shardmerge_b200.writer import ShardLayer
+    from shardmerge_b200.writer import ModelWriter, ShardLayer
 
     a = ARCH[args.workload]
     M = args.finetunes
@@ -233,20 +270,28 @@ def main():
     bytes_layer = params_layer * 2 * (M + 2)                      # base + M finetunes + output, bf16
     max_params = max(numel(s) for _, s in per_layer)
     ws_bytes = 5 * 4 * 4 * max_params                             # workspaces of the distinct shapes (generous)
-    fit = int((free_b * 0.85 - ws_bytes) // bytes_layer)
+    fit = (free_b * 0.85 - ws_bytes) / bytes_layer                # layers of this architecture one GPU can hold
     L = a["L"] if args.layers <= 0 else min(args.layers, a["L"])
-    L = max(1, min(L, fit))
+    L = max(1, min(L, int(fit * world * 0.97)))                   # ONE model of L layers, split over the ranks
 
-    # ---- resident synthetic model -------------------------------------------------------
-    tensors = []                                                  # (name, base, [fts])
-    idx = 0
+    # ---- the model's merged tensors, and this rank's share (whole tensors, LPT; same answer on every rank) ------
+    catalog = []                                                  # (name, shape, seed index)
     for layer in range(L):
         for nm, shape in per_layer:
+            catalog.append((f"model.layers.{layer}.{nm}", shape, len(catalog)))
+    numels = {name: numel(shape) for name, shape, _ in catalog}
+    parts = schedule.tensor_partition(numels, world, n_models=M)
+    mine = set(parts[rank])
+    cost = {n: schedule.merge_cost(v, M) for n, v in numels.items()}
+    imbalance = schedule.imbalance(parts, cost) if world > 1 else 0.0
+    tensors = []                                                  # (name, base, [fts]) resident on this rank
+    for name, shape, idx in catalog:
+        if name in mine:
             base, fts = synth_tensor(torch, shape, idx, M, dev)
-            tensors.append((f"model.layers.{layer}.{nm}", base, fts))
-            idx += 1
+            tensors.append((name, base, fts))
     torch.cuda.synchronize(dev)
-    merged_params = L * params_layer
+    merged_params = sum(numels.values())                          # whole job, all ranks
+    my_params = sum(numels[n] for n in mine)
 
     cfg = MergeConfig(finetune_merge=[MergeModel(model=f"synth/ft{k}", base="synth/base", alpha=ALPHAS[k],
                                                  is_input=(k == 0), is_output=(k == 1)) for k in range(M)],
@@ -266,6 +311,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    def max_over_ranks(x):
+        if world > 1:
+            t = torch.tensor([x], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
+
     for _ in range(args.warmup):
         step()
     barrier()
@@ -282,12 +334,12 @@ def main():
     gpu_launches = E.PROFILER.launches
     E.PROFILER = None
     clocks = sampler.stop()
-    elapsed_ms = sum(s0.elapsed_time(s1) for s0, s1 in ev)
+    elapsed_ms = max_over_ranks(sum(s0.elapsed_time(s1) for s0, s1 in ev))
+    value = merged_params * args.steps / (elapsed_ms / 1000.0)
     if world > 1:
-        t = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t.item())
-    value = world * merged_params * args.steps / (elapsed_ms / 1000.0)
+        t = torch.tensor([float(gpu_launches)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        gpu_launches = int(t.item())
 
     # ---- per-kernel pass: the same steps on ONE stream with a CUDA-event pair around every kernel class ----------
     # (with several lanes the kernels of different tensors overlap, and an event pair around one of them would also
@@ -305,7 +357,7 @@ def main():
     E.PROFILER = None
     fm.lanes = lanes_used
     serial_ms = sum(s0.elapsed_time(s1) for s0, s1 in pv)
-    value_serial = merged_params * args.steps / (serial_ms / 1000.0)
+    value_serial = my_params * args.steps / (serial_ms / 1000.0)
 
     # ---- roofline of the dominant kernel class ---------------------------------------------
     summ = prof.summary()
@@ -314,10 +366,15 @@ def main():
         peak, peak_src = float(json.loads(peaks_path.read_text())["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    col_bytes = sum(summ[t]["bytes"] for t in ("col_fwd", "col_inv") if t in summ)
+    col_moved = sum(summ[t]["bytes"] for t in ("col_fwd", "col_inv") if t in summ)     # what the sweeps really move
     col_ms = sum(summ[t]["ms"] for t in ("col_fwd", "col_inv") if t in summ)
     col_launch = sum(summ[t]["launches"] for t in ("col_fwd", "col_inv") if t in summ)
-    achieved = col_bytes / (col_ms / 1000.0) / 1e9 if col_ms else None
+    # a column transform is 8N bytes (read + write the 4N-byte half spectrum once); a pair merge has three
+    # (two forward, one inverse).  Tensors with a single sweep or none (R <= 256, 1-D) move exactly that already.
+    n2d = sum(numels[n] for n in mine if len(next(sh for nm, sh, _ in catalog if nm == n)) == 2)
+    col_alg = 24.0 * n2d * (M - 1) * args.steps                  # M - 1 pair merges per tensor (pair tree for M > 2)
+    achieved = col_alg / (col_ms / 1000.0) / 1e9 if col_ms else None
+    per_sweep = col_moved / (col_ms / 1000.0) / 1e9 if col_ms else None
     kernel_ms_total = sum(v["ms"] or 0.0 for v in summ.values())
     traffic, traffic_note = None, None
     tpath = ROOT / "profiles" / "r01_traffic.json"
@@ -325,90 +382,99 @@ def main():
         tj = json.loads(tpath.read_text())
         traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
         traffic_note = dict(launch=tj["kernel"], algorithmic_bytes_of_that_launch=tj["algorithmic_bytes"], source=tj["source"])
+    pipeline_alg = 64.0 * n2d * (M - 1) * args.steps              # 64N bytes per pair merge
     roofline = dict(bound="hbm", kernel="k_col_p3 / k_col_p (column FFT sweeps, forward+inverse)", achieved=achieved, peak=peak,
                     unit="GB/s", frac=(achieved / peak if achieved else None), traffic=traffic, traffic_note=traffic_note,
                     peak_source=peak_src,
-                    bytes_per_launch=(col_bytes / col_launch if col_launch else None),
+                    bytes_model="SURVEY 8(d): 8N per column transform x 3 transforms per pair = 24N; the two-sweep "
+                                "four-step kernels move 16N per transform (per_sweep)",
+                    per_sweep=dict(gbs=per_sweep, frac=(per_sweep / peak if per_sweep else None),
+                                   bytes_per_launch=(col_moved / col_launch if col_launch else None)),
+                    bytes_per_launch=(col_alg / col_launch if col_launch else None),
                     share_of_kernel_time=(col_ms / kernel_ms_total if kernel_ms_total else None),
+                    whole_pipeline=dict(gbs=(pipeline_alg / (serial_ms / 1000.0) / 1e9),
+                                        frac=(pipeline_alg / (serial_ms / 1000.0) / 1e9 / peak),
+                                        note="64N algorithmic bytes per pair merge over the serial pass"),
                     measured="CUDA events around every kernel class during a serial (one stream) pass of the same steps "
-                             "inside this run; the timed region overlaps kernels of consecutive tensors on several streams",
+                             "inside this run (rank 0's share of the tensors); the timed region overlaps kernels of "
+                             "consecutive tensors on several streams",
                     serial_pass=dict(ms_per_step=serial_ms / args.steps, params_per_s_per_gpu=value_serial),
                     per_class={k: dict(calls=v["calls"], launches=v["launches"], ms=v["ms"],
                                        gbs=(v["bytes"] / (v["ms"] / 1000.0) / 1e9 if v["ms"] else None),
                                        frac=(v["bytes"] / (v["ms"] / 1000.0) / 1e9 / peak if v["ms"] and v["bytes"] else None))
                                for k, v in summ.items()})
 
-    # ---- e2e: host tensors through _merge_layer ----------------------------------------------
+    # ---- e2e: host tensors through _process_layers + ModelWriter ---------------------------------
     e2e = None
     if not args.no_e2e:
+        import shutil
+        import tempfile
         Le = max(1, min(args.e2e_layers, L))
-        host = {"synth/base": {}}
-        for k in range(M):
-            host[f"synth/ft{k}"] = {}
+        # this rank's tensors among the first Le layers (the same partition as above restricted to those layers)
+        e2e_catalog = [(n, sh, i) for n, sh, i in catalog if int(n.split(".")[2]) < Le]
+        e2e_parts = schedule.tensor_partition({n: numel(sh) for n, sh, _ in e2e_catalog}, world, n_models=M)
+        e2e_mine = set(e2e_parts[rank])
+        del tensors[:]
+        outputs.clear()
+        E.clear_caches()
+        torch.cuda.empty_cache()
+        host = {"synth/base": {}, **{f"synth/ft{k}": {} for k in range(M)}}
         names = []
-        for name, base, fts in tensors[: Le * len(per_layer)]:
+        for name, shape, idx in e2e_catalog:
+            if name not in e2e_mine:
+                continue
+            base, fts = synth_tensor(torch, shape, idx, M, dev)
             host["synth/base"][name] = base.cpu().pin_memory()
             for k, ft in enumerate(fts):
                 host[f"synth/ft{k}"][name] = ft.cpu().pin_memory()
             names.append(name)
-        fm2 = FourierMerge(cfg, index_manager=InMemoryIndex(host))
-        out_host = {n: torch.empty(host["synth/base"][n].shape, dtype=torch.bfloat16).pin_memory() for n in names}
+            del base, fts
+        # one output shard per transformer layer (as HF checkpoints roughly do), files on tmpfs when there is one
+        index = InMemoryIndex(host)
+        fm2 = FourierMerge(cfg, index_manager=index)
+        weight_map = {n: f"model-{int(n.split('.')[2]) + 1:05d}-of-{Le:05d}.safetensors" for n in names}
+        tmp_root = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+        out_root = Path(tempfile.mkdtemp(prefix=f"shardmerge_bench_r{rank}_", dir=tmp_root))
         h2d = sum(t.numel() * 2 for n in names for t in [host["synth/base"][n]] + [host[f"synth/ft{k}"][n] for k in range(M)])
-        d2h = sum(out_host[n].numel() * 2 for n in names)
-
-        class HostSink:
-            """Stands in for ModelWriter.add_tensor (shard/writer.py:115-149) without the file write: every result
-            is copied device -> pinned host on a side stream, like ModelWriter._stage does."""
-
-            def __init__(self):
-                self.stream = torch.cuda.Stream(device=dev)
-                self.events = []
-
-            def add_tensor(self, name, tensor):
-                produced = torch.cuda.current_stream(dev).record_event()
-                with torch.cuda.stream(self.stream):
-                    self.stream.wait_event(produced)
-                    out_host[name].copy_(tensor, non_blocking=True)
-                    tensor.record_stream(self.stream)
-                    self.events.append(self.stream.record_event())
-
-            def wait(self):
-                for ev in self.events:
-                    ev.synchronize()
-                self.events.clear()
-
-        sink = HostSink()
-        layers_e2e = [ShardLayer(i, "s", n, False) for i, n in enumerate(names)]
+        d2h = sum(host["synth/base"][n].numel() * 2 for n in names)
+        layers_e2e = [ShardLayer(i, weight_map[n], n, False) for i, n in enumerate(names)]
         fm2.defer_checks = True                    # what MergeTensorsBase.merge() sets: checks settle one tensor behind
+        pool = {}                                  # the writer's pinned pool survives from step to step, like within one merge
 
-        async def e2e_step():
-            # the reference's hot loop (shard/merge/base.py:212-223): _merge_layer + writer.add_tensor per tensor;
-            # here the next tensor's upload, this tensor's kernels and the previous tensor's download overlap
-            await fm2._process_layers(sink, layers_e2e, str(dev))
-            sink.wait()
+        async def e2e_step(k):
+            # the reference's hot loop (shard/merge/base.py:212-223): _merge_layer + writer.add_tensor per tensor; here
+            # the uploads of the next tensors, this tensor's kernels, the previous tensor's download and the shard file
+            # writes (writer thread) overlap.  finalize() waits for the last file.
+            out = out_root / f"step{k}"
+            writer = ModelWriter(base_index={"metadata": {}, "weight_map": weight_map}, output_path=out, layer_order=names,
+                                 output_astype=torch.bfloat16, pinned_pool=pool.get("pool"))
+            pool["pool"] = writer._pool
+            await fm2._process_layers(writer, layers_e2e, str(dev))
+            writer.finalize()
             torch.cuda.synchronize(dev)
+            shutil.rmtree(out, ignore_errors=True)
 
         loop = asyncio.new_event_loop()
-        for _ in range(min(args.warmup, 2)):
-            loop.run_until_complete(e2e_step())
+        for k in range(max(1, min(args.warmup, 2))):
+            loop.run_until_complete(e2e_step(-1 - k))
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(args.steps):
-            loop.run_until_complete(e2e_step())
+        t_e2e0 = time.perf_counter()
+        for k in range(args.steps):
+            loop.run_until_complete(e2e_step(k))
         e1.record()
         barrier()
-        ems = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ems], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ems = float(t.item())
+        e2e_wall = time.perf_counter() - t_e2e0
+        my_ems = e0.elapsed_time(e1)
+        ems = max_over_ranks(my_ems)
+        shutil.rmtree(out_root, ignore_errors=True)
         # what plain pinned copies achieve on this box, both directions at once (the e2e path moves 6 B in and 2 B out
-        # per merged parameter, so it is bounded by the host link, not by the kernels)
+        # per merged parameter, so it is bounded by the host link, not by the kernels); all ranks probe at the same time
         pin_in = torch.empty(1 << 29, dtype=torch.uint8).pin_memory(); dev_in = torch.empty(1 << 29, dtype=torch.uint8, device=dev)
         pin_out = torch.empty(1 << 28, dtype=torch.uint8).pin_memory(); dev_out = torch.empty(1 << 28, dtype=torch.uint8, device=dev)
         s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
-        torch.cuda.synchronize(dev)
+        barrier()
         p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         p0.record()
         s_in.wait_event(p0); s_out.wait_event(p0)
@@ -422,34 +488,46 @@ def main():
         p1.record(); torch.cuda.synchronize(dev)
         link_ms = p0.elapsed_time(p1)
         link = dict(h2d_gbs=2 * (1 << 29) / link_ms / 1e6, d2h_gbs=2 * (1 << 28) / link_ms / 1e6,
-                    note="1 GiB in + 0.5 GiB out, pinned, concurrent (the 3:1 ratio of the merge)")
+                    note="per rank, all ranks at once: 1 GiB in + 0.5 GiB out, pinned, concurrent (the 3:1 ratio of the merge)")
         del pin_in, dev_in, pin_out, dev_out
-        e2e_params = sum(numel(host["synth/base"][n].shape) for n in names)
-        e2e = dict(value=world * e2e_params * args.steps / (ems / 1000.0), unit="params/s",
-                   h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, layers=Le, host_link_probe=link,
-                   h2d_gbs_achieved=world * h2d * args.steps / (ems / 1000.0) / 1e9 / world,
-                   api="MergeTensorsBase._process_layers (FourierMerge._merge_layer + writer.add_tensor per tensor) on "
-                       "pinned host tensors: H2D of base + finetunes and D2H of the merged tensor inside the timed region")
+        e2e_params = sum(numel(sh) for _, sh, _ in e2e_catalog)         # whole job
+        h2d_all, d2h_all = h2d, d2h
+        if world > 1:
+            t = torch.tensor([float(h2d), float(d2h)], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            h2d_all, d2h_all = int(t[0].item()), int(t[1].item())
+        e2e = dict(value=e2e_params * args.steps / (ems / 1000.0), unit="params/s",
+                   h2d_bytes_per_step=h2d_all, d2h_bytes_per_step=d2h_all, layers=Le, host_link_probe=link,
+                   h2d_gbs_achieved_rank0=h2d * args.steps / (my_ems / 1000.0) / 1e9,
+                   wall_s=e2e_wall, files="safetensors shards, one per layer, written by ModelWriter's writer thread to " +
+                                           ("tmpfs (/dev/shm)" if tmp_root else "the default temp directory"),
+                   api="MergeTensorsBase._process_layers (FourierMerge._merge_layer + ModelWriter.add_tensor per tensor, "
+                       "ModelWriter.finalize per step) on pinned host tensors: H2D of base + finetunes, D2H of the merged "
+                       "tensor into pinned staging and the shard file writes are inside the timed region")
 
     # ---- CPU baseline (rank 0, N = 1 only) -----------------------------------------------------
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        shape = (a["KV"], a["H"])
-        r, dt = cpu_port_rate(shape, M, 1, repeats=5)
-        cpu_baseline = dict(value=r, unit="params/s", cores=1, kind="port",
-                            sample=f"5 x k_proj {shape[0]}x{shape[1]} through oracle/oracle_np.merge_layer "
-                                   f"(numpy, single thread), {dt:.1f} s")
+        shapes = reference_sample_shapes(a)
+        r, dt, threads, kind, per = cpu_reference_rate(shapes, M)
+        cpu_baseline = dict(value=r, unit="params/s", cores=threads, kind=kind,
+                            sample=f"one tensor each of {' and '.join(f'{s[0]}x{s[1]}' for s in shapes)} through "
+                                   + ("the reference's FourierMerge._merge_layer(device='cpu') (oracle/_ref)" if kind == "reference"
+                                      else "oracle/oracle_np.merge_layer (numpy port; oracle/_ref absent)")
+                                   + f", torch threads = {threads}, {dt:.1f} s; seconds per tensor {per}")
 
     if rank == 0:
         line = dict(metric="merged_params_per_sec", value=value, unit="params/s", n_gpus=world, steps=args.steps,
-                    warmup=args.warmup, ms_per_step=elapsed_ms / args.steps, higher_is_better=True, scaling="weak",
+                    warmup=args.warmup, ms_per_step=elapsed_ms / args.steps, higher_is_better=True, scaling="strong",
                     vs_baseline=None, dtype="f32", data="synthetic",
                     merged_gb_per_s=value * 2 / 1e9,
                     config=dict(workload=workload_name(args.workload, M),
-                                layers_resident=L, layers_of_model=a["L"], merged_params_per_step_per_gpu=merged_params,
-                                tensors_per_step=len(tensors), l2="inputs per step (%.1f GB) exceed the 126 MB L2" %
-                                                                 (merged_params * 2 * (M + 1) / 1e9),
-                                partition="whole tensors per rank, no collective", streams_per_gpu=lanes_used),
+                                layers_resident=L, layers_of_model=a["L"], merged_params_per_step=merged_params,
+                                tensors_per_step=len(catalog), tensors_on_rank0=len(mine),
+                                l2="inputs per step and rank (%.1f GB) exceed the 126 MB L2" % (my_params * 2 * (M + 1) / 1e9),
+                                partition="whole tensors, longest-processing-time-first over the ranks "
+                                          "(schedule.tensor_partition), no collective on the data path",
+                                partition_imbalance=imbalance, streams_per_gpu=lanes_used),
                     roofline=roofline, cpu_baseline=cpu_baseline, e2e=e2e, gpu_launches=gpu_launches, clocks=clocks,
                     wall_s=wall)
         print(json.dumps(line))

@@ -173,6 +173,7 @@ class ModelWriter:
     only_shards: Optional[Set[str]] = None       # multi-GPU merge: the shards this process owns (schedule.py)
     write_index: bool = True                     # multi-GPU merge: rank 0 writes the index copy, the others only read it
     async_write: bool = True
+    pinned_pool: Optional["_PinnedPool"] = None  # share staging buffers between writers (successive merges in one process)
 
     def __post_init__(self):
         self.output_path = Path(self.output_path)
@@ -195,7 +196,7 @@ class ModelWriter:
         self._bufs: Dict[str, list] = {}                           # shard -> pinned buffers to give back
         self._events: Dict[str, list] = {}
         self._copy_stream = None
-        self._pool = _PinnedPool()
+        self._pool = self.pinned_pool if self.pinned_pool is not None else _PinnedPool()
         self._worker: Optional[_ShardWriter] = None
         self._lock = threading.Lock()
         self._check_existing_shards()

@@ -265,8 +265,16 @@ def test_merge_vs_reference_on_cuda(E, shape, seed):
     met = parity_metrics(out_bits, ref_bits, bb, shape)
     basef = O.bf16_to_f32(bb)
     raw, resid, share = flip_accounted(O.bf16_to_f32(out_bits) - basef, O.bf16_to_f32(ref_bits) - basef, k=16)
+    floor = {}
+    if shape[0] * shape[1] <= 1024 * 4096:
+        # the floor any implementation faces: the SAME reference code, CPU (MKL) against CUDA (cuFFT), same metric
+        # (at larger sizes the CPU reference's biased fp32 norms make the comparison meaningless)
+        ref_cpu = bits(RR.merge_layer(base.cpu(), [f.cpu() for f in fts], [0.3, 0.5], device="cpu"))
+        fm_ = parity_metrics(ref_cpu, ref_bits, bb, shape)
+        floor = dict(reference_cpu_vs_cuda_within_1ulp=fm_["within_1ulp"], reference_cpu_vs_cuda_exact=fm_["exact"])
     record("merge_vs_reference_cuda", f"{shape[0]}x{shape[1]}", reference_seconds=round(ref_s, 2),
-           reference_equals_base_fraction=degenerate, bf16_delta_rel_l2_raw=raw, bf16_delta_rel_l2_flip_accounted=resid, **met)
+           reference_equals_base_fraction=degenerate, bf16_delta_rel_l2_raw=raw, bf16_delta_rel_l2_flip_accounted=resid,
+           **floor, **met)
     if degenerate > 0.5:
         pytest.skip("the reference degenerates on CUDA for this input (NaN imaginary path, SURVEY 7.3-2): recorded only")
     # the bf16 outputs quantise the delta (|delta| ~ 0.1 ulp of |base|), so the delta comparison resolves ~1e-2 only;
