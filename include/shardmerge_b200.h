@@ -229,6 +229,25 @@ typedef struct sm_pair_args {
 
 int sm_pair_merge_slerp_async(const sm_plan* plan, const void* tables, const sm_pair_args* args, void* stream);
 
+/* The same chain as one pair merge INSIDE the pairwise tree that FourierMerge._merge_layer builds for more than two
+ * finetunes (shard/merge/fast_fourier.py:171-254: round 1 merges pairs of deltas, later rounds merge the fp32 results,
+ * cull_pct halves per round, target_norm is the mean over ALL models' norms, :165).  `ext` adds what the tree needs:
+ *   x32_0 / x32_1  non-NULL: that input is an fp32 [R][C] tensor (an earlier round's result) instead of (base, ft);
+ *   rows_done      1: the row passes of both inputs already ran into (re[k], im[k]) and `sumsq` holds their sums of
+ *                  squares (round 1: the caller transforms every model once, reads the norms, pairs them on the host
+ *                  like correlated_pairs does, :180-186);
+ *   target_norm    > 0: use it instead of the mean of the two norms;
+ *   out_f32        non-NULL: write merged * target_norm as fp32 (no base add, no bf16 cast): an intermediate of the tree.
+ * Branch / role decisions stay on the device as in sm_pair_merge_slerp_async. */
+typedef struct sm_pair_ext {
+  const float* x32_0; const float* x32_1;
+  int rows_done;
+  double sumsq[2];
+  double target_norm;
+  float* out_f32;
+} sm_pair_ext;
+int sm_pair_merge_tree_async(const sm_plan* plan, const void* tables, const sm_pair_args* args, const sm_pair_ext* ext, void* stream);
+
 /* Per-kernel-class CUDA-event timing of the fused chain (bench.py roofline).  Classes: */
 #define SM_CLS_ROW_FWD 0
 #define SM_CLS_COL_FWD 1

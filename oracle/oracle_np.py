@@ -277,7 +277,7 @@ def merge_layer(base_out_bf16, models, target_norm_offset=1e-10, cull_start_pct=
         raise ValueError("Inf in merged tensor")
     if info is not None:
         info.update(branches=branches, target_norm=target_norm, norms=[float(x) for x in norms],
-                    merged_f32=cache[stack[0]])          # the fp32 tree result before the base is added (:256-257)
+                    merged_f32=cache[stack[0]], intermediates={k: v for k, v in cache.items() if "_" in k})          # the fp32 tree result before the base is added (:256-257)
     return f32_to_bf16(result)                                               # :276
 
 

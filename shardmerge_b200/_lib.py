@@ -48,6 +48,7 @@ SIGNATURES = {
     "sm_expand_full": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "sm_pack_half": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "sm_pair_merge_slerp_async": (_i, [_vp, _vp, _vp, _vp]),
+    "sm_pair_merge_tree_async": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "sm_profile_enable": (_i, [_i]),
     "sm_profile_collect": (_i, [_vp, _vp, _vp, _i]),
 }
@@ -59,6 +60,11 @@ class PairArgs(C.Structure):
                 ("re", _vp * 3), ("im", _vp * 2), ("ctl", _vp), ("sel_ws", _vp), ("sel_ws_bytes", _sz),
                 ("t", _d), ("t_sum", _f), ("cutoff_pct", _d), ("cull_pct", _d), ("target_norm_offset", _d),
                 ("select_mode", _i)]
+
+
+class PairExt(C.Structure):
+    """sm_pair_ext of include/shardmerge_b200.h"""
+    _fields_ = [("x32_0", _vp), ("x32_1", _vp), ("rows_done", _i), ("sumsq", _d * 2), ("target_norm", _d), ("out_f32", _vp)]
 
 
 CLS_NAMES = ["row_fwd", "col_fwd", "stats_cutoff", "reduce", "scalars", "blend_cull", "select1", "col_inv", "row_inv"]

@@ -2102,6 +2102,16 @@ int sm_inv_rows_bf16_sel(const sm_plan* plan, const void* tables, const float* r
   return launch_row_inv(plan->p, tables, a, (cudaStream_t)stream);
 }
 
+int sm_inv_rows_f32_sel(const sm_plan* plan, const void* tables, const float* re, const float* im, const float* im_alt,
+                        const int* sel, const float* cull_thr, float* out, const float* scale_dev, float scale_host,
+                        int check_ifft, uint32_t* flags4, void* stream) {
+  RowInvArgs a{};
+  a.check_ifft = check_ifft; a.im_alt = im_alt; a.sel = sel;
+  a.re = re; a.im = im; a.cull_thr = cull_thr; a.out_mode = 1; a.out_f32 = out;
+  a.scale_ptr = scale_dev; a.scale_host = scale_host; a.flags = flags4;
+  return launch_row_inv(plan->p, tables, a, (cudaStream_t)stream);
+}
+
 extern "C" int sm_inv_rows_bf16(const sm_plan* plan, const void* tables, const float* re, const float* im,
                                 const float* cull_thr, const void* base_bf16, void* out_bf16,
                                 const float* scale_dev, float scale_host, int check_ifft, uint32_t* flags4,

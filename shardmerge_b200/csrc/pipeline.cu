@@ -15,8 +15,11 @@
 
 namespace {
 
-__global__ void k_prepare(unsigned char* ctl, double target_norm_offset) {
-  const double* sumsq = reinterpret_cast<const double*>(ctl + SM_CTL_SUMSQ);
+// ext_tn > 0: the target norm is given (the mean over ALL models of the layer in a pair tree, fast_fourier.py:165);
+// use_host_sumsq: the row passes ran earlier and the host passes their sums of squares in (tree round 1)
+__global__ void k_prepare(unsigned char* ctl, double target_norm_offset, double ext_tn, int use_host_sumsq, double hs0, double hs1) {
+  double* sumsq = reinterpret_cast<double*>(ctl + SM_CTL_SUMSQ);
+  if (use_host_sumsq) { sumsq[0] = hs0; sumsq[1] = hs1; }
   float* flt = reinterpret_cast<float*>(ctl + SM_CTL_FLT);
   int* ints = reinterpret_cast<int*>(ctl + SM_CTL_INT);
   double* tn_out = reinterpret_cast<double*>(ctl + SM_CTL_TN);
@@ -25,7 +28,7 @@ __global__ void k_prepare(unsigned char* ctl, double target_norm_offset) {
   const int swap = fabsf(nx) < fabsf(ny) ? 1 : 0;              // fast_fourier.py:212
   const double na = swap ? (double)ny : (double)nx, nb = swap ? (double)nx : (double)ny;
   const float mean32 = (nx + ny) / 2.0f;                        // torch.tensor(layer_norms).mean()  (:165)
-  const double tn = (double)mean32 + target_norm_offset;
+  const double tn = ext_tn > 0.0 ? ext_tn : (double)mean32 + target_norm_offset;
   const double cnorm_a = fabs(na / tn), cnorm_b = fabs(nb / tn);
   const double n_ratio = cnorm_b / (cnorm_a + 1e-10);
   int branch = SM_BRANCH_SLERP;
@@ -81,7 +84,18 @@ extern "C" int sm_profile_collect(double* ms, double* bytes, int* launches, int 
   return 0;
 }
 
+static int pair_chain(const sm_plan* plan, const void* tables, const sm_pair_args* a, const sm_pair_ext* x, void* stream);
+
 extern "C" int sm_pair_merge_slerp_async(const sm_plan* plan, const void* tables, const sm_pair_args* a, void* stream) {
+  return pair_chain(plan, tables, a, nullptr, stream);
+}
+
+extern "C" int sm_pair_merge_tree_async(const sm_plan* plan, const void* tables, const sm_pair_args* a, const sm_pair_ext* x,
+                                        void* stream) {
+  return pair_chain(plan, tables, a, x, stream);
+}
+
+static int pair_chain(const sm_plan* plan, const void* tables, const sm_pair_args* a, const sm_pair_ext* x, void* stream) {
   const SmPlan& p = plan->p;
   cudaStream_t st = (cudaStream_t)stream;
   const double N = (double)p.R * (double)p.C;
@@ -96,14 +110,21 @@ extern "C" int sm_pair_merge_slerp_async(const sm_plan* plan, const void* tables
   const int col_launches = sm_plan_col_launches(plan);
   int rc;
   SM_CUDA_CHECK(cudaMemsetAsync(ctl, 0, SM_CTL_BYTES, st));
-  {
+  const bool rows_done = x != nullptr && x->rows_done != 0;
+  if (!rows_done) {
+    // bf16 (base, finetune) pairs: 2N + 2N read, 4N written; fp32 tree intermediates: 4N read, 4N written
     Scope s(st, SM_CLS_ROW_FWD, 16.0 * N, 2);
-    if ((rc = sm_fwd_rows_bf16(plan, tables, a->base0, a->ft0, a->re[0], a->im[0], dbl + 0, st))) return rc;
-    if ((rc = sm_fwd_rows_bf16(plan, tables, a->base1, a->ft1, a->re[1], a->im[1], dbl + 1, st))) return rc;
+    if (x != nullptr && x->x32_0 != nullptr) {
+      if ((rc = sm_fwd_rows_f32(plan, tables, x->x32_0, 1.f, 1.f, a->re[0], a->im[0], dbl + 0, st))) return rc;
+    } else if ((rc = sm_fwd_rows_bf16(plan, tables, a->base0, a->ft0, a->re[0], a->im[0], dbl + 0, st))) return rc;
+    if (x != nullptr && x->x32_1 != nullptr) {
+      if ((rc = sm_fwd_rows_f32(plan, tables, x->x32_1, 1.f, 1.f, a->re[1], a->im[1], dbl + 1, st))) return rc;
+    } else if ((rc = sm_fwd_rows_bf16(plan, tables, a->base1, a->ft1, a->re[1], a->im[1], dbl + 1, st))) return rc;
   }
   {
     Scope s(st, SM_CLS_SCALARS, 0.0, 1);
-    k_prepare<<<1, 1, 0, st>>>(ctl, a->target_norm_offset);
+    k_prepare<<<1, 1, 0, st>>>(ctl, a->target_norm_offset, x ? x->target_norm : 0.0, rows_done ? 1 : 0,
+                               rows_done ? x->sumsq[0] : 0.0, rows_done ? x->sumsq[1] : 0.0);
     SM_LAUNCH_CHECK();
   }
   {
@@ -161,8 +182,12 @@ extern "C" int sm_pair_merge_slerp_async(const sm_plan* plan, const void* tables
   }
   {
     Scope s(st, SM_CLS_ROW_INV, 8.0 * N, 1);
-    if ((rc = sm_inv_rows_bf16_sel(plan, tables, a->re[2], a->im[0], a->im[1], swap, cull ? flt + SM_F_THR_CULL : nullptr,
-                                   a->base_out, a->out_bf16, flt + SM_F_OUT_SCALE, 1.f, 1, flags, st))) return rc;
+    if (x != nullptr && x->out_f32 != nullptr) {
+      // an intermediate of the pair tree: merged * target_norm as fp32, the base is added after the last round only
+      if ((rc = sm_inv_rows_f32_sel(plan, tables, a->re[2], a->im[0], a->im[1], swap, cull ? flt + SM_F_THR_CULL : nullptr,
+                                    x->out_f32, flt + SM_F_OUT_SCALE, 1.f, 1, flags, st))) return rc;
+    } else if ((rc = sm_inv_rows_bf16_sel(plan, tables, a->re[2], a->im[0], a->im[1], swap, cull ? flt + SM_F_THR_CULL : nullptr,
+                                          a->base_out, a->out_bf16, flt + SM_F_OUT_SCALE, 1.f, 1, flags, st))) return rc;
   }
   return 0;
 }

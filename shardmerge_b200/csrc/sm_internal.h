@@ -63,3 +63,6 @@ int sm_inv_rows_bf16_sel(const sm_plan* plan, const void* tables, const float* r
                          const float* im_alt, const int* sel, const float* cull_thr, const void* base_bf16,
                          void* out_bf16, const float* scale_dev, float scale_host, int check_ifft, uint32_t* flags4,
                          void* stream);
+int sm_inv_rows_f32_sel(const sm_plan* plan, const void* tables, const float* re, const float* im, const float* im_alt,
+                        const int* sel, const float* cull_thr, float* out, const float* scale_dev, float scale_host,
+                        int check_ifft, uint32_t* flags4, void* stream);

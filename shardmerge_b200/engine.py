@@ -520,17 +520,38 @@ class PendingPair:
         return self.info
 
 
-def pair_merge_async(ws: Workspace, s0: Source, s1: Source, base_out: torch.Tensor, out: torch.Tensor, *, t: float,
+def pair_merge_async(ws: Workspace, s0: Source, s1: Source, base_out: Optional[torch.Tensor], out: torch.Tensor, *, t: float,
                      t_sum: float = 1.0, cutoff_pct: float = 0.08, cull_pct: float = 0.20,
-                     target_norm_offset: float = 1e-10, layer_name: str = "") -> PendingPair:
+                     target_norm_offset: float = 1e-10, layer_name: str = "", slots=(0, 1), rows_done: bool = False,
+                     sumsq=None, target_norm: float = 0.0) -> PendingPair:
+    """Enqueue one pair merge as a single stream-ordered chain (csrc/pipeline.cu).  `out` is bf16 (base_out is added,
+    the end of _merge_layer) or fp32 (merged * target_norm: an intermediate of the pair tree, base_out unused).  A source
+    is a bf16 (base, finetune) pair or an fp32 tensor; with rows_done the row spectra already sit in `slots` and `sumsq`
+    carries their sums of squares.  target_norm > 0 overrides the mean of the two norms (tree: mean over all models)."""
     global _ring
     pl, lib = ws.plan, ws.plan.lib
     dev = pl.device
     a = _lib.PairArgs()
-    a.base0, a.ft0, a.base1, a.ft1 = s0.base.data_ptr(), s0.ft.data_ptr(), s1.base.data_ptr(), s1.ft.data_ptr()
-    a.base_out, a.out_bf16 = base_out.data_ptr(), out.data_ptr()
-    a.re[0], a.re[1], a.re[2] = ws.re[0].data_ptr(), ws.re[1].data_ptr(), ws.re_out.data_ptr()
-    a.im[0], a.im[1] = ws.im[0].data_ptr(), ws.im[1].data_ptr()
+    x = _lib.PairExt()
+    use_ext = rows_done or target_norm > 0 or out.dtype == torch.float32 or not s0.is_bf16 or not s1.is_bf16
+    if s0.is_bf16:
+        a.base0, a.ft0 = s0.base.data_ptr(), s0.ft.data_ptr()
+    else:
+        x.x32_0 = s0.x32.data_ptr()
+    if s1.is_bf16:
+        a.base1, a.ft1 = s1.base.data_ptr(), s1.ft.data_ptr()
+    else:
+        x.x32_1 = s1.x32.data_ptr()
+    if out.dtype == torch.bfloat16:
+        a.base_out, a.out_bf16 = base_out.data_ptr(), out.data_ptr()
+    else:
+        x.out_f32 = out.data_ptr()
+    x.rows_done = 1 if rows_done else 0
+    if rows_done:
+        x.sumsq[0], x.sumsq[1] = float(sumsq[0]), float(sumsq[1])
+    x.target_norm = float(target_norm)
+    a.re[0], a.re[1], a.re[2] = ws.re[slots[0]].data_ptr(), ws.re[slots[1]].data_ptr(), ws.re_out.data_ptr()
+    a.im[0], a.im[1] = ws.im[slots[0]].data_ptr(), ws.im[slots[1]].data_ptr()
     a.ctl = ws.ctl.data_ptr()
     a.sel_ws, a.sel_ws_bytes = ws.sel_ws.data_ptr(), ws.sel_ws.numel()
     a.t, a.t_sum, a.cutoff_pct, a.cull_pct = float(t), float(t_sum), float(cutoff_pct), float(cull_pct)
@@ -540,10 +561,13 @@ def pair_merge_async(ws: Workspace, s0: Source, s1: Source, base_out: torch.Tens
     if PROFILER is not None:
         fs = lib.sm_fstats_supported(pl.handle) and not ws.safe_select
         cl = lib.sm_plan_col_launches(pl.handle)          # launches of one column transform (column bands x sweeps)
-        PROFILER.launches += 2 + 1 + 2 * cl + ((2 + 2) if fs else (11 + 2 + 1 + 11)) + (cl if sweeps else 0) + 1
+        PROFILER.launches += (0 if rows_done else 2) + 1 + 2 * cl + ((2 + 2) if fs else (11 + 2 + 1 + 11)) + (cl if sweeps else 0) + 1
         PROFILER.fused_calls += 1
-    _lib.check(lib.sm_pair_merge_slerp_async(pl.handle, pl.tables.data_ptr(), ctypes.byref(a), _stream(dev)),
-               "sm_pair_merge_slerp_async")
+    if use_ext:
+        rc = lib.sm_pair_merge_tree_async(pl.handle, pl.tables.data_ptr(), ctypes.byref(a), ctypes.byref(x), _stream(dev))
+    else:
+        rc = lib.sm_pair_merge_slerp_async(pl.handle, pl.tables.data_ptr(), ctypes.byref(a), _stream(dev))
+    _lib.check(rc, "sm_pair_merge_async")
     if _ring is None:
         _ring = _PinnedPool()
     host = _ring.take()

@@ -47,6 +47,26 @@ def clamp(value: float, min_value: float, max_value: float) -> float:
     return max(min_value, min(value, max_value))
 
 
+class _PendingTree:
+    """Deferred check of a pair tree: the per-pair handles of engine.pair_merge_async behind the interface of one."""
+
+    def __init__(self, out, parts, layer_name, norms, target_norm):
+        self.out, self.parts, self.layer_name = out, parts, layer_name
+        self.norms, self.target_norm = norms, target_norm
+        self.redo = None
+
+    def resolve(self) -> dict:
+        infos = [p.resolve() for p in self.parts]
+        sticky = 0
+        flags = [0, 0, 0, 0]
+        for i in infos:
+            sticky |= i["select_sticky"]
+            flags = [f + g for f, g in zip(flags, i["flags"])]
+        branch = next((i["branch"] for i in infos if i["branch"] != "slerp"), "slerp")
+        return dict(norms=list(self.norms), target_norm=self.target_norm, swap=[i["swap"] for i in infos], branch=branch,
+                    branches=[i["branch"] for i in infos], select_sticky=sticky, flags=flags)
+
+
 class FourierMerge(MergeTensorsBase):
     pipeline_depth = 1           # merge(): one tensor stays in flight while the previous one is settled / written
     # Consecutive tensors alternate between `lanes` CUDA streams (each with its own workspace): every kernel of the
@@ -65,6 +85,9 @@ class FourierMerge(MergeTensorsBase):
         self.defer_checks = False        # True inside merge(): _merge_layer returns before the check
         self._lane_streams: dict = {}    # device index -> [streams]
         self._lane_next = 0
+        self.fused_tree = os.environ.get("SHARDMERGE_FUSED_TREE", "1") != "0"   # 0: pair tree on the step-by-step path (A-B)
+        self.keep_intermediates = False  # tests: keep the tree's fp32 round results in self.last_tree
+        self.last_tree: list = []
 
     def get_readme(self) -> str:
         models = "\n".join(f"- {m.model} (vs {m.base})" for m in self.config.finetune_merge)
@@ -149,8 +172,11 @@ class FourierMerge(MergeTensorsBase):
                 raise ValueError(f"finetune / base shape mismatch for {layer_name}: {tuple(src.ft.shape)} vs {shp}")
             if int(torch.tensor(shp).prod()) != base_out.numel():
                 raise ValueError(f"tensor shape mismatch for {layer_name}: {shp} vs output base {tuple(base_out.shape)}")
-        fused_ok = (len(sources) == 2 and not safe_select and base_out.dtype == torch.bfloat16
-                    and sources[0].is_bf16 and sources[1].is_bf16 and base_out.ndim in (1, 2))
+        all_bf16 = (not safe_select and base_out.dtype == torch.bfloat16 and base_out.ndim in (1, 2)
+                    and all(src.is_bf16 for src in sources))
+        if all_bf16 and len(sources) >= 3 and self.fused_tree:
+            return self._merge_sources_tree(sources, base_out, dev, layer_name, defer)
+        fused_ok = len(sources) == 2 and all_bf16
         if not fused_ok:
             return self._merge_sources_steps(sources, base_out, dev, layer_name, safe_select)
         R, C = E.shape_rc(base_out)
@@ -162,12 +188,7 @@ class FourierMerge(MergeTensorsBase):
         if self.lanes > 1 and defer:
             # the chain runs on this tensor's lane; the caller's stream is not made to wait for it -- whoever
             # consumes `out` does so after resolve (a host-side wait for the lane's last event)
-            streams = self._lane_streams.get(dev.index)
-            if streams is None:
-                streams = self._lane_streams[dev.index] = [torch.cuda.Stream(device=dev) for _ in range(self.lanes)]
-            lane_i = self._lane_next % self.lanes
-            self._lane_next += 1
-            lane = streams[lane_i]
+            lane_i, lane = self._next_lane(dev)
             ws = E.get_workspace(R, C, dev, n_spectra=2, lane=lane_i)
             lane.wait_event(torch.cuda.current_stream(dev).record_event())      # inputs are ready on the caller's stream
             with torch.cuda.stream(lane):
@@ -184,6 +205,90 @@ class FourierMerge(MergeTensorsBase):
         self._resolve(pend)
         return out
 
+    def _next_lane(self, dev):
+        streams = self._lane_streams.get(dev.index)
+        if streams is None:
+            streams = self._lane_streams[dev.index] = [torch.cuda.Stream(device=dev) for _ in range(self.lanes)]
+        lane_i = self._lane_next % self.lanes
+        self._lane_next += 1
+        return lane_i, streams[lane_i]
+
+    # -------------------------------------------------------------------------------------
+    def _merge_sources_tree(self, sources: List[E.Source], base_out: torch.Tensor, dev, layer_name: str = "",
+                            defer: bool = False) -> torch.Tensor:
+        """Three or more bf16 finetunes: the pairwise tree of fast_fourier.py:171-254 with every pair merge on the fused
+        chain.  One host read per tensor -- the models' norms, which pair them up (correlated_pairs over norm products,
+        :180-186; later rounds keep using the ORIGINAL norms list, the reference's stale-norms quirk) and give
+        target_norm (:165).  Round 1 merges row spectra that are already in the workspace into fp32 intermediates,
+        later rounds read fp32 tensors, the last pair writes base + merged as bf16; role / branch decisions of every
+        pair are made on the device and checked afterwards (a non-SLERP branch anywhere redoes the tensor step by step)."""
+        R, C = E.shape_rc(base_out)
+        M = len(sources)
+        out = torch.empty(base_out.shape, dtype=torch.bfloat16, device=dev)
+        base_c = base_out.contiguous()
+        caller = torch.cuda.current_stream(dev)
+        if self.lanes > 1 and defer:
+            lane_i, lane = self._next_lane(dev)
+            lane.wait_event(caller.record_event())               # inputs are ready on the caller's stream
+        else:
+            lane_i, lane = 0, caller
+        parts = []
+        with torch.cuda.stream(lane):
+            ws = E.get_workspace(R, C, dev, n_spectra=M, lane=lane_i)
+            sums = torch.zeros(M, dtype=torch.float64, device=dev)
+            for i, src in enumerate(sources):
+                E.fwd_rows_ptr(ws, i, src, sums.data_ptr() + 8 * i)
+            sumsq = sums.to("cpu").tolist()                       # the one host wait (this lane only; the others keep running)
+            norms = [E.f32(v ** 0.5) for v in sumsq]
+            target_norm = torch.tensor(norms, dtype=torch.float32).mean().item() + self.target_norm_offset   # :165
+            # stack entry: (source, slot holding its row spectrum or None, sum of squares or None)
+            stack = [(src, i, sumsq[i]) for i, src in enumerate(sources)]
+            weights = [src.weight for src in sources]
+            cull_pct = self.cull_start_pct
+            kept = []
+            while len(stack) > 1:
+                n = len(stack)
+                corr = torch.zeros((n, n), dtype=torch.float32)
+                for i in range(n):
+                    for j in range(i + 1, n):
+                        corr[i, j] = torch.tensor(norms[i], dtype=torch.float32) * torch.tensor(norms[j], dtype=torch.float32)
+                pairs = list(correlated_pairs(corr, way="least"))
+                last_round = len(pairs) == 1 and pairs[0][1] >= 0
+                nxt, nxt_w = [], []
+                for x, y, _ in pairs:
+                    if y < 0:
+                        src, _, _ = stack[x]
+                        nxt.append((src, None, None)); nxt_w.append(weights[x])   # carried over; its rows are redone when it is paired
+                        continue
+                    (sa, slot_a, ss_a), (sb, slot_b, ss_b) = stack[x], stack[y]
+                    a_w, b_w = weights[x], weights[y]
+                    rows_done = slot_a is not None and slot_b is not None
+                    res = out if last_round else torch.empty((R, C), dtype=torch.float32, device=dev)
+                    parts.append(E.pair_merge_async(
+                        ws, sa, sb, base_c, res, t=a_w / (a_w + b_w), t_sum=1.0, cutoff_pct=0.08, cull_pct=cull_pct,
+                        target_norm_offset=self.target_norm_offset, layer_name=layer_name,
+                        slots=(slot_a, slot_b) if rows_done else (0, 1), rows_done=rows_done,
+                        sumsq=(ss_a, ss_b) if rows_done else None, target_norm=target_norm))
+                    if not last_round:
+                        inter = E.Source(x32=res, weight=(a_w + b_w) / 2.0, name=name_hash(f"{sa.name}_{sb.name}"))
+                        nxt.append((inter, None, None)); nxt_w.append((a_w + b_w) / 2.0)
+                        if self.keep_intermediates:
+                            kept.append((sa.name, sb.name, res))
+                stack, weights = nxt, nxt_w
+                cull_pct = cull_pct / 2.0                         # :254
+        if lane is not caller:
+            for t_ in [out, base_c] + [t for src in sources for t in (src.base, src.ft)]:
+                t_.record_stream(lane)
+        if self.keep_intermediates:
+            self.last_tree = kept
+        pend = _PendingTree(out, parts, layer_name, norms, target_norm)
+        pend.redo = lambda: self._merge_sources_steps(sources, base_out, dev, layer_name, False)
+        if defer:
+            self.pending.append(pend)
+            return out
+        self._resolve(pend)
+        return out
+
     def _resolve(self, pend):
         info = pend.resolve()
         if info["branch"] != "slerp" or info["select_sticky"] != 0:
@@ -192,7 +297,7 @@ class FourierMerge(MergeTensorsBase):
                 logger.warning(f"select window miss on {pend.layer_name}; re-running step by step")
             pend.out.copy_(pend.redo().reshape(pend.out.shape))
             return
-        self.last_info = dict(branches=["slerp"], layer=pend.layer_name, norms=info["norms"],
+        self.last_info = dict(branches=info.get("branches", ["slerp"]), layer=pend.layer_name, norms=info["norms"],
                               target_norm=info["target_norm"], flags=info["flags"], swap=info["swap"])
         if info["flags"][1] > 0:
             raise ValueError("Inf in ifft output")                          # functions.py:215-217

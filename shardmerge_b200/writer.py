@@ -26,6 +26,7 @@ from __future__ import annotations
 
 import json
 import logging
+import mmap
 import os
 import queue
 import struct
@@ -79,10 +80,15 @@ _ST_DTYPES = {
 }
 
 
-def write_safetensors(path, tensors: Dict[str, torch.Tensor], metadata: Optional[Dict[str, str]] = None):
+_CHUNK = 32 << 20          # bytes per positional write handed to the I/O pool
+
+
+def write_safetensors(path, tensors: Dict[str, torch.Tensor], metadata: Optional[Dict[str, str]] = None, io_pool=None):
     """Write `tensors` (contiguous CPU tensors) as one safetensors file.  Same bytes as
     safetensors.torch.save_file(tensors, path, metadata) (tests/test_host_logic.py checks that), but the data goes
-    from the tensors' own (pinned) memory to the file: no per-tensor bytes() copy."""
+    from the tensors' own (pinned) memory to the file: no per-tensor bytes() copy.  With `io_pool` (a
+    concurrent.futures executor) the data is written as positional 32 MB chunks in parallel -- a single writer thread
+    moves ~3 GB/s into the page cache, a merge on one B200 produces ~15 GB/s."""
     items = []
     for name, t in tensors.items():
         if t.device.type != "cpu" or not t.is_contiguous():
@@ -101,12 +107,49 @@ def write_safetensors(path, tensors: Dict[str, torch.Tensor], metadata: Optional
         off += n
     blob = json.dumps(header, separators=(",", ":"), ensure_ascii=False).encode("utf-8")
     blob += b" " * (-len(blob) % 8)
-    with open(path, "wb") as fh:
-        fh.write(struct.pack("<Q", len(blob)))
-        fh.write(blob)
-        for _, t in items:
-            if t.numel():
-                fh.write(memoryview(t.reshape(-1).view(torch.uint8).numpy()))
+    head = struct.pack("<Q", len(blob)) + blob
+    total = len(head) + off
+    fd = os.open(str(path), os.O_RDWR | os.O_CREAT | os.O_TRUNC, 0o644)
+    try:
+        if io_pool is None or total < (4 << 20):
+            os.pwrite(fd, head, 0)
+            pos = len(head)
+            for _, t in items:
+                n = t.numel() * t.element_size()
+                if n:
+                    _pwrite_all(fd, memoryview(t.reshape(-1).view(torch.uint8).numpy()), pos)
+                pos += n
+        else:
+            # writes to ONE file serialise on its inode lock; stores through a shared mapping do not: map the file and
+            # let the pool copy 32 MB chunks in parallel (torch's copy releases the GIL)
+            os.ftruncate(fd, total)
+            mm = mmap.mmap(fd, total)
+            try:
+                mm[: len(head)] = head
+                dst = torch.frombuffer(mm, dtype=torch.uint8)
+                pos = len(head)
+                futures = []
+                for _, t in items:
+                    n = t.numel() * t.element_size()
+                    if n:
+                        src = t.reshape(-1).view(torch.uint8)
+                        for c0 in range(0, n, _CHUNK):
+                            c1 = min(c0 + _CHUNK, n)
+                            futures.append(io_pool.submit(dst[pos + c0: pos + c1].copy_, src[c0:c1]))
+                    pos += n
+                for f in futures:
+                    f.result()
+                del dst, futures
+            finally:
+                mm.close()
+    finally:
+        os.close(fd)
+
+
+def _pwrite_all(fd: int, data, offset: int):
+    done = 0
+    while done < len(data):
+        done += os.pwrite(fd, data[done:], offset + done)
 
 
 class _PinnedPool:
@@ -130,14 +173,18 @@ class _PinnedPool:
 
 
 class _ShardWriter:
-    """One worker thread that turns (shard, staged tensors) jobs into files.  At most `depth` jobs wait in the queue, so
-    the pinned memory a merge holds is bounded by depth + 2 shards."""
+    """Worker threads that turn (shard, staged tensors) jobs into files: `workers` shards are in progress at a time, their
+    data is written as parallel positional chunks by `io_threads` more threads (file writes release the GIL).  At most
+    `depth` jobs wait in the queue, so the pinned memory a merge holds is bounded by depth + workers + 1 shards."""
 
-    def __init__(self, depth: int = 2):
+    def __init__(self, depth: int = 4, workers: int = 4, io_threads: int = 8):
+        from concurrent.futures import ThreadPoolExecutor
         self.jobs: "queue.Queue" = queue.Queue(maxsize=depth)
         self.errors: list = []
-        self.thread = threading.Thread(target=self._run, name="shardmerge-writer", daemon=True)
-        self.thread.start()
+        self.io_pool = ThreadPoolExecutor(max_workers=io_threads, thread_name_prefix="shardmerge-io")
+        self.threads = [threading.Thread(target=self._run, name=f"shardmerge-writer-{i}", daemon=True) for i in range(workers)]
+        for t in self.threads:
+            t.start()
 
     def _run(self):
         while True:
@@ -158,8 +205,11 @@ class _ShardWriter:
         self.jobs.join()
 
     def close(self):
-        self.jobs.put(None)
-        self.thread.join()
+        for _ in self.threads:
+            self.jobs.put(None)
+        for t in self.threads:
+            t.join()
+        self.io_pool.shutdown(wait=True)
 
 
 @dataclass
@@ -195,6 +245,7 @@ class ModelWriter:
         self._staged: Dict[str, Dict[str, torch.Tensor]] = {}      # shard -> {tensor: host tensor (view of a pinned buffer)}
         self._bufs: Dict[str, list] = {}                           # shard -> pinned buffers to give back
         self._events: Dict[str, list] = {}
+        self._recent_events: list = []                            # device -> host copies since the last wait_staged()
         self._copy_stream = None
         self._pool = self.pinned_pool if self.pinned_pool is not None else _PinnedPool()
         self._worker: Optional[_ShardWriter] = None
@@ -236,6 +287,7 @@ class ModelWriter:
                 src.record_stream(self._copy_stream)
                 done = self._copy_stream.record_event()
             self._events.setdefault(shard_name, []).append(done)
+            self._recent_events.append(done)
             self._bufs.setdefault(shard_name, []).append(buf)
         else:
             host = t.clone().to(self.output_astype).contiguous()
@@ -274,7 +326,8 @@ class ModelWriter:
         ordered = {n: tensors[n] for n in sorted(tensors, key=lambda n: self._order_pos.get(n, 1 << 30))}
         tmp = path.with_name(path.name + f".tmp{os.getpid()}")
         try:
-            write_safetensors(tmp, ordered, metadata={"format": "pt"})
+            write_safetensors(tmp, ordered, metadata={"format": "pt"},
+                              io_pool=self._worker.io_pool if self._worker is not None else None)
             os.replace(tmp, path)
             with self._lock:
                 for name in staged:
@@ -297,6 +350,13 @@ class ModelWriter:
         self._stage(shard_name, layer_name, tensor)
         if on_disk | set(self._staged[shard_name]) >= self.shard_to_tensors[shard_name]:
             self._flush(shard_name)
+
+    def wait_staged(self):
+        """Block until every tensor handed to add_tensor so far has arrived in pinned host memory (the device -> host
+        part of the hand-over; shard files may still be in the writer threads)."""
+        events, self._recent_events = self._recent_events, []
+        for ev in events:
+            ev.synchronize()
 
     def wait(self):
         """Block until every shard handed to the writer thread is on disk."""

@@ -718,3 +718,114 @@ def test_elementwise_kernel_bandwidth(E):
         gbs = 10 * numel * 2 * 4 / (e0.elapsed_time(e1) / 1e3) / 1e9
         print(f"\n[elem mode {mode}] {numel} elements x 2 finetunes: {gbs:.0f} GB/s of algorithmic traffic")
         assert gbs > 1500
+
+
+@pytest.mark.parametrize("n_models,shape", [(4, (512, 2048)), (3, (1024, 2048)), (4, (1, 8192)), (5, (256, 4096))])
+def test_fused_tree_matches_step_path(E, n_models, shape):
+    """BASELINE config 4: the pair tree with every pair merge on the fused chain (FourierMerge._merge_sources_tree: fp32
+    intermediates, external target norm, device-side role / branch decisions) against the host-driven step path on the
+    same kernels -- same spectra, same exact thresholds, so the same tensor."""
+    R, C = shape
+    sh = (R, C) if R > 1 else (C,)
+    g = torch.Generator(device=DEV).manual_seed(77 + n_models + R)
+    mean, bs = (1.0, 0.1) if R == 1 else (0.0, 0.02)
+    base = (mean + bs * torch.randn(sh, generator=g, device=DEV)).to(torch.bfloat16)
+    sig = (0.002, 0.0026, 0.0023, 0.0029, 0.0021)[:n_models]
+    if R == 1:
+        sig = tuple(5 * s for s in sig)
+    alphas = (0.3, 0.5, 0.4, 0.2, 0.6)[:n_models]
+    fts = [(base.float() + s * torch.randn(sh, generator=g, device=DEV)).to(torch.bfloat16) for s in sig]
+    srcs = lambda: [E.make_source(base, ft, weight=a, name=f"m{k}") for k, (ft, a) in enumerate(zip(fts, alphas))]
+    fm = _merger()
+    assert fm.fused_tree
+    got = fm.merge_sources(srcs(), base, torch.device(DEV), layer_name="model.layers.0.x")
+    info = dict(fm.last_info)
+    assert info["branches"] == ["slerp"] * (n_models - 1)
+    # deferred on the lanes as merge() does it
+    fm.defer_checks = True
+    got2 = fm.merge_sources(srcs(), base, torch.device(DEV), layer_name="model.layers.0.x", defer=True)
+    fm.resolve_all()
+    torch.cuda.synchronize()
+    assert np.array_equal(bits(got), bits(got2))
+    fm_steps = _merger()
+    fm_steps.fused_tree = False
+    want = fm_steps.merge_sources(srcs(), base, torch.device(DEV), layer_name="model.layers.0.x")
+    assert fm_steps.last_info["branches"] == ["slerp"] * (n_models - 1)
+    assert abs(info["target_norm"] / fm_steps.last_info["target_norm"] - 1) < 1e-7
+    # Rounds >= 2 blend spectra whose culled bins hold rounding noise: the last bit of a round-1 scalar decides ~10 % of
+    # the later rounds' bins (in the reference as well, see test_tree_of_four_finetunes_vs_oracle), so two correct
+    # evaluations agree on the final tensor only loosely ...
+    basef = base.float().cpu().numpy()
+    dg, dw = got.float().cpu().numpy() - basef, want.float().cpu().numpy() - basef
+    assert rel_l2(dg, dw) < 0.5 and abs(np.linalg.norm(dg) / np.linalg.norm(dw) - 1) < 0.05
+    if n_models != 4 or R == 1:
+        return
+    # ... but the LAST round of the fused tree can be pinned exactly: feed its two fp32 inputs (the tree's own round-1
+    # results) to the step-by-step tensor function with the same t and cull: same kernels' arithmetic on identical
+    # inputs -> the same bf16 tensor.
+    from shardmerge_b200.tensor import functions as F
+    fm.keep_intermediates = True
+    got3 = fm.merge_sources(srcs(), base, torch.device(DEV), layer_name="model.layers.0.x")
+    assert np.array_equal(bits(got3), bits(got))
+    (a0, a1, ta), (b0, b1, tb) = fm.last_tree                 # round-1 results in the order round 2 stacks them
+    w = {f"m{k}": a for k, a in enumerate(alphas)}
+    wa, wb = (w[a0] + w[a1]) / 2, (w[b0] + w[b1]) / 2
+    x, y = (ta, tb) if float(ta.norm()) >= float(tb.norm()) else (tb, ta)     # larger norm takes role v0; t is not swapped
+    m, _, _ = F.merge_tensors_fft2_slerp(x, y, t=wa / (wa + wb), device=DEV, t_sum=1.0, cutoff_pct=0.08, cull_pct=0.10)
+    final = (base.float() + m.to(DEV) * E.f32(info["target_norm"])).to(torch.bfloat16)
+    u = bf16_ulp_distance(bits(got), bits(final))
+    assert float((u == 0).mean()) >= 0.9999 and int(u.max()) <= 1, (float((u == 0).mean()), int(u.max()))
+
+
+def test_fused_tree_rounds_vs_oracle(E):
+    """pin what is deterministic in a tree.  Round 1 (pairs of deltas, cull 0.20): the fp32
+    intermediates against the oracle's, flip-accounted <= 1e-5.  Round 2 (cull 0.10) blends spectra whose culled bins
+    hold rounding noise, so ~10 % of its output bins are decided by noise in the reference itself: given IDENTICAL fp32
+    inputs (the oracle's round-1 results) our pair merge must agree with the oracle's on every bin whose two inputs are
+    above the noise floor."""
+    from shardmerge_b200.tensor import functions as F
+    R, C = 512, 2048
+    g = torch.Generator(device=DEV).manual_seed(991)
+    base = (0.02 * torch.randn((R, C), generator=g, device=DEV)).to(torch.bfloat16)
+    sig, alphas = (0.002, 0.0026, 0.0023, 0.0029), (0.3, 0.5, 0.4, 0.2)
+    fts = [(base.float() + s * torch.randn((R, C), generator=g, device=DEV)).to(torch.bfloat16) for s in sig]
+    fm = _merger()
+    fm.keep_intermediates = True
+    srcs = [E.make_source(base, ft, weight=a, name=f"m{k}") for k, (ft, a) in enumerate(zip(fts, alphas))]
+    fm.merge_sources(srcs, base, torch.device(DEV), layer_name="model.layers.0.x")
+    assert len(fm.last_tree) == 2
+    models = [dict(base=bits(base), ft=bits(ft), alpha=a, name=f"m{k}") for k, (ft, a) in enumerate(zip(fts, alphas))]
+    info = {}
+    O.merge_layer(bits(base), models, info=info, interp_imag=False)
+    inter = info["intermediates"]
+    assert len(inter) == 3                                  # two round-1 results and the final one
+    round1 = {}
+    for na, nb, t in fm.last_tree:
+        key = next(k for k in inter if set(k.split("_")) == {na, nb})
+        raw, resid, share = flip_accounted(t.cpu().numpy(), inter[key].reshape(R, C), k=16)
+        print(f"\n[tree round 1 {key}] raw {raw:.3e} flip-accounted {resid:.3e}")
+        assert resid <= 1e-5, (key, raw, resid)
+        round1[key] = inter[key].reshape(R, C)
+    # round 2 on the oracle's own round-1 results
+    (ka, a), (kb, b) = sorted(round1.items(), key=lambda kv: -float(np.linalg.norm(kv[1])))
+    t2 = 0.5                                                # both weights are (w_x + w_y) / 2 -> ratio of the two means
+    wa = {k: (alphas[int(k.split("_")[0][1:])] + alphas[int(k.split("_")[1][1:])]) / 2 for k in round1}
+    first, second = list(round1)                            # stack order of round 2 = order the pairs were produced
+    t2 = wa[first] / (wa[first] + wa[second])
+    ours, _, _ = F.merge_tensors_fft2_slerp(torch.from_numpy(a), torch.from_numpy(b), t=t2, device=DEV, t_sum=1.0,
+                                            cutoff_pct=0.08, cull_pct=0.10)
+    ref, n0, n1 = O.merge_tensors_fft2_slerp(a, b, t2, t_sum=1.0, cutoff_pct=0.08, cull_pct=0.10, interp_imag=False)
+    So, Sr = np.fft.rfft2(ours.numpy().astype(np.float64)), np.fft.rfft2(np.asarray(ref, dtype=np.float64))
+    A, B = np.fft.rfft2(a.astype(np.float64) / n0), np.fft.rfft2(b.astype(np.float64) / n1)
+    floor = 1e-3 * np.median(np.abs(A.real))
+    solid = (np.abs(A.real) > floor) & (np.abs(B.real) > floor)           # bins not decided by rounding noise
+    frac_solid = float(solid.mean())
+    d = (So.real - Sr.real)[solid]
+    # a handful of decisions next to the thresholds may still flip: set the largest differences aside like flip_accounted
+    e = np.sort(d ** 2)[::-1]
+    resid = float(np.sqrt(e[64:].sum() / (Sr.real[solid] ** 2).sum()))
+    print(f"[tree round 2] bins above the noise floor {frac_solid:.3f}; Re rel-L2 on them {np.sqrt(e.sum() / (Sr.real[solid] ** 2).sum()):.3e}, "
+          f"without the 64 largest {resid:.3e}")
+    assert 0.55 < frac_solid < 0.75                         # two inputs with 20 % culled bins each: ~0.64 solid
+    assert resid <= 1e-4, resid
+    assert rel_l2(So.imag, Sr.imag) <= 1e-5                 # imaginary part: Im X0, untouched by the blend

@@ -162,6 +162,14 @@ def test_write_safetensors_matches_save_file(tmp_path):
         assert (tmp_path / "a.safetensors").read_bytes() == (tmp_path / "b.safetensors").read_bytes()
     with pytest.raises(ValueError):
         write_safetensors(tmp_path / "c.safetensors", {"nc": torch.zeros(4, 4).t()[1:]})
+    # the parallel path (shared mapping + chunk copies by a thread pool) for files above 4 MB
+    from concurrent.futures import ThreadPoolExecutor
+    big = {"w.b": torch.randn(1100, 1024, generator=g).to(torch.bfloat16), "w.a": torch.randn(700, 1024, generator=g),
+           "w.c": torch.randn(3, generator=g)}
+    save_file(big, str(tmp_path / "a.safetensors"), metadata={"format": "pt"})
+    with ThreadPoolExecutor(4) as pool:
+        write_safetensors(tmp_path / "b.safetensors", big, metadata={"format": "pt"}, io_pool=pool)
+    assert (tmp_path / "a.safetensors").read_bytes() == (tmp_path / "b.safetensors").read_bytes()
 
 
 def test_writer_flush_partial_resumes_at_tensor_granularity(tmp_path):
