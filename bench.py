@@ -236,6 +236,8 @@ def main():
     ap.add_argument("--e2e-layers", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-files", type=int, default=1, help="0: skip the second e2e measurement that writes the shard files")
+    ap.add_argument("--prefetch-depth", type=int, default=-1, help="tensors whose uploads run ahead in the e2e loop (-1: the strategy's default)")
     ap.add_argument("--profile-json", default="", help="write the per-kernel-class summary here")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -443,43 +445,67 @@ def main():
 
         writers = []
 
-        async def e2e_step(k):
-            # the reference's hot loop (shard/merge/base.py:212-223): _merge_layer + writer.add_tensor per tensor; here
-            # the uploads of the next tensors, this tensor's kernels, the previous tensor's download and the shard file
-            # writes (writer threads) overlap.  The step ends when every result sits in the writer's pinned host memory.
-            out = out_root / f"step{k}"
-            writer = ModelWriter(base_index={"metadata": {}, "weight_map": weight_map}, output_path=out, layer_order=names,
-                                 output_astype=torch.bfloat16, pinned_pool=pool.get("pool"))
-            pool["pool"] = writer._pool
-            await fm2._process_layers(writer, layers_e2e, str(dev))
-            writer.wait_staged()
-            torch.cuda.synchronize(dev)
-            writers.append(writer)
+        class StagingOnlyWriter(ModelWriter):      # the whole hand-over (pinned pool, side-stream D2H, shard assembly) minus the file
+            def _write_shard(self, shard_name, staged):
+                with self._lock:
+                    for n_ in staged:
+                        self.written_shard_layers.add((shard_name, n_))
 
-        def finish_files():
-            for w in writers:
-                w.finalize()                       # waits until the last shard file is complete, checks completeness
-            del writers[:]
-
+        if args.prefetch_depth >= 0:
+            fm2.prefetch_depth = args.prefetch_depth
         loop = asyncio.new_event_loop()
-        for k in range(max(1, min(args.warmup, 2))):
-            loop.run_until_complete(e2e_step(-1 - k))
+
+        def measure(WriterCls, tag):
+            """-> (ms until every result of every timed step sits in pinned host memory, ms until all files are complete)"""
+
+            async def e2e_step(k):
+                # the reference's hot loop (shard/merge/base.py:212-223): _merge_layer + writer.add_tensor per tensor; here
+                # the uploads of the next tensors, this tensor's kernels, the previous tensor's download and the shard
+                # assembly (writer threads) overlap.  The step ends when every result sits in the writer's pinned host memory.
+                out = out_root / f"{tag}{k}"
+                writer = WriterCls(base_index={"metadata": {}, "weight_map": weight_map}, output_path=out, layer_order=names,
+                                   output_astype=torch.bfloat16, pinned_pool=pool.get("pool"), queue_depth=2 * Le,
+                                   writer_threads=min(8, Le), io_threads=min(16, os.cpu_count() or 8))
+                pool["pool"] = writer._pool
+                await fm2._process_layers(writer, layers_e2e, str(dev))
+                writer.wait_staged()
+                torch.cuda.synchronize(dev)
+                writers.append(writer)
+
+            def finish_files():
+                for w in writers:
+                    w.finalize()                   # waits until the last shard file is complete, checks completeness
+                del writers[:]
+
+            # warm-up: as many steps as will be timed, their files finished only afterwards, so that the writer's pinned
+            # pool ends up holding the staging buffers of that many steps (no cudaHostAlloc inside the timed region)
+            n_warm = max(args.steps, min(args.warmup, 2), 1)
+            for k in range(n_warm):
+                loop.run_until_complete(e2e_step(-1 - k))
             finish_files()
-            shutil.rmtree(out_root / f"step{-1 - k}", ignore_errors=True)      # bench housekeeping, outside the timed region
-        barrier()
-        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-        e0.record()
+            for k in range(n_warm):
+                shutil.rmtree(out_root / f"{tag}{-1 - k}", ignore_errors=True)     # bench housekeeping, outside the timed region
+            barrier()
+            e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            e0.record()
+            for k in range(args.steps):
+                loop.run_until_complete(e2e_step(k))
+            e1.record()
+            finish_files()
+            e2.record()
+            barrier()
+            for k in range(args.steps):
+                shutil.rmtree(out_root / f"{tag}{k}", ignore_errors=True)
+            return e0.elapsed_time(e1), e0.elapsed_time(e2)
+
         t_e2e0 = time.perf_counter()
-        for k in range(args.steps):
-            loop.run_until_complete(e2e_step(k))
-        e1.record()
-        finish_files()
-        e2.record()
-        barrier()
-        e2e_wall = time.perf_counter() - t_e2e0
-        my_ems = e0.elapsed_time(e1)
+        my_ems, _ = measure(StagingOnlyWriter, "s")
         ems = max_over_ranks(my_ems)
-        ems_files = max_over_ranks(e0.elapsed_time(e2))
+        ems_files = None
+        if args.e2e_files:
+            _, my_files = measure(ModelWriter, "f")
+            ems_files = max_over_ranks(my_files)
+        e2e_wall = time.perf_counter() - t_e2e0
         shutil.rmtree(out_root, ignore_errors=True)
         # what plain pinned copies achieve on this box, both directions at once (the e2e path moves 6 B in and 2 B out
         # per merged parameter, so it is bounded by the host link, not by the kernels); all ranks probe at the same time
@@ -511,14 +537,18 @@ def main():
         e2e = dict(value=e2e_params * args.steps / (ems / 1000.0), unit="params/s",
                    h2d_bytes_per_step=h2d_all, d2h_bytes_per_step=d2h_all, layers=Le, host_link_probe=link,
                    h2d_gbs_achieved_rank0=h2d * args.steps / (my_ems / 1000.0) / 1e9,
-                   with_files=dict(value=e2e_params * args.steps / (ems_files / 1000.0), unit="params/s",
-                                   note="the same steps until ModelWriter.finalize() has returned for every step: all safetensors "
-                                        "shards (one per layer) complete on " + ("tmpfs (/dev/shm)" if tmp_root else "the default temp directory")),
-                   wall_s=e2e_wall,
+                   with_files=(dict(value=e2e_params * args.steps / (ems_files / 1000.0), unit="params/s",
+                                    note="a second set of the same steps with the unmodified ModelWriter, timed until finalize() has "
+                                         "returned for every step: all safetensors shards (one per layer) complete on "
+                                         + ("tmpfs (/dev/shm)" if tmp_root else "the default temp directory")
+                                         + "; the file copies compete with the DMA for host memory bandwidth")
+                               if ems_files else None),
+                   wall_s=e2e_wall, prefetch_depth=fm2.prefetch_depth,
                    api="MergeTensorsBase._process_layers (FourierMerge._merge_layer + ModelWriter.add_tensor per tensor) on pinned "
-                       "host tensors: H2D of base + finetunes and D2H of every merged tensor into the writer's pinned staging are "
-                       "inside the timed region, which ends when the last result has arrived in host memory; the writer threads "
-                       "write the shard files concurrently (with_files: until they are complete)")
+                       "host tensors: H2D of base + finetunes and D2H of every merged tensor into ModelWriter's pinned staging "
+                       "(pool, side stream, shard assembly on the writer threads) are inside the timed region, which ends when "
+                       "the last result has arrived in host memory; `value` leaves the file system out (the shard's file write is "
+                       "skipped), `with_files` is the same through the unmodified ModelWriter until the files are complete")
 
     # ---- CPU baseline (rank 0, N = 1 only) -----------------------------------------------------
     cpu_baseline = None

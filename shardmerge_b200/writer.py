@@ -224,6 +224,9 @@ class ModelWriter:
     write_index: bool = True                     # multi-GPU merge: rank 0 writes the index copy, the others only read it
     async_write: bool = True
     pinned_pool: Optional["_PinnedPool"] = None  # share staging buffers between writers (successive merges in one process)
+    queue_depth: int = 4                         # shards waiting for a writer thread before add_tensor blocks (bounds pinned memory)
+    writer_threads: int = 4                      # shard files written at a time
+    io_threads: int = 8                          # threads copying chunks into the files' mappings
 
     def __post_init__(self):
         self.output_path = Path(self.output_path)
@@ -311,7 +314,7 @@ class ModelWriter:
 
         if self.async_write:
             if self._worker is None:
-                self._worker = _ShardWriter()
+                self._worker = _ShardWriter(self.queue_depth, self.writer_threads, self.io_threads)
             self._worker.submit(job)
         else:
             job()
