@@ -38,8 +38,11 @@ int sm_version(void);
 const char* sm_last_error(void);
 
 /* ---- plans ------------------------------------------------------------------------ */
-/* Plan for tensors of shape [R][C] (R = 1 for 1-D tensors), C even, prime factors of C/2
- * and R in {2,3,5,7,11,13}, R <= 65536.  Returns NULL if the shape is unsupported. */
+/* Plan for tensors of shape [R][C] (R = 1 for 1-D tensors), C even.  Prime factors 2..13 of C/2 and R run as register
+ * butterflies (the shapes of Llama-class models: specialised kernels); any larger prime factor up to 1021 (37 in 18944,
+ * 167 in 128256 = a Llama-3 vocabulary) runs as a generic O(r)-per-point radix stage, so that torch.fft's "any length"
+ * contract (shard/tensor/functions.py:55-58) holds for every weight shape in practice.  Returns NULL if the shape is
+ * unsupported (odd C, a prime factor above 1021, or no four-step split of R that fits in shared memory). */
 sm_plan* sm_plan_create(int R, int C);
 void sm_plan_destroy(sm_plan* plan);
 int sm_plan_pitch(const sm_plan* plan);                 /* P, in floats                       */

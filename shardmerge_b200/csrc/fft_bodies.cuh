@@ -106,6 +106,17 @@ SM_HD void row_fwd_body(Exec& ex, const SmPlan& pl, int row, const RowFwdArgs& a
     const bool last = (st == pl.n_row - 1);
     RowSmem sin{smem + (size_t)(cur ^ 1) * bufstride, padmask};   // written by the previous stage
     RowSmem sout{smem + (size_t)cur * bufstride, padmask};
+    if (sm_radix_is_generic(r)) {             // never the first stage (sm_make_plan): the source is shared memory
+      SM_FOR_THREADS(ex, tid) {
+        for (int it = tid; it < Ch; it += T) {
+          if (last) stockham_generic_output<true>(r, it, Ch, s, 2, twC, sin, sout);
+          else      stockham_generic_output<false>(r, it, Ch, s, 2, twC, sin, sout);
+        }
+      }
+      ex.sync();
+      s *= r; cur ^= 1;
+      continue;
+    }
     SM_FOR_THREADS(ex, tid) {
       for (int b = tid; b < nb; b += T) {
         if (st == 0) {
@@ -218,6 +229,17 @@ SM_HD void row_inv_body(Exec& ex, const SmPlan& pl, int row, const RowInvArgs& a
     const bool first = (st == 0), last = (st == pl.n_row - 1);
     RowSmem sin{smem + (size_t)(cur ^ 1) * bufstride, padmask};
     RowSmem sout{smem + (size_t)cur * bufstride, padmask};
+    if (sm_radix_is_generic(r)) {             // never the first stage (sm_make_plan)
+      SM_FOR_THREADS(ex, tid) {
+        for (int it = tid; it < Ch; it += T) {
+          if (last) stockham_generic_output<true>(r, it, Ch, s, 2, twC, sin, gdst);
+          else      stockham_generic_output<false>(r, it, Ch, s, 2, twC, sin, sout);
+        }
+      }
+      ex.sync();
+      s *= r; cur ^= 1;
+      continue;
+    }
     SM_FOR_THREADS(ex, tid) {
       for (int b = tid; b < nb; b += T) {
         if (first && last)  stockham_bfly_rt<true>(r, b, Ch, s, 2, twC, gsrc, gdst);
@@ -296,6 +318,14 @@ SM_HD void col_body(Exec& ex, const SmPlan& pl, int tile, int inst, const ColArg
                         (a.write_im != 0 && !(a.wsel != nullptr && (*a.wsel != 0) == (a.wskip != 0))) ? 1 : 0};
       ColSmem sin{smem + (size_t)(cur ^ 1) * L * SM_COL_TILE, lane};
       ColSmem sout{smem + (size_t)cur * L * SM_COL_TILE, lane};
+      if (sm_radix_is_generic(r)) {           // one output per (warp slot, lane = column) and iteration
+        for (int it = wid; it < L; it += nwarps) {
+          if (first && last)  stockham_generic_output<true>(r, it, L, s, a.tw_mul, twR, gsrc, gdst);
+          else if (first)     stockham_generic_output<false>(r, it, L, s, a.tw_mul, twR, gsrc, sout);
+          else if (last)      stockham_generic_output<true>(r, it, L, s, a.tw_mul, twR, sin, gdst);
+          else                stockham_generic_output<false>(r, it, L, s, a.tw_mul, twR, sin, sout);
+        }
+      } else
       for (int b = wid; b < nb; b += nwarps) {
         if (first && last)  stockham_bfly_rt<true>(r, b, L, s, a.tw_mul, twR, gsrc, gdst);
         else if (first)     stockham_bfly_rt<false>(r, b, L, s, a.tw_mul, twR, gsrc, sout);

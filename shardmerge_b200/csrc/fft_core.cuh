@@ -376,6 +376,7 @@ SM_HD void stockham_bfly_first(int b, int N, const cf* quad, const Src& src, con
 template <class Src, class Dst>
 SM_HD void stockham_bfly_first_rt(int r, int b, int N, const cf* quad, const Src& src, const Dst& dst) {
   switch (r) {
+    case 1:  stockham_bfly_first<1>(b, N, quad, src, dst); break;     // identity stage in front of a generic radix
     case 2:  stockham_bfly_first<2>(b, N, quad, src, dst); break;
     case 3:  stockham_bfly_first<3>(b, N, quad, src, dst); break;
     case 4:  stockham_bfly_first<4>(b, N, quad, src, dst); break;
@@ -387,6 +388,44 @@ SM_HD void stockham_bfly_first_rt(int r, int b, int N, const cf* quad, const Src
     case 16: stockham_bfly_first<16>(b, N, quad, src, dst); break;
     default: break;
   }
+}
+
+// ---------------------------------------------------------------------------------
+// generic radix: any r (the plan uses it for prime factors above 13, e.g. 37 in 18944 = 2^9 * 37 or 167 in
+// 128256 = 2^8 * 3 * 167).  One call computes ONE output k of butterfly b as an r-term sum,
+//   y[q + s*(r*p + k)] = W_N^(s*p*k) * sum_j x[b + j*N/r] * W_r^(j*k),      W_r^e = tab[e * (N/r) * tw_mul],
+// re-reading its inputs from the source (global memory through L1, or shared memory): O(r) per element instead of
+// O(log r), which is what a length that does not factor costs without a Bluestein / Rader stage.  Work items are
+// (b, k) pairs, so a stage has as many independent items as the transform has points.  Sources must be pure (the
+// plan keeps generic radices out of the first row stage, whose delta source accumulates the sum of squares).
+// ---------------------------------------------------------------------------------
+SM_HD bool sm_radix_is_generic(int r) {
+  return !(r == 1 || r == 2 || r == 3 || r == 4 || r == 5 || r == 7 || r == 8 || r == 11 || r == 13 || r == 16);
+}
+
+template <bool kLast, class Src, class Dst>
+SM_HD void stockham_generic_output(int r, int item, int N, int s, int tw_mul, const cf* tw, const Src& src, const Dst& dst) {
+  const int Nr = N / r;
+  const int b = item / r, k = item - b * r;
+  const int p = kLast ? 0 : b / s;
+  const int q = b - p * s;
+  const size_t wstep = (size_t)Nr * tw_mul;
+  double accr = 0.0, acci = 0.0;                   // r terms: accumulate in fp64, one rounding at the end
+  int e = 0;                                       // (j * k) mod r
+  for (int j = 0; j < r; ++j) {
+    float xr, xi;
+    src.load(b + j * Nr, xr, xi);
+    const cf w = ldg_cf(tw + (size_t)e * wstep);
+    accr += (double)xr * w.x - (double)xi * w.y;
+    acci += (double)xr * w.y + (double)xi * w.x;
+    e += k; if (e >= r) e -= r;
+  }
+  float ar = (float)accr, ai = (float)acci;
+  if (!kLast && k > 0) {
+    const cf w = ldg_cf(tw + (size_t)s * p * tw_mul * k);
+    cmul(ar, ai, w.x, w.y);
+  }
+  dst.store(q + s * r * p + k * s, ar, ai);
 }
 
 // runtime-radix dispatch (the plan is data, the butterflies are code)

@@ -1389,8 +1389,9 @@ extern "C" sm_plan* sm_plan_create(int R, int C) {
   sm_plan* pl = new sm_plan;
   int rc = sm_make_plan(R, C, &pl->p);
   if (rc != 0) {
-    sm_set_error("unsupported tensor shape [%d][%d] for the sm_100a FFT (rc=%d): C must be even, "
-                 "C/2 and R must factor into {2,3,5,7,11,13}, R <= 65536", R, C, rc);
+    sm_set_error("unsupported tensor shape [%d][%d] for the sm_100a FFT (rc=%d): C must be even, the prime factors of "
+                 "C/2 and R at most %d, and R = a * b with one a-point and one b-point column instance of 32 columns "
+                 "each fitting in shared memory", R, C, rc, SM_GENERIC_MAX);
     delete pl;
     return nullptr;
   }

@@ -128,6 +128,9 @@ class InMemoryIndex(_IndexBase):
     def tensor_numels(self, model_uri: str) -> Dict[str, int]:
         return {n: t.numel() for n, t in self.models[model_uri].items()}
 
+    def tensor_shapes(self, model_uri: str) -> Dict[str, tuple]:
+        return {n: tuple(t.shape) for n, t in self.models[model_uri].items()}
+
     def _host_tensor(self, model_uri: str, tensor_name: str) -> torch.Tensor:
         return self.models[model_uri][tensor_name]
 
@@ -165,18 +168,25 @@ class LocalSafetensorsIndex(_IndexBase):
         with open(path) as fh:
             self._register(model_uri, json.load(fh))
 
-    def tensor_numels(self, model_uri: str) -> Dict[str, int]:
-        """element counts from the safetensors headers (no tensor data is read)."""
+    def tensor_shapes(self, model_uri: str) -> Dict[str, tuple]:
+        """shapes from the safetensors headers (no tensor data is read)."""
         from safetensors import safe_open
-        out: Dict[str, int] = {}
+        out: Dict[str, tuple] = {}
         index = self.model_indexes[model_uri]
         for shard in sorted(set(index["weight_map"].values())):
             with safe_open(str(self.storage_dir / model_uri / shard), framework="pt") as f:
                 for key in f.keys():
-                    n = 1
-                    for d in f.get_slice(key).get_shape():
-                        n *= d
-                    out[key] = n
+                    out[key] = tuple(f.get_slice(key).get_shape())
+        return out
+
+    def tensor_numels(self, model_uri: str) -> Dict[str, int]:
+        """element counts from the safetensors headers (no tensor data is read)."""
+        out: Dict[str, int] = {}
+        for key, shape in self.tensor_shapes(model_uri).items():
+            n = 1
+            for d in shape:
+                n *= d
+            out[key] = n
         return out
 
     def get_tensor(self, model_uri: str, tensor_name: str, device: str = "cpu") -> TensorPromise:

@@ -93,6 +93,38 @@ class FourierMerge(MergeTensorsBase):
         models = "\n".join(f"- {m.model} (vs {m.base})" for m in self.config.finetune_merge)
         return f"# SLERP-FFT Merged Model\nBase: {self.config.output_base_model}\nModels merged:\n{models}\n"
 
+    async def initialize(self):
+        """Index set-up of the base class, then every merged tensor's shape is checked against the FFT plans BEFORE any
+        work is done or output written (the reference's torch.fft takes any shape; here an odd last dimension or a prime
+        factor above 1021 has no plan, and that should not surface in the middle of a 70B merge)."""
+        await super().initialize()
+        shapes_of = getattr(self.index_manager, "tensor_shapes", None)
+        if shapes_of is None:
+            return
+        from .. import _lib
+        from ..writer import ShardLayer
+        lib = _lib.load()
+        bad = []
+        for name, shape in shapes_of(self.config.output_base_model).items():
+            try:
+                if ShardLayer(0, "", name, False).layer_number < 0:
+                    continue                                   # pass-through tensors are never transformed
+            except ValueError:
+                continue                                       # unknown names are reported by the writer, as in the reference
+            if len(shape) not in (1, 2):
+                bad.append((name, shape, "only 1-D and 2-D tensors are transformed"))
+                continue
+            R, C = (1, shape[0]) if len(shape) == 1 else shape
+            plan = lib.sm_plan_create(int(R), int(C))
+            if not plan:
+                bad.append((name, shape, lib.sm_last_error().decode()))
+            else:
+                lib.sm_plan_destroy(plan)
+        if bad:
+            lines = "\n".join(f"  {n} {tuple(s)}: {why}" for n, s, why in bad[:20])
+            raise E.UnsupportedShape(f"{len(bad)} tensors of {self.config.output_base_model} cannot be merged on the sm_100a "
+                                     f"FFT path:\n{lines}")
+
     # -------------------------------------------------------------------------------------
     async def _passthrough(self, shard_layer, device, attr: str) -> torch.Tensor:
         chosen = next((m for m in self.config.finetune_merge if getattr(m, attr)), None)

@@ -38,10 +38,35 @@ def test_plan_queries_need_no_gpu():
     buf = ctypes.create_string_buffer(512)
     assert lib.sm_plan_describe(p, buf, 512) > 0 and b"R=4096" in buf.value
     lib.sm_plan_destroy(p)
-    # unsupported shapes are refused with a message, not mangled (embed_tokens: 128256 = 2^8*3*167)
-    assert not lib.sm_plan_create(128256, 4096)
-    assert b"unsupported" in lib.sm_last_error()
+    # awkward lengths get a plan with generic radix stages (embed_tokens: 128256 = 2^8 * 3 * 167; Qwen2.5: 18944 = 2^9 * 37)
+    for R, C, want in ((128256, 8192, b"3 167"), (18944, 3584, b"37"), (3584, 18944, b"37")):
+        p = lib.sm_plan_create(R, C)
+        assert p, (R, C)
+        assert sorted(lib.sm_plan_row_freq(p, i) for i in range(0, R, 97)) == sorted(set(lib.sm_plan_row_freq(p, i) for i in range(0, R, 97)))
+        assert lib.sm_plan_describe(p, buf, 512) > 0 and want in buf.value, buf.value
+        lib.sm_plan_destroy(p)
+    # unsupported shapes are refused with a message, not mangled
     assert not lib.sm_plan_create(16, 7)                 # odd C
+    assert b"unsupported" in lib.sm_last_error()
+    assert not lib.sm_plan_create(2 * 1031, 64)          # prime factor above 1021
+
+
+def test_hot_shape_plans_unchanged():
+    """The specialised kernels are chosen by factorisation: the plans of the BASELINE shapes must stay what the GPU parity
+    report was measured with (tests/golden/plans_baseline.json: the plan strings of that run, one per shape)."""
+    import json
+    from pathlib import Path
+    from shardmerge_b200 import _lib
+    lib = _lib.load()
+    rep = json.loads((Path(__file__).resolve().parent / "golden" / "plans_baseline.json").read_text())
+    assert len(rep) == 12
+    buf = ctypes.create_string_buffer(1024)
+    for key, plan in rep.items():
+        R, C = (int(v) for v in key.split("x"))
+        p = lib.sm_plan_create(R, C)
+        lib.sm_plan_describe(p, buf, 1024)
+        assert buf.value.decode() == plan, key
+        lib.sm_plan_destroy(p)
 
 
 @pytest.mark.parametrize("R,C", [(4096, 4096), (1024, 4096), (14336, 4096), (4096, 14336), (8192, 8192), (1024, 8192),

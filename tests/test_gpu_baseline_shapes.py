@@ -306,3 +306,79 @@ def test_tensor_function_vs_reference_on_cuda(E, shape, seed):
     if float((r == 0).mean()) > 0.5:
         pytest.skip("the reference degenerates on CUDA for this input: recorded only")
     assert resid <= 1e-5, (raw, resid, share)
+
+
+# ------------------------------------------------------------------------------------------ lengths that do not factor
+AWKWARD = [(74, 296), (1002, 668), (18944, 3584), (3584, 18944), (16032, 8192), (1, 18944), (167, 4096)]
+
+
+@pytest.mark.parametrize("shape", AWKWARD)
+def test_generic_radix_lengths_vs_fp64_fft(E, shape):
+    """VERDICT r1 missing #1: the reference's torch.fft takes any length (functions.py:55-58).  Prime factors above 13
+    (37 in Qwen2.5's 18944, 167 in Llama-3's 128256-row embeddings; 16032 = 2^5 * 3 * 167 is the CI-sized stand-in for
+    those) run as generic radix stages: forward and inverse against the fp64 FFT like every other shape."""
+    if shape[0] == 1:
+        R, C = shape
+        g = torch.Generator(device=DEV).manual_seed(C)
+        x = torch.randn((1, C), generator=g, device=DEV, dtype=torch.float32)
+        ws = E.get_workspace(1, C, DEV)
+        ws.ctl.zero_()
+        E.fwd_rows(ws, 0, E.Source(x32=x), E.D_SUMSQ0)
+        E.fwd_cols(ws, 0, scale=1.0)
+        ref = torch.fft.rfft(x.double(), dim=1)
+        got = torch.complex(ws.re[0][:, : C // 2 + 1].double(), ws.im[0][:, : C // 2 + 1].double())
+        fwd = _rel(got, ref)
+        out = torch.empty((1, C), dtype=torch.float32, device=DEV)
+        E.inv_rows(ws, ws.re[0], ws.im[0], False, 1.0, None, out, check_ifft=True)
+        inv = _rel(out.double(), x.double())
+        desc = ws.plan.describe()
+    else:
+        fwd, inv, pad_ok, desc = forward_inverse_check(E, shape, seed=3)
+        assert pad_ok
+    record("fft_vs_fp64_generic_radix", f"{shape[0]}x{shape[1]}", forward_rel_l2=fwd, inverse_rel_l2=inv, plan=desc)
+    assert fwd <= 1e-6 and inv <= 1e-6, (fwd, inv)
+    E.clear_caches()
+    torch.cuda.empty_cache()
+
+
+def test_config5_embedding_shape_merge(E):
+    """BASELINE config 5: the 128256 x 8192 embedding / lm_head shape (1.05 G elements) through the tensor-level merge on
+    ONE B200 (it fits: 17 GB of planes).  CI-sized stand-in 16032 x 8192 (same awkward factors 3 * 167) is checked
+    against the reference itself on device="cuda" when oracle/_ref is present; the full shape is merged, timed, and
+    checked through size-independent properties (finite, norm of the merged delta, output = base where both deltas
+    are zero is covered elsewhere)."""
+    from oracle import ref_runner as RR
+    fm = _merger()
+    # --- CI size vs the reference on CUDA
+    shape = (16032, 8192)
+    base, fts = synth(shape, 61)
+    srcs = [E.make_source(base, fts[k], weight=a, name=f"m{k}") for k, a in enumerate((0.3, 0.5))]
+    out = fm.merge_sources(srcs, base, torch.device(DEV), layer_name="model.layers.0.x")
+    assert fm.last_info["branches"] == ["slerp"]
+    if RR.available():
+        ref = RR.merge_layer(base, fts, [0.3, 0.5], device=DEV)
+        met = parity_metrics(bits(out), bits(ref), bits(base), shape)
+        record("config5", "16032x8192_vs_reference_cuda", **met)
+        assert met["within_1ulp"] >= 0.99, met
+        del ref
+    del base, fts, srcs, out
+    E.clear_caches(); torch.cuda.empty_cache()
+    # --- full size
+    shape = (128256, 8192)
+    base, fts = synth(shape, 62)
+    srcs = [E.make_source(base, fts[k], weight=a, name=f"m{k}") for k, a in enumerate((0.3, 0.5))]
+    out = fm.merge_sources(srcs, base, torch.device(DEV), layer_name="model.layers.0.x")      # warm-up: plans, tables
+    torch.cuda.synchronize()
+    t0 = time.time()
+    out = fm.merge_sources(srcs, base, torch.device(DEV), layer_name="model.layers.0.x")
+    torch.cuda.synchronize()
+    dt = time.time() - t0
+    assert fm.last_info["branches"] == ["slerp"]
+    d = out.float() - base.float()
+    d0 = fts[0].float() - base.float()
+    ratio = float(d.norm() / d0.norm())
+    finite = bool(torch.isfinite(out.float()).all())
+    record("config5", "128256x8192_one_gpu", seconds=round(dt, 3), params_per_s=shape[0] * shape[1] / dt,
+           merged_delta_norm_over_delta0_norm=ratio, finite=finite, plan=E.get_plan(*shape, DEV).describe())
+    assert finite and 0.3 < ratio < 1.5
+    E.clear_caches(); torch.cuda.empty_cache()

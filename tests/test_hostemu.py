@@ -45,7 +45,9 @@ def natural(emu, a, R, C):
 
 
 SHAPES = [(1, 2), (1, 4), (1, 16), (1, 2048), (2, 4), (4, 4), (8, 8), (16, 16), (32, 64), (3, 10), (7, 22), (256, 64),
-          (512, 64), (1024, 32), (4096, 8), (5632, 8), (896, 8), (96, 40), (1, 5632), (143, 26), (300, 12), (1, 7168)]
+          (512, 64), (1024, 32), (4096, 8), (5632, 8), (896, 8), (96, 40), (1, 5632), (143, 26), (300, 12), (1, 7168),
+          # generic radix stages (prime factors above 13): 37, 167, 17 * 19, in rows and in one- and two-sweep columns
+          (1, 74), (1, 296), (1, 18944), (37, 8), (74, 26), (167, 4), (2004, 4), (18944, 4), (128256, 2), (323, 646)]
 
 
 @pytest.mark.parametrize("shape", SHAPES)
@@ -59,7 +61,8 @@ def test_forward_and_roundtrip(emu, shape):
     got = natural(emu, re[:, : Ch + 1] + 1j * im[:, : Ch + 1], R, C)
     assert rel_l2(got, ref) < 5e-7
     # fp32 partial sums (per thread on the device, per row in the emulation), widened to fp64
-    assert abs(ss / float((x.astype(np.float64) ** 2).sum()) - 1) < 2e-6
+    # (the emulation keeps ONE fp32 partial per row where the device keeps one per thread: a long single row needs slack)
+    assert abs(ss / float((x.astype(np.float64) ** 2).sum()) - 1) < (2e-6 if C <= 8192 else 1e-5)
     out = np.zeros((R, C), np.float32); fl = (ctypes.c_uint * 4)()
     rc = emu.emu_inverse(R, C, P(re, c_fp), P(im, c_fp), ctypes.c_float(0.0), 1, None, None, P(out, c_fp), ctypes.c_float(1.0), fl)
     assert rc == 0 and list(fl) == [0, 0, 0, 0]
