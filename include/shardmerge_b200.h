@@ -275,6 +275,11 @@ int sm_profile_collect(double* ms, double* bytes, int* launches, int n_classes);
  * bf16 in / out, n elements, `fts` = HOST array of n_models (<= 8) device pointers; all 16-byte aligned. */
 int sm_elem_merge_bf16(int mode, size_t n, const void* base, const void* const* fts, int n_models, void* out, void* stream);
 
+/* correlate_pairs (shard/tensor/functions.py:304-314), one pair: *out_sum = sum over the C columns of the cosine similarity
+ * along dim 0 of two [R][C] device tensors (a 1-D tensor is [n][1]); the caller divides by C (torch's .mean()).
+ * dtype 0: fp32, 1: bf16.  Both tensors are read once (HBM-bound). */
+int sm_cosine_cols(int dtype, int R, int C, const void* a, const void* b, double* out_sum, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

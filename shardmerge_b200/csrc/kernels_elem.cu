@@ -115,7 +115,54 @@ __global__ void __launch_bounds__(256) k_elem_merge(const __grid_constant__ Elem
   }
 }
 
+// ---- correlate_pairs (shard/tensor/functions.py:304-314): mean over the columns of the cosine similarity of two [R][C]
+// tensors along dim 0.  One CTA per 32 adjacent columns walks all rows (coalesced 128-byte row segments for fp32, 64 for
+// bf16), three fp32 sums per column, one atomic per CTA.  torch: (x / max(||x||, eps)) . (y / max(||y||, eps)), eps = 1e-8,
+// NaN -> 0 (nan_to_num), then .mean().  HBM-bound: both tensors are read once.
+template <class T> __device__ __forceinline__ float ld_as_f32(const T* p, size_t i);
+template <> __device__ __forceinline__ float ld_as_f32<float>(const float* p, size_t i) { return __ldg(p + i); }
+template <> __device__ __forceinline__ float ld_as_f32<uint16_t>(const uint16_t* p, size_t i) { return __uint_as_float((uint32_t)__ldg(p + i) << 16); }
+
+template <class T>
+__global__ void __launch_bounds__(256) k_cosine_cols(const T* __restrict__ a, const T* __restrict__ b, int R, int C, double* out_sum) {
+  __shared__ float sab[8][33], saa[8][33], sbb[8][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  float ab = 0.f, aa = 0.f, bb = 0.f;
+  if (c < C) {
+    for (int r = w; r < R; r += 8) {
+      const float x = ld_as_f32<T>(a, (size_t)r * C + c), y = ld_as_f32<T>(b, (size_t)r * C + c);
+      ab = fmaf(x, y, ab); aa = fmaf(x, x, aa); bb = fmaf(y, y, bb);
+    }
+  }
+  sab[w][lane] = ab; saa[w][lane] = aa; sbb[w][lane] = bb;
+  __syncthreads();
+  if (w == 0) {
+    float cs = 0.f;
+    if (c < C) {
+      for (int k = 1; k < 8; ++k) { ab += sab[k][lane]; aa += saa[k][lane]; bb += sbb[k][lane]; }
+      cs = ab / (fmaxf(sqrtf(aa), 1e-8f) * fmaxf(sqrtf(bb), 1e-8f));
+      if (cs != cs) cs = 0.f;
+    }
+    double v = (double)cs;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) atomicAdd(out_sum, v);
+  }
+}
+
 }  // namespace
+
+extern "C" int sm_cosine_cols(int dtype, int R, int C, const void* a, const void* b, double* out_sum, void* stream) {
+  if (R < 1 || C < 1) { sm_set_error("cosine_cols: empty tensor"); return -2; }
+  cudaStream_t st = (cudaStream_t)stream;
+  SM_CUDA_CHECK(cudaMemsetAsync(out_sum, 0, sizeof(double), st));
+  const unsigned int grid = (unsigned int)((C + 31) / 32);
+  if (dtype == 0) k_cosine_cols<float><<<grid, 256, 0, st>>>((const float*)a, (const float*)b, R, C, out_sum);
+  else if (dtype == 1) k_cosine_cols<uint16_t><<<grid, 256, 0, st>>>((const uint16_t*)a, (const uint16_t*)b, R, C, out_sum);
+  else { sm_set_error("cosine_cols: dtype 0 (fp32) or 1 (bf16)"); return -2; }
+  SM_LAUNCH_CHECK();
+  return 0;
+}
 
 extern "C" int sm_elem_merge_bf16(int mode, size_t n, const void* base, const void* const* fts, int n_models, void* out,
                                   void* stream) {

@@ -151,10 +151,12 @@ def interpolate_fft_components(v0_fft: torch.Tensor, v1_fft: torch.Tensor, t: fl
 
 
 def merge_tensors_fft2_slerp(v0: torch.Tensor, v1: torch.Tensor, t: float, device: str, b: float = .1,
-                             t_sum: float = 1.0, cutoff_pct: float = 0.0, cull_pct: float = 0.0
+                             t_sum: float = 1.0, cutoff_pct: float = 0.0, cull_pct: float = 0.0, _result_device=None
                              ) -> tuple[torch.Tensor, float, float]:
-    """Normalise, FFT, blend, inverse FFT (functions.py:164-221) -> (merged fp32 on CPU, ||v0||, ||v1||)."""
+    """Normalise, FFT, blend, inverse FFT (functions.py:164-221) -> (merged fp32 on CPU, ||v0||, ||v1||).
+    `_result_device` (not in the reference): leave the result there instead of copying it to the CPU."""
     dev = _dev(device)
+    _cpu = "cpu" if _result_device is None else _result_device
     R, C = _as_rows(v0)
     x0 = v0.to(dev).to(torch.float32).contiguous()
     x1 = v1.to(dev).to(torch.float32).contiguous()
@@ -167,10 +169,10 @@ def merge_tensors_fft2_slerp(v0: torch.Tensor, v1: torch.Tensor, t: float, devic
     n1 = E.f32(float(dbl[E.D_SUMSQ1]) ** 0.5)
     v0n = (x0 * E.inv_norm_f32(n0)) if n0 != 0 else x0
     if n1 < .0001:                                            # functions.py:184-185
-        return v0n.reshape(v0.shape).to("cpu"), n0, n1
+        return v0n.reshape(v0.shape).to(_cpu), n0, n1
     if n0 < .0001:                                            # functions.py:187-190
         logger.info(f"Warning: Small norm v0 ({n0})")
-        return v0n.reshape(v0.shape).to("cpu"), n0, n1
+        return v0n.reshape(v0.shape).to(_cpu), n0, n1
     ratio = n1 / (n0 + 1e-10)
     out = torch.empty((R, C), dtype=torch.float32, device=dev)
     if ratio < b:                                             # functions.py:199-202 (linear: no blend needed)
@@ -189,12 +191,14 @@ def merge_tensors_fft2_slerp(v0: torch.Tensor, v1: torch.Tensor, t: float, devic
     if int(flags[1]) > 0:                                     # functions.py:215-217
         logger.info(f"Warning: Inf in ifft output: {int(flags[1])}")
         raise ValueError("Inf in ifft output")
-    return out.reshape(v0.shape).to("cpu"), n0, n1
+    return out.reshape(v0.shape).to(_cpu), n0, n1
 
 
-def task_arithmetic_fft2(v0: torch.Tensor, v1: torch.Tensor, t: float, device: str, agreement: bool = True) -> torch.Tensor:
+def task_arithmetic_fft2(v0: torch.Tensor, v1: torch.Tensor, t: float, device: str, agreement: bool = True,
+                         _result_device=None) -> torch.Tensor:
     """Sign-agreement arithmetic in the frequency domain (functions.py:224-254) -> fp32 on CPU."""
     dev = _dev(device)
+    _cpu = "cpu" if _result_device is None else _result_device
     R, C = _as_rows(v0)
     x0 = v0.to(dev).to(torch.float32).contiguous()
     x1 = v1.to(dev).to(torch.float32).contiguous()
@@ -205,7 +209,7 @@ def task_arithmetic_fft2(v0: torch.Tensor, v1: torch.Tensor, t: float, device: s
     out = torch.empty((R, C), dtype=torch.float32, device=dev)
     E.spectral_pair(ws, 0, 1, scale0=1.0, scale1=1.0, mode="arith", t=t, agreement=agreement, out_scale=1.0,
                     out=out, check_ifft=False)
-    return out.reshape(v0.shape).to("cpu")
+    return out.reshape(v0.shape).to(_cpu)
 
 
 def arithmetic_fft_components(v0_fft: torch.Tensor, v1_fft: torch.Tensor, t: float, agreement: bool, device: str,
@@ -225,13 +229,27 @@ def arithmetic_fft_components(v0_fft: torch.Tensor, v1_fft: torch.Tensor, t: flo
 
 
 def correlate_pairs(tensors: torch.Tensor, work_device: str, store_device: str) -> torch.Tensor:
-    """Symmetric matrix of mean cosine similarities between stacked tensors (functions.py:304-314)."""
+    """Symmetric matrix of mean cosine similarities (along dim 0) between stacked tensors (functions.py:304-314).
+    One streaming kernel per pair on `work_device` (sm_cosine_cols); fp32 and bf16 stacks, anything else is upcast."""
+    dev = _dev(work_device)
+    lib = E._lib.load()
     n = tensors.shape[0]
     m = torch.zeros(n, n, device=store_device)
+    items = []
     for i in range(n):
-        a = tensors[i].to(work_device)
+        t = tensors[i].to(dev)
+        if t.dtype not in (torch.float32, torch.bfloat16):
+            t = t.to(torch.float32)
+        items.append(t.contiguous())
+    acc = torch.zeros(1, dtype=torch.float64, device=dev)
+    for i in range(n):
+        a = items[i]
+        R, C = (a.shape[0], a[0].numel()) if a.ndim >= 2 else (a.shape[0], 1)
         for j in range(i + 1, n):
-            c = torch.nn.functional.cosine_similarity(a, tensors[j].to(work_device), dim=0).nan_to_num(0).mean().item()
+            b = items[j] if items[j].dtype == a.dtype else items[j].to(a.dtype)
+            E._lib.check(lib.sm_cosine_cols(0 if a.dtype == torch.float32 else 1, int(R), int(C), a.data_ptr(), b.data_ptr(),
+                                            acc.data_ptr(), E._stream(dev)), "sm_cosine_cols")
+            c = acc.item() / C
             m[i, j] = m[j, i] = c
     return m
 

@@ -172,3 +172,65 @@ def test_files_in_files_out_vs_reference_cli(E, tmp_path):
                 # small tensors (<= 98 K elements): one flipped spectrum bin shows in a few % of the roundings
                 assert frac >= 0.97, (k, frac)
     print(f"\nfiles-in/files-out vs reference CLI: worst within-1-ulp fraction {worst:.5f}")
+
+
+def _legacy_case(E, d):
+    from shardmerge_b200.config import MergeConfig, MergeModel
+    from shardmerge_b200.index import InMemoryIndex
+    from shardmerge_b200.merge.fourier import FourierMerge as LegacyFourierMerge
+    from shardmerge_b200.writer import ShardLayer
+    layer = str(d["layer"])
+    fb = lambda u: torch.from_numpy(u.view(np.int16).copy()).view(torch.bfloat16)
+    n = len(d["alphas"])
+    models = {"org/base": {layer: fb(d["base"])}, **{f"org/ft{k}": {layer: fb(d[f"ft{k}"])} for k in range(n)}}
+    cfg = MergeConfig(finetune_merge=[MergeModel(model=f"org/ft{k}", base="org/base", alpha=float(a), is_input=(k == 0),
+                                                 is_output=(k == 1)) for k, a in enumerate(d["alphas"])],
+                      output_base_model="org/base", output_dir="/tmp/unused")
+    fm = LegacyFourierMerge(cfg, task_add_models=[f"org/ft{int(k)}" for k in d["task_add"]], index_manager=InMemoryIndex(models))
+    out = asyncio.run(fm._merge_layer(ShardLayer(0, "s", layer, False), DEV))
+    return out, fm.last_info
+
+
+@pytest.mark.parametrize("name,branches", [("legacy_slerp_256x512", ["slerp"]), ("legacy_arith_128x256", ["arith"]),
+                                           ("legacy_tree3_128x256", None), ("legacy_taskadd_128x256", None)])
+def test_legacy_fourier_merge_vs_reference_fixture(E, golden_dir, name, branches):
+    """the earlier FourierMerge (shard/merge/fourier.py:58-205: dtype-of-the-model deltas, cosine pairing,
+    median target norm, task_add_models, fp32 result) against fixtures the reference itself produced
+    (oracle/make_golden_legacy.py)."""
+    from tests.parity_util import flip_accounted
+    d = np.load(golden_dir / f"{name}.npz")
+    out, info = _legacy_case(E, d)
+    assert str(out.dtype) == str(d["out_dtype"]) == "torch.float32"              # no bf16 cast in this variant (:205)
+    base = torch.from_numpy(d["base"].view(np.int16).copy()).view(torch.bfloat16).float().numpy()
+    got, ref = out.cpu().numpy() - base, d["out_f32"] - base
+    assert np.isfinite(got).all()
+    if branches is not None:
+        assert info["branches"] == branches
+        raw, resid, share = flip_accounted(got, ref, k=8)
+        print(f"\n[{name}] merged delta rel-L2 raw {raw:.3e} flip-accounted {resid:.3e}")
+        # the fp32 sum base + merged quantises the delta at ~2^-24 of |base|: 1e-5 of the delta is what it can resolve
+        assert resid < 3e-5, (raw, resid, share)
+    else:
+        # later tree rounds / the task-add pass blend spectra with culled (rounding-noise) bins: pinned loosely, like
+        # every tree (see test_tree_of_four_finetunes_vs_oracle)
+        rel = float(np.linalg.norm(got - ref) / np.linalg.norm(ref))
+        print(f"\n[{name}] branches {info['branches']} merged delta rel-L2 {rel:.3f}")
+        assert rel < 0.6 and abs(np.linalg.norm(got) / np.linalg.norm(ref) - 1) < 0.1
+
+
+def test_correlate_pairs_kernel_vs_torch(E):
+    """sm_cosine_cols behind correlate_pairs (functions.py:304-314) against the torch expression it replaces."""
+    from shardmerge_b200.tensor import functions as F
+    g = torch.Generator(device=DEV).manual_seed(8)
+    for shape, dtype in (((3, 300, 70), torch.float32), ((4, 129, 2048), torch.bfloat16), ((3, 5000), torch.float32)):
+        t = torch.randn(shape, generator=g, device=DEV).to(dtype)
+        t[1] = (t[0].float() * 0.5 + 0.1 * t[1].float()).to(dtype)              # a correlated pair
+        if len(shape) == 3:
+            t[0][:, 3] = 0                                                        # a zero column: 0 / eps -> 0
+        m = F.correlate_pairs(t, work_device=DEV, store_device="cpu")
+        n = shape[0]
+        for i in range(n):
+            for j in range(i + 1, n):
+                want = torch.nn.functional.cosine_similarity(t[i].float(), t[j].float(), dim=0).nan_to_num(0).mean().item()
+                assert abs(m[i, j].item() - want) < 2e-5 and m[j, i] == m[i, j], (shape, i, j, m[i, j].item(), want)
+        assert (m.diagonal() == 0).all()

@@ -253,6 +253,42 @@ def test_fourier_merge_validates_shapes_up_front(tmp_path):
     assert "q_proj" in str(exc.value) and not (tmp_path / "out").exists()
 
 
+def test_verify_output_and_copy_model_files(tmp_path):
+    """the index / file alignment check of scripts/verify_safetensors.py plus dtype / shape / finiteness,
+    and the local counterpart of `shard copy-model`."""
+    from safetensors.torch import save_file
+    from shardmerge_b200.validate import copy_model_files, verify_output
+    out = tmp_path / "out"
+    out.mkdir()
+    a, b = torch.ones(4, 4, dtype=torch.bfloat16), torch.ones(8, dtype=torch.bfloat16)
+    save_file({"model.layers.0.a": a, "model.layers.0.b": b}, str(out / "s1.safetensors"), metadata={"format": "pt"})
+    save_file({"model.layers.1.a": a}, str(out / "s2.safetensors"), metadata={"format": "pt"})
+    wm = {"model.layers.0.a": "s1.safetensors", "model.layers.0.b": "s1.safetensors", "model.layers.1.a": "s2.safetensors"}
+    (out / "model.safetensors.index.json").write_text(json.dumps({"metadata": {}, "weight_map": wm}))
+    rep = verify_output(out, expected_dtype=torch.bfloat16, expected_shapes={"model.layers.0.a": (4, 4)})
+    assert rep.ok and rep.tensors == 3 and "align" in rep.summary()
+    # break it: a NaN, a wrong dtype, a key the index does not know, a shard the index names but that is gone, an extra file
+    bad = a.clone(); bad[0, 0] = float("nan")
+    save_file({"model.layers.0.a": bad, "model.layers.0.b": b.float(), "stray": a}, str(out / "s1.safetensors"))
+    (out / "s2.safetensors").unlink()
+    save_file({"x": a}, str(out / "s9.safetensors"))
+    rep = verify_output(out, expected_dtype=torch.bfloat16, expected_shapes={"model.layers.0.a": (2, 8)})
+    assert not rep.ok
+    assert rep.missing_files == ["s2.safetensors"] and rep.extra_files == ["s9.safetensors"]
+    assert rep.extra_keys == {"s1.safetensors": ["stray"]} and rep.non_finite == {"model.layers.0.a": 1}
+    assert rep.wrong_dtype == {"model.layers.0.b": "torch.float32"} and rep.wrong_shape == {"model.layers.0.a": (4, 4)}
+    # copy-model: configuration / tokenizer files only
+    src = tmp_path / "org" / "m"
+    src.mkdir(parents=True)
+    for n in ("config.json", "tokenizer.json", "generation_config.json", "model-00001-of-00001.safetensors",
+              "model.safetensors.index.json", "pytorch_model.bin"):
+        (src / n).write_text("{}")
+    assert copy_model_files(src, out) == ["config.json", "generation_config.json", "tokenizer.json"]
+    assert copy_model_files(src, out) == []                 # nothing is overwritten
+    with pytest.raises(FileNotFoundError):
+        copy_model_files(tmp_path / "nope", out)
+
+
 def test_local_safetensors_index(tmp_path):
     from safetensors.torch import save_file
     model = _toy_model(1)
