@@ -112,34 +112,51 @@ def _run(tag, launches, nbytes, dev, fn):
 
 
 class Plan:
-    """FFT plan + twiddle tables for tensors of shape [R][C] on one device."""
+    """FFT plan + twiddle tables for tensors of shape [R][C] on one device, or for a stack of `batch` such matrices
+    (a tensor with leading dimensions: the reference's fftn(dim=(-2, -1)) transforms every [R][C] slice on its own while
+    norms, order statistics and SLERP sums run over the WHOLE tensor, shard/tensor/functions.py:58,85,113-141).  A stack
+    is laid out as one [batch * R][C] matrix: row passes and statistics use a plan over all its rows, the column sweeps a
+    plan over R rows applied to every slice in turn."""
 
-    def __init__(self, R: int, C: int, device):
+    def __init__(self, R: int, C: int, device, batch: int = 1):
         self.lib = _lib.load()
         self.device = _require_cuda(device)
-        self.R, self.C, self.Ch = R, C, C // 2
-        self.handle = self.lib.sm_plan_create(R, C)
+        self.Rin, self.batch = R, batch
+        self.R, self.C, self.Ch = R * batch, C, C // 2
+        self.handle = self.lib.sm_plan_create(self.R, C)
         if not self.handle:
             raise UnsupportedShape(self.lib.sm_last_error().decode())
         self.P = self.lib.sm_plan_pitch(self.handle)
         with torch.cuda.device(self.device):
             self.tables = torch.empty(self.lib.sm_plan_table_bytes(self.handle), dtype=torch.uint8, device=self.device)
             _lib.check(self.lib.sm_plan_init_tables(self.handle, self.tables.data_ptr(), _stream(self.device)), "init_tables")
+            self.col_handle, self.col_tables = self.handle, self.tables
+            if batch > 1:
+                self.col_handle = self.lib.sm_plan_create(R, C)
+                if not self.col_handle:
+                    raise UnsupportedShape(self.lib.sm_last_error().decode())
+                self.col_tables = torch.empty(self.lib.sm_plan_table_bytes(self.col_handle), dtype=torch.uint8, device=self.device)
+                _lib.check(self.lib.sm_plan_init_tables(self.col_handle, self.col_tables.data_ptr(), _stream(self.device)),
+                           "init_tables")
+        self.col_passes = self.lib.sm_plan_col_passes(self.col_handle)
+        self.slice_bytes = R * self.P * 4                          # one [R][P] fp32 plane slice
 
     def describe(self) -> str:
         buf = ctypes.create_string_buffer(1024)
-        self.lib.sm_plan_describe(self.handle, buf, 1024)
-        return buf.value.decode()
+        self.lib.sm_plan_describe(self.col_handle, buf, 1024)
+        return buf.value.decode() + (f" x {self.batch} slices" if self.batch > 1 else "")
 
     def row_freq(self) -> torch.Tensor:
-        """stored row -> frequency index (CPU int64 tensor)."""
-        return torch.tensor([self.lib.sm_plan_row_freq(self.handle, i) for i in range(self.R)], dtype=torch.int64)
+        """stored row -> frequency index within its slice (CPU int64 tensor, one slice)."""
+        return torch.tensor([self.lib.sm_plan_row_freq(self.col_handle, i) for i in range(self.Rin)], dtype=torch.int64)
 
     def __del__(self):
         try:
             if getattr(self, "handle", None):
+                if getattr(self, "col_handle", None) and self.col_handle != self.handle:
+                    self.lib.sm_plan_destroy(self.col_handle)
                 self.lib.sm_plan_destroy(self.handle)
-                self.handle = None
+                self.handle = self.col_handle = None
         except Exception:
             pass
 
@@ -197,27 +214,34 @@ _plans: dict = {}
 _workspaces: dict = {}
 
 
-def get_plan(R: int, C: int, device) -> Plan:
+def get_plan(R: int, C: int, device, batch: int = 1) -> Plan:
     dev = _require_cuda(device)
-    key = (dev.index, R, C)
+    key = (dev.index, R, C, batch)
     pl = _plans.get(key)
     if pl is None:
-        pl = _plans[key] = Plan(R, C, dev)
+        pl = _plans[key] = Plan(R, C, dev, batch)
     return pl
 
 
-def get_workspace(R: int, C: int, device, n_spectra: int = 2, safe_select: bool = False, lane: int = 0) -> Workspace:
+def get_workspace(R: int, C: int, device, n_spectra: int = 2, safe_select: bool = False, lane=0, batch: int = 1) -> Workspace:
     """Workspaces are cached per (device, shape, select mode, lane); a lane is one of the streams FourierMerge
-    spreads consecutive tensors over, and two tensors in flight must not share planes."""
+    spreads consecutive tensors over, and two tensors in flight must not share planes.  `batch` > 1: a stack of
+    [R][C] matrices (see Plan)."""
     dev = _require_cuda(device)
-    key = (dev.index, R, C, safe_select, lane)
+    key = (dev.index, R, C, batch, safe_select, lane)
     ws = _workspaces.get(key)
     if ws is None or ws.n_spectra < n_spectra:
         if ws is not None:
             # the planes being replaced may still be read by kernels enqueued on another stream
             torch.cuda.synchronize(dev)
-        ws = _workspaces[key] = Workspace(get_plan(R, C, dev), n_spectra, safe_select)
+        ws = _workspaces[key] = Workspace(get_plan(R, C, dev, batch), n_spectra, safe_select)
     return ws
+
+
+def ws_for(t: torch.Tensor, device, **kw) -> Workspace:
+    """Workspace for a tensor's shape: 1-D -> one row, 2-D -> [R][C], more dimensions -> a stack of [R][C] slices."""
+    R, C, B = shape_rcb(t)
+    return get_workspace(R, C, device, batch=B, **kw)
 
 
 def clear_caches():
@@ -225,12 +249,22 @@ def clear_caches():
     _plans.clear()
 
 
-def shape_rc(t: torch.Tensor):
+def shape_rcb(t: torch.Tensor):
+    """-> (rows, columns, slices) of the matrices the reference's fft / fftn(dim=(-2, -1)) transforms (functions.py:55-58)."""
+    if t.ndim == 0:
+        raise UnsupportedShape("a 0-d tensor has nothing to transform")
     if t.ndim == 1:
-        return 1, t.shape[0]
-    if t.ndim == 2:
-        return t.shape[0], t.shape[1]
-    raise UnsupportedShape(f"only 1-D and 2-D tensors are supported by the sm_100a FFT path, got {tuple(t.shape)}")
+        return 1, t.shape[0], 1
+    b = 1
+    for d in t.shape[:-2]:
+        b *= d
+    return t.shape[-2], t.shape[-1], b
+
+
+def shape_rc(t: torch.Tensor):
+    """rows x columns of the tensor seen as ONE matrix (a stack of slices counts all its rows)."""
+    R, C, B = shape_rcb(t)
+    return R * B, C
 
 
 # ------------------------------------------------------------------------------------------
@@ -294,12 +328,20 @@ def fwd_rows_ptr(ws: Workspace, slot: int, src: Source, sumsq_ptr: int, m1: floa
 def fwd_cols(ws: Workspace, slot: int, scale: float = 1.0, scale_slot: Optional[int] = None, write_im: bool = True):
     pl, lib = ws.plan, ws.plan.lib
     N = pl.R * pl.C
-    sweeps = max(1, pl.lib.sm_plan_col_passes(pl.handle))
+    sweeps = max(1, pl.col_passes)
     nbytes = 8 * N * sweeps - (0 if write_im else 2 * N)
-    rc = _run("col_fwd", pl.lib.sm_plan_col_launches(pl.handle), nbytes, pl.device, lambda: lib.sm_fwd_cols(
-        pl.handle, pl.tables.data_ptr(), ws.re[slot].data_ptr(), ws.im[slot].data_ptr(),
-        None if scale_slot is None else ws.fptr(scale_slot), float(scale), 1 if write_im else 0, _stream(pl.device)))
-    _lib.check(rc, "sm_fwd_cols")
+    sptr = None if scale_slot is None else ws.fptr(scale_slot)
+
+    def run():
+        for b in range(pl.batch):
+            off = b * pl.slice_bytes
+            rc = lib.sm_fwd_cols(pl.col_handle, pl.col_tables.data_ptr(), ws.re[slot].data_ptr() + off,
+                                 ws.im[slot].data_ptr() + off, sptr, float(scale), 1 if write_im else 0, _stream(pl.device))
+            if rc:
+                return rc
+        return 0
+
+    _lib.check(_run("col_fwd", pl.batch * lib.sm_plan_col_launches(pl.col_handle), nbytes, pl.device, run), "sm_fwd_cols")
 
 
 def select_kth(ws: Workspace, plane0: torch.Tensor, plane1: Optional[torch.Tensor], rank: int, out_slot: int,
@@ -354,12 +396,22 @@ def fstats_blend_cull(ws: Workspace, reX: torch.Tensor, reY: torch.Tensor, t_sum
 
 def inv_cols(ws: Workspace, re: torch.Tensor, im: torch.Tensor, cull: bool):
     pl, lib = ws.plan, ws.plan.lib
-    sweeps = pl.lib.sm_plan_col_passes(pl.handle)
+    sweeps = pl.col_passes
     if sweeps == 0:
         return
-    _lib.check(_run("col_inv", pl.lib.sm_plan_col_launches(pl.handle), 8 * pl.R * pl.C * sweeps, pl.device, lambda: lib.sm_inv_cols(
-        pl.handle, pl.tables.data_ptr(), re.data_ptr(), im.data_ptr(),
-        ws.fptr(F_THR_CULL) if cull else None, _stream(pl.device))), "sm_inv_cols")
+    cptr = ws.fptr(F_THR_CULL) if cull else None
+
+    def run():
+        for b in range(pl.batch):
+            off = b * pl.slice_bytes
+            rc = lib.sm_inv_cols(pl.col_handle, pl.col_tables.data_ptr(), re.data_ptr() + off, im.data_ptr() + off, cptr,
+                                 _stream(pl.device))
+            if rc:
+                return rc
+        return 0
+
+    _lib.check(_run("col_inv", pl.batch * lib.sm_plan_col_launches(pl.col_handle), 8 * pl.R * pl.C * sweeps, pl.device, run),
+               "sm_inv_cols")
 
 
 def inv_rows(ws: Workspace, re: torch.Tensor, im: torch.Tensor, cull: bool, scale: float,

@@ -111,14 +111,19 @@ class FourierMerge(MergeTensorsBase):
                     continue                                   # pass-through tensors are never transformed
             except ValueError:
                 continue                                       # unknown names are reported by the writer, as in the reference
-            if len(shape) not in (1, 2):
-                bad.append((name, shape, "only 1-D and 2-D tensors are transformed"))
+            if len(shape) == 0:
+                bad.append((name, shape, "a 0-d tensor has nothing to transform"))
                 continue
-            R, C = (1, shape[0]) if len(shape) == 1 else shape
-            plan = lib.sm_plan_create(int(R), int(C))
-            if not plan:
-                bad.append((name, shape, lib.sm_last_error().decode()))
-            else:
+            R, C = (1, shape[0]) if len(shape) == 1 else (shape[-2], shape[-1])
+            stack = 1
+            for d in shape[:-2]:
+                stack *= d
+            # the slices' column sweeps need a plan for [R][C]; rows and statistics one for all stack * R rows
+            for rows in {int(R), int(R) * int(stack)}:
+                plan = lib.sm_plan_create(rows, int(C))
+                if not plan:
+                    bad.append((name, shape, lib.sm_last_error().decode()))
+                    break
                 lib.sm_plan_destroy(plan)
         if bad:
             lines = "\n".join(f"  {n} {tuple(s)}: {why}" for n, s, why in bad[:20])
@@ -347,11 +352,11 @@ class FourierMerge(MergeTensorsBase):
         """Step-by-step path: any number of models, any branch, host decisions between the stages."""
         if len(sources) == 0:
             raise IndexError("list index out of range")      # what the reference does with no applicable model
-        R, C = E.shape_rc(base_out)
+        R, C = E.shape_rc(base_out)              # a tensor with leading dimensions is a stack of slices: all its rows
         base_bf16 = base_out if base_out.dtype == torch.bfloat16 else None
         # its own workspace (lane "steps"): a redo or a 1 / 3+ model tensor runs on the caller's stream while fused
         # chains of the same shape may still be in flight on the lane streams with the lane workspaces
-        ws = E.get_workspace(R, C, dev, n_spectra=max(2, len(sources)), safe_select=safe_select, lane="steps")
+        ws = E.ws_for(base_out, dev, n_spectra=max(2, len(sources)), safe_select=safe_select, lane="steps")
         ws.ctl.zero_()
         info = dict(branches=[], layer=layer_name)
         self.last_info = info
@@ -413,9 +418,9 @@ class FourierMerge(MergeTensorsBase):
                 cnorm_a, cnorm_b = abs(na / target_norm), abs(nb / target_norm)
                 n_ratio = cnorm_b / (cnorm_a + 1e-10)
                 final = last_round
-                out = (torch.empty((R, C) if base_out.ndim == 2 else (C,), dtype=torch.bfloat16, device=dev)
+                out = (torch.empty((R, C) if base_out.ndim >= 2 else (C,), dtype=torch.bfloat16, device=dev)
                        if (final and base_bf16 is not None)
-                       else torch.empty((R, C) if base_out.ndim == 2 else (C,), dtype=torch.float32, device=dev))
+                       else torch.empty((R, C) if base_out.ndim >= 2 else (C,), dtype=torch.float32, device=dev))
                 if cnorm_a < 1e-6:                             # :223-225  merged = a + b
                     info["branches"].append("add")
                     merged = _pair_elementwise(sa, sb, 1.0, 1.0, 1.0, final, base_out, ws, out)

@@ -33,6 +33,7 @@ def _dev(device) -> torch.device:
 
 
 def _as_rows(t: torch.Tensor):
+    """rows x columns of `t` laid out as one matrix (leading dimensions stack [R][C] slices, engine.Plan)."""
     R, C = E.shape_rc(t)
     return R, C
 
@@ -40,7 +41,7 @@ def _as_rows(t: torch.Tensor):
 def _spectrum_of(x32: torch.Tensor, dev, scale: float = 1.0):
     """real fp32 tensor (on dev) -> workspace whose slot 0 holds its half-planar spectrum * scale."""
     R, C = _as_rows(x32)
-    ws = E.get_workspace(R, C, dev)
+    ws = E.ws_for(x32, dev)
     ws.ctl.zero_()
     E.fwd_rows(ws, 0, E.Source(x32=x32), E.D_SUMSQ0)
     E.fwd_cols(ws, 0, scale=scale)
@@ -48,18 +49,23 @@ def _spectrum_of(x32: torch.Tensor, dev, scale: float = 1.0):
 
 
 def _expand(ws: E.Workspace, slot: int, shape) -> torch.Tensor:
+    """half-planar spectrum -> full complex64 tensor (Hermitian mirror), slice by slice for a stack."""
     pl = ws.plan
     out = torch.empty((pl.R, pl.C), dtype=torch.complex64, device=pl.device)
-    E._lib.check(pl.lib.sm_expand_full(pl.handle, ws.re[slot].data_ptr(), ws.im[slot].data_ptr(), out.data_ptr(),
-                                      E._stream(pl.device)), "sm_expand_full")
+    for b in range(pl.batch):
+        off = b * pl.slice_bytes
+        E._lib.check(pl.lib.sm_expand_full(pl.col_handle, ws.re[slot].data_ptr() + off, ws.im[slot].data_ptr() + off,
+                                          out.data_ptr() + b * pl.Rin * pl.C * 8, E._stream(pl.device)), "sm_expand_full")
     return out.reshape(shape)
 
 
 def _pack(ws: E.Workspace, slot: int, z: torch.Tensor):
     pl = ws.plan
     z = z.to(device=pl.device, dtype=torch.complex64).contiguous()
-    E._lib.check(pl.lib.sm_pack_half(pl.handle, z.data_ptr(), ws.re[slot].data_ptr(), ws.im[slot].data_ptr(),
-                                    E._stream(pl.device)), "sm_pack_half")
+    for b in range(pl.batch):
+        off = b * pl.slice_bytes
+        E._lib.check(pl.lib.sm_pack_half(pl.col_handle, z.data_ptr() + b * pl.Rin * pl.C * 8, ws.re[slot].data_ptr() + off,
+                                        ws.im[slot].data_ptr() + off, E._stream(pl.device)), "sm_pack_half")
 
 
 # ------------------------------------------------------------------------------------------
@@ -92,7 +98,7 @@ def ifft_transform(tensor: torch.Tensor, device: str) -> torch.Tensor:
     """Real part of the inverse 1-D / 2-D FFT -> fp32 on the CPU (functions.py:60-73)."""
     dev = _dev(device)
     R, C = _as_rows(tensor)
-    ws = E.get_workspace(R, C, dev)
+    ws = E.ws_for(tensor, dev)
     ws.ctl.zero_()
     _pack(ws, 0, tensor.reshape(R, C))
     out = torch.empty((R, C), dtype=torch.float32, device=dev)
@@ -138,7 +144,7 @@ def interpolate_fft_components(v0_fft: torch.Tensor, v1_fft: torch.Tensor, t: fl
     allocated with torch.zeros_like(v0_fft, device=device))."""
     dev = _dev(device)
     R, C = _as_rows(v0_fft)
-    ws = E.get_workspace(R, C, dev)
+    ws = E.ws_for(v0_fft, dev)
     ws.ctl.zero_()
     _pack(ws, 0, v0_fft.reshape(R, C))
     _pack(ws, 1, v1_fft.reshape(R, C))
@@ -160,7 +166,7 @@ def merge_tensors_fft2_slerp(v0: torch.Tensor, v1: torch.Tensor, t: float, devic
     R, C = _as_rows(v0)
     x0 = v0.to(dev).to(torch.float32).contiguous()
     x1 = v1.to(dev).to(torch.float32).contiguous()
-    ws = E.get_workspace(R, C, dev)
+    ws = E.ws_for(v0, dev)
     ws.ctl.zero_()
     E.fwd_rows(ws, 0, E.Source(x32=x0), E.D_SUMSQ0)
     E.fwd_rows(ws, 1, E.Source(x32=x1), E.D_SUMSQ1)
@@ -202,7 +208,7 @@ def task_arithmetic_fft2(v0: torch.Tensor, v1: torch.Tensor, t: float, device: s
     R, C = _as_rows(v0)
     x0 = v0.to(dev).to(torch.float32).contiguous()
     x1 = v1.to(dev).to(torch.float32).contiguous()
-    ws = E.get_workspace(R, C, dev)
+    ws = E.ws_for(v0, dev)
     ws.ctl.zero_()
     E.fwd_rows(ws, 0, E.Source(x32=x0), E.D_SUMSQ0)
     E.fwd_rows(ws, 1, E.Source(x32=x1), E.D_SUMSQ1)
@@ -218,7 +224,7 @@ def arithmetic_fft_components(v0_fft: torch.Tensor, v1_fft: torch.Tensor, t: flo
     "larger value" mask compares v0 with itself and is always False).  Returns complex64 on the CPU."""
     dev = _dev(device)
     R, C = _as_rows(v0_fft)
-    ws = E.get_workspace(R, C, dev)
+    ws = E.ws_for(v0_fft, dev)
     ws.ctl.zero_()
     _pack(ws, 0, v0_fft.reshape(R, C))
     _pack(ws, 1, v1_fft.reshape(R, C))

@@ -234,3 +234,39 @@ def test_correlate_pairs_kernel_vs_torch(E):
                 want = torch.nn.functional.cosine_similarity(t[i].float(), t[j].float(), dim=0).nan_to_num(0).mean().item()
                 assert abs(m[i, j].item() - want) < 2e-5 and m[j, i] == m[i, j], (shape, i, j, m[i, j].item(), want)
         assert (m.diagonal() == 0).all()
+
+
+def test_stacked_tensor_is_batched_like_fftn(E):
+    """VERDICT r1 missing #8: a tensor with leading dimensions (stacked experts) -- the reference transforms every
+    [R][C] slice on its own (fftn(dim=(-2, -1)), functions.py:58) while the norms, both order statistics and the SLERP
+    sums run over the WHOLE tensor.  Checked against the oracle (numpy fft2 over the last two axes does the same)."""
+    from oracle import oracle_np as O
+    from shardmerge_b200.tensor import functions as F
+    from tests.parity_util import flip_accounted, rel_l2
+    g = torch.Generator(device=DEV).manual_seed(12)
+    shape = (3, 352, 512)
+    v0 = 0.0026 * torch.randn(shape, generator=g, device=DEV)
+    v1 = 0.0020 * torch.randn(shape, generator=g, device=DEV)
+    X = F.fft_transform(v0, DEV)
+    assert rel_l2(X.numpy(), np.fft.fft2(v0.double().cpu().numpy(), axes=(-2, -1))) < 1e-6
+    assert rel_l2(F.ifft_transform(X, DEV).numpy(), v0.cpu().numpy()) < 1e-6
+    m, n0, n1 = F.merge_tensors_fft2_slerp(v0, v1, t=0.375, device=DEV, t_sum=1.0, cutoff_pct=0.08, cull_pct=0.20)
+    mo, o0, o1 = O.merge_tensors_fft2_slerp(v0.cpu().numpy(), v1.cpu().numpy(), 0.375, t_sum=1.0, cutoff_pct=0.08, cull_pct=0.20,
+                                            interp_imag=False)
+    assert abs(n0 / o0 - 1) < 1e-6 and abs(n1 / o1 - 1) < 1e-6
+    assert m.shape == shape
+    raw, resid, share = flip_accounted(m.numpy().reshape(-1, shape[-1]), np.asarray(mo).reshape(-1, shape[-1]), k=16)
+    assert resid <= 1e-5, (raw, resid, share)
+    # and through the merge driver (step path), bf16 in / out
+    from shardmerge_b200.config import MergeConfig
+    from shardmerge_b200.index import InMemoryIndex
+    from shardmerge_b200.merge.fast_fourier import FourierMerge
+    base = (0.02 * torch.randn(shape, generator=g, device=DEV)).to(torch.bfloat16)
+    fts = [(base.float() + s * torch.randn(shape, generator=g, device=DEV)).to(torch.bfloat16) for s in (0.002, 0.0026)]
+    fm = FourierMerge(MergeConfig(finetune_merge=[], output_base_model="b", output_dir="/tmp/unused"), index_manager=InMemoryIndex({}))
+    out = fm.merge_sources([E.make_source(base, ft, weight=a, name=f"m{k}") for k, (ft, a) in enumerate(zip(fts, (0.3, 0.5)))],
+                           base, torch.device(DEV), layer_name="model.layers.0.experts")
+    assert out.shape == shape and out.dtype == torch.bfloat16 and fm.last_info["branches"] == ["slerp"]
+    oo = O.merge_layer(bits(base), [dict(base=bits(base), ft=bits(ft), alpha=a, name=f"m{k}") for k, (ft, a) in enumerate(zip(fts, (0.3, 0.5)))])
+    u = bf16_ulp_distance(bits(out), oo.reshape(shape))
+    assert float((u <= 1).mean()) >= 0.985, float((u <= 1).mean())
