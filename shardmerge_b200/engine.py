@@ -420,6 +420,7 @@ def inv_rows(ws: Workspace, re: torch.Tensor, im: torch.Tensor, cull: bool, scal
     st = _stream(pl.device)
     cptr = ws.fptr(F_THR_CULL) if cull else None
     N = pl.R * pl.C
+    scale = float(scale) * pl.batch          # the kernel's 1 / (rows * C) counts all rows of a stack; one slice has rows / batch
     if out.dtype == torch.bfloat16:
         rc = _run("row_inv", 1, 8 * N, pl.device, lambda: lib.sm_inv_rows_bf16(
             pl.handle, pl.tables.data_ptr(), re.data_ptr(), im.data_ptr(), cptr, base.data_ptr(),

@@ -164,16 +164,29 @@ def merge_tensors_fft2_slerp(v0: torch.Tensor, v1: torch.Tensor, t: float, devic
     dev = _dev(device)
     _cpu = "cpu" if _result_device is None else _result_device
     R, C = _as_rows(v0)
-    x0 = v0.to(dev).to(torch.float32).contiguous()
-    x1 = v1.to(dev).to(torch.float32).contiguous()
     ws = E.ws_for(v0, dev)
     ws.ctl.zero_()
-    E.fwd_rows(ws, 0, E.Source(x32=x0), E.D_SUMSQ0)
-    E.fwd_rows(ws, 1, E.Source(x32=x1), E.D_SUMSQ1)
-    dbl, _, _, _ = ws.read_ctl()
-    n0 = E.f32(float(dbl[E.D_SUMSQ0]) ** 0.5)
-    n1 = E.f32(float(dbl[E.D_SUMSQ1]) ** 0.5)
-    v0n = (x0 * E.inv_norm_f32(n0)) if n0 != 0 else x0
+    if v0.dtype != torch.float32 or v1.dtype != torch.float32:
+        # normalize_tensor works in the tensors' OWN dtype (functions.py:85-88: a bf16 norm, a bf16 quotient -- what the
+        # earlier FourierMerge feeds in, shard/merge/fourier.py:120,179); only fft_transform widens to fp32 (:55).  Those
+        # roundings are 2^-9 relative per element, far above FFT rounding, so they are reproduced with the same torch ops.
+        d0, d1 = v0.to(dev), v1.to(dev)
+        n0, n1 = d0.norm().item(), d1.norm().item()
+        x0 = (d0 / n0 if n0 != 0 else d0).to(torch.float32).contiguous()
+        x1 = (d1 / n1 if n1 != 0 else d1).to(torch.float32).contiguous()
+        E.fwd_rows(ws, 0, E.Source(x32=x0), E.D_SUMSQ0)
+        E.fwd_rows(ws, 1, E.Source(x32=x1), E.D_SUMSQ1)
+        v0n, inv0, inv1 = x0, 1.0, 1.0
+    else:
+        x0 = v0.to(dev).contiguous()
+        x1 = v1.to(dev).contiguous()
+        E.fwd_rows(ws, 0, E.Source(x32=x0), E.D_SUMSQ0)
+        E.fwd_rows(ws, 1, E.Source(x32=x1), E.D_SUMSQ1)
+        dbl, _, _, _ = ws.read_ctl()
+        n0 = E.f32(float(dbl[E.D_SUMSQ0]) ** 0.5)
+        n1 = E.f32(float(dbl[E.D_SUMSQ1]) ** 0.5)
+        v0n = (x0 * E.inv_norm_f32(n0)) if n0 != 0 else x0
+        inv0, inv1 = E.inv_norm_f32(n0), E.inv_norm_f32(n1)
     if n1 < .0001:                                            # functions.py:184-185
         return v0n.reshape(v0.shape).to(_cpu), n0, n1
     if n0 < .0001:                                            # functions.py:187-190
@@ -183,13 +196,13 @@ def merge_tensors_fft2_slerp(v0: torch.Tensor, v1: torch.Tensor, t: float, devic
     out = torch.empty((R, C), dtype=torch.float32, device=dev)
     if ratio < b:                                             # functions.py:199-202 (linear: no blend needed)
         logger.info(f"Small norm v1 ({n1})")
-        E.fwd_cols(ws, 0, scale=E.inv_norm_f32(n0))
-        E.fwd_cols(ws, 1, scale=E.inv_norm_f32(n1))
+        E.fwd_cols(ws, 0, scale=inv0)
+        E.fwd_cols(ws, 1, scale=inv1)
         ws.re[0].add_(ws.re[1], alpha=float(t)); ws.im[0].add_(ws.im[1], alpha=float(t))
         E.inv_cols(ws, ws.re[0], ws.im[0], cull=False)
         E.inv_rows(ws, ws.re[0], ws.im[0], False, 1.0, None, out, check_ifft=True)
     else:
-        E.spectral_pair(ws, 0, 1, scale0=E.inv_norm_f32(n0), scale1=E.inv_norm_f32(n1), mode="slerp", t=t,
+        E.spectral_pair(ws, 0, 1, scale0=inv0, scale1=inv1, mode="slerp", t=t,
                         t_sum=t_sum, cutoff_pct=cutoff_pct, cull_pct=cull_pct, out_scale=1.0, out=out)
     _, _, flags, _ = ws.read_ctl()
     if int(flags[0]) > 0:
