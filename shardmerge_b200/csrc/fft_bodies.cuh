@@ -490,6 +490,29 @@ struct ColCtSrcP {
     }
   }
 };
+// first-stage source of the bulk-copy fed sweeps (kernels_fft.cu: k_col_pb): one instance x 32 columns of both planes staged
+// in shared memory as [element][32 floats]; the padding columns behind Ch are zero in the planes themselves
+SM_HD pf lds_pf(const float* p) {
+#if defined(__CUDA_ARCH__)
+  const float2 v = *reinterpret_cast<const float2*>(p);
+  return pf_make(v.x, v.y);
+#else
+  return pf_make(p[0], p[1]);
+#endif
+}
+template <bool kInverse>
+struct ColStagedSrcP {
+  const float* s0; const float* s1; int lane; float thr;
+  SM_HD void load(int i, pf& a, pf& b) const {
+    a = lds_pf(s0 + i * SM_COL_TILE + 2 * lane); b = lds_pf(s1 + i * SM_COL_TILE + 2 * lane);
+    if (kInverse) {                                        // p1 is the real plane in the inverse: cull on load
+      float b0 = pf_lo(b), b1 = pf_hi(b);
+      if (b0 < thr && -b0 < thr) b0 = 0.f;
+      if (b1 < thr && -b1 < thr) b1 = 0.f;
+      b = pf_make(b0, b1);
+    }
+  }
+};
 template <bool kBigTw>
 struct ColCtDstP {
   float* p0; float* p1; size_t row0; size_t estride; bool valid; const cf* twR; int inst; float scale; bool write_p1;
@@ -503,8 +526,9 @@ struct ColCtDstP {
 };
 
 // one CTA (NW warps = 2*NW butterfly slots) = one instance x 32 columns, L = R1*R2
-template <int R1, int R2, int NW, bool kInverse, bool kBigTw, class Exec>
-SM_HD void col_ct_body_p(Exec& ex, int tile, int inst, const ColCtArgs a, const cf* twR, pf4* smem) {
+template <int R1, int R2, int NW, bool kInverse, bool kBigTw, class Exec, bool kStaged = false>
+SM_HD void col_ct_body_p(Exec& ex, int tile, int inst, const ColCtArgs a, const cf* twR, pf4* smem,
+                         const float* st0 = nullptr, const float* st1 = nullptr) {
   constexpr int L = R1 * R2;
   constexpr int NS = 2 * NW;
   const int col0 = (tile + a.tile0) * SM_COL_TILE;
@@ -518,13 +542,17 @@ SM_HD void col_ct_body_p(Exec& ex, int tile, int inst, const ColCtArgs a, const 
     const float scale = a.scale_ptr ? *a.scale_ptr : a.scale;
     float* const p0 = (a.sel != nullptr && *a.sel != 0) ? a.p0_alt : a.p0;
     ColCtSrcP<kInverse> gsrc{p0, a.p1, row0, estride, valid, thr};
+    ColStagedSrcP<kInverse> ssrc{st0, st1, lane, thr};
     ColCtDstP<kBigTw> gdst{p0, a.p1, row0, estride, valid, twR, inst, scale, kInverse ? true : SM_COL_WRITE_P1(a)};
     if constexpr (R2 == 1) {
       for (int b = slot; b < 1; b += NS) stockham_bfly<R1, true, pf>(b, L, 1, a.tw_mul, twR, gsrc, gdst);
     } else {
       ColSmemP sout{smem, lane};
 #pragma unroll
-      for (int b = slot; b < R2; b += NS) stockham_bfly<R1, false, pf>(b, L, 1, a.tw_mul, twR, gsrc, sout);
+      for (int b = slot; b < R2; b += NS) {
+        if constexpr (kStaged) stockham_bfly<R1, false, pf>(b, L, 1, a.tw_mul, twR, ssrc, sout);
+        else stockham_bfly<R1, false, pf>(b, L, 1, a.tw_mul, twR, gsrc, sout);
+      }
     }
   }
   if constexpr (R2 > 1) {
@@ -548,8 +576,9 @@ SM_HD void col_ct_body_p(Exec& ex, int tile, int inst, const ColCtArgs a, const 
 // three register stages (radices <= 8) with the middle one in place: the two-stage sweeps of the long instances (L = 112 /
 // 128) need a radix-16 butterfly of packed values, 80 registers, 6 CTAs per SM; radices <= 8 need ~56 (the L = 64 sweeps
 // run at 6.0 TB/s with 9-10 CTAs per SM against 4.8 TB/s, profiles/r01).  L = R1*R2*R3, L / R1 <= 2 NW and L / R2 <= 2 NW.
-template <int R1, int R2, int R3, int NW, bool kInverse, bool kBigTw, class Exec>
-SM_HD void col_ct_body_p3(Exec& ex, int tile, int inst, const ColCtArgs a, const cf* twR, pf4* smem) {
+template <int R1, int R2, int R3, int NW, bool kInverse, bool kBigTw, class Exec, bool kStaged = false>
+SM_HD void col_ct_body_p3(Exec& ex, int tile, int inst, const ColCtArgs a, const cf* twR, pf4* smem,
+                          const float* st0 = nullptr, const float* st1 = nullptr) {
   constexpr int L = R1 * R2 * R3;
   constexpr int NS = 2 * NW;
   static_assert(L / R2 <= NS, "col_ct_body_p3: at most one middle-stage butterfly per slot (it runs in place)");
@@ -564,9 +593,13 @@ SM_HD void col_ct_body_p3(Exec& ex, int tile, int inst, const ColCtArgs a, const
     const float thr = (kInverse && a.thr_ptr) ? *a.thr_ptr : 0.f;
     float* const p0 = (a.sel != nullptr && *a.sel != 0) ? a.p0_alt : a.p0;
     ColCtSrcP<kInverse> gsrc{p0, a.p1, row0, estride, valid, thr};
+    ColStagedSrcP<kInverse> ssrc{st0, st1, lane, thr};
     ColSmemP sm{smem, lane};
 #pragma unroll
-    for (int b = slot; b < L / R1; b += NS) stockham_bfly<R1, false, pf>(b, L, 1, a.tw_mul, twR, gsrc, sm);
+    for (int b = slot; b < L / R1; b += NS) {
+      if constexpr (kStaged) stockham_bfly<R1, false, pf>(b, L, 1, a.tw_mul, twR, ssrc, sm);
+      else stockham_bfly<R1, false, pf>(b, L, 1, a.tw_mul, twR, gsrc, sm);
+    }
   }
   ex.sync();
   SM_FOR_THREADS(ex, tid) {

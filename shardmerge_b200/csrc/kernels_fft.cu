@@ -86,6 +86,79 @@ __global__ void __launch_bounds__(NW * 32) k_col_p3(const __grid_constant__ ColC
   col_ct_body_p3<R1, R2, R3, NW, kInverse, kBigTw>(ex, (int)blockIdx.x, (int)blockIdx.y, a, twR, reinterpret_cast<pf4*>(g_dyn_smem));
 }
 
+// ---- mbarrier / bulk-copy primitives (cp.async.bulk, the 1-D TMA path) used by the bulk-copy fed kernels below ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  } while (!ok);
+}
+
+
+// ---- column sweeps fed by the bulk-copy engine (persistent) ---------------------------------------------------------
+// k_col_p / k_col_p3 above spend most of their stall cycles waiting for the global loads of their first stage
+// (long_scoreboard 5 - 8 of ~13 stall cycles per issue, profiles/r01 and r02): a CTA lives for one instance x 32 columns
+// and the loads of the next CTA start only when a slot frees up.  Here a CTA is persistent over the (tile, instance)
+// items, and the 2 L row segments (128 bytes each) of its NEXT item are copied global -> shared by cp.async.bulk into
+// one of two staging buffers while it transforms the current one; the first stage reads the staged planes, everything
+// after it is the body of k_col_p / k_col_p3.  No thread waits on a global load.  R3 == 1 selects the two-stage body.
+template <int R1, int R2, int R3, int NW, bool kInverse, bool kBigTw>
+__global__ void __launch_bounds__(NW * 32) k_col_pb(const __grid_constant__ ColCtArgs a, const cf* __restrict__ twR, int ntiles,
+                                                    int n_items) {
+  constexpr int L = R1 * R2 * R3;
+  constexpr int T = NW * 32;
+  constexpr int kPlane = L * SM_COL_TILE;                 // floats per staged plane
+  DeviceExec ex;
+  __shared__ uint64_t bar[2];
+  pf4* work = reinterpret_cast<pf4*>(g_dyn_smem);                              // L x 16 pf4 = L x 256 bytes
+  float* stage = reinterpret_cast<float*>(g_dyn_smem) + (size_t)L * 64;        // 2 buffers x 2 planes x L x 32 floats
+  const int tid = threadIdx.x;
+  if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
+  __syncthreads();
+  const float* p0 = (a.sel != nullptr && *a.sel != 0) ? a.p0_alt : a.p0;
+  const float* p1 = a.p1;
+  auto issue = [&](int item, int buf) {
+    const int inst = item / ntiles, tile = item - inst * ntiles;
+    if (tid == 0) mbar_expect_tx(&bar[buf], 2u * (uint32_t)L * 128u);
+    float* dst = stage + (size_t)buf * 2 * kPlane;
+    const size_t col = (size_t)(tile + a.tile0) * SM_COL_TILE;
+    for (int i = tid; i < 2 * L; i += T) {
+      const int pl = i >= L ? 1 : 0, e = i - pl * L;
+      const float* src = (pl ? p1 : p0) + ((size_t)inst * a.inst_mul + (size_t)e * a.elem_mul) * a.P + col;
+      bulk_g2s(dst + (size_t)pl * kPlane + (size_t)e * SM_COL_TILE, src, 128u, &bar[buf]);
+    }
+  };
+  int item = (int)blockIdx.x, n = 0;
+  if (item < n_items) issue(item, 0);
+  for (; item < n_items; item += (int)gridDim.x, ++n) {
+    const int buf = n & 1;
+    const int next = item + (int)gridDim.x;
+    if (next < n_items) issue(next, buf ^ 1);            // that buffer was last read before the barrier that ended item n - 1
+    mbar_wait(&bar[buf], (uint32_t)(n >> 1) & 1u);
+    const int inst = item / ntiles, tile = item - inst * ntiles;
+    const float* s0 = stage + (size_t)buf * 2 * kPlane;
+    if constexpr (R3 == 1) col_ct_body_p<R1, R2, NW, kInverse, kBigTw, DeviceExec, true>(ex, tile, inst, a, twR, work, s0, s0 + kPlane);
+    else col_ct_body_p3<R1, R2, R3, NW, kInverse, kBigTw, DeviceExec, true>(ex, tile, inst, a, twR, work, s0, s0 + kPlane);
+    __syncthreads();                                     // the work buffer and this staging buffer are free again
+  }
+}
+
 // ---- both column sweeps of a four-step transform in ONE launch, the second one fed from L2 ----------------
 // A separate launch per sweep streams the whole spectrum through DRAM twice (16N bytes per transform).  Here the
 // CTAs of both sweeps share one 1-D grid, ordered so that the second-sweep CTAs of column tile t are dispatched
@@ -166,29 +239,6 @@ __global__ void __launch_bounds__(T) k_row_inv_ct(int C, int P, const RowInvArgs
 // copied global -> shared by the copy engine while it computes the current one: one elected thread
 // issues the copy as soon as the stage-1 barrier has released the staging buffer, every thread waits
 // on the mbarrier before stage 1 of the next row.  No thread ever stalls on a global load.
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_fence_init() {
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  do {
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-  } while (!ok);
-}
-
 struct FwdStageHook {          // refill the input staging buffer with the CTA's next row
   const RowFwdArgs* a; int next_row, R, C; char* stage; uint64_t* bar;
   __device__ __forceinline__ void after_first_stage() const {
@@ -1490,8 +1540,12 @@ static int launch_col_ct_pair(bool inverse, bool big_tw, dim3 grid, const ColCtA
   return 0;
 }
 
+template <int R1, int R2, int R3, int NW>
+static int launch_col_pb(bool inverse, bool big_tw, dim3 grid, const ColCtArgs& a, const cf* twR, cudaStream_t st);
+
 template <int R1, int R2, int NW>
 static int launch_col_p(bool inverse, bool big_tw, dim3 grid, const ColCtArgs& a, const cf* twR, cudaStream_t st) {
+  if constexpr (R2 > 1) { const int rc = launch_col_pb<R1, R2, 1, NW>(inverse, big_tw, grid, a, twR, st); if (rc <= 0) return rc; }
   static bool done[4] = {false, false, false, false};
   const int smem = (R2 > 1) ? R1 * R2 * SM_COL_TILE * 8 : 0;
   cudaError_t e;
@@ -1510,6 +1564,7 @@ static int launch_col_p(bool inverse, bool big_tw, dim3 grid, const ColCtArgs& a
 
 template <int R1, int R2, int R3, int NW>
 static int launch_col_p3(bool inverse, bool big_tw, dim3 grid, const ColCtArgs& a, const cf* twR, cudaStream_t st) {
+  { const int rc = launch_col_pb<R1, R2, R3, NW>(inverse, big_tw, grid, a, twR, st); if (rc <= 0) return rc; }
   static bool done[4] = {false, false, false, false};
   const int smem = R1 * R2 * R3 * SM_COL_TILE * 8;
   cudaError_t e;
@@ -1522,6 +1577,49 @@ static int launch_col_p3(bool inverse, bool big_tw, dim3 grid, const ColCtArgs& 
   else if (big_tw) { SM_COLP3_CASE(true, true, 2) }
   else { SM_COLP3_CASE(true, false, 3) }
 #undef SM_COLP3_CASE
+  SM_LAUNCH_CHECK();
+  return 0;
+}
+
+static int num_sms();
+// SM_COL_BULK=1 selects the persistent, bulk-copy fed sweeps (k_col_pb).  OFF by default: measured on the Llama-8B-shaped
+// bench (profiles/r02_ab_col_bulk.log) they move 3.5 TB/s against 5.1 TB/s for k_col_p / k_col_p3 -- 2 L bulk copies of
+// 128 bytes per item keep the copy engine busier than the data is worth, and the staging buffers cut the CTAs per SM from
+// 7 to 2.  Kept as an A-B switch (and as the skeleton for a tensor-map variant with one copy per plane).
+static bool use_col_bulk() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SM_COL_BULK"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v != 0;
+}
+
+// persistent, bulk-copy fed variant of launch_col_p (R3 == 1) / launch_col_p3; returns 1 if it does not apply
+template <int R1, int R2, int R3, int NW>
+static int launch_col_pb(bool inverse, bool big_tw, dim3 grid, const ColCtArgs& a, const cf* twR, cudaStream_t st) {
+  constexpr int L = R1 * R2 * R3;
+  constexpr int smem = L * 768;                         // work (L x 256) + two staging buffers of two planes (L x 128 each)
+  if (!use_col_bulk() || smem > 110 * 1024) return 1;
+  static bool done[4] = {false, false, false, false};
+  static int occ[4] = {0, 0, 0, 0};
+  const int ntiles = (int)grid.x, n_items = (int)(grid.x * grid.y);
+  cudaError_t e;
+#define SM_COLPB_CASE(INV, BIG, IDX)                                                                        \
+  e = opt_in(k_col_pb<R1, R2, R3, NW, INV, BIG>, &done[IDX]);                                               \
+  if (e != cudaSuccess) { sm_set_error("opt_in: %s", cudaGetErrorString(e)); return -100; }               \
+  if (occ[IDX] == 0) {                                                                                    \
+    int o = 0;                                                                                            \
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, k_col_pb<R1, R2, R3, NW, INV, BIG>, NW * 32, smem) != cudaSuccess || o < 1) o = 1; \
+    occ[IDX] = o;                                                                                         \
+  }                                                                                                       \
+  {                                                                                                       \
+    int ctas = num_sms() * occ[IDX];                                                                      \
+    if (ctas > n_items) ctas = n_items;                                                                   \
+    k_col_pb<R1, R2, R3, NW, INV, BIG><<<ctas, NW * 32, smem, st>>>(a, twR, ntiles, n_items);             \
+  }
+  if (!inverse && big_tw) { SM_COLPB_CASE(false, true, 0) }
+  else if (!inverse) { SM_COLPB_CASE(false, false, 1) }
+  else if (big_tw) { SM_COLPB_CASE(true, true, 2) }
+  else { SM_COLPB_CASE(true, false, 3) }
+#undef SM_COLPB_CASE
   SM_LAUNCH_CHECK();
   return 0;
 }
