@@ -1,0 +1,73 @@
+"""BASELINE config 5: one tensor's rows spread over several GPUs (shardmerge_b200/rowsplit.py).  `pytest -m gpu`.
+The one-rank case runs everywhere (everything but the NCCL calls); the two-rank case needs two GPUs and runs the worker
+under torchrun."""
+import json
+import os
+import socket
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from tests.parity_util import bf16_ulp_distance
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def bits(t):
+    return t.contiguous().view(torch.int16).cpu().numpy().view(np.uint16)
+
+
+@pytest.mark.parametrize("shape", [(2048, 2048), (2004, 296), (1024, 4096)])
+def test_rowsplit_one_rank_matches_fused_chain(shape):
+    """One rank = the whole tensor as a single slab: the torch-side order statistics (exact radix select with Hermitian
+    multiplicities), masked fp64 sums and the host-side role / target-norm decisions against the fused chain's."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from shardmerge_b200 import engine as E
+    from shardmerge_b200.config import MergeConfig
+    from shardmerge_b200.index import InMemoryIndex
+    from shardmerge_b200.merge.fast_fourier import FourierMerge
+    from shardmerge_b200.rowsplit import merge_rowsplit
+    g = torch.Generator(device=DEV).manual_seed(shape[0] + shape[1])
+    base = (0.02 * torch.randn(shape, generator=g, device=DEV)).to(torch.bfloat16)
+    # second case: the SECOND model has the larger norm (roles swap, weights do not)
+    for sig in ((0.002, 0.0026), (0.0026, 0.002)):
+        fts = [(base.float() + s * torch.randn(shape, generator=g, device=DEV)).to(torch.bfloat16) for s in sig]
+        info = {}
+        got = merge_rowsplit(base, fts, (0.3, 0.5), info=info)
+        fm = FourierMerge(MergeConfig(finetune_merge=[], output_base_model="b", output_dir="/tmp/unused"), index_manager=InMemoryIndex({}))
+        want = fm.merge_sources([E.make_source(base, f, weight=a, name=f"m{k}") for k, (f, a) in enumerate(zip(fts, (0.3, 0.5)))],
+                                base, torch.device(DEV), layer_name="model.layers.0.x")
+        assert fm.last_info["branches"] == ["slerp"] and info["swap"] == fm.last_info["swap"]
+        assert abs(info["target_norm"] / fm.last_info["target_norm"] - 1) < 1e-7
+        u = bf16_ulp_distance(bits(got), bits(want))
+        assert float((u == 0).mean()) >= 0.9999 and int(u.max()) <= 1, (shape, sig, float((u == 0).mean()), int(u.max()))
+
+
+def _torchrun(n, *args, timeout=900):
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), str(ROOT / "tests" / "rowsplit_worker.py"), *[str(a) for a in args]]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=str(ROOT))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    line = [l for l in r.stdout.splitlines() if l.startswith("ROWSPLIT ")][-1]
+    return json.loads(line[len("ROWSPLIT "):])
+
+
+@pytest.mark.parametrize("shape", [(4096, 2048), (16032, 1024)])
+def test_rowsplit_two_ranks(shape):
+    """Rows on two GPUs (NCCL all-to-all of the half spectrum, all-reduced histograms and sums) against the one-GPU merge of
+    the whole tensor: same spectra, same exact thresholds -> the same bf16 tensor."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    res = _torchrun(2, *shape)
+    print("\n[rowsplit x2]", res)
+    assert res["vs_one_gpu_exact"] >= 0.9999 and res["vs_one_gpu_within_1ulp"] == 1.0, res
