@@ -66,9 +66,15 @@ def main():
             if RR.available():
                 del one
                 E.clear_caches(); torch.cuda.empty_cache()
-                ref = RR.merge_layer(base, fts, [0.3, 0.5], device=str(dev))
-                ur = bf16_ulp_distance(bits(got), bits(ref))
-                res.update(vs_reference_cuda_exact=float((ur == 0).mean()), vs_reference_cuda_within_1ulp=float((ur <= 1).mean()))
+                try:
+                    t1 = time.perf_counter()
+                    ref = RR.merge_layer(base, fts, [0.3, 0.5], device=str(dev))
+                    torch.cuda.synchronize()
+                    ur = bf16_ulp_distance(bits(got), bits(ref))
+                    res.update(vs_reference_cuda_exact=float((ur == 0).mean()), vs_reference_cuda_within_1ulp=float((ur <= 1).mean()),
+                               reference_cuda_seconds=round(time.perf_counter() - t1, 2))
+                except Exception as exc:                     # e.g. the reference's sorts / temporaries do not fit at 1 G elements
+                    res.update(reference_cuda_error=f"{type(exc).__name__}: {str(exc)[:200]}")
         print("ROWSPLIT " + json.dumps(res), flush=True)
     dist.barrier()
     dist.destroy_process_group()
