@@ -435,7 +435,17 @@ def main():
         index = InMemoryIndex(host)
         fm2 = FourierMerge(cfg, index_manager=index)
         weight_map = {n: f"model-{int(n.split('.')[2]) + 1:05d}-of-{Le:05d}.safetensors" for n in names}
-        tmp_root = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+        # shard files of the with_files measurement: tmpfs if it has room for the steps' output (twice over), else the default
+        # temp directory, else that measurement is skipped (it must never take the bench line down)
+        need_bytes = 2 * max(args.steps, 2) * sum(host["synth/base"][n].numel() * 2 for n in names)
+        tmp_root, files_ok = None, False
+        for cand in ("/dev/shm", tempfile.gettempdir()):
+            try:
+                if os.path.isdir(cand) and os.access(cand, os.W_OK) and shutil.disk_usage(cand).free > need_bytes * (world if cand == "/dev/shm" else 1):
+                    tmp_root, files_ok = cand, True
+                    break
+            except OSError:
+                pass
         out_root = Path(tempfile.mkdtemp(prefix=f"shardmerge_bench_r{rank}_", dir=tmp_root))
         h2d = sum(t.numel() * 2 for n in names for t in [host["synth/base"][n]] + [host[f"synth/ft{k}"][n] for k in range(M)])
         d2h = sum(host["synth/base"][n].numel() * 2 for n in names)
@@ -502,9 +512,19 @@ def main():
         my_ems, _ = measure(StagingOnlyWriter, "s")
         ems = max_over_ranks(my_ems)
         ems_files = None
-        if args.e2e_files:
-            _, my_files = measure(ModelWriter, "f")
+        if world > 1:                                   # every rank must take the same branch: all measure, or none
+            t = torch.tensor([1.0 if files_ok else 0.0], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            files_ok = bool(t.item() > 0.5)
+        if args.e2e_files and files_ok:
+            try:
+                _, my_files = measure(ModelWriter, "f")
+            except Exception as exc:                    # a full file system must not take the bench line down
+                print(f"[bench] with_files measurement failed: {exc}", file=sys.stderr)
+                my_files = float("nan")
             ems_files = max_over_ranks(my_files)
+            if ems_files != ems_files:
+                ems_files = None
         e2e_wall = time.perf_counter() - t_e2e0
         shutil.rmtree(out_root, ignore_errors=True)
         # what plain pinned copies achieve on this box, both directions at once (the e2e path moves 6 B in and 2 B out
@@ -540,7 +560,7 @@ def main():
                    with_files=(dict(value=e2e_params * args.steps / (ems_files / 1000.0), unit="params/s",
                                     note="a second set of the same steps with the unmodified ModelWriter, timed until finalize() has "
                                          "returned for every step: all safetensors shards (one per layer) complete on "
-                                         + ("tmpfs (/dev/shm)" if tmp_root else "the default temp directory")
+                                         + ("tmpfs (/dev/shm)" if tmp_root == "/dev/shm" else str(tmp_root))
                                          + "; the file copies compete with the DMA for host memory bandwidth")
                                if ems_files else None),
                    wall_s=e2e_wall, prefetch_depth=fm2.prefetch_depth,

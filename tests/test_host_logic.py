@@ -382,3 +382,55 @@ def test_merge_distributed_world2_gloo(tmp_path):
                 assert torch.equal(sf.get_tensor(k), (ref[k].float() * 2).to(torch.bfloat16))
                 seen.add(k)
     assert seen == set(ref) and (out / "README.md").read_text() == "readme"
+
+
+SELECT_WORKER = textwrap.dedent("""
+    import sys, numpy as np, torch, torch.distributed as dist
+    sys.path.insert(0, %(root)r)
+    from shardmerge_b200.rowsplit import dist_select_kth
+    rank = int(sys.argv[1])
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%(port)d", rank=rank, world_size=2)
+    rng = np.random.default_rng(5)
+    full = rng.standard_normal((64, 96)).astype(np.float32)
+    full[3, 7] = 0.0; full[10, 80] = np.float32(1e-30); full[20, 5] = full[21, 6]        # zero, tiny, a tie
+    Ch = 90                                                   # columns 0..Ch valid, 91..95 padding
+    full[:, Ch + 1:] = 0.0
+    w = 48                                                    # two column slabs of 48
+    mine = torch.from_numpy(full[:, rank * w:(rank + 1) * w].copy())
+    col = rank * w + torch.arange(w)
+    mult = torch.where(col <= Ch, torch.where((col == 0) | (col == Ch), 1, 2), 0).to(torch.int64)
+    keys = mine.view(torch.int32) & 0x7FFFFFFF
+    # reference: every valid bin with its multiplicity, sorted
+    allmult = np.where(np.arange(96) <= Ch, np.where((np.arange(96) == 0) | (np.arange(96) == Ch), 1, 2), 0)
+    ref = np.sort(np.repeat(np.abs(full), allmult, axis=1).ravel())
+    ok = True
+    for k in (0, 1, 17, len(ref) // 5, len(ref) // 2, len(ref) - 1):
+        bits = dist_select_kth([keys], mult, k)
+        val = np.array([bits], dtype=np.int32).view(np.float32)[0]
+        ok = ok and (val == ref[k])
+    # two planes at once (the cutoff statistic runs over cat(|re0|, |re1|))
+    ref2 = np.sort(np.concatenate([ref, ref * np.float32(0.5)]))
+    bits = dist_select_kth([keys, (mine * 0.5).view(torch.int32) & 0x7FFFFFFF], mult, len(ref2) // 12)
+    ok = ok and (np.array([bits], dtype=np.int32).view(np.float32)[0] == ref2[len(ref2) // 12])
+    print("RANK", rank, "OK" if ok else "MISMATCH", flush=True)
+    dist.barrier(); dist.destroy_process_group()
+""")
+
+
+def test_distributed_order_statistic_world2_gloo(tmp_path):
+    """The exact radix select the row-split merge uses for its two global order statistics (shardmerge_b200/rowsplit.py:
+    weighted histograms per rank, all-reduce, three rounds), two ranks over gloo on CPU against a sort."""
+    import socket
+    script = tmp_path / "sel_worker.py"
+    for attempt in range(3):
+        with socket.socket() as sk:
+            sk.bind(("127.0.0.1", 0))
+            port = sk.getsockname()[1]
+        script.write_text(SELECT_WORKER % dict(root=str(ROOT), port=port))
+        procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+                 for r in range(2)]
+        logs = [p.communicate(timeout=180)[0] for p in procs]
+        if all(p.returncode == 0 for p in procs):
+            break
+    assert all(p.returncode == 0 for p in procs), logs
+    assert all("OK" in l and "MISMATCH" not in l for l in logs), logs
