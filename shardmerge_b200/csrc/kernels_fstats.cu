@@ -65,7 +65,8 @@ struct FsState {                     // SM_FS_STATE_BYTES device bytes
   unsigned int bstar;
   double s_in[3];                    // decided part of the SLERP sums (s00, s11, s01)
   unsigned int sticky;               // OR of every status this state has ended with (kernels never clear it)   (SM_FS_STICKY_OFF)
-  unsigned int pad[13];
+  unsigned int dense;                // the sample found > 1.6 % of the keys inside the window: tied keys, combine per warp
+  unsigned int pad[12];
 };
 static_assert(sizeof(FsState) == SM_FS_STATE_BYTES, "FsState layout");
 static_assert(offsetof(FsState, status) == SM_FS_STATUS_OFF, "FsState status offset");
@@ -306,6 +307,10 @@ __global__ void __launch_bounds__(kSampleThreads) k_fs_sample(const __grid_const
     unsigned int l2 = 0;
     while ((1ull << l2) < width) ++l2;
     if (width == 0ull || l2 > kFineLog) status |= 4u;    // the fine histogram has one counter per bit pattern
+    unsigned int in_window = 0u;                           // sample keys inside the window (at most 17 bins wide when it is usable)
+    if (status == 0u)
+      for (unsigned int b = lo >> kSampleShift; b <= (hi >> kSampleShift) && b < (unsigned int)kSampleBins; ++b) in_window += s_h[b];
+    st->dense = (in_window > (ns >> 6)) ? 1u : 0u;         // > 1.6 % of the sample
     st->rank = rank; st->below = 0ull; st->lo = lo; st->hi = hi;
     st->shift = l2 > 11 ? l2 - 11 : 0;
     st->status = status; st->key = 0u; st->value = 0.f; st->bstar = 0u;
@@ -330,7 +335,7 @@ constexpr int kQCap = 64;            // entries per warp queue: < 32 left after 
 
 struct PassCtx {
   float lo_f, hi_f;                  // the window as floats: for non-NaN keys, float order == bit-pattern order
-  unsigned int lo, shift, scap;
+  unsigned int lo, shift, scap, dense;
   unsigned int* fine;
   float2* slist;                     // this CTA's side list
   unsigned int* status;
@@ -373,10 +378,17 @@ __device__ __forceinline__ float fs_blend(const BlendScal& bs, float a, float b,
 // NaN-propagating minimum (fminf would drop a NaN operand)
 __device__ __forceinline__ float fmin_nan(float x, float y) { float r; asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(x), "f"(y)); return r; }
 
-// true if no product a_i * b_i of the item is zero (incl. underflow) or NaN
+// The fast path decides torch.sign(a) == torch.sign(b) by a * b > 0.  That is wrong only if the product is NaN or if it
+// underflowed to zero with both operands non-zero.  An operand that IS zero needs no care: sign(0) = 0 differs from the sign
+// of any non-zero value (a * b = 0 -> false, right), and if both are zero the element is in no SLERP sum (|re1| = 0 is below
+// or inside every window), counts as a key below the window either way, and blends to zero under either mask.  (Spectra of
+// later pair-tree rounds hold ~1 % exact zeros: with the stricter "no zero product" test 10 % of their items were queued.)
+__device__ __forceinline__ float fs_pq(float a, float b) { return (a == 0.f || b == 0.f) ? 1.f : fabsf(a * b); }
 __device__ __forceinline__ bool fs_item_plain(const float4& a, const float4& b) {
   const float m = fmin_nan(fmin_nan(fabsf(a.x * b.x), fabsf(a.y * b.y)), fmin_nan(fabsf(a.z * b.z), fabsf(a.w * b.w)));
-  return m > 0.f;                  // false for NaN
+  if (m > 0.f) return true;        // the common case costs what it always did: four products and three minima
+  const float q = fmin_nan(fmin_nan(fs_pq(a.x, b.x), fs_pq(a.y, b.y)), fmin_nan(fs_pq(a.z, b.z), fs_pq(a.w, b.w)));
+  return q > 0.f;                  // false for NaN
 }
 
 struct Acc { unsigned int below; float p00, p11, p01; bool anyw; };
@@ -410,10 +422,25 @@ __device__ __forceinline__ float fs_elem(const PassCtx& x, const BlendScal& bs, 
 
 // one key inside the window, multiplicity w: a fire-and-forget global reduction into its own counter (the window spans
 // ~2 M counters, so two keys rarely meet) and a shared-memory one into the CTA's coarse histogram
+// Lanes of the warp that carry the SAME key (and multiplicity) combine first: rounding-noise keys -- the culled bins of an
+// earlier pair-tree round, a few ulps of the transform's largest terms -- take a handful of distinct values, and 2 % of a
+// tensor's keys reducing into ten counters serialise in L2 (the cutoff pass of a round-2 spectrum took 5x as long).
+// The sample tells the two cases apart (FsState::dense): a smooth density puts ~1 % of the keys into the window, a tied one
+// more; the match costs ~7 % of the pass when keys are distinct, so it is only done where it pays.
 __device__ __forceinline__ void fs_red_key(const PassCtx& x, unsigned int key, unsigned int w) {
   const unsigned int d = key - x.lo;
-  atomicAdd(x.fine + d, w);
-  atomicAdd(&g_fs_coarse[d >> x.shift], w);
+  if (x.dense) {                                                             // uniform over the grid
+    const unsigned int act = __activemask();
+    const unsigned int peers = __match_any_sync(act, (d << 2) | w);          // d < 2^22, w in {1, 2}
+    if ((int)(threadIdx.x & 31u) == __ffs((int)peers) - 1) {
+      const unsigned int tot = w * (unsigned int)__popc(peers);
+      atomicAdd(x.fine + d, tot);
+      atomicAdd(&g_fs_coarse[d >> x.shift], tot);
+    }
+  } else {
+    atomicAdd(x.fine + d, w);
+    atomicAdd(&g_fs_coarse[d >> x.shift], w);
+  }
 }
 
 // what the drain adds to the block totals (only touched out of line)
@@ -491,7 +518,7 @@ __global__ void __launch_bounds__(kPassThreads, kPassCtasPerSm) k_fs_pass(const 
   const float* __restrict__ re0 = sw ? c.reY : c.reX;
   const float* __restrict__ re1 = sw ? c.reX : c.reY;
   PassCtx x;
-  x.lo = st->lo; x.shift = st->shift; x.scap = ws.scap;
+  x.lo = st->lo; x.shift = st->shift; x.scap = ws.scap; x.dense = st->dense;
   x.lo_f = __uint_as_float(x.lo); x.hi_f = __uint_as_float(st->hi);       // hi <= +inf (k_fs_sample)
   x.fine = ws.fine; x.slist = ws.sbkt + (size_t)blockIdx.x * ws.scap;
   x.status = &st->status; x.out = out; x.Ch = pl.Ch;
