@@ -6,6 +6,7 @@
 #include <cstdarg>
 #include <cstdlib>
 #include <mutex>
+#include <cuda.h>            // CUtensorMap (types only: the encoder is fetched through cudaGetDriverEntryPoint)
 #include "fft_bodies.cuh"
 #include "sm_internal.h"
 
@@ -118,9 +119,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // items, and the 2 L row segments (128 bytes each) of its NEXT item are copied global -> shared by cp.async.bulk into
 // one of two staging buffers while it transforms the current one; the first stage reads the staged planes, everything
 // after it is the body of k_col_p / k_col_p3.  No thread waits on a global load.  R3 == 1 selects the two-stage body.
+// use == 1: the staging copies are TWO tensor-map TMA loads per item (cp.async.bulk.tensor.3d, one box of L rows x 32 columns
+// per plane) instead of 2 L bulk copies of 128 bytes.  The maps describe a plane as (column, b, a) with row = a * Rb + b.
+struct ColMaps { CUtensorMap p0, p0_alt, p1; int use; };
+
+__device__ __forceinline__ void tma_load_3d(void* dst_smem, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+               ::"r"(smem_u32(dst_smem)), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
+}
+
 template <int R1, int R2, int R3, int NW, bool kInverse, bool kBigTw>
 __global__ void __launch_bounds__(NW * 32) k_col_pb(const __grid_constant__ ColCtArgs a, const cf* __restrict__ twR, int ntiles,
-                                                    int n_items) {
+                                                    int n_items, const __grid_constant__ ColMaps maps) {
   constexpr int L = R1 * R2 * R3;
   constexpr int T = NW * 32;
   constexpr int kPlane = L * SM_COL_TILE;                 // floats per staged plane
@@ -138,6 +148,15 @@ __global__ void __launch_bounds__(NW * 32) k_col_pb(const __grid_constant__ ColC
     if (tid == 0) mbar_expect_tx(&bar[buf], 2u * (uint32_t)L * 128u);
     float* dst = stage + (size_t)buf * 2 * kPlane;
     const size_t col = (size_t)(tile + a.tile0) * SM_COL_TILE;
+    if (maps.use) {
+      if (tid == 0) {
+        const bool alt = (a.sel != nullptr && *a.sel != 0);
+        const int cb = a.elem_mul == 1 ? 0 : inst, ca = a.elem_mul == 1 ? inst : 0;     // sweep B / single sweep : sweep A
+        tma_load_3d(dst, alt ? &maps.p0_alt : &maps.p0, (int)col, cb, ca, &bar[buf]);
+        tma_load_3d(dst + kPlane, &maps.p1, (int)col, cb, ca, &bar[buf]);
+      }
+      return;
+    }
     for (int i = tid; i < 2 * L; i += T) {
       const int pl = i >= L ? 1 : 0, e = i - pl * L;
       const float* src = (pl ? p1 : p0) + ((size_t)inst * a.inst_mul + (size_t)e * a.elem_mul) * a.P + col;
@@ -1582,14 +1601,49 @@ static int launch_col_p3(bool inverse, bool big_tw, dim3 grid, const ColCtArgs& 
 }
 
 static int num_sms();
-// SM_COL_BULK=1 selects the persistent, bulk-copy fed sweeps (k_col_pb).  OFF by default: measured on the Llama-8B-shaped
-// bench (profiles/r02_ab_col_bulk.log) they move 3.5 TB/s against 5.1 TB/s for k_col_p / k_col_p3 -- 2 L bulk copies of
-// 128 bytes per item keep the copy engine busier than the data is worth, and the staging buffers cut the CTAs per SM from
-// 7 to 2.  Kept as an A-B switch (and as the skeleton for a tensor-map variant with one copy per plane).
+// SM_COL_BULK=1 selects the persistent, bulk-copy fed sweeps (k_col_pb), SM_COL_BULK=2 the same fed by two tensor-map TMA
+// loads per item.  OFF by default: measured on the Llama-8B-shaped bench (profiles/r02_ab_col_bulk.log) they move 3.5 TB/s
+// (2 L bulk copies of 128 bytes per item) and 4.4 TB/s (tensor maps) against 5.1 TB/s for k_col_p / k_col_p3: the plain-load
+// kernels already keep 5 CTAs x 8 warps x 14 loads in flight per SM, the staging buffers cut the CTAs per SM to 2, and with
+// them the warps that cover the shared-memory latency of the butterflies.  Kept as A-B switches.
 static bool use_col_bulk() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("SM_COL_BULK"); v = (e && e[0] == '1') ? 1 : 0; }
+  if (v < 0) { const char* e = getenv("SM_COL_BULK"); v = (e && (e[0] == '1' || e[0] == '2')) ? 1 : 0; }
   return v != 0;
+}
+
+// SM_COL_BULK=2: the same with tensor-map TMA loads (two per item)
+static int col_bulk_mode() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SM_COL_BULK"); v = e ? atoi(e) : 0; if (v < 0 || v > 2) v = 0; }
+  return v;
+}
+
+typedef CUresult (*SmEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static SmEncodeTiled tensor_map_encoder() {
+  static SmEncodeTiled fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    cudaDriverEntryPointQueryResult q;
+    void* p = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<SmEncodeTiled>(p);
+  }
+  return fn;
+}
+// plane [R][P] seen as (column, b, a) with row = a * Rb + b; box = 32 columns x (bb x ba) rows
+static bool make_col_map(CUtensorMap* m, const float* plane, int P, int Ra, int Rb, int bb, int ba) {
+  SmEncodeTiled enc = tensor_map_encoder();
+  if (!enc || plane == nullptr) return false;
+  cuuint64_t dims[3] = {(cuuint64_t)P, (cuuint64_t)Rb, (cuuint64_t)Ra};
+  cuuint64_t strides[2] = {(cuuint64_t)P * 4, (cuuint64_t)P * 4 * (cuuint64_t)Rb};
+  cuuint32_t box[3] = {SM_COL_TILE, (cuuint32_t)bb, (cuuint32_t)ba};
+  cuuint32_t es[3] = {1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(plane), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // persistent, bulk-copy fed variant of launch_col_p (R3 == 1) / launch_col_p3; returns 1 if it does not apply
@@ -1598,6 +1652,19 @@ static int launch_col_pb(bool inverse, bool big_tw, dim3 grid, const ColCtArgs& 
   constexpr int L = R1 * R2 * R3;
   constexpr int smem = L * 768;                         // work (L x 256) + two staging buffers of two planes (L x 128 each)
   if (!use_col_bulk() || smem > 110 * 1024) return 1;
+  ColMaps maps;
+  maps.use = 0;
+  if (col_bulk_mode() == 2 && L <= 256) {
+    // sweep A (element stride Rb rows): box (32, 1, L) over dims (P, Rb, Ra = L); sweep B / single sweep (contiguous rows):
+    // box (32, L, 1) over dims (P, Rb = L, Ra = instances)
+    const bool contiguous = a.elem_mul == 1;
+    const int Rb = contiguous ? L : a.elem_mul, Ra = contiguous ? (int)grid.y : L;
+    const int bb = contiguous ? L : 1, ba = contiguous ? 1 : L;
+    bool ok = make_col_map(&maps.p0, a.p0, a.P, Ra, Rb, bb, ba) && make_col_map(&maps.p1, a.p1, a.P, Ra, Rb, bb, ba);
+    if (ok && a.p0_alt != nullptr) ok = make_col_map(&maps.p0_alt, a.p0_alt, a.P, Ra, Rb, bb, ba);
+    else if (ok) maps.p0_alt = maps.p0;
+    maps.use = ok ? 1 : 0;
+  }
   static bool done[4] = {false, false, false, false};
   static int occ[4] = {0, 0, 0, 0};
   const int ntiles = (int)grid.x, n_items = (int)(grid.x * grid.y);
@@ -1613,7 +1680,7 @@ static int launch_col_pb(bool inverse, bool big_tw, dim3 grid, const ColCtArgs& 
   {                                                                                                       \
     int ctas = num_sms() * occ[IDX];                                                                      \
     if (ctas > n_items) ctas = n_items;                                                                   \
-    k_col_pb<R1, R2, R3, NW, INV, BIG><<<ctas, NW * 32, smem, st>>>(a, twR, ntiles, n_items);             \
+    k_col_pb<R1, R2, R3, NW, INV, BIG><<<ctas, NW * 32, smem, st>>>(a, twR, ntiles, n_items, maps);       \
   }
   if (!inverse && big_tw) { SM_COLPB_CASE(false, true, 0) }
   else if (!inverse) { SM_COLPB_CASE(false, false, 1) }

@@ -116,7 +116,7 @@ def test_forward_and_inverse_vs_fp64_fft(E, shape):
 
 
 FALLBACKS = [{"SM_COL_PAIRS": "0"}, {"SM_ROW_PAIRS": "0"}, {"SM_ROW_TMA": "0"}, {"SM_ROW_EO": "0"}, {"SM_COL_FUSED": "1"},
-             {"SM_COL_BULK": "1"}]
+             {"SM_COL_BULK": "1"}, {"SM_COL_BULK": "2"}]
 
 
 @pytest.mark.parametrize("env", FALLBACKS, ids=lambda e: ",".join(f"{k}={v}" for k, v in e.items()))
