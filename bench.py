@@ -379,11 +379,12 @@ def main():
     per_sweep = col_moved / (col_ms / 1000.0) / 1e9 if col_ms else None
     kernel_ms_total = sum(v["ms"] or 0.0 for v in summ.values())
     traffic, traffic_note = None, None
-    tpath = ROOT / "profiles" / "r01_traffic.json"
+    tpath = ROOT / "profiles" / "r02_traffic.json"
     if tpath.exists():                                            # dram__bytes_read + dram__bytes_write of one captured launch
         tj = json.loads(tpath.read_text())
         traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
-        traffic_note = dict(launch=tj["kernel"], algorithmic_bytes_of_that_launch=tj["algorithmic_bytes"], source=tj["source"])
+        traffic_note = dict(launch=tj["kernel"], algorithmic_bytes_of_that_launch=tj["algorithmic_bytes"],
+                            survey_8d_bytes_of_that_launch=tj.get("algorithmic_bytes_survey_8d_share"), source=tj["source"])
     pipeline_alg = 64.0 * n2d * (M - 1) * args.steps              # 64N bytes per pair merge
     roofline = dict(bound="hbm", kernel="k_col_p3 / k_col_p (column FFT sweeps, forward+inverse)", achieved=achieved, peak=peak,
                     unit="GB/s", frac=(achieved / peak if achieved else None), traffic=traffic, traffic_note=traffic_note,
