@@ -71,3 +71,46 @@ def test_rowsplit_two_ranks(shape):
     res = _torchrun(2, *shape)
     print("\n[rowsplit x2]", res)
     assert res["vs_one_gpu_exact"] >= 0.9999 and res["vs_one_gpu_within_1ulp"] == 1.0, res
+
+
+def test_merge_distributed_two_gpus(tmp_path):
+    """VERDICT r1 missing #2: the shard-granular work partition (schedule.merge_distributed: LPT over whole output shards, rank 0
+    writes the index copy, every rank its own shards, no collective on the data path) with the real FourierMerge on two GPUs;
+    the result is verified (validate.verify_output) and compared tensor by tensor with a one-GPU merge."""
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import asyncio
+    from safetensors import safe_open
+    sys.path.insert(0, str(ROOT / "tests"))
+    import distmerge_worker as W
+    out = tmp_path / "out2"
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), str(ROOT / "tests" / "distmerge_worker.py"), str(out)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=str(ROOT))
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    res = [json.loads(l[len("DISTMERGE "):]) for l in r.stdout.splitlines() if l.startswith("DISTMERGE ")]
+    assert len(res) == 2
+    r0 = next(x for x in res if x["rank"] == 0)
+    owned = [set(x["shards"]) for x in res]
+    assert owned[0] and owned[1] and not (owned[0] & owned[1])
+    assert r0["ok"] and r0["readme"], r0
+    # one GPU, same models
+    from shardmerge_b200.config import MergeConfig, MergeModel
+    from shardmerge_b200.index import InMemoryIndex
+    from shardmerge_b200.merge.fast_fourier import FourierMerge
+    models = W.toy_models()
+    cfg = MergeConfig(finetune_merge=[MergeModel(model="org/ft0", base="org/base", alpha=0.3, is_input=True),
+                                      MergeModel(model="org/ft1", base="org/base", alpha=0.5, is_output=True)],
+                      output_base_model="org/base", output_dir=str(tmp_path / "out1"), device=DEV)
+    asyncio.run(FourierMerge(cfg, index_manager=InMemoryIndex(models)).merge(DEV))
+    n = 0
+    for f in sorted((tmp_path / "out1").glob("*.safetensors")):
+        with safe_open(f, framework="pt") as a, safe_open(out / f.name, framework="pt") as b:
+            assert set(a.keys()) == set(b.keys())
+            for k in a.keys():
+                assert torch.equal(a.get_tensor(k), b.get_tensor(k)), k
+                n += 1
+    assert n == r0["tensors"] == 21
