@@ -382,3 +382,46 @@ def test_config5_embedding_shape_merge(E):
            merged_delta_norm_over_delta0_norm=ratio, finite=finite, plan=E.get_plan(*shape, DEV).describe())
     assert finite and 0.3 < ratio < 1.5
     E.clear_caches(); torch.cuda.empty_cache()
+
+
+@pytest.mark.parametrize("case", ["arith_1024x4096", "tree4_512x2048", "norm_1d_8192", "norm_1d_4096"])
+def test_other_branches_vs_reference_on_cuda(E, case):
+    """The branches the BASELINE inputs do not take, against the unmodified reference on device="cuda": the arithmetic-FFT
+    branch (norm ratio < 0.1, fast_fourier.py:226-232), a 4-finetune pair tree (:171-254; pinned loosely) and 1-D
+    tensors (layer norms; SURVEY 7.3-2 asked whether the reference's nested imaginary path degenerates there on CUDA)."""
+    RR = _ref()
+    g = torch.Generator(device=DEV).manual_seed(len(case) * 17)
+    if case.startswith("norm_1d"):
+        n = int(case.split("_")[-1])
+        base = (1.0 + 0.1 * torch.randn((n,), generator=g, device=DEV)).to(torch.bfloat16)
+        sig, alphas = (0.01, 0.013), (0.3, 0.5)
+        shape = (n,)
+    elif case.startswith("arith"):
+        shape, sig, alphas = (1024, 4096), (0.0026, 0.0001), (0.3, 0.5)
+        base = (0.02 * torch.randn(shape, generator=g, device=DEV)).to(torch.bfloat16)
+    else:
+        shape, sig, alphas = (512, 2048), (0.002, 0.0026, 0.0023, 0.0029), (0.3, 0.5, 0.4, 0.2)
+        base = (0.02 * torch.randn(shape, generator=g, device=DEV)).to(torch.bfloat16)
+    fts = [(base.float() + s * torch.randn(shape, generator=g, device=DEV)).to(torch.bfloat16) for s in sig]
+    fm = _merger()
+    srcs = [E.make_source(base, f, weight=a, name=f"m{k}") for k, (f, a) in enumerate(zip(fts, alphas))]
+    layer = "model.layers.0.input_layernorm.weight" if len(shape) == 1 else "model.layers.0.mlp.up_proj.weight"
+    out = fm.merge_sources(srcs, base, torch.device(DEV), layer_name=layer)
+    ref = RR.merge_layer(base, fts, list(alphas), device=DEV, layer=layer)
+    ob, rb, bb = bits(out), bits(ref), bits(base)
+    met = parity_metrics(ob, rb, bb, shape)
+    degenerate = float((rb == bb).mean())
+    basef = O.bf16_to_f32(bb)
+    do, dr = O.bf16_to_f32(ob) - basef, O.bf16_to_f32(rb) - basef
+    rel = float(np.linalg.norm(do - dr) / max(np.linalg.norm(dr), 1e-30))
+    record("other_branches_vs_reference_cuda", case, branches=fm.last_info["branches"], reference_equals_base_fraction=degenerate,
+           bf16_delta_rel_l2=rel, **met)
+    if degenerate > 0.5:
+        pytest.skip("the reference degenerates on CUDA for this input (merged delta = 0): recorded only")
+    if case.startswith("arith"):
+        assert fm.last_info["branches"] == ["arith"] and met["within_1ulp"] >= 0.999, met
+    elif case.startswith("tree4"):
+        assert fm.last_info["branches"] == ["slerp"] * 3
+        assert rel < 0.6 and abs(np.linalg.norm(do) / np.linalg.norm(dr) - 1) < 0.1, rel
+    else:
+        assert fm.last_info["branches"] == ["slerp"] and met["within_1ulp"] >= 0.97, met
