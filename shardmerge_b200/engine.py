@@ -534,6 +534,19 @@ class _PinnedPool:
 _ring: Optional[_PinnedPool] = None
 
 
+def take_pinned_slot() -> torch.Tensor:
+    """A 1 KiB pinned host block (uint8) from the scalar-block pool; hand it back with give_pinned_slot()."""
+    global _ring
+    if _ring is None:
+        _ring = _PinnedPool()
+    return _ring.take()
+
+
+def give_pinned_slot(slot: torch.Tensor):
+    if _ring is not None:
+        _ring.give(slot)
+
+
 class PendingPair:
     """Result of pair_merge_async: the output tensor is already enqueued; `resolve()` waits for the
     scalar block, and reports what the device decided."""

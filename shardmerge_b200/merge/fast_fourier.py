@@ -54,8 +54,15 @@ class _PendingTree:
         self.out, self.parts, self.layer_name = out, parts, layer_name
         self.norms, self.target_norm = norms, target_norm
         self.redo = None
+        self.phase_b = None            # enqueues the pair merges once the norms are on the host (FourierMerge._merge_sources_tree)
+
+    def run_phase_b(self):
+        fn, self.phase_b = self.phase_b, None
+        if fn is not None:
+            fn()
 
     def resolve(self) -> dict:
+        self.run_phase_b()
         infos = [p.resolve() for p in self.parts]
         sticky = 0
         flags = [0, 0, 0, 0]
@@ -86,6 +93,7 @@ class FourierMerge(MergeTensorsBase):
         self._lane_streams: dict = {}    # device index -> [streams]
         self._lane_next = 0
         self.fused_tree = os.environ.get("SHARDMERGE_FUSED_TREE", "1") != "0"   # 0: pair tree on the step-by-step path (A-B)
+        self._tree_waiting: list = []    # pair trees whose row passes are enqueued but whose norms have not been read yet
         self.keep_intermediates = False  # tests: keep the tree's fp32 round results in self.last_tree
         self.last_tree: list = []
 
@@ -191,6 +199,8 @@ class FourierMerge(MergeTensorsBase):
             if pend.out is tensor:
                 head, self.pending = self.pending[: i + 1], self.pending[i + 1:]
                 for p in head:
+                    if p in self._tree_waiting:
+                        self._tree_waiting.remove(p)
                     self._resolve(p)
                 return
 
@@ -211,7 +221,14 @@ class FourierMerge(MergeTensorsBase):
                 raise ValueError(f"tensor shape mismatch for {layer_name}: {shp} vs output base {tuple(base_out.shape)}")
         all_bf16 = (not safe_select and base_out.dtype == torch.bfloat16 and base_out.ndim in (1, 2)
                     and all(src.is_bf16 for src in sources))
-        if all_bf16 and len(sources) >= 3 and self.fused_tree:
+        is_tree = all_bf16 and 3 <= len(sources) <= 120 and self.fused_tree
+        if self._tree_waiting and not is_tree:
+            # a pair tree whose norms have not been read yet keeps its row spectra in its lane's workspace: enqueue its
+            # pair merges before anything else may be given that lane
+            waiting, self._tree_waiting = self._tree_waiting, []
+            for pend in waiting:
+                pend.run_phase_b()
+        if is_tree:
             return self._merge_sources_tree(sources, base_out, dev, layer_name, defer)
         fused_ok = len(sources) == 2 and all_bf16
         if not fused_ok:
@@ -269,60 +286,81 @@ class FourierMerge(MergeTensorsBase):
             lane.wait_event(caller.record_event())               # inputs are ready on the caller's stream
         else:
             lane_i, lane = 0, caller
-        parts = []
+        # ---- phase A (enqueue only): every model's row pass, the sums of squares on their way to pinned host memory
         with torch.cuda.stream(lane):
             ws = E.get_workspace(R, C, dev, n_spectra=M, lane=lane_i)
             sums = torch.zeros(M, dtype=torch.float64, device=dev)
             for i, src in enumerate(sources):
                 E.fwd_rows_ptr(ws, i, src, sums.data_ptr() + 8 * i)
-            sumsq = sums.to("cpu").tolist()                       # the one host wait (this lane only; the others keep running)
-            norms = [E.f32(v ** 0.5) for v in sumsq]
-            target_norm = torch.tensor(norms, dtype=torch.float32).mean().item() + self.target_norm_offset   # :165
-            # stack entry: (source, slot holding its row spectrum or None, sum of squares or None)
-            stack = [(src, i, sumsq[i]) for i, src in enumerate(sources)]
-            weights = [src.weight for src in sources]
-            cull_pct = self.cull_start_pct
-            kept = []
-            while len(stack) > 1:
-                n = len(stack)
-                corr = torch.zeros((n, n), dtype=torch.float32)
-                for i in range(n):
-                    for j in range(i + 1, n):
-                        corr[i, j] = torch.tensor(norms[i], dtype=torch.float32) * torch.tensor(norms[j], dtype=torch.float32)
-                pairs = list(correlated_pairs(corr, way="least"))
-                last_round = len(pairs) == 1 and pairs[0][1] >= 0
-                nxt, nxt_w = [], []
-                for x, y, _ in pairs:
-                    if y < 0:
-                        src, _, _ = stack[x]
-                        nxt.append((src, None, None)); nxt_w.append(weights[x])   # carried over; its rows are redone when it is paired
-                        continue
-                    (sa, slot_a, ss_a), (sb, slot_b, ss_b) = stack[x], stack[y]
-                    a_w, b_w = weights[x], weights[y]
-                    rows_done = slot_a is not None and slot_b is not None
-                    res = out if last_round else torch.empty((R, C), dtype=torch.float32, device=dev)
-                    parts.append(E.pair_merge_async(
-                        ws, sa, sb, base_c, res, t=a_w / (a_w + b_w), t_sum=1.0, cutoff_pct=0.08, cull_pct=cull_pct,
-                        target_norm_offset=self.target_norm_offset, layer_name=layer_name,
-                        slots=(slot_a, slot_b) if rows_done else (0, 1), rows_done=rows_done,
-                        sumsq=(ss_a, ss_b) if rows_done else None, target_norm=target_norm))
-                    if not last_round:
-                        inter = E.Source(x32=res, weight=(a_w + b_w) / 2.0, name=name_hash(f"{sa.name}_{sb.name}"))
-                        nxt.append((inter, None, None)); nxt_w.append((a_w + b_w) / 2.0)
-                        if self.keep_intermediates:
-                            kept.append((sa.name, sb.name, res))
-                stack, weights = nxt, nxt_w
-                cull_pct = cull_pct / 2.0                         # :254
+            slot = E.take_pinned_slot()                       # pinned landing zone from the pool (no cudaHostAlloc per tensor)
+            sums_host = slot[: 8 * M].view(torch.float64)
+            sums_host.copy_(sums, non_blocking=True)
+            sums_ready = torch.cuda.Event()
+            sums_ready.record(lane)
         if lane is not caller:
             for t_ in [out, base_c] + [t for src in sources for t in (src.base, src.ft)]:
                 t_.record_stream(lane)
-        if self.keep_intermediates:
-            self.last_tree = kept
-        pend = _PendingTree(out, parts, layer_name, norms, target_norm)
+        pend = _PendingTree(out, [], layer_name, None, None)
+
+        # ---- phase B: the one host wait (norms), pairing on the host, every pair merge as a fused chain on the lane
+        def phase_b():
+            sums_ready.synchronize()
+            sumsq = sums_host.tolist()
+            E.give_pinned_slot(slot)
+            norms = [E.f32(v ** 0.5) for v in sumsq]
+            target_norm = torch.tensor(norms, dtype=torch.float32).mean().item() + self.target_norm_offset   # :165
+            pend.norms, pend.target_norm = norms, target_norm
+            with torch.cuda.stream(lane):
+                # stack entry: (source, slot holding its row spectrum or None, sum of squares or None)
+                stack = [(src, i, sumsq[i]) for i, src in enumerate(sources)]
+                weights = [src.weight for src in sources]
+                cull_pct = self.cull_start_pct
+                kept = []
+                while len(stack) > 1:
+                    n = len(stack)
+                    corr = torch.zeros((n, n), dtype=torch.float32)
+                    for i in range(n):
+                        for j in range(i + 1, n):
+                            corr[i, j] = torch.tensor(norms[i], dtype=torch.float32) * torch.tensor(norms[j], dtype=torch.float32)
+                    pairs = list(correlated_pairs(corr, way="least"))
+                    last_round = len(pairs) == 1 and pairs[0][1] >= 0
+                    nxt, nxt_w = [], []
+                    for x, y, _ in pairs:
+                        if y < 0:
+                            src, _, _ = stack[x]
+                            nxt.append((src, None, None)); nxt_w.append(weights[x])   # carried over; its rows are redone when it is paired
+                            continue
+                        (sa, slot_a, ss_a), (sb, slot_b, ss_b) = stack[x], stack[y]
+                        a_w, b_w = weights[x], weights[y]
+                        rows_done = slot_a is not None and slot_b is not None
+                        res = out if last_round else torch.empty((R, C), dtype=torch.float32, device=dev)
+                        pend.parts.append(E.pair_merge_async(
+                            ws, sa, sb, base_c, res, t=a_w / (a_w + b_w), t_sum=1.0, cutoff_pct=0.08, cull_pct=cull_pct,
+                            target_norm_offset=self.target_norm_offset, layer_name=layer_name,
+                            slots=(slot_a, slot_b) if rows_done else (0, 1), rows_done=rows_done,
+                            sumsq=(ss_a, ss_b) if rows_done else None, target_norm=target_norm))
+                        if not last_round:
+                            inter = E.Source(x32=res, weight=(a_w + b_w) / 2.0, name=name_hash(f"{sa.name}_{sb.name}"))
+                            nxt.append((inter, None, None)); nxt_w.append((a_w + b_w) / 2.0)
+                            if self.keep_intermediates:
+                                kept.append((sa.name, sb.name, res))
+                    stack, weights = nxt, nxt_w
+                    cull_pct = cull_pct / 2.0                         # :254
+            if self.keep_intermediates:
+                self.last_tree = kept
+
+        pend.phase_b = phase_b
         pend.redo = lambda: self._merge_sources_steps(sources, base_out, dev, layer_name, False)
         if defer:
+            # The host wait for this tensor's norms is put off until the NEXT tree tensor's row passes are enqueued (on
+            # another lane), so the GPU has work while the host waits; at most one tensor waits (its row spectra occupy its
+            # lane's workspace until its chains are enqueued, and the lanes take turns).
+            self._tree_waiting.append(pend)
+            while len(self._tree_waiting) > (1 if self.lanes > 1 else 0):
+                self._tree_waiting.pop(0).run_phase_b()
             self.pending.append(pend)
             return out
+        pend.run_phase_b()
         self._resolve(pend)
         return out
 
@@ -344,6 +382,9 @@ class FourierMerge(MergeTensorsBase):
     def resolve_all(self):
         """Check every deferred fused merge (one wait per tensor, all already in flight)."""
         pending, self.pending = self.pending, []
+        waiting, self._tree_waiting = self._tree_waiting, []
+        for pend in waiting:                      # enqueue what is still held back, oldest first, before any wait
+            pend.run_phase_b()
         for pend in pending:
             self._resolve(pend)
 
