@@ -11,4 +11,4 @@ for mode in ("all", "no1d"):
     with contextlib.redirect_stdout(buf):
         bench.main()
     d = json.loads(buf.getvalue().strip().splitlines()[-1])
-    print(mode, "value %.2f G ms/step %.3f params %d" % (d["value"] / 1e9, d["ms_per_step"], d["config"]["merged_params_per_step_per_gpu"]))
+    print(mode, "value %.2f G ms/step %.3f params %d" % (d["value"] / 1e9, d["ms_per_step"], d["config"]["merged_params_per_step"]))
