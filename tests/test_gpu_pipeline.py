@@ -270,3 +270,40 @@ def test_stacked_tensor_is_batched_like_fftn(E):
     oo = O.merge_layer(bits(base), [dict(base=bits(base), ft=bits(ft), alpha=a, name=f"m{k}") for k, (ft, a) in enumerate(zip(fts, (0.3, 0.5)))])
     u = bf16_ulp_distance(bits(out), oo.reshape(shape))
     assert float((u <= 1).mean()) >= 0.985, float((u <= 1).mean())
+
+
+def test_local_index_reader_threads_and_pinned_pool(E, tmp_path):
+    """LocalSafetensorsIndex.prefetch reads straight from the safetensors file into pooled pinned buffers on
+    reader threads and uploads from there; every tensor must arrive bit for bit (several dtypes, more tensors than
+    buffers in flight so the pool recycles), announced or not."""
+    from safetensors.torch import save_file
+    from shardmerge_b200.index import LocalSafetensorsIndex
+    g = torch.Generator().manual_seed(2)
+    d = tmp_path / "org" / "m"
+    d.mkdir(parents=True)
+    tensors, wm = {}, {}
+    for s in range(3):
+        shard = {}
+        for i in range(8):
+            n = f"model.layers.{s * 8 + i}.mlp.up_proj.weight"
+            shard[n] = torch.randn((256, 1024) if i % 2 == 0 else (512, 768), generator=g).to(torch.bfloat16 if i % 3 else torch.float32)
+            wm[n] = f"model-{s + 1:05d}-of-00003.safetensors"
+        tensors.update(shard)
+        save_file(shard, str(d / f"model-{s + 1:05d}-of-00003.safetensors"), metadata={"format": "pt"})
+    (d / "model.safetensors.index.json").write_text(json.dumps({"metadata": {}, "weight_map": wm}))
+    idx = LocalSafetensorsIndex(tmp_path, reader_threads=3)
+    asyncio.run(idx.add_model("org/m"))
+    assert idx.tensor_shapes("org/m") == {n: tuple(t.shape) for n, t in tensors.items()}
+    names = list(tensors)
+    for rnd in range(2):                                   # second round: the pinned pool is warm
+        for k, n in enumerate(names):
+            if k % 4 != 3:
+                idx.prefetch("org/m", n, DEV)              # most are announced ahead, some are asked for cold
+        for n in names:
+            t = asyncio.run(idx.get_tensor("org/m", n, device=DEV).get())
+            assert t.device.type == "cuda" and t.dtype == tensors[n].dtype
+            torch.cuda.current_stream().synchronize()
+            assert torch.equal(t.cpu(), tensors[n]), n
+    assert sum(len(v) for v in idx._pin_free.values()) + len(idx._pin_busy) <= 8    # buffers were recycled, not one per tensor
+    with pytest.raises(KeyError):
+        idx.get_tensor("org/m", "nope")
