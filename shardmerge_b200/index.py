@@ -166,7 +166,7 @@ class LocalSafetensorsIndex(_IndexBase):
     once per shard) into a POOLED pinned buffer, then the host-to-device copy on a copy stream, issued from that thread --
     file read, upload and the merge kernels of earlier tensors overlap, nothing is pinned per tensor and nothing is kept."""
 
-    def __init__(self, storage_dir, reader_threads: int = 4):
+    def __init__(self, storage_dir, reader_threads: int = 8):
         super().__init__()
         self.storage_dir = Path(storage_dir)
         self._shard_meta: Dict[str, tuple] = {}          # shard path -> (data start, {name: (dtype, shape, begin, end)})
