@@ -510,7 +510,13 @@ def main():
             return e0.elapsed_time(e1), e0.elapsed_time(e2)
 
         t_e2e0 = time.perf_counter()
+        index.copy_events = []                     # (start, end) events of every upload: how busy the H2D copy engine is
         my_ems, _ = measure(StagingOnlyWriter, "s")
+        copy_pairs, index.copy_events = index.copy_events, None
+        # the last args.steps * len(uploads per step) pairs belong to the timed steps (warm-up steps come first)
+        per_step = len(names) * (M + 1)
+        timed = copy_pairs[-args.steps * per_step:] if per_step else []
+        h2d_busy_ms = sum(a_.elapsed_time(b_) for a_, b_ in timed)
         ems = max_over_ranks(my_ems)
         ems_files = None
         if world > 1:                                   # every rank must take the same branch: all measure, or none
@@ -558,6 +564,8 @@ def main():
         e2e = dict(value=e2e_params * args.steps / (ems / 1000.0), unit="params/s",
                    h2d_bytes_per_step=h2d_all, d2h_bytes_per_step=d2h_all, layers=Le, host_link_probe=link,
                    h2d_gbs_achieved_rank0=h2d * args.steps / (my_ems / 1000.0) / 1e9,
+                   h2d_copy_engine_rank0=dict(busy_ms=h2d_busy_ms, busy_fraction_of_timed_region=h2d_busy_ms / my_ems if my_ems else None,
+                                              gbs_while_busy=(h2d * args.steps / (h2d_busy_ms / 1000.0) / 1e9) if h2d_busy_ms else None),
                    with_files=(dict(value=e2e_params * args.steps / (ems_files / 1000.0), unit="params/s",
                                     note="a second set of the same steps with the unmodified ModelWriter, timed until finalize() has "
                                          "returned for every step: all safetensors shards (one per layer) complete on "

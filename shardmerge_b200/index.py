@@ -56,6 +56,7 @@ class _IndexBase:
         self._order: Dict[str, List[str]] = {}
         self._prefetched: dict = {}
         self._copy_streams: dict = {}
+        self.copy_events = None          # set to a list to collect (start, end) CUDA events of every upload (bench.py)
 
     def _register(self, model_uri: str, index: dict):
         self.model_indexes[model_uri] = index
@@ -94,7 +95,13 @@ class _IndexBase:
         if stream is None:
             stream = self._copy_streams[str(dev)] = torch.cuda.Stream(device=dev)
         with torch.cuda.stream(stream):
+            if self.copy_events is not None:
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
             t = host.to(dev, non_blocking=True)
+            if self.copy_events is not None:
+                e1.record(stream)
+                self.copy_events.append((e0, e1))
             ev = stream.record_event()
         self._prefetched[key] = (t, ev, host)
 
