@@ -123,7 +123,8 @@ int sm_blend(const sm_plan* plan, int mode, int agreement, const float* re0, con
  * u32 at byte SM_FS_STATUS_OFF that is non-zero afterwards if the window missed / was too wide / a bucket
  * overflowed -- the thresholds are NaN then and the caller redoes the tensor with the step-by-step kernels
  * (sm_select_kth_abs mode 1).  ws: at least sm_fstats_ws_bytes() device bytes, zero-filled before the first use;
- * the kernels use the LAST sm_fstats_ws_bytes() of it and leave their histograms zeroed for the next call, so one
+ * the kernels use the LAST sm_fstats_ws_bytes() of it and keep their histograms there from call to call (each call
+ * clears what the previous one touched: nobody else may write to that part, and a buffer serves ONE plan), so one
  * buffer of sm_select_ws_bytes() + sm_fstats_ws_bytes() serves both families.  sm_fstats_supported() == 0: tensor
  * too small (launch bound; use the step-by-step kernels) or too large (>= 2^31 elements). */
 #define SM_FS_STATE_BYTES 128

@@ -39,6 +39,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 // ------------------------------------------------------------------ kernels
 __global__ void __launch_bounds__(512) k_row_fwd(const __grid_constant__ SmPlan pl, const __grid_constant__ RowFwdArgs a, const cf* __restrict__ twC,
                                                  const cf* __restrict__ twQ, double* __restrict__ sumsq) {
+  sm_pdl_enter();
   DeviceExec ex;
   float accf = 0.f;
   row_fwd_body(ex, pl, (int)blockIdx.x, a, twC, twQ, reinterpret_cast<cf*>(g_dyn_smem), &accf);
@@ -57,11 +58,13 @@ __global__ void __launch_bounds__(512) k_row_fwd(const __grid_constant__ SmPlan 
 
 __global__ void __launch_bounds__(512) k_row_inv(const __grid_constant__ SmPlan pl, const __grid_constant__ RowInvArgs a, const cf* __restrict__ twC,
                                                  const cf* __restrict__ twQ) {
+  sm_pdl_enter();
   DeviceExec ex;
   row_inv_body(ex, pl, (int)blockIdx.x, a, twC, twQ, reinterpret_cast<cf*>(g_dyn_smem));
 }
 
 __global__ void __launch_bounds__(512) k_col(const __grid_constant__ SmPlan pl, const __grid_constant__ ColArgs a, const cf* __restrict__ twR) {
+  sm_pdl_enter();
   DeviceExec ex;
   col_body(ex, pl, (int)blockIdx.x, (int)blockIdx.y, a, twR, reinterpret_cast<cf*>(g_dyn_smem));
 }
@@ -69,6 +72,7 @@ __global__ void __launch_bounds__(512) k_col(const __grid_constant__ SmPlan pl, 
 // ---- compile-time specialised kernels for the hot shapes (Llama / TinyLlama factorizations)
 template <int R1, int R2, int NW, bool kInverse, bool kBigTw>
 __global__ void __launch_bounds__(NW * 32, (R1 >= 11 || R2 >= 11) ? 3 : 4) k_col_ct(const ColCtArgs a, const cf* __restrict__ twR) {
+  sm_pdl_enter();
   DeviceExec ex;
   col_ct_body<R1, R2, NW, kInverse, kBigTw>(ex, (int)blockIdx.x, (int)blockIdx.y, a, twR, reinterpret_cast<cf*>(g_dyn_smem));
 }
@@ -77,12 +81,14 @@ __global__ void __launch_bounds__(NW * 32, (R1 >= 11 || R2 >= 11) ? 3 : 4) k_col
 // resident CTA was measured slower (spills), so the compiler's own allocation (<= 80 registers) stands
 template <int R1, int R2, int NW, bool kInverse, bool kBigTw>
 __global__ void __launch_bounds__(NW * 32) k_col_p(const __grid_constant__ ColCtArgs a, const cf* __restrict__ twR) {
+  sm_pdl_enter();
   DeviceExec ex;
   col_ct_body_p<R1, R2, NW, kInverse, kBigTw>(ex, (int)blockIdx.x, (int)blockIdx.y, a, twR, reinterpret_cast<pf4*>(g_dyn_smem));
 }
 
 template <int R1, int R2, int R3, int NW, bool kInverse, bool kBigTw>
 __global__ void __launch_bounds__(NW * 32) k_col_p3(const __grid_constant__ ColCtArgs a, const cf* __restrict__ twR) {
+  sm_pdl_enter();
   DeviceExec ex;
   col_ct_body_p3<R1, R2, R3, NW, kInverse, kBigTw>(ex, (int)blockIdx.x, (int)blockIdx.y, a, twR, reinterpret_cast<pf4*>(g_dyn_smem));
 }
@@ -207,6 +213,7 @@ template <int R1, int R2, int S1, int S2, int NW, bool kInverse>
 __global__ void __launch_bounds__(NW * 32, (R1 >= 11 || R2 >= 11 || S1 >= 11 || S2 >= 11) ? 3 : 4)
 k_col2_ct(const __grid_constant__ ColCtArgs a1, const __grid_constant__ ColCtArgs a2, const __grid_constant__ Col2Sched s,
           const cf* __restrict__ twR) {
+  sm_pdl_enter();
   DeviceExec ex;
   int phase, tile, inst;
   col2_decode(s, blockIdx.x, &phase, &tile, &inst);
@@ -231,6 +238,7 @@ k_col2_ct(const __grid_constant__ ColCtArgs a1, const __grid_constant__ ColCtArg
 template <int R1, int R2, int R3, int R4, int T, bool kPad>
 __global__ void __launch_bounds__(T) k_row_fwd_ct(int C, int P, const RowFwdArgs a, const cf* __restrict__ twC,
                                                   const cf* __restrict__ twQ, double* __restrict__ sumsq) {
+  sm_pdl_enter();
   DeviceExec ex;
   float accf = 0.f;
   row_fwd_ct_body<R1, R2, R3, R4, T, kPad>(ex, (int)blockIdx.x, C, P, a, twC, twQ, reinterpret_cast<cf*>(g_dyn_smem), &accf);
@@ -249,6 +257,7 @@ __global__ void __launch_bounds__(T) k_row_fwd_ct(int C, int P, const RowFwdArgs
 template <int R1, int R2, int R3, int R4, int T, bool kPad>
 __global__ void __launch_bounds__(T) k_row_inv_ct(int C, int P, const RowInvArgs a, const cf* __restrict__ twC,
                                                   const cf* __restrict__ twQ) {
+  sm_pdl_enter();
   DeviceExec ex;
   row_inv_ct_body<R1, R2, R3, R4, T, kPad>(ex, (int)blockIdx.x, C, P, a, twC, twQ, reinterpret_cast<cf*>(g_dyn_smem));
 }
@@ -278,6 +287,7 @@ template <int R1, int R2, int R3, int R4, int T, bool kPad>
 __global__ void __launch_bounds__(T) k_row_fwd_tma(int R, int C, int P, const __grid_constant__ RowFwdArgs a,
                                                    const cf* __restrict__ twC, const cf* __restrict__ twQ,
                                                    double* __restrict__ sumsq, int work_bytes) {
+  sm_pdl_enter();
   DeviceExec ex;
   __shared__ uint64_t full;
   __shared__ double wsum[16];
@@ -327,6 +337,7 @@ struct InvStageHook {          // refill the spectrum staging (re, im rows) with
 template <int R1, int R2, int R3, int R4, int T, bool kPad>
 __global__ void __launch_bounds__(T) k_row_inv_tma(int R, int C, int P, const __grid_constant__ RowInvArgs a,
                                                    const cf* __restrict__ twC, const cf* __restrict__ twQ, int work_bytes) {
+  sm_pdl_enter();
   constexpr int CH = R1 * R2 * R3 * R4;
   DeviceExec ex;
   __shared__ uint64_t full_spec, full_base;
@@ -439,6 +450,7 @@ template <int R1, int R2, int R3, int T, bool kEO>
 __global__ void __launch_bounds__(T, 3) k_row2_fwd(int R, int C, int P, const __grid_constant__ RowFwdArgs a,
                                                 const cf* __restrict__ twC, const cf* __restrict__ twQ,
                                                 double* __restrict__ sumsq, int work_bytes) {
+  sm_pdl_enter();
   constexpr int CH = R1 * R2 * R3;
   constexpr int S3 = CH / R3;                       // stride (and butterfly count) of the last stage
   static_assert(CH / R1 == T && CH / R2 == T && S3 == 2 * T, "k_row2_fwd: one butterfly per thread in stages 1-2, two in stage 3");
@@ -637,6 +649,7 @@ template <int R1, int R2, int R3, int R4, int T, bool kPad, int kCtas>
 __global__ void __launch_bounds__(T, kCtas) k_row2_fwd4(int R, int C, int P, const __grid_constant__ RowFwdArgs a,
                                                     const cf* __restrict__ twC, const cf* __restrict__ twQ,
                                                     double* __restrict__ sumsq) {
+  sm_pdl_enter();
   constexpr int CH = R1 * R2 * R3 * R4;
   constexpr int NB1 = CH / R1, NB2 = CH / R2, NB3 = CH / R3, S4 = CH / R4;
   constexpr int s2 = R1, s3 = R1 * R2;
@@ -805,6 +818,7 @@ template <int R1, int R2, int R3, int R4, int T, int kCtas>
 __global__ void __launch_bounds__(T, kCtas) k_row1_fwd_eo(int R, int C, int P, const __grid_constant__ RowFwdArgs a,
                                                       const cf* __restrict__ twC, const cf* __restrict__ twQ2,
                                                       double* __restrict__ sumsq) {
+  sm_pdl_enter();
   constexpr int CH = R1 * R2 * R3 * R4;             // length of the even / odd transforms = Ch / 2
   constexpr int NB1 = CH / R1, NB2 = CH / R2, NB3 = CH / R3, S4 = CH / R4;
   constexpr int s2 = R1, s3 = R1 * R2;
@@ -1001,6 +1015,7 @@ struct RowTangleStagedEO {       // staged spectrum row (re, im), H = Ch / 2
 template <int R1, int R2, int R3, int T, bool kEO>
 __global__ void __launch_bounds__(T, 3) k_row2_inv(int R, int C, int P, const __grid_constant__ RowInvArgs a,
                                                    const cf* __restrict__ twC, const cf* __restrict__ twQ, int work_bytes) {
+  sm_pdl_enter();
   constexpr int CH = R1 * R2 * R3;
   constexpr int S3 = CH / R3;
   constexpr int kRows = kEO ? 1 : 2;
@@ -1148,6 +1163,7 @@ struct RowTangleGlobal2 {
 template <int R1, int R2, int R3, int R4, int T, bool kPad, int kCtas>
 __global__ void __launch_bounds__(T, kCtas) k_row2_inv4(int R, int C, int P, const __grid_constant__ RowInvArgs a,
                                                     const cf* __restrict__ twC, const cf* __restrict__ twQ) {
+  sm_pdl_enter();
   constexpr int CH = R1 * R2 * R3 * R4;
   constexpr int NB1 = CH / R1, NB2 = CH / R2, NB3 = CH / R3, S4 = CH / R4;
   constexpr int s2 = R1, s3 = R1 * R2;
@@ -1300,6 +1316,7 @@ __device__ __forceinline__ void epilogue_store_eo(const RowInvArgs& a, float sca
 template <int R1, int R2, int R3, int R4, int T, int kCtas>
 __global__ void __launch_bounds__(T, kCtas) k_row1_inv_eo(int R, int C, int P, const __grid_constant__ RowInvArgs a,
                                                       const cf* __restrict__ twC, const cf* __restrict__ twQ2) {
+  sm_pdl_enter();
   constexpr int CH = R1 * R2 * R3 * R4;             // length of the two lane transforms = Ch / 2
   constexpr int NB1 = CH / R1, NB2 = CH / R2, NB3 = CH / R3, S4 = CH / R4;
   constexpr int s2 = R1, s3 = R1 * R2;
@@ -1397,6 +1414,7 @@ __global__ void __launch_bounds__(T, kCtas) k_row1_inv_eo(int R, int C, int P, c
 
 // scale a 1-D spectrum (no column sweep exists to fold the normalisation into)
 __global__ void k_scale_row(float* re, float* im, int n, const float* scale_dev, float scale_host, int write_im) {
+  sm_pdl_enter();
   const float s = scale_dev ? *scale_dev : scale_host;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     re[i] *= s;
@@ -1425,6 +1443,7 @@ __global__ void k_init_quads(cf* quad, int n_b, int N) {
 }
 
 __global__ void k_inv_norm(const double* sumsq, float* out) {
+  sm_pdl_enter();
   const double ss = *sumsq;
   const float nrm = (float)sqrt(ss);
   *out = (nrm != 0.f) ? (1.0f / nrm) : 1.0f;
@@ -1549,7 +1568,7 @@ static int launch_col_ct_pair(bool inverse, bool big_tw, dim3 grid, const ColCtA
 #define SM_COL_CASE(INV, BIG, IDX)                                                        \
   e = opt_in(k_col_ct<R1, R2, NW, INV, BIG>, &done[IDX]);                                 \
   if (e != cudaSuccess) { sm_set_error("opt_in: %s", cudaGetErrorString(e)); return -100; } \
-  k_col_ct<R1, R2, NW, INV, BIG><<<grid, NW * 32, smem, st>>>(a, twR);
+  sm_launch(k_col_ct<R1, R2, NW, INV, BIG>, dim3(grid), dim3(NW * 32), (size_t)(smem), st, a, twR);
   if (!inverse && big_tw) { SM_COL_CASE(false, true, 0) }
   else if (!inverse) { SM_COL_CASE(false, false, 1) }
   else if (big_tw) { SM_COL_CASE(true, true, 2) }
@@ -1571,7 +1590,7 @@ static int launch_col_p(bool inverse, bool big_tw, dim3 grid, const ColCtArgs& a
 #define SM_COLP_CASE(INV, BIG, IDX)                                                       \
   e = opt_in(k_col_p<R1, R2, NW, INV, BIG>, &done[IDX]);                                  \
   if (e != cudaSuccess) { sm_set_error("opt_in: %s", cudaGetErrorString(e)); return -100; } \
-  k_col_p<R1, R2, NW, INV, BIG><<<grid, NW * 32, smem, st>>>(a, twR);
+  sm_launch(k_col_p<R1, R2, NW, INV, BIG>, dim3(grid), dim3(NW * 32), (size_t)(smem), st, a, twR);
   if (!inverse && big_tw) { SM_COLP_CASE(false, true, 0) }
   else if (!inverse) { SM_COLP_CASE(false, false, 1) }
   else if (big_tw) { SM_COLP_CASE(true, true, 2) }
@@ -1590,7 +1609,7 @@ static int launch_col_p3(bool inverse, bool big_tw, dim3 grid, const ColCtArgs& 
 #define SM_COLP3_CASE(INV, BIG, IDX)                                                      \
   e = opt_in(k_col_p3<R1, R2, R3, NW, INV, BIG>, &done[IDX]);                             \
   if (e != cudaSuccess) { sm_set_error("opt_in: %s", cudaGetErrorString(e)); return -100; } \
-  k_col_p3<R1, R2, R3, NW, INV, BIG><<<grid, NW * 32, smem, st>>>(a, twR);
+  sm_launch(k_col_p3<R1, R2, R3, NW, INV, BIG>, dim3(grid), dim3(NW * 32), (size_t)(smem), st, a, twR);
   if (!inverse && big_tw) { SM_COLP3_CASE(false, true, 0) }
   else if (!inverse) { SM_COLP3_CASE(false, false, 1) }
   else if (big_tw) { SM_COLP3_CASE(true, true, 2) }
@@ -1780,8 +1799,8 @@ static int launch_col2(bool inverse, const ColCtArgs& a1, const ColCtArgs& a2, C
   if (lag > s.ntiles) lag = s.ntiles;
   s.lag = lag;
   const unsigned int grid = (unsigned int)s.ntiles * (unsigned int)(s.n1 + s.n2);
-  if (!inverse) k_col2_ct<R1, R2, S1, S2, NW, false><<<grid, NW * 32, smem, st>>>(a1, a2, s, twR);
-  else k_col2_ct<R1, R2, S1, S2, NW, true><<<grid, NW * 32, smem, st>>>(a1, a2, s, twR);
+  if (!inverse) sm_launch(k_col2_ct<R1, R2, S1, S2, NW, false>, dim3(grid), dim3(NW * 32), (size_t)(smem), st, a1, a2, s, twR);
+  else sm_launch(k_col2_ct<R1, R2, S1, S2, NW, true>, dim3(grid), dim3(NW * 32), (size_t)(smem), st, a1, a2, s, twR);
   SM_LAUNCH_CHECK();
   return 0;
 }
@@ -1828,7 +1847,7 @@ static int try_row2_fwd(const SmPlan& p, const RowFwdArgs& fa, const cf* twC, co
     if (e != cudaSuccess) { sm_set_error("row2 setup: %s", cudaGetErrorString(e)); return -100; }
     int grid = num_sms() * (occ > 0 ? occ : 1);
     if (grid > p.R / 2) grid = p.R / 2;
-    k_row2_fwd<R1, R2, R3, T, false><<<grid, T, smem, st>>>(p.R, p.C, p.P, fa, twC, twQ, sumsq, work_bytes);
+    sm_launch(k_row2_fwd<R1, R2, R3, T, false>, dim3(grid), dim3(T), (size_t)(smem), st, p.R, p.C, p.P, fa, twC, twQ, sumsq, work_bytes);
     SM_LAUNCH_CHECK();
     return 0;
   } else {
@@ -1850,7 +1869,7 @@ static int launch_row2_fwd4(const SmPlan& p, const RowFwdArgs& fa, const cf* twC
   if (e != cudaSuccess) { sm_set_error("row2 fwd4 setup: %s", cudaGetErrorString(e)); return -100; }
   int grid = num_sms() * kCtas;
   if (grid > p.R / 2) grid = p.R / 2;
-  k_row2_fwd4<R1, R2, R3, R4, T, kPad, kCtas><<<grid, T, smem, st>>>(p.R, p.C, p.P, fa, twC, twQ, sumsq);
+  sm_launch(k_row2_fwd4<R1, R2, R3, R4, T, kPad, kCtas>, dim3(grid), dim3(T), (size_t)(smem), st, p.R, p.C, p.P, fa, twC, twQ, sumsq);
   SM_LAUNCH_CHECK();
   return 0;
 }
@@ -1866,7 +1885,7 @@ static int launch_row2_inv4(const SmPlan& p, const RowInvArgs& ia, const cf* twC
   if (e != cudaSuccess) { sm_set_error("row2 inv4 setup: %s", cudaGetErrorString(e)); return -100; }
   int grid = num_sms() * kCtas;
   if (grid > p.R / 2) grid = p.R / 2;
-  k_row2_inv4<R1, R2, R3, R4, T, kPad, kCtas><<<grid, T, smem, st>>>(p.R, p.C, p.P, ia, twC, twQ);
+  sm_launch(k_row2_inv4<R1, R2, R3, R4, T, kPad, kCtas>, dim3(grid), dim3(T), (size_t)(smem), st, p.R, p.C, p.P, ia, twC, twQ);
   SM_LAUNCH_CHECK();
   return 0;
 }
@@ -1890,7 +1909,7 @@ static int launch_row1_fwd_eo(const SmPlan& p, const RowFwdArgs& fa, const cf* t
   if (e != cudaSuccess) { sm_set_error("row1 fwd eo setup: %s", cudaGetErrorString(e)); return -100; }
   int grid = num_sms() * kCtas;
   if (grid > p.R) grid = p.R;
-  k_row1_fwd_eo<R1, R2, R3, R4, T, kCtas><<<grid, T, smem, st>>>(p.R, p.C, p.P, fa, twC, twQ, sumsq);
+  sm_launch(k_row1_fwd_eo<R1, R2, R3, R4, T, kCtas>, dim3(grid), dim3(T), (size_t)(smem), st, p.R, p.C, p.P, fa, twC, twQ, sumsq);
   SM_LAUNCH_CHECK();
   return 0;
 }
@@ -1909,7 +1928,7 @@ static int launch_row1_fwd_eo3(const SmPlan& p, const RowFwdArgs& fa, const cf* 
   if (e != cudaSuccess) { sm_set_error("row1 fwd eo3 setup: %s", cudaGetErrorString(e)); return -100; }
   int grid = num_sms() * (occ > 0 ? occ : 1);
   if (grid > p.R) grid = p.R;
-  k_row2_fwd<R1, R2, R3, T, true><<<grid, T, smem, st>>>(p.R, p.C, p.P, fa, twC, twQ, sumsq, work_bytes);
+  sm_launch(k_row2_fwd<R1, R2, R3, T, true>, dim3(grid), dim3(T), (size_t)(smem), st, p.R, p.C, p.P, fa, twC, twQ, sumsq, work_bytes);
   SM_LAUNCH_CHECK();
   return 0;
 }
@@ -1935,7 +1954,7 @@ static int launch_row1_inv_eo(const SmPlan& p, const RowInvArgs& ia, const cf* t
   if (e != cudaSuccess) { sm_set_error("row1 inv eo setup: %s", cudaGetErrorString(e)); return -100; }
   int grid = num_sms() * kCtas;
   if (grid > p.R) grid = p.R;
-  k_row1_inv_eo<R1, R2, R3, R4, T, kCtas><<<grid, T, smem, st>>>(p.R, p.C, p.P, ia, twC, twQ);
+  sm_launch(k_row1_inv_eo<R1, R2, R3, R4, T, kCtas>, dim3(grid), dim3(T), (size_t)(smem), st, p.R, p.C, p.P, ia, twC, twQ);
   SM_LAUNCH_CHECK();
   return 0;
 }
@@ -1953,7 +1972,7 @@ static int launch_row1_inv_eo3(const SmPlan& p, const RowInvArgs& ia, const cf* 
   if (e != cudaSuccess) { sm_set_error("row1 inv eo3 setup: %s", cudaGetErrorString(e)); return -100; }
   int grid = num_sms() * (occ > 0 ? occ : 1);
   if (grid > p.R) grid = p.R;
-  k_row2_inv<R1, R2, R3, T, true><<<grid, T, smem, st>>>(p.R, p.C, p.P, ia, twC, twQ, work_bytes);
+  sm_launch(k_row2_inv<R1, R2, R3, T, true>, dim3(grid), dim3(T), (size_t)(smem), st, p.R, p.C, p.P, ia, twC, twQ, work_bytes);
   SM_LAUNCH_CHECK();
   return 0;
 }
@@ -1985,7 +2004,7 @@ static int try_row2_inv(const SmPlan& p, const RowInvArgs& ia, const cf* twC, co
     if (e != cudaSuccess) { sm_set_error("row2 inv setup: %s", cudaGetErrorString(e)); return -100; }
     int grid = num_sms() * (occ > 0 ? occ : 1);
     if (grid > p.R / 2) grid = p.R / 2;
-    k_row2_inv<R1, R2, R3, T, false><<<grid, T, smem, st>>>(p.R, p.C, p.P, ia, twC, twQ, work_bytes);
+    sm_launch(k_row2_inv<R1, R2, R3, T, false>, dim3(grid), dim3(T), (size_t)(smem), st, p.R, p.C, p.P, ia, twC, twQ, work_bytes);
     SM_LAUNCH_CHECK();
     return 0;
   } else {
@@ -2039,19 +2058,19 @@ static int launch_row_ct(bool inverse, const SmPlan& p, const RowFwdArgs* fa, co
     }
     int grid = num_sms() * per_sm;
     if (grid > p.R) grid = p.R;
-    if (!inverse) k_row_fwd_tma<R1, R2, R3, R4, T, kPad><<<grid, T, smem, st>>>(p.R, p.C, p.P, *fa, twC, twQ, sumsq, work_bytes);
-    else k_row_inv_tma<R1, R2, R3, R4, T, kPad><<<grid, T, smem, st>>>(p.R, p.C, p.P, *ia, twC, twQ, work_bytes);
+    if (!inverse) sm_launch(k_row_fwd_tma<R1, R2, R3, R4, T, kPad>, dim3(grid), dim3(T), (size_t)(smem), st, p.R, p.C, p.P, *fa, twC, twQ, sumsq, work_bytes);
+    else sm_launch(k_row_inv_tma<R1, R2, R3, R4, T, kPad>, dim3(grid), dim3(T), (size_t)(smem), st, p.R, p.C, p.P, *ia, twC, twQ, work_bytes);
     SM_LAUNCH_CHECK();
     return 0;
   }
   if (!inverse) {
     e = opt_in(k_row_fwd_ct<R1, R2, R3, R4, T, kPad>, &done[0]);
     if (e != cudaSuccess) { sm_set_error("opt_in: %s", cudaGetErrorString(e)); return -100; }
-    k_row_fwd_ct<R1, R2, R3, R4, T, kPad><<<p.R, T, p.row_smem_fwd, st>>>(p.C, p.P, *fa, twC, twQ, sumsq);
+    sm_launch(k_row_fwd_ct<R1, R2, R3, R4, T, kPad>, dim3(p.R), dim3(T), (size_t)(p.row_smem_fwd), st, p.C, p.P, *fa, twC, twQ, sumsq);
   } else {
     e = opt_in(k_row_inv_ct<R1, R2, R3, R4, T, kPad>, &done[1]);
     if (e != cudaSuccess) { sm_set_error("opt_in: %s", cudaGetErrorString(e)); return -100; }
-    k_row_inv_ct<R1, R2, R3, R4, T, kPad><<<p.R, T, p.row_smem_inv, st>>>(p.C, p.P, *ia, twC, twQ);
+    sm_launch(k_row_inv_ct<R1, R2, R3, R4, T, kPad>, dim3(p.R), dim3(T), (size_t)(p.row_smem_inv), st, p.C, p.P, *ia, twC, twQ);
   }
   SM_LAUNCH_CHECK();
   return 0;
@@ -2080,7 +2099,7 @@ static int launch_row_fwd(const SmPlan& p, const void* tables, const RowFwdArgs&
     const int rc = try_row_ct(false, p, &a, nullptr, tabC(p, tables), tabQ(p, tables), sumsq, st);
     if (rc <= 0) return rc;
   }
-  k_row_fwd<<<p.R, p.row_threads, p.row_smem_fwd, st>>>(p, a, tabC(p, tables), tabQ(p, tables), sumsq);
+  sm_launch(k_row_fwd, dim3(p.R), dim3(p.row_threads), (size_t)(p.row_smem_fwd), st, p, a, tabC(p, tables), tabQ(p, tables), sumsq);
   SM_LAUNCH_CHECK();
   return 0;
 }
@@ -2126,7 +2145,7 @@ static int launch_col(const SmPlan& p, const void* tables, int sweep, int invers
   }
   const int threads = (sweep == 0) ? p.thrA : p.thrB;
   const int smem = (sweep == 0) ? p.smemA : p.smemB;
-  k_col<<<dim3(ntiles, n_inst), threads, smem, st>>>(p, ca, tabR(p, tables));
+  sm_launch(k_col, dim3(dim3(ntiles, n_inst)), dim3(threads), (size_t)(smem), st, p, ca, tabR(p, tables));
   SM_LAUNCH_CHECK();
   return 0;
 }
@@ -2193,7 +2212,7 @@ int sm_fwd_cols_sel(const sm_plan* plan, const void* tables, float* re, float* i
     if (rc <= 0) return rc;
   }
   if (p.col_passes == 0) {
-    k_scale_row<<<(p.Ch + 1 + 255) / 256, 256, 0, st>>>(re, im, p.Ch + 1, scale_dev, scale_host, write_im);
+    sm_launch(k_scale_row, dim3((p.Ch + 1 + 255) / 256), dim3(256), (size_t)(0), st, re, im, p.Ch + 1, scale_dev, scale_host, write_im);
     SM_LAUNCH_CHECK();
     return 0;
   }
@@ -2212,7 +2231,7 @@ int sm_fwd_cols_sel(const sm_plan* plan, const void* tables, float* re, float* i
 }
 
 extern "C" int sm_inv_norm(const double* sumsq, float* out, void* stream) {
-  k_inv_norm<<<1, 1, 0, (cudaStream_t)stream>>>(sumsq, out);
+  sm_launch(k_inv_norm, dim3(1), dim3(1), (size_t)(0), (cudaStream_t)stream, sumsq, out);
   SM_LAUNCH_CHECK();
   return 0;
 }
@@ -2251,7 +2270,7 @@ static int launch_row_inv(const SmPlan& p, const void* tables, RowInvArgs& a, cu
     const int rc = try_row_ct(true, p, nullptr, &a, tabC(p, tables), tabQ(p, tables), nullptr, st);
     if (rc <= 0) return rc;
   }
-  k_row_inv<<<p.R, p.row_threads, p.row_smem_inv, st>>>(p, a, tabC(p, tables), tabQ(p, tables));
+  sm_launch(k_row_inv, dim3(p.R), dim3(p.row_threads), (size_t)(p.row_smem_inv), st, p, a, tabC(p, tables), tabQ(p, tables));
   SM_LAUNCH_CHECK();
   return 0;
 }

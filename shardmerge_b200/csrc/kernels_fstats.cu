@@ -76,11 +76,13 @@ constexpr int kSampleShift = 18;                         // sample histogram dig
 constexpr int kSampleBins = 1 << (31 - kSampleShift);    // 8192
 
 struct FsWs {                        // carved out of the caller's workspace
-  // one contiguous block; the caller hands it over zero-filled once, afterwards k_fs_sample keeps it so:
+  // one contiguous block; the caller hands it over zero-filled once, afterwards k_fs_sample keeps it so (coarse and scnt
+  // are cleared by every sample kernel; of `fine` only the counters the previous pass can have touched, meta[0] of them):
   unsigned int* shist;               // [kSampleBins] sample histogram
   unsigned int* coarse;              // [kBins]  keys (with multiplicity) per coarse bin
   unsigned int* scnt;                // [kMaxLists]  entries in the side list of pass CTA i
   unsigned int* fine;                // [kFineMax] keys (with multiplicity) per bit pattern of the window
+  unsigned int* meta;                // [16]  [0]: how many leading `fine` counters the last pass may have left non-zero
   size_t zero_bytes;                 // size of that block
   // not zeroed (guarded by scnt):
   float2* sbkt;                      // [n_lists][scap]  (|re0| with "multiplicity 1" in the sign bit, |re1|)
@@ -229,6 +231,7 @@ template <int MODE>
 __global__ void __launch_bounds__(kSampleThreads) k_fs_sample(const __grid_constant__ SmPlan pl, const __grid_constant__ FsCommon c,
                                                               FsState* st, const __grid_constant__ FsWs ws, unsigned long long rank,
                                                               long long k_lo, long long k_hi) {
+  sm_pdl_enter();
   __shared__ Pick out_a, out_b;
   __shared__ unsigned int s_h[kSampleBins];
   const unsigned int ns = kNS;
@@ -243,9 +246,12 @@ __global__ void __launch_bounds__(kSampleThreads) k_fs_sample(const __grid_const
 #pragma unroll
   for (int j = 0; j < kSampleBins / kSampleThreads; ++j) s_h[threadIdx.x + kSampleThreads * j] = 0u;
   {  // this kernel also clears the histograms of the pass that follows (fire-and-forget stores, done long before it starts):
-     // no memset node in the chain.  The sample histogram itself is left clean by the last CTA below.
+     // no memset node in the chain.  The sample histogram itself is left clean by the last CTA below.  Of the 16 MB of
+     // `fine` only the first meta[0] counters can be non-zero: the window of the previous pass (usually 2 - 4 MB).
     uint4* const z = reinterpret_cast<uint4*>(ws.coarse);          // [coarse | scnt | fine] is one contiguous block
-    const size_t n16 = ((size_t)kBins + kMaxLists + kFineMax) / 4;
+    unsigned int dirty = __ldcg(ws.meta);                          // read before this CTA's ticket: the last CTA rewrites it
+    if (dirty > kFineMax) dirty = kFineMax;
+    const size_t n16 = ((size_t)kBins + kMaxLists + dirty + 3) / 4;
     const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) z[i] = zero;
   }
@@ -316,6 +322,7 @@ __global__ void __launch_bounds__(kSampleThreads) k_fs_sample(const __grid_const
     st->status = status; st->key = 0u; st->value = 0.f; st->bstar = 0u;
     st->s_in[0] = 0.0; st->s_in[1] = 0.0; st->s_in[2] = 0.0;
     st->ticket = 0u;
+    ws.meta[0] = status == 0u ? (unsigned int)width : 0u;   // the counters the pass that follows may touch (a dead pass: none)
   }
   FS_STAMP(4);
 }
@@ -506,6 +513,7 @@ template <int MODE>
 __global__ void __launch_bounds__(kPassThreads, kPassCtasPerSm) k_fs_pass(const __grid_constant__ SmPlan pl, const __grid_constant__ FsCommon c,
                                                             FsState* st, const __grid_constant__ FsWs ws, float* out,
                                                             float* thr_out) {
+  sm_pdl_enter();
   __shared__ unsigned long long s_below[kPassWarps];
   __shared__ double s_red[32];
   __shared__ Pick pick;
@@ -693,6 +701,7 @@ __global__ void __launch_bounds__(kPassThreads, kPassCtasPerSm) k_fs_pass(const 
 // into the scalars of slerp().
 __global__ void __launch_bounds__(SM_EW_THREADS) k_fs_close(FsState* st, const __grid_constant__ FsWs ws, double t, float* scal4,
                                                             double* sums_out) {
+  sm_pdl_enter();
   __shared__ double s_red[32];
   const bool ok = st->status == 0u;
   const unsigned int key = st->key;
@@ -762,7 +771,7 @@ extern "C" int sm_fstats_supported(const sm_plan* plan) {
 }
 
 static size_t fs_zero_bytes() {
-  return (size_t)kSampleBins * 4 + (size_t)kBins * 4 + (size_t)kMaxLists * 4 + (size_t)kFineMax * 4;
+  return (size_t)kSampleBins * 4 + (size_t)kBins * 4 + (size_t)kMaxLists * 4 + (size_t)kFineMax * 4 + 64;
 }
 
 extern "C" size_t sm_fstats_ws_bytes(const sm_plan* plan) {
@@ -787,6 +796,7 @@ static int fs_carve(const sm_plan* plan, void* wsp, size_t ws_bytes, FsWs* w) {
   w->coarse = reinterpret_cast<unsigned int*>(b); b += (size_t)kBins * 4;
   w->scnt = reinterpret_cast<unsigned int*>(b); b += (size_t)kMaxLists * 4;
   w->fine = reinterpret_cast<unsigned int*>(b); b += (size_t)kFineMax * 4;
+  w->meta = reinterpret_cast<unsigned int*>(b); b += 64;
   w->zero_bytes = (size_t)(b - z0);
   w->n_lists = fs_grid(p).x;
   w->scap = fs_scap(p, w->n_lists);
@@ -823,14 +833,14 @@ extern "C" int sm_fstats_cutoff(const sm_plan* plan, const float* reX, const flo
   FsCommon c{reX, reY, sel, nullptr, nullptr, 1.f};
   long long k_lo = 0, k_hi = 0;
   fs_sample_ranks(rank, total, &k_lo, &k_hi);
-  k_fs_sample<0><<<fs_sample_grid(), kSampleThreads, 0, s>>>(p, c, st, w, rank, k_lo, k_hi);
+  sm_launch(k_fs_sample<0>, dim3(fs_sample_grid()), dim3(kSampleThreads), (size_t)(0), s, p, c, st, w, rank, k_lo, k_hi);
   SM_LAUNCH_CHECK();
   if (getenv("SM_FS_ONLY_SAMPLE")) return 0;
   if ((rc = fs_pass_attr())) return rc;
-  k_fs_pass<0><<<w.n_lists, kPassThreads, kPassDynSmem, s>>>(p, c, st, w, nullptr, thr_cut_out);
+  sm_launch(k_fs_pass<0>, dim3(w.n_lists), dim3(kPassThreads), (size_t)(kPassDynSmem), s, p, c, st, w, nullptr, thr_cut_out);
   SM_LAUNCH_CHECK();
   const unsigned int close_grid = w.n_lists < 148u ? w.n_lists : 148u;
-  k_fs_close<<<close_grid, SM_EW_THREADS, 0, s>>>(st, w, t, scal4_out, sums3_out);
+  sm_launch(k_fs_close, dim3(close_grid), dim3(SM_EW_THREADS), (size_t)(0), s, st, w, t, scal4_out, sums3_out);
   SM_LAUNCH_CHECK();
   return 0;
 }
@@ -850,10 +860,10 @@ extern "C" int sm_fstats_blend_cull(const sm_plan* plan, const float* reX, const
   FsCommon c{reX, reY, sel, thr_cut, scal4, t_sum};
   long long k_lo = 0, k_hi = 0;
   fs_sample_ranks(rank, total, &k_lo, &k_hi);
-  k_fs_sample<1><<<fs_sample_grid(), kSampleThreads, 0, s>>>(p, c, st, w, rank, k_lo, k_hi);
+  sm_launch(k_fs_sample<1>, dim3(fs_sample_grid()), dim3(kSampleThreads), (size_t)(0), s, p, c, st, w, rank, k_lo, k_hi);
   SM_LAUNCH_CHECK();
   if ((rc = fs_pass_attr())) return rc;
-  k_fs_pass<1><<<w.n_lists, kPassThreads, kPassDynSmem, s>>>(p, c, st, w, out_re, thr_cull_out);
+  sm_launch(k_fs_pass<1>, dim3(w.n_lists), dim3(kPassThreads), (size_t)(kPassDynSmem), s, p, c, st, w, out_re, thr_cull_out);
   SM_LAUNCH_CHECK();
   return 0;
 }

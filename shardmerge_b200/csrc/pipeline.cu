@@ -10,14 +10,22 @@
 // from there.  The chain always continues down the SLERP branch (what the BASELINE configs
 // take); if k_prepare found another branch, or an order-statistic window missed, the caller sees
 // it in the scalar block afterwards and re-runs that tensor on the step-by-step path.
+#include <cstdlib>
 #include <vector>
 #include "sm_internal.h"
+
+bool sm_pdl_enabled() {              // SM_PDL=0: plain stream-ordered launches (A-B switch, sm_internal.h)
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SM_PDL"); v = (e != nullptr && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
 
 namespace {
 
 // ext_tn > 0: the target norm is given (the mean over ALL models of the layer in a pair tree, fast_fourier.py:165);
 // use_host_sumsq: the row passes ran earlier and the host passes their sums of squares in (tree round 1)
 __global__ void k_prepare(unsigned char* ctl, double target_norm_offset, double ext_tn, int use_host_sumsq, double hs0, double hs1) {
+  sm_pdl_enter();
   double* sumsq = reinterpret_cast<double*>(ctl + SM_CTL_SUMSQ);
   if (use_host_sumsq) { sumsq[0] = hs0; sumsq[1] = hs1; }
   float* flt = reinterpret_cast<float*>(ctl + SM_CTL_FLT);
@@ -123,7 +131,7 @@ static int pair_chain(const sm_plan* plan, const void* tables, const sm_pair_arg
   }
   {
     Scope s(st, SM_CLS_SCALARS, 0.0, 1);
-    k_prepare<<<1, 1, 0, st>>>(ctl, a->target_norm_offset, x ? x->target_norm : 0.0, rows_done ? 1 : 0,
+    sm_launch(k_prepare, dim3(1), dim3(1), (size_t)(0), st, ctl, a->target_norm_offset, x ? x->target_norm : 0.0, rows_done ? 1 : 0,
                                rows_done ? x->sumsq[0] : 0.0, rows_done ? x->sumsq[1] : 0.0);
     SM_LAUNCH_CHECK();
   }

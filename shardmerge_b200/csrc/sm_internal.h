@@ -30,6 +30,31 @@ void sm_set_error(const char* fmt, ...);
     }                                                                                  \
   } while (0)
 
+// ---- programmatic dependent launch (sm_90+): every kernel of the fused chain starts with sm_pdl_enter() -- wait until the
+// preceding kernel of the stream has completed and its writes are visible -- and is launched through sm_launch(), which sets
+// the programmatic stream serialization attribute.  Semantics are those of plain stream order (nothing is read before the
+// wait); what is saved is the launch latency of kernel k+1, which is set up while kernel k still runs: ~2 us per boundary on
+// B200 (tools/ubench_pdl.cu), 17 boundaries per pair merge.  No kernel issues griddepcontrol.launch_dependents: with an early
+// trigger the next kernel's CTAs become resident and sit in the wait while the current one runs, which saves nothing more in
+// a single stream (same ubench) and, with several lanes, takes the SM slots the OTHER lanes' kernels would have filled
+// (value 53.0 -> 49.7 Gparam/s, profiles/r02_ab_pdl.log).  SM_PDL=0 launches plainly (A-B switch).
+#ifdef __CUDACC__
+__device__ __forceinline__ void sm_pdl_enter() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+bool sm_pdl_enabled();
+template <class... KA, class... A>
+static inline void sm_launch(void (*kernel)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = sm_pdl_enabled() ? 1 : 0;
+  (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<A&&>(args)...);      // errors surface in SM_LAUNCH_CHECK()
+}
+#endif
+
 // table layout inside the caller's buffer: [W_C : C entries][W_R : R entries][quads : 4 * (Ch / row_rad[0])]
 // of float2; the quad table (fft_core.cuh: first-stage twiddles) starts 32-byte aligned.
 static inline size_t sm_tab_off_R(const SmPlan& p) { return (size_t)p.C * 8; }

@@ -24,7 +24,7 @@ total = ws.plan.lib.sm_fstats_ws_bytes(ws.plan.handle)
 base = ws.sel_ws.data_ptr() + ws.sel_ws.numel() - total          # fs_carve: the last `total` bytes of the buffer
 al = (base + 63) // 64 * 64 - base
 off = (base + al + total - 512 - 65536 + 63) // 64 * 64 - base      # fs_carve: the stamps follow the side lists
-nc = 64 if only_sample else 592
+nc = 256 if only_sample else 296
 o0 = ws.sel_ws.numel() - total + off
 st = ws.sel_ws[o0: o0 + nc * 8 * 8].view(torch.int64).cpu().reshape(nc, 8).numpy()
 t0 = st[:, 0][st[:, 0] > 0].min()
