@@ -270,10 +270,14 @@ int sm_profile_collect(double* ms, double* bytes, int* launches, int n_classes);
 
 /* ---- element-wise strategies (next to the spectral path: the reference's other MergeTensorsBase subclasses) ----------
  * mode 0: AdditionMerge._merge_layer (shard/merge/addition.py:44-83): out = sum_k (ft_k - base), every op rounded to
- *         bf16 like the reference's in-dtype arithmetic; the base is NOT added back.
+ *         the tensors' dtype like the reference's in-dtype arithmetic; the base is NOT added back.
  * mode 1: TaskAdditionMerge._merge_layer (shard/merge/taskaddition.py:44-83): deltas whose sign differs from the
  *         majority sign are zeroed, the rest summed (fp32 accumulation in model order, one rounding).
- * bf16 in / out, n elements, `fts` = HOST array of n_models (<= 8) device pointers; all 16-byte aligned. */
+ * n elements, `fts` = HOST array of n_models device pointers; all 16-byte aligned.
+ * sm_elem_merge: dtype 0 fp32, 1 bf16, 2 fp16 (every op in the tensors' own dtype, as torch does), 1..64 models; from 16
+ * models on, mode 1 sums like torch.sum on the CPU (16-row groups folded into a second fp32 accumulator).  bf16 with <= 8
+ * models runs kernels with a compile-time model count.  sm_elem_merge_bf16 = sm_elem_merge(dtype 1). */
+int sm_elem_merge(int mode, int dtype, size_t n, const void* base, const void* const* fts, int n_models, void* out, void* stream);
 int sm_elem_merge_bf16(int mode, size_t n, const void* base, const void* const* fts, int n_models, void* out, void* stream);
 
 /* correlate_pairs (shard/tensor/functions.py:304-314), one pair: *out_sum = sum over the C columns of the cosine similarity

@@ -287,31 +287,71 @@ def _bf16_round(x: np.ndarray) -> np.ndarray:
     return bf16_to_f32(f32_to_bf16(np.asarray(x, dtype=np.float32)))
 
 
-def addition_merge(base_bf16: np.ndarray, fts_bf16) -> np.ndarray:
+def _elem_codec(dtype: str):
+    """(widen to fp32, round fp32 to the storage dtype and widen again, narrow to storage) for the element-wise strategies:
+    'bf16' tensors travel as uint16 bit patterns, 'f16' as np.float16, 'f32' as np.float32."""
+    if dtype == "bf16":
+        return bf16_to_f32, _bf16_round, f32_to_bf16
+    if dtype == "f16":
+        return (lambda a: np.asarray(a, dtype=np.float16).astype(np.float32),
+                lambda x: np.asarray(x, dtype=np.float32).astype(np.float16).astype(np.float32),
+                lambda x: np.asarray(x, dtype=np.float32).astype(np.float16))
+    if dtype == "f32":
+        ident = lambda a: np.asarray(a, dtype=np.float32)
+        return ident, ident, ident
+    raise ValueError(dtype)
+
+
+def _cascade_sum_rows(x: np.ndarray) -> np.ndarray:
+    """torch.sum(x, dim=0) of a CPU float tensor [M, ...] (ATen SumKernel.cpp, cascade_sum -> multi_row_sum over the outer
+    dimension, fp32 accumulators): rows are added one by one into a level-0 accumulator; after every 16 rows it is
+    folded into level 1 (after 256 into level 2, ...), and the levels are added at the end.  Up to 15 rows this is the plain
+    sequential sum; from 16 rows on the association differs."""
+    M = x.shape[0]
+    acc = [np.zeros(x.shape[1:], dtype=np.float32) for _ in range(4)]
+    i = 0
+    while i + 16 <= M:
+        for _ in range(16):
+            acc[0] = acc[0] + x[i]
+            i += 1
+        for j in range(1, 4):
+            acc[j] = acc[j] + acc[j - 1]
+            acc[j - 1] = np.zeros_like(acc[0])
+            if i & (15 << (4 * j)):
+                break
+    while i < M:
+        acc[0] = acc[0] + x[i]
+        i += 1
+    for j in range(1, 4):
+        acc[0] = acc[0] + acc[j]
+    return acc[0]
+
+
+def addition_merge(base, fts, dtype: str = "bf16") -> np.ndarray:
     """AdditionMerge._merge_layer (shard/merge/addition.py:44-83): out = 0; out += (ft - base) per model, every
-    operation in the tensors' own dtype (bf16: computed in fp32, rounded to bf16 after each op).  The summed
-    delta is returned -- the base is NOT added back.  uint16 bit patterns in, uint16 out."""
+    operation in the tensors' own dtype (bf16 / fp16: computed in fp32, rounded to the dtype after each op).  The summed
+    delta is returned -- the base is NOT added back.  Storage as in _elem_codec (bf16: uint16 bit patterns in and out)."""
+    widen, rnd, narrow = _elem_codec(dtype)
     with np.errstate(invalid="ignore", over="ignore"):
-        b = bf16_to_f32(base_bf16)
+        b = widen(base)
         out = np.zeros(b.shape, dtype=np.float32)
-        for ft in fts_bf16:
-            delta = _bf16_round(bf16_to_f32(ft) - b)               # :72
-            out = _bf16_round(out + delta)                         # :73
-    return f32_to_bf16(out)
+        for ft in fts:
+            delta = rnd(widen(ft) - b)                             # :72
+            out = rnd(out + delta)                                 # :73
+    return narrow(out)
 
 
-def taskaddition_merge(base_bf16: np.ndarray, fts_bf16) -> np.ndarray:
-    """TaskAdditionMerge._merge_layer (shard/merge/taskaddition.py:44-83): bf16 deltas, majority sign over the models
-    (sign of the sum of signs), deltas whose sign differs from it zeroed, the rest summed (torch.sum over bf16
-    accumulates in fp32 in model order and rounds once)."""
+def taskaddition_merge(base, fts, dtype: str = "bf16") -> np.ndarray:
+    """TaskAdditionMerge._merge_layer (shard/merge/taskaddition.py:44-83): deltas in the tensors' dtype, majority sign over
+    the models (sign of the sum of signs), deltas whose sign differs from it zeroed, the rest summed (torch.sum on CPU:
+    fp32 accumulators in model order -- cascaded from 16 models on, _cascade_sum_rows -- one rounding at the end)."""
+    widen, rnd, narrow = _elem_codec(dtype)
     with np.errstate(invalid="ignore", over="ignore"):
-        b = bf16_to_f32(base_bf16)
-        d = np.stack([_bf16_round(bf16_to_f32(ft) - b) for ft in fts_bf16], axis=0)      # :68
+        b = widen(base)
+        d = np.stack([rnd(widen(ft) - b) for ft in fts], axis=0)   # :68
         sgn = np.sign(d)                                            # :71   (NaN stays NaN)
-        w = np.sign(sgn.sum(axis=0, dtype=np.float32))             # :73
+        w = np.sign(_cascade_sum_rows(sgn))                        # :73   (small integers: exact in any order)
         mask = (sgn == w[None]).astype(np.float32)                 # :75   (NaN == NaN is False)
-        masked = _bf16_round(d * mask)                             # :76
-        acc = np.zeros(b.shape, dtype=np.float32)
-        for k in range(masked.shape[0]):                           # :78
-            acc = acc + masked[k]
-    return f32_to_bf16(acc)
+        masked = rnd(d * mask)                                     # :76
+        acc = _cascade_sum_rows(masked)                            # :78
+    return narrow(acc)

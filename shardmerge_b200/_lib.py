@@ -43,6 +43,7 @@ SIGNATURES = {
     "sm_inv_rows_bf16": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _vp, _vp]),
     "sm_inv_rows_f32": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _i, _vp, _vp]),
     "sm_delta_axpby_bf16": (_i, [_sz, _vp, _vp, _vp, _f, _vp, _vp, _f, _f, _vp, _vp, _vp]),
+    "sm_elem_merge": (_i, [_i, _i, _sz, _vp, _vp, _i, _vp, _vp]),
     "sm_elem_merge_bf16": (_i, [_i, _sz, _vp, _vp, _i, _vp, _vp]),
     "sm_cosine_cols": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp]),
     "sm_copy_bytes": (_i, [_vp, _vp, _sz, _vp]),

@@ -9,6 +9,7 @@
 // that rounding sequence, so the results are bit-identical to the reference's (tests/golden/elem_*.npz), NaN payloads
 // aside.  HBM-bound: (M + 1) reads and one write of 2 bytes per element; 8 elements (16 bytes per tensor) per thread.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "sm_internal.h"
 
 namespace {
@@ -115,6 +116,114 @@ __global__ void __launch_bounds__(256) k_elem_merge(const __grid_constant__ Elem
   }
 }
 
+// ---- any storage dtype, up to 64 models (the reference takes whatever the checkpoints hold; the compile-time kernels above
+// cover the common case, bf16 and <= 8 finetunes).  Run-time loop over the models, four consecutive elements per thread;
+// the sign-agreement mode reads the finetunes twice (sum of signs, then the masked sum).  torch.sum on the CPU (where
+// taskaddition.py:69 puts the stack) keeps fp32 accumulators in model order and, from 16 rows on, folds every 16 rows
+// into a second accumulator that is added at the end (ATen SumKernel.cpp multi_row_sum; oracle_np._cascade_sum_rows):
+// reproduced here so that fp32 checkpoints come out bit-identical as well.
+constexpr int kMaxAny = 64;
+struct ElemAnyArgs { const void* base; const void* ft[kMaxAny]; void* out; int M; size_t n; };
+
+template <int DT> struct ElemCodec;
+template <> struct ElemCodec<0> {                    // fp32
+  __device__ static float load(const void* p, size_t i) { return __ldg(reinterpret_cast<const float*>(p) + i); }
+  __device__ static void load4(const void* p, size_t i4, float (&f)[4]) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p) + i4); f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+  }
+  __device__ static float rnd(float x) { return x; }
+  __device__ static void store(void* p, size_t i, float v) { reinterpret_cast<float*>(p)[i] = v; }
+  __device__ static void store4(void* p, size_t i4, const float (&o)[4]) { reinterpret_cast<float4*>(p)[i4] = make_float4(o[0], o[1], o[2], o[3]); }
+};
+template <> struct ElemCodec<1> {                    // bf16
+  __device__ static float load(const void* p, size_t i) { return __uint_as_float((uint32_t)__ldg(reinterpret_cast<const uint16_t*>(p) + i) << 16); }
+  __device__ static void load4(const void* p, size_t i4, float (&f)[4]) {
+    const uint2 v = __ldg(reinterpret_cast<const uint2*>(p) + i4);
+    f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+  }
+  __device__ static float rnd(float x) { return bf16r(x); }
+  __device__ static void store(void* p, size_t i, float v) { __nv_bfloat16 h = __float2bfloat16_rn(v); reinterpret_cast<uint16_t*>(p)[i] = *reinterpret_cast<uint16_t*>(&h); }
+  __device__ static void store4(void* p, size_t i4, const float (&o)[4]) { reinterpret_cast<uint2*>(p)[i4] = make_uint2(pack2(o[0], o[1]), pack2(o[2], o[3])); }
+};
+template <> struct ElemCodec<2> {                    // fp16
+  __device__ static float h2f(uint16_t u) { return __half2float(*reinterpret_cast<const __half*>(&u)); }
+  __device__ static uint16_t f2h(float x) { __half h = __float2half_rn(x); return *reinterpret_cast<uint16_t*>(&h); }
+  __device__ static float load(const void* p, size_t i) { return h2f(__ldg(reinterpret_cast<const uint16_t*>(p) + i)); }
+  __device__ static void load4(const void* p, size_t i4, float (&f)[4]) {
+    const uint2 v = __ldg(reinterpret_cast<const uint2*>(p) + i4);
+    f[0] = h2f((uint16_t)(v.x & 0xffffu)); f[1] = h2f((uint16_t)(v.x >> 16)); f[2] = h2f((uint16_t)(v.y & 0xffffu)); f[3] = h2f((uint16_t)(v.y >> 16));
+  }
+  __device__ static float rnd(float x) { return h2f(f2h(x)); }
+  __device__ static void store(void* p, size_t i, float v) { reinterpret_cast<uint16_t*>(p)[i] = f2h(v); }
+  __device__ static void store4(void* p, size_t i4, const float (&o)[4]) {
+    reinterpret_cast<uint2*>(p)[i4] = make_uint2((uint32_t)f2h(o[0]) | ((uint32_t)f2h(o[1]) << 16), (uint32_t)f2h(o[2]) | ((uint32_t)f2h(o[3]) << 16));
+  }
+};
+
+// W elements (4: vector body, 1: tail) starting at element e0; `get(p, f)` loads them from tensor p
+template <int MODE, int DT, int W, class Get>
+__device__ __forceinline__ void merge_any(const ElemAnyArgs& a, const Get& get, float (&o)[W]) {
+  using Cd = ElemCodec<DT>;
+  float b[W], f[W];
+  get(a.base, b);
+  if (MODE == 0) {
+#pragma unroll
+    for (int e = 0; e < W; ++e) o[e] = 0.f;
+    for (int k = 0; k < a.M; ++k) {
+      get(a.ft[k], f);
+#pragma unroll
+      for (int e = 0; e < W; ++e) o[e] = Cd::rnd(o[e] + Cd::rnd(f[e] - b[e]));          // addition.py:72-73
+    }
+  } else {
+    float ssum[W], a0[W], a1[W];
+#pragma unroll
+    for (int e = 0; e < W; ++e) { ssum[e] = 0.f; a0[e] = 0.f; a1[e] = 0.f; }
+    for (int k = 0; k < a.M; ++k) {                      // taskaddition.py:68-73
+      get(a.ft[k], f);
+#pragma unroll
+      for (int e = 0; e < W; ++e) ssum[e] += sgnf(Cd::rnd(f[e] - b[e]));
+    }
+#pragma unroll
+    for (int e = 0; e < W; ++e) ssum[e] = sgnf(ssum[e]);
+    for (int k = 0; k < a.M; ++k) {                      // :75-78
+      get(a.ft[k], f);
+#pragma unroll
+      for (int e = 0; e < W; ++e) {
+        const float d = Cd::rnd(f[e] - b[e]);
+        a0[e] += Cd::rnd(d * ((sgnf(d) == ssum[e]) ? 1.f : 0.f));
+      }
+      if (((k + 1) & 15) == 0) {                         // a full group of 16 rows: fold into the next level
+#pragma unroll
+        for (int e = 0; e < W; ++e) { a1[e] += a0[e]; a0[e] = 0.f; }
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < W; ++e) o[e] = a0[e] + a1[e];
+  }
+}
+
+template <int MODE, int DT>
+__global__ void __launch_bounds__(256) k_elem_merge_any(const __grid_constant__ ElemAnyArgs a) {
+  using Cd = ElemCodec<DT>;
+  const size_t n4 = a.n / 4, stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float o[4];
+    merge_any<MODE, DT, 4>(a, [&](const void* p, float (&f)[4]) { Cd::load4(p, i, f); }, o);
+    if (MODE == 1) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[e] = Cd::rnd(o[e]);
+    }
+    Cd::store4(a.out, i, o);
+  }
+  if (blockIdx.x == 0) {
+    for (size_t j = n4 * 4 + threadIdx.x; j < a.n; j += blockDim.x) {
+      float o[1];
+      merge_any<MODE, DT, 1>(a, [&](const void* p, float (&f)[1]) { f[0] = Cd::load(p, j); }, o);
+      Cd::store(a.out, j, o[0]);
+    }
+  }
+}
+
 // ---- correlate_pairs (shard/tensor/functions.py:304-314): mean over the columns of the cosine similarity of two [R][C]
 // tensors along dim 0.  One CTA per 32 adjacent columns walks all rows (coalesced 128-byte row segments for fp32, 64 for
 // bf16), three fp32 sums per column, one atomic per CTA.  torch: (x / max(||x||, eps)) . (y / max(||y||, eps)), eps = 1e-8,
@@ -164,34 +273,60 @@ extern "C" int sm_cosine_cols(int dtype, int R, int C, const void* a, const void
   return 0;
 }
 
-extern "C" int sm_elem_merge_bf16(int mode, size_t n, const void* base, const void* const* fts, int n_models, void* out,
-                                  void* stream) {
-  if (mode < 0 || mode > 1) { sm_set_error("elem_merge: unknown mode %d", mode); return -2; }
-  if (n_models < 1 || n_models > kMaxModels) { sm_set_error("elem_merge: 1..%d models, got %d", kMaxModels, n_models); return -2; }
-  ElemArgs a{};
-  a.base = reinterpret_cast<const uint4*>(base); a.out = reinterpret_cast<uint4*>(out); a.M = n_models;
-  a.n = n; a.n8 = n / 8;
-  bool aligned = ((uintptr_t)base % 16 == 0) && ((uintptr_t)out % 16 == 0);
-  for (int k = 0; k < n_models; ++k) { a.ft[k] = reinterpret_cast<const uint4*>(fts[k]); aligned = aligned && ((uintptr_t)fts[k] % 16 == 0); }
-  if (!aligned) { sm_set_error("elem_merge: tensors must be 16-byte aligned"); return -2; }
-  if (n == 0) return 0;
+static int elem_grid(size_t vec_items) {
   int dev = 0, sms = 148;
   if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
-  size_t need = (a.n8 + 255) / 256;
+  size_t need = (vec_items + 255) / 256;
   if (need < 1) need = 1;
   const size_t cap = (size_t)sms * 16;                  // two resident waves of 8 CTAs per SM, grid-stride over the rest
-  const unsigned int grid = (unsigned int)(need < cap ? need : cap);
+  return (int)(need < cap ? need : cap);
+}
+
+extern "C" int sm_elem_merge(int mode, int dtype, size_t n, const void* base, const void* const* fts, int n_models, void* out,
+                             void* stream) {
+  if (mode < 0 || mode > 1) { sm_set_error("elem_merge: unknown mode %d", mode); return -2; }
+  if (dtype < 0 || dtype > 2) { sm_set_error("elem_merge: dtype 0 (fp32), 1 (bf16) or 2 (fp16), got %d", dtype); return -2; }
+  if (n_models < 1 || n_models > kMaxAny) { sm_set_error("elem_merge: 1..%d models, got %d", kMaxAny, n_models); return -2; }
+  bool aligned = ((uintptr_t)base % 16 == 0) && ((uintptr_t)out % 16 == 0);
+  for (int k = 0; k < n_models; ++k) aligned = aligned && ((uintptr_t)fts[k] % 16 == 0);
+  if (!aligned) { sm_set_error("elem_merge: tensors must be 16-byte aligned"); return -2; }
+  if (n == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == 1 && n_models <= kMaxModels) {            // the common case: compile-time model count, 8 elements per thread
+    ElemArgs a{};
+    a.base = reinterpret_cast<const uint4*>(base); a.out = reinterpret_cast<uint4*>(out); a.M = n_models;
+    a.n = n; a.n8 = n / 8;
+    for (int k = 0; k < n_models; ++k) a.ft[k] = reinterpret_cast<const uint4*>(fts[k]);
+    const unsigned int grid = (unsigned int)elem_grid(a.n8);
 #define SM_ELEM_CASE(MM)                                                 \
   case MM:                                                               \
     if (mode == 0) k_elem_merge<0, MM><<<grid, 256, 0, st>>>(a);         \
     else k_elem_merge<1, MM><<<grid, 256, 0, st>>>(a);                   \
     break;
-  switch (n_models) {
-    SM_ELEM_CASE(1) SM_ELEM_CASE(2) SM_ELEM_CASE(3) SM_ELEM_CASE(4)
-    SM_ELEM_CASE(5) SM_ELEM_CASE(6) SM_ELEM_CASE(7) SM_ELEM_CASE(8)
-  }
+    switch (n_models) {
+      SM_ELEM_CASE(1) SM_ELEM_CASE(2) SM_ELEM_CASE(3) SM_ELEM_CASE(4)
+      SM_ELEM_CASE(5) SM_ELEM_CASE(6) SM_ELEM_CASE(7) SM_ELEM_CASE(8)
+    }
 #undef SM_ELEM_CASE
+    SM_LAUNCH_CHECK();
+    return 0;
+  }
+  ElemAnyArgs a{};
+  a.base = base; a.out = out; a.M = n_models; a.n = n;
+  for (int k = 0; k < n_models; ++k) a.ft[k] = fts[k];
+  const unsigned int grid = (unsigned int)elem_grid(n / 4);
+#define SM_ELEM_ANY(DT)                                                  \
+  case DT:                                                               \
+    if (mode == 0) k_elem_merge_any<0, DT><<<grid, 256, 0, st>>>(a);     \
+    else k_elem_merge_any<1, DT><<<grid, 256, 0, st>>>(a);               \
+    break;
+  switch (dtype) { SM_ELEM_ANY(0) SM_ELEM_ANY(1) SM_ELEM_ANY(2) }
+#undef SM_ELEM_ANY
   SM_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int sm_elem_merge_bf16(int mode, size_t n, const void* base, const void* const* fts, int n_models, void* out,
+                                  void* stream) {
+  return sm_elem_merge(mode, 1, n, base, fts, n_models, out, stream);
 }

@@ -64,3 +64,30 @@ def bf16_ulp_distance(a_bits, b_bits):
         u = u.astype(np.int32)
         return np.where(u & 0x8000, 0x8000 - (u & 0x7FFF), u + 0x8000)
     return np.abs(key(np.asarray(a_bits)) - key(np.asarray(b_bits)))
+
+
+# ---- tests/golden/elem_*.npz (oracle/make_golden_elem.py): the element-wise strategies' fixtures ----------------------------
+def _bf16_to_f32(u):
+    return (np.asarray(u, dtype=np.uint16).astype(np.uint32) << 16).view(np.float32)
+
+
+ELEM_CASES = ["elem_addition_3x_64x128", "elem_addition_2x_special_32x64", "elem_taskaddition_3x_64x128",
+              "elem_taskaddition_4x_96x40", "elem_taskaddition_2x_special_32x64",
+              # other storage dtypes, more than 8 models (torch.sum on the CPU cascades from 16 rows on)
+              "elem_addition_f16_3x_64x128", "elem_addition_f32_2x_special_32x64", "elem_addition_10x_48x64",
+              "elem_taskaddition_f16_3x_special_64x128", "elem_taskaddition_f32_4x_96x40", "elem_taskaddition_12x_48x64",
+              "elem_taskaddition_20x_48x64", "elem_taskaddition_f32_35x_24x64"]
+
+
+def elem_case(golden_dir, name):
+    """-> (dtype tag, base, finetunes, expected) of a tests/golden/elem_*.npz fixture (bf16 as uint16 bit patterns)"""
+    d = np.load(golden_dir / f"{name}.npz")
+    dt = str(d["dtype"]) if "dtype" in d.files else "bf16"
+    return dt, d["base"], [d[f"ft{k}"] for k in range(int(d["n"]))], d["out"]
+
+
+def elem_same(dt, got, want):
+    """bit-identical, NaN == NaN"""
+    wide = _bf16_to_f32 if dt == "bf16" else (lambda a: np.asarray(a, dtype=np.float32))
+    fa, fb = wide(got), wide(want)
+    return (got == want) | ((fa != fa) & (fb != fb))

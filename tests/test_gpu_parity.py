@@ -661,29 +661,65 @@ def _nan_equal_bits(a, b):
     return (a == b) | ((fa != fa) & (fb != fb))
 
 
-@pytest.mark.parametrize("name", ["elem_addition_3x_64x128", "elem_addition_2x_special_32x64", "elem_taskaddition_3x_64x128",
-                                  "elem_taskaddition_4x_96x40", "elem_taskaddition_2x_special_32x64"])
+from tests.parity_util import ELEM_CASES, elem_case as _elem_case, elem_same as _elem_same
+
+_ELEM_TORCH = {"bf16": torch.bfloat16, "f16": torch.float16, "f32": torch.float32}
+
+
+def _elem_to_torch(dt, a):
+    return torch.from_numpy(a.view(np.int16).copy()).view(torch.bfloat16) if dt == "bf16" else torch.from_numpy(a.copy())
+
+
+def _elem_to_numpy(dt, t):
+    return bits(t) if dt == "bf16" else t.detach().cpu().numpy()
+
+
+@pytest.mark.parametrize("name", ELEM_CASES)
 def test_elementwise_strategies_golden(E, golden_dir, name):
     """AdditionMerge / TaskAdditionMerge through the reference's class interface (`_merge_layer`) on the reference's own
-    inputs: bit-identical to the reference's bf16 output (NaN payloads aside)."""
+    inputs: bit-identical to the reference's output (NaN payloads aside) for bf16, fp16 and fp32 models, 2..35 finetunes."""
     import asyncio
     from shardmerge_b200.config import MergeConfig, MergeModel
     from shardmerge_b200.index import InMemoryIndex
     from shardmerge_b200.merge import AdditionMerge, TaskAdditionMerge
     from shardmerge_b200.writer import ShardLayer
-    d = np.load(golden_dir / f"{name}.npz")
-    n = int(d["n"])
+    dt, base, fts, want = _elem_case(golden_dir, name)
+    n = len(fts)
     layer = "model.layers.3.mlp.up_proj.weight"
-    to_t = lambda u: torch.from_numpy(u.view(np.int16).copy()).view(torch.bfloat16)
-    models = {"org/base": {layer: to_t(d["base"])}}
+    models = {"org/base": {layer: _elem_to_torch(dt, base)}}
     for k in range(n):
-        models[f"org/ft{k}"] = {layer: to_t(d[f"ft{k}"])}
+        models[f"org/ft{k}"] = {layer: _elem_to_torch(dt, fts[k])}
     cfg = MergeConfig(finetune_merge=[MergeModel(model=f"org/ft{k}", base="org/base", alpha=1.0) for k in range(n)],
                       output_base_model="org/base", output_dir="/tmp/unused")
     cls = TaskAdditionMerge if "taskaddition" in name else AdditionMerge
     out = asyncio.run(cls(cfg, index_manager=InMemoryIndex(models))._merge_layer(ShardLayer(0, "s", layer, False), DEV))
-    assert out.dtype == torch.bfloat16 and out.is_cuda
-    assert _nan_equal_bits(bits(out), d["out"]).all()
+    assert out.dtype == _ELEM_TORCH[dt] and out.is_cuda
+    assert _elem_same(dt, _elem_to_numpy(dt, out), want).all()
+
+
+@pytest.mark.parametrize("mode,n_models,numel,dt", [(0, 3, 1 << 20, "f32"), (1, 17, (1 << 20) + 3, "f32"), (1, 5, (1 << 21) + 1, "f16"),
+                                                     (1, 9, (1 << 20) + 7, "bf16"), (0, 12, 1000003, "bf16"), (1, 33, 300001, "f16")])
+def test_elementwise_general_kernel_vs_oracle(E, mode, n_models, numel, dt):
+    """The run-time-model-count kernel (any dtype, > 8 models) at ragged sizes against the numpy oracle, bit for bit."""
+    from shardmerge_b200.merge._elementwise import elem_merge
+    td = _ELEM_TORCH[dt]
+    g = torch.Generator(device=DEV).manual_seed(950 + mode * 100 + n_models)
+    base = (0.02 * torch.randn(numel, generator=g, device=DEV)).to(td)
+    fts = [(base.float() + 0.003 * torch.randn(numel, generator=g, device=DEV)).to(td) for _ in range(n_models)]
+    fts[0][:64] = base[:64]                                           # zero deltas
+    fts[1][100] = float("nan"); fts[0][101] = float("inf")
+    out = elem_merge(mode, base, fts, torch.device(DEV))
+    want = (O.taskaddition_merge if mode == 1 else O.addition_merge)(_elem_to_numpy(dt, base), [_elem_to_numpy(dt, t) for t in fts], dt)
+    assert _elem_same(dt, _elem_to_numpy(dt, out), want).all()
+
+
+def test_elementwise_rejects_mixed_dtypes(E):
+    from shardmerge_b200.merge._elementwise import elem_merge
+    base = torch.zeros(64, dtype=torch.bfloat16, device=DEV)
+    with pytest.raises(NotImplementedError):
+        elem_merge(0, base, [base.float()], torch.device(DEV))
+    with pytest.raises(NotImplementedError):
+        elem_merge(0, base.double(), [base.double()], torch.device(DEV))
 
 
 @pytest.mark.parametrize("mode,n_models,numel", [(0, 2, 4096 * 4096), (1, 3, 4096 * 4096), (1, 4, 1024 * 4096 + 5), (0, 8, 1000003)])

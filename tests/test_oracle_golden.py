@@ -142,15 +142,17 @@ def _nan_equal_bits(a, b):
     return (a == b) | ((fa != fa) & (fb != fb))
 
 
-@pytest.mark.parametrize("name", ["elem_addition_3x_64x128", "elem_addition_2x_special_32x64", "elem_taskaddition_3x_64x128",
-                                  "elem_taskaddition_4x_96x40", "elem_taskaddition_2x_special_32x64"])
+from tests.parity_util import ELEM_CASES, elem_case as _elem_case, elem_same as _elem_same
+
+
+@pytest.mark.parametrize("name", ELEM_CASES)
 def test_elementwise_strategies_match_reference_bit_for_bit(golden_dir, name):
     """AdditionMerge / TaskAdditionMerge (shard/merge/addition.py, taskaddition.py) run by the reference on CPU
-    (oracle/make_golden_elem.py): the numpy restatement reproduces every bf16 rounding, incl. zeros, inf, NaN."""
-    d = np.load(golden_dir / f"{name}.npz")
-    fts = [d[f"ft{k}"] for k in range(int(d["n"]))]
-    got = O.taskaddition_merge(d["base"], fts) if "taskaddition" in name else O.addition_merge(d["base"], fts)
-    assert _nan_equal_bits(got, d["out"]).all()
+    (oracle/make_golden_elem.py): the numpy restatement reproduces every rounding in the tensors' own dtype (bf16, fp16,
+    fp32), incl. zeros, inf, NaN, and torch.sum's cascade from 16 models on."""
+    dt, base, fts, want = _elem_case(golden_dir, name)
+    got = (O.taskaddition_merge if "taskaddition" in name else O.addition_merge)(base, fts, dt)
+    assert _elem_same(dt, got, want).all()
 
 
 def test_oracle_vs_reference_cli_fixture(golden_dir):
