@@ -1832,6 +1832,15 @@ static bool use_row_pairs() {       // SM_ROW_PAIRS=0: one row per CTA iteration
 }
 
 // paired-row forward pass (k_row2_fwd); returns 1 if this shape / mode has none
+// SM_ROW2_OCC=n caps the resident CTAs per SM of the persistent paired-row kernels (default: what fits, 3): fewer leave
+// shared memory for another lane's kernels on the same SM (A-B switch)
+static int row2_occ(int occ) {
+  static int cap = -1;
+  if (cap < 0) { const char* e = getenv("SM_ROW2_OCC"); cap = e ? atoi(e) : 0; }
+  if (occ < 1) occ = 1;
+  return (cap > 0 && cap < occ) ? cap : occ;
+}
+
 template <int R1, int R2, int R3, int R4, int T, bool kPad>
 static int try_row2_fwd(const SmPlan& p, const RowFwdArgs& fa, const cf* twC, const cf* twQ, double* sumsq, cudaStream_t st) {
   if constexpr (R4 == 1 && kPad && (R1 * R2 * R3) / R3 == 2 * T && (R1 * R2 * R3) / R1 == T && (R1 * R2 * R3) / R2 == T) {
@@ -1845,7 +1854,7 @@ static int try_row2_fwd(const SmPlan& p, const RowFwdArgs& fa, const cf* twC, co
     cudaError_t e = opt_in(k_row2_fwd<R1, R2, R3, T, false>, &done);
     if (e == cudaSuccess && occ == 0) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_row2_fwd<R1, R2, R3, T, false>, T, smem);
     if (e != cudaSuccess) { sm_set_error("row2 setup: %s", cudaGetErrorString(e)); return -100; }
-    int grid = num_sms() * (occ > 0 ? occ : 1);
+    int grid = num_sms() * row2_occ(occ);
     if (grid > p.R / 2) grid = p.R / 2;
     sm_launch(k_row2_fwd<R1, R2, R3, T, false>, dim3(grid), dim3(T), (size_t)(smem), st, p.R, p.C, p.P, fa, twC, twQ, sumsq, work_bytes);
     SM_LAUNCH_CHECK();
@@ -1926,7 +1935,7 @@ static int launch_row1_fwd_eo3(const SmPlan& p, const RowFwdArgs& fa, const cf* 
   cudaError_t e = opt_in(k_row2_fwd<R1, R2, R3, T, true>, &done);
   if (e == cudaSuccess && occ == 0) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_row2_fwd<R1, R2, R3, T, true>, T, smem);
   if (e != cudaSuccess) { sm_set_error("row1 fwd eo3 setup: %s", cudaGetErrorString(e)); return -100; }
-  int grid = num_sms() * (occ > 0 ? occ : 1);
+  int grid = num_sms() * row2_occ(occ);
   if (grid > p.R) grid = p.R;
   sm_launch(k_row2_fwd<R1, R2, R3, T, true>, dim3(grid), dim3(T), (size_t)(smem), st, p.R, p.C, p.P, fa, twC, twQ, sumsq, work_bytes);
   SM_LAUNCH_CHECK();
@@ -1970,7 +1979,7 @@ static int launch_row1_inv_eo3(const SmPlan& p, const RowInvArgs& ia, const cf* 
   cudaError_t e = opt_in(k_row2_inv<R1, R2, R3, T, true>, &done);
   if (e == cudaSuccess && occ == 0) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_row2_inv<R1, R2, R3, T, true>, T, smem);
   if (e != cudaSuccess) { sm_set_error("row1 inv eo3 setup: %s", cudaGetErrorString(e)); return -100; }
-  int grid = num_sms() * (occ > 0 ? occ : 1);
+  int grid = num_sms() * row2_occ(occ);
   if (grid > p.R) grid = p.R;
   sm_launch(k_row2_inv<R1, R2, R3, T, true>, dim3(grid), dim3(T), (size_t)(smem), st, p.R, p.C, p.P, ia, twC, twQ, work_bytes);
   SM_LAUNCH_CHECK();
@@ -2002,7 +2011,7 @@ static int try_row2_inv(const SmPlan& p, const RowInvArgs& ia, const cf* twC, co
     cudaError_t e = opt_in(k_row2_inv<R1, R2, R3, T, false>, &done);
     if (e == cudaSuccess && occ == 0) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_row2_inv<R1, R2, R3, T, false>, T, smem);
     if (e != cudaSuccess) { sm_set_error("row2 inv setup: %s", cudaGetErrorString(e)); return -100; }
-    int grid = num_sms() * (occ > 0 ? occ : 1);
+    int grid = num_sms() * row2_occ(occ);
     if (grid > p.R / 2) grid = p.R / 2;
     sm_launch(k_row2_inv<R1, R2, R3, T, false>, dim3(grid), dim3(T), (size_t)(smem), st, p.R, p.C, p.P, ia, twC, twQ, work_bytes);
     SM_LAUNCH_CHECK();

@@ -123,6 +123,8 @@ class FourierMerge(MergeTensorsBase):
                 bad.append((name, shape, "a 0-d tensor has nothing to transform"))
                 continue
             R, C = (1, shape[0]) if len(shape) == 1 else (shape[-2], shape[-1])
+            if len(shape) == 2 and C % 2 == 1 and R % 2 == 0:
+                R, C = C, R                                    # merged as its transpose (merge_sources)
             stack = 1
             for d in shape[:-2]:
                 stack *= d
@@ -219,6 +221,16 @@ class FourierMerge(MergeTensorsBase):
                 raise ValueError(f"finetune / base shape mismatch for {layer_name}: {tuple(src.ft.shape)} vs {shp}")
             if int(torch.tensor(shp).prod()) != base_out.numel():
                 raise ValueError(f"tensor shape mismatch for {layer_name}: {shp} vs output base {tuple(base_out.shape)}")
+        if base_out.ndim == 2 and base_out.shape[1] % 2 == 1 and base_out.shape[0] % 2 == 0:
+            # The packed real row transform needs an even row length.  fft2(X^T) = fft2(X)^T, and everything between the two
+            # transforms is element-wise or a statistic over all bins, so an [R][odd C] tensor is merged as its [C][R]
+            # transpose (contiguous copies: a rare shape, no LLM weight has it) and the result transposed back.
+            tr = lambda x: None if x is None else x.t().contiguous()
+            t_sources = [E.Source(base=tr(sr.base), ft=tr(sr.ft), x32=tr(sr.x32), weight=sr.weight, name=sr.name) for sr in sources]
+            merged_t = self.merge_sources(t_sources, tr(base_out), dev, layer_name, safe_select, defer=False)
+            for sr, ts in zip(sources, t_sources):
+                sr.norm = ts.norm
+            return merged_t.t().contiguous()
         all_bf16 = (not safe_select and base_out.dtype == torch.bfloat16 and base_out.ndim in (1, 2)
                     and all(src.is_bf16 for src in sources))
         is_tree = all_bf16 and 3 <= len(sources) <= 120 and self.fused_tree

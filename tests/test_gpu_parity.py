@@ -408,6 +408,30 @@ def test_golden_layer_cases(E, golden_dir, name, branches, min_within1):
         assert resid < 0.05, (name, raw, resid, share)
 
 
+@pytest.mark.parametrize("shape,seed", [((256, 333), 61), ((1024, 1001), 62)])
+def test_pair_merge_odd_row_length_vs_oracle(E, shape, seed):
+    """[R][odd C] tensors have no packed real row transform; they are merged as their transpose (fft2(X^T) = fft2(X)^T and
+    the blend is element-wise / global).  Against the oracle, which transforms the tensor as it is."""
+    R, C = shape
+    g = torch.Generator(device=DEV).manual_seed(1234 + seed)
+    base = (0.02 * torch.randn(shape, generator=g, device=DEV)).to(torch.bfloat16)
+    fts = [(base.float() + sg * torch.randn(shape, generator=g, device=DEV)).to(torch.bfloat16) for sg in (0.002, 0.0026)]
+    fm = _merger()
+    srcs = [E.make_source(base, fts[k], weight=a, name=f"m{k}") for k, a in enumerate((0.3, 0.5))]
+    out = fm.merge_sources(srcs, base, torch.device(DEV), layer_name="model.layers.0.x")
+    assert tuple(out.shape) == shape and out.dtype == torch.bfloat16 and fm.last_info["branches"] == ["slerp"]
+    models = [dict(base=bits(base), ft=bits(fts[k]), alpha=a, name=f"m{k}") for k, a in enumerate((0.3, 0.5))]
+    info = {}
+    oo = O.merge_layer(bits(base), models, info=info)
+    assert abs(fm.last_info["target_norm"] / info["target_norm"] - 1) < 1e-6
+    basef = O.bf16_to_f32(bits(base))
+    raw, resid, share = flip_accounted(O.bf16_to_f32(bits(out)) - basef, O.bf16_to_f32(oo) - basef, k=16)
+    u = bf16_ulp_distance(bits(out), oo)
+    frac1 = float((u <= 1).mean())
+    print(f"\n[{shape}] odd row length: raw {raw:.3e} flip-accounted {resid:.3e} within 1 ulp {frac1:.6f}")
+    assert resid < 0.05 and frac1 >= 0.98, (raw, resid, share, frac1)
+
+
 def test_golden_layer_range(E, golden_dir):
     d = np.load(golden_dir / "layer_layer_range_64x128.npz")
     got, info = _run_layer_case(E, d, n_models=2)

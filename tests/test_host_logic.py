@@ -236,18 +236,19 @@ def test_process_layers_finalizes_each_tensor_before_the_writer_sees_it():
 
 
 def test_fourier_merge_validates_shapes_up_front(tmp_path):
-    """a tensor whose shape has no FFT plan (odd last dimension here) is reported by initialize(), before
+    """a tensor whose shape has no FFT plan (both dimensions odd here) is reported by initialize(), before
     any output exists; awkward but supported lengths (37, 167 as prime factors) pass."""
     from shardmerge_b200.engine import UnsupportedShape
     from shardmerge_b200.merge.fast_fourier import FourierMerge
     ok = {"model.embed_tokens.weight": torch.zeros(7, 3, dtype=torch.bfloat16),          # pass-through: never transformed
           "model.layers.0.mlp.up_proj.weight": torch.zeros(74, 334, dtype=torch.bfloat16),
+          "model.layers.0.mlp.down_proj.weight": torch.zeros(16, 7, dtype=torch.bfloat16),  # odd rows: merged as the transpose
           "model.layers.0.input_layernorm.weight": torch.zeros(74, dtype=torch.bfloat16)}
     cfg = MergeConfig(finetune_merge=[MergeModel(model="org/a", base="org/base")], output_base_model="org/base",
                       output_dir=str(tmp_path / "out"))
     asyncio.run(FourierMerge(cfg, index_manager=InMemoryIndex({"org/base": ok, "org/a": ok})).initialize())
     bad = dict(ok)
-    bad["model.layers.0.self_attn.q_proj.weight"] = torch.zeros(16, 7, dtype=torch.bfloat16)
+    bad["model.layers.0.self_attn.q_proj.weight"] = torch.zeros(15, 7, dtype=torch.bfloat16)
     with pytest.raises(UnsupportedShape) as exc:
         asyncio.run(FourierMerge(cfg, index_manager=InMemoryIndex({"org/base": bad, "org/a": bad})).initialize())
     assert "q_proj" in str(exc.value) and not (tmp_path / "out").exists()
