@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(kSampleThreads) k_fs_sample(const __grid_const
 // the generic per-element code (weights, exact signs, histogram reductions, side list).  The first two versions
 // branched per key inside the loop: with 32 lanes x 8 keys some lane takes every branch, so the rare code ran
 // at 1/32 efficiency and made up half of the executed instructions (88 per element pair; now ~25).
-constexpr int kQCap = 64;            // entries per warp queue: < 32 left after a drain, <= 32 pushed per item
+constexpr int kQCap = 96;            // entries per warp queue: < 32 left after a drain, <= 64 pushed per iteration (two items)
 
 struct PassCtx {
   float lo_f, hi_f;                  // the window as floats: for non-NaN keys, float order == bit-pattern order
@@ -358,7 +358,7 @@ __shared__ unsigned int g_fs_nside;
 // one CTA of 1024 threads per SM: a quarter of the CTAs means a quarter of the end-of-kernel reductions into the
 // same 64 cache lines of the global coarse histogram (they serialise in L2: 3.5 us with 592 CTAs, measured)
 constexpr int kPassThreads = 512, kPassCtasPerSm = 2, kPassWarps = kPassThreads / 32;
-// the warp queues live in dynamic shared memory (80 KB): [kPassWarps][kQCap] of float4 a, float4 b, uint2 meta
+// the warp queues live in dynamic shared memory (60 KB): [kPassWarps][kQCap] of float4 a, float4 b, uint2 meta
 extern __shared__ __align__(16) unsigned char g_fs_dyn[];
 __device__ __forceinline__ float4* fs_qa(int wid) { return reinterpret_cast<float4*>(g_fs_dyn) + wid * kQCap; }
 __device__ __forceinline__ float4* fs_qb(int wid) { return reinterpret_cast<float4*>(g_fs_dyn) + (kPassWarps + wid) * kQCap; }
@@ -391,38 +391,47 @@ __device__ __forceinline__ float fmin_nan(float x, float y) { float r; asm("min.
 // or inside every window), counts as a key below the window either way, and blends to zero under either mask.  (Spectra of
 // later pair-tree rounds hold ~1 % exact zeros: with the stricter "no zero product" test 10 % of their items were queued.)
 __device__ __forceinline__ float fs_pq(float a, float b) { return (a == 0.f || b == 0.f) ? 1.f : fabsf(a * b); }
-__device__ __forceinline__ bool fs_item_plain(const float4& a, const float4& b) {
-  const float m = fmin_nan(fmin_nan(fabsf(a.x * b.x), fabsf(a.y * b.y)), fmin_nan(fabsf(a.z * b.z), fabsf(a.w * b.w)));
-  if (m > 0.f) return true;        // the common case costs what it always did: four products and three minima
+// p = the four products a_i * b_i of the item (the same values decide `same` in fs_elem: computed once)
+__device__ __forceinline__ bool fs_item_plain(const float4& a, const float4& b, const float4& p) {
+  const float m = fmin_nan(fmin_nan(fabsf(p.x), fabsf(p.y)), fmin_nan(fabsf(p.z), fabsf(p.w)));
+  if (m > 0.f) return true;        // the common case: three minima and a compare
   const float q = fmin_nan(fmin_nan(fs_pq(a.x, b.x), fs_pq(a.y, b.y)), fmin_nan(fs_pq(a.z, b.z), fs_pq(a.w, b.w)));
   return q > 0.f;                  // false for NaN
 }
 
-struct Acc { unsigned int below; float p00, p11, p01; bool anyw; };
+struct Acc { unsigned int below, anyw; float p00, p11, p01; };
 
-// interior element pair of a plain item, multiplicity 2 (the caller doubles counts and sums at the end).  Window tests
-// are float compares on |v| (free abs modifier); NaN keys compare false everywhere, i.e. they sit above the window like
-// their bit patterns do.  A key inside the window only raises a flag (the item is then queued as well).
+// Classify one key against the window in four instructions: |v| < lo -> ++below; else |v| <= hi -> anyw = 1.  (Written in PTX
+// because the compiler, short of predicate registers for the 16 keys of an iteration, recomputed every compare where the
+// count was consumed: 5.5 instructions per key.)  NaN keys compare false both times: above the window, like their bit
+// patterns.
+__device__ __forceinline__ void fs_key(float v, float lo, float hi, unsigned int& below, unsigned int& anyw) {
+  asm("{\n\t.reg .pred p, q;\n\t.reg .f32 t;\n\t"
+      "abs.f32 t, %2;\n\t"
+      "setp.lt.f32 p, t, %3;\n\t"
+      "@p add.u32 %0, %0, 1;\n\t"
+      "setp.le.and.f32 q, t, %4, !p;\n\t"
+      "@q mov.u32 %1, 1;\n\t}"
+      : "+r"(below), "+r"(anyw) : "f"(v), "f"(lo), "f"(hi));
+}
+
+// interior element pair of a plain item, multiplicity 2 (the caller doubles counts and sums at the end); p = a * b.
+// A key inside the window only raises a flag (the item is then queued as well).
 template <int MODE>
-__device__ __forceinline__ float fs_elem(const PassCtx& x, const BlendScal& bs, float a, float b, Acc& c) {
-  const bool same = a * b > 0.f;
+__device__ __forceinline__ float fs_elem(const PassCtx& x, const BlendScal& bs, float a, float b, float p, Acc& c) {
+  const bool same = p > 0.f;
   if (MODE == 0) {
-    const float fa = fabsf(a), fb = fabsf(b);
-    const bool la = fa < x.lo_f, lb = fb < x.lo_f;
-    c.below += (la ? 1u : 0u) + (lb ? 1u : 0u);
-    c.anyw |= (!la && fa <= x.hi_f) | (!lb && fb <= x.hi_f);
+    fs_key(a, x.lo_f, x.hi_f, c.below, c.anyw);
+    fs_key(b, x.lo_f, x.hi_f, c.below, c.anyw);
     // |re1| >= thr for every thr in the window (NaN: never < thr) -> the element is in the SLERP sums; masked operands
     // instead of a branch (2 selects + 3 FMAs)
-    const bool in = same && !(fb <= x.hi_f);
+    const bool in = same && !(fabsf(b) <= x.hi_f);
     const float ma = in ? a : 0.f, mb = in ? b : 0.f;
     c.p00 = fmaf(ma, ma, c.p00); c.p11 = fmaf(mb, mb, c.p11); c.p01 = fmaf(ma, mb, c.p01);
     return 0.f;
   } else {
     const float o = fs_blend(bs, a, b, same);
-    const float fo = fabsf(o);
-    const bool lo_ = fo < x.lo_f;
-    c.below += lo_ ? 1u : 0u;
-    c.anyw |= (!lo_ && fo <= x.hi_f);
+    fs_key(o, x.lo_f, x.hi_f, c.below, c.anyw);
     return o;
   }
 }
@@ -567,33 +576,45 @@ __global__ void __launch_bounds__(kPassThreads, kPassCtasPerSm) k_fs_pass(const 
         float4 a0, b0, a1, b1;                           // both items in flight before the first is consumed
         a0 = *reinterpret_cast<const float4*>(re0 + off0); b0 = *reinterpret_cast<const float4*>(re1 + off0);
         a1 = *reinterpret_cast<const float4*>(re0 + off1); b1 = *reinterpret_cast<const float4*>(re1 + off1);
+        bool want[2];
+        unsigned int meta[2];
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
           const float4 av = r == 0 ? a0 : a1, bv = r == 0 ? b0 : b1;
           const bool valid = r == 0 ? v0 : v1;
           const unsigned int gg = r == 0 ? g : g1;
           const size_t off = r == 0 ? off0 : off1;
-          const bool generic = (gg == 0u) || (gg == G - 1u) || !fs_item_plain(av, bv);
-          Acc ac{0u, 0.f, 0.f, 0.f, false};              // fp32 over one float4, fp64 across
+          const float4 pv = make_float4(av.x * bv.x, av.y * bv.y, av.z * bv.z, av.w * bv.w);
+          const bool edge = (gg == 0u) | (gg == G - 1u);
+          const bool generic = edge | !fs_item_plain(av, bv, pv);
+          Acc ac{0u, 0u, 0.f, 0.f, 0.f};                 // fp32 over one float4, fp64 across
           float4 o;
-          o.x = fs_elem<MODE>(x, bs, av.x, bv.x, ac); o.y = fs_elem<MODE>(x, bs, av.y, bv.y, ac);
-          o.z = fs_elem<MODE>(x, bs, av.z, bv.z, ac); o.w = fs_elem<MODE>(x, bs, av.w, bv.w, ac);
+          o.x = fs_elem<MODE>(x, bs, av.x, bv.x, pv.x, ac); o.y = fs_elem<MODE>(x, bs, av.y, bv.y, pv.y, ac);
+          o.z = fs_elem<MODE>(x, bs, av.z, bv.z, pv.z, ac); o.w = fs_elem<MODE>(x, bs, av.w, bv.w, pv.w, ac);
           const bool fast = valid && !generic;
           if (fast) {
             below_in += ac.below;
             if (MODE == 0) { d00 += (double)ac.p00; d11 += (double)ac.p11; d01 += (double)ac.p01; }
             else *reinterpret_cast<float4*>(out + off) = o;
           }
-          const bool want = valid && (generic || ac.anyw);
-          const unsigned int m = __ballot_sync(0xffffffffu, want);
-          if (m) {                                       // warp-uniform
-            if (want) {
-              const int slot = qn + __popc(m & ((1u << lane) - 1u));
-              qa[slot] = av; qb[slot] = bv;
-              qm[slot] = make_uint2((unsigned int)off, 4u * gg | (generic ? 0x80000000u : 0u));
+          want[r] = valid && (generic || ac.anyw != 0u);
+          meta[r] = 4u * gg | (generic ? 0x80000000u : 0u);
+        }
+        {  // both items of the iteration join the queue in one step (some lane wants to in 9 iterations out of 10)
+          const unsigned int m0 = __ballot_sync(0xffffffffu, want[0]), m1 = __ballot_sync(0xffffffffu, want[1]);
+          if (m0 | m1) {                                 // warp-uniform
+            const unsigned int lt = (1u << lane) - 1u;
+            if (want[0]) {
+              const int slot = qn + __popc(m0 & lt);
+              qa[slot] = a0; qb[slot] = b0; qm[slot] = make_uint2((unsigned int)off0, meta[0]);
             }
-            qn += __popc(m);
-            if (qn >= 32) { qn -= 32; fs_drain<MODE>(wid, qn, 32, da); }
+            qn += __popc(m0);
+            if (want[1]) {
+              const int slot = qn + __popc(m1 & lt);
+              qa[slot] = a1; qb[slot] = b1; qm[slot] = make_uint2((unsigned int)off1, meta[1]);
+            }
+            qn += __popc(m1);
+            while (qn >= 32) { qn -= 32; fs_drain<MODE>(wid, qn, 32, da); }
           }
         }
         // advance by 64 items
@@ -806,7 +827,7 @@ static int fs_carve(const sm_plan* plan, void* wsp, size_t ws_bytes, FsWs* w) {
   return 0;
 }
 
-static int fs_pass_attr() {          // opt in to the 80 KB of dynamic shared memory of k_fs_pass, once
+static int fs_pass_attr() {          // opt in to the dynamic shared memory of k_fs_pass (the warp queues), once
   static int rc = 1;
   if (rc == 1) {
     cudaError_t e = cudaFuncSetAttribute((const void*)k_fs_pass<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPassDynSmem);
