@@ -450,9 +450,16 @@ SM_HD void col_ct_body(Exec& ex, int tile, int inst, const ColCtArgs a, const cf
 // packed value: half the FP / load-store / index instructions per element, 8-byte global accesses, 16-byte
 // shared-memory accesses.  Lane mapping: 16 lanes x 2 columns = one 32-column tile row (128 B), two butterfly
 // slots per warp.  The pair (Ch, Ch+1) touches one zero-filled padding column, whose transform is zero again.
+#ifndef SM_COL_LD_EF
+#define SM_COL_LD_EF 0     // 1: the column sweeps' loads are streaming loads (ld.global.cs, evict-first; experiment: keep a sweep's OUTPUT in L2 for the next)
+#endif
 SM_HD pf ldcg_pf(const float* p) {
 #if defined(__CUDA_ARCH__)
+#if SM_COL_LD_EF
+  const float2 v = __ldcs(reinterpret_cast<const float2*>(p));     // ld.global.cs: evict-first in L1 and L2
+#else
   const float2 v = __ldcg(reinterpret_cast<const float2*>(p));
+#endif
   return pf_make(v.x, v.y);
 #else
   return pf_make(p[0], p[1]);
