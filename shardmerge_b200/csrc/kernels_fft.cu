@@ -965,27 +965,45 @@ __device__ __forceinline__ bool any_not_finite4(float a, float b, float c, float
   return not_finite(fmax_nan(fmax_nan(fabsf(a), fabsf(b)), fmax_nan(fabsf(c), fabsf(d))));
 }
 
+// y = x * scale (+ base) for four values with the reference's two checks -- ifft output (NaN -> 0, Inf counted: flags 0 / 1),
+// merged value (flags 2 / 3).  ONE test on the results covers both in the common case: a non-finite x makes its y non-finite
+// too (NaN and Inf propagate through x * scale + base, Inf * 0 = NaN), so only a non-finite y replays the checks in order.
+__device__ __forceinline__ void epi_finish4(const RowInvArgs& a, float scale, bool add_base, float x0, float x1, float x2, float x3,
+                                            float b0, float b1, float b2, float b3, float& y0, float& y1, float& y2, float& y3) {
+  // __fmul_rn / __fadd_rn: one rounding per torch op, never contracted into an FMA
+  y0 = __fmul_rn(x0, scale); y1 = __fmul_rn(x1, scale); y2 = __fmul_rn(x2, scale); y3 = __fmul_rn(x3, scale);
+  if (add_base) { y0 = __fadd_rn(b0, y0); y1 = __fadd_rn(b1, y1); y2 = __fadd_rn(b2, y2); y3 = __fadd_rn(b3, y3); }
+  if (any_not_finite4(y0, y1, y2, y3)) {                   // exceptional
+    if (a.check_ifft && any_not_finite4(x0, x1, x2, x3)) {
+      x0 = epi_fix(x0, a.flags, 0); x1 = epi_fix(x1, a.flags, 0); x2 = epi_fix(x2, a.flags, 0); x3 = epi_fix(x3, a.flags, 0);
+    }
+    y0 = __fmul_rn(x0, scale); y1 = __fmul_rn(x1, scale); y2 = __fmul_rn(x2, scale); y3 = __fmul_rn(x3, scale);
+    if (add_base) {
+      y0 = __fadd_rn(b0, y0); y1 = __fadd_rn(b1, y1); y2 = __fadd_rn(b2, y2); y3 = __fadd_rn(b3, y3);
+      if (any_not_finite4(y0, y1, y2, y3)) {
+        y0 = epi_fix(y0, a.flags, 2); y1 = epi_fix(y1, a.flags, 2); y2 = epi_fix(y2, a.flags, 2); y3 = epi_fix(y3, a.flags, 2);
+      }
+    }
+  }
+}
+
 // element j of the pair: (a, b) = swapped engine output -> x[2j] = b / N, x[2j+1] = a / N for both rows
 __device__ __forceinline__ void epilogue_store2(const RowInvArgs& a, float scale, uint32_t bb0, uint32_t bb1, uint32_t* out0,
                                                 uint32_t* out1, float* of0, float* of1, int j, pf va, pf vb) {
   const pf n = pf_bcast(a.inv_n);
   pf x0 = vb * n, x1 = va * n;
   float x00 = pf_lo(x0), x01 = pf_hi(x0), x10 = pf_lo(x1), x11 = pf_hi(x1);   // xRC: element R of the pair, row C
-  if (a.check_ifft && any_not_finite4(x00, x01, x10, x11)) {     // exceptional: one rarely taken branch for the four values
-    x00 = epi_fix(x00, a.flags, 0); x01 = epi_fix(x01, a.flags, 0); x10 = epi_fix(x10, a.flags, 0); x11 = epi_fix(x11, a.flags, 0);
-  }
-  x00 *= scale; x01 *= scale; x10 *= scale; x11 *= scale;
-  if (a.out_mode == 0) {
-    x00 = bf16_bits_to_f32(bb0 & 0xffffu) + x00; x10 = bits_f32(bb0 & 0xffff0000u) + x10;
-    x01 = bf16_bits_to_f32(bb1 & 0xffffu) + x01; x11 = bits_f32(bb1 & 0xffff0000u) + x11;
-    if (any_not_finite4(x00, x01, x10, x11)) {
-      x00 = epi_fix(x00, a.flags, 2); x10 = epi_fix(x10, a.flags, 2); x01 = epi_fix(x01, a.flags, 2); x11 = epi_fix(x11, a.flags, 2);
-    }
-    out0[j] = pack_bf16x2_rne(x00, x10);
-    out1[j] = pack_bf16x2_rne(x01, x11);
+  const bool add_base = a.out_mode == 0;
+  const float b00 = add_base ? bf16_bits_to_f32(bb0 & 0xffffu) : 0.f, b10 = add_base ? bits_f32(bb0 & 0xffff0000u) : 0.f;
+  const float b01 = add_base ? bf16_bits_to_f32(bb1 & 0xffffu) : 0.f, b11 = add_base ? bits_f32(bb1 & 0xffff0000u) : 0.f;
+  float y00, y01, y10, y11;
+  epi_finish4(a, scale, add_base, x00, x01, x10, x11, b00, b01, b10, b11, y00, y01, y10, y11);
+  if (add_base) {
+    out0[j] = pack_bf16x2_rne(y00, y10);
+    out1[j] = pack_bf16x2_rne(y01, y11);
   } else {
-    reinterpret_cast<float2*>(of0)[j] = make_float2(x00, x10);
-    reinterpret_cast<float2*>(of1)[j] = make_float2(x01, x11);
+    reinterpret_cast<float2*>(of0)[j] = make_float2(y00, y10);
+    reinterpret_cast<float2*>(of1)[j] = make_float2(y01, y11);
   }
 }
 
@@ -1296,21 +1314,14 @@ struct RowTangleGlobalEO {
 __device__ __forceinline__ void epilogue_store_eo(const RowInvArgs& a, float scale, uint2 bb, uint2* out64, float4* of, int m, pf va, pf vb) {
   const pf n = pf_bcast(a.inv_n);
   const pf x0 = vb * n, x1 = va * n;
-  float x00 = pf_lo(x0), x01 = pf_hi(x0), x10 = pf_lo(x1), x11 = pf_hi(x1);   // xEL: element E of the complex pair, lane L
-  if (a.check_ifft && any_not_finite4(x00, x01, x10, x11)) {     // exceptional: one rarely taken branch for the four values
-    x00 = epi_fix(x00, a.flags, 0); x01 = epi_fix(x01, a.flags, 0); x10 = epi_fix(x10, a.flags, 0); x11 = epi_fix(x11, a.flags, 0);
-  }
-  x00 *= scale; x01 *= scale; x10 *= scale; x11 *= scale;
-  if (a.out_mode == 0) {
-    x00 = bf16_bits_to_f32(bb.x & 0xffffu) + x00; x10 = bits_f32(bb.x & 0xffff0000u) + x10;
-    x01 = bf16_bits_to_f32(bb.y & 0xffffu) + x01; x11 = bits_f32(bb.y & 0xffff0000u) + x11;
-    if (any_not_finite4(x00, x01, x10, x11)) {
-      x00 = epi_fix(x00, a.flags, 2); x10 = epi_fix(x10, a.flags, 2); x01 = epi_fix(x01, a.flags, 2); x11 = epi_fix(x11, a.flags, 2);
-    }
-    out64[m] = make_uint2(pack_bf16x2_rne(x00, x10), pack_bf16x2_rne(x01, x11));
-  } else {
-    of[m] = make_float4(x00, x10, x01, x11);
-  }
+  const float x00 = pf_lo(x0), x01 = pf_hi(x0), x10 = pf_lo(x1), x11 = pf_hi(x1);   // xEL: element E of the complex pair, lane L
+  const bool add_base = a.out_mode == 0;
+  const float b00 = add_base ? bf16_bits_to_f32(bb.x & 0xffffu) : 0.f, b10 = add_base ? bits_f32(bb.x & 0xffff0000u) : 0.f;
+  const float b01 = add_base ? bf16_bits_to_f32(bb.y & 0xffffu) : 0.f, b11 = add_base ? bits_f32(bb.y & 0xffff0000u) : 0.f;
+  float y00, y01, y10, y11;
+  epi_finish4(a, scale, add_base, x00, x01, x10, x11, b00, b01, b10, b11, y00, y01, y10, y11);
+  if (add_base) out64[m] = make_uint2(pack_bf16x2_rne(y00, y10), pack_bf16x2_rne(y01, y11));
+  else of[m] = make_float4(y00, y10, y01, y11);
 }
 
 template <int R1, int R2, int R3, int R4, int T, int kCtas>
