@@ -1007,6 +1007,42 @@ __device__ __forceinline__ void epilogue_store2(const RowInvArgs& a, float scale
   }
 }
 
+// Branch-free variants for the last stage's loop over its outputs: store what comes out and fold the magnitudes into `bad`
+// (NaN-propagating maximum); the caller tests `bad` ONCE per batch of outputs and, if it is not finite, runs the exact
+// epilogue above over the batch again (same addresses: the corrected values overwrite, the flags are counted there only).
+// Keeps the batch one basic block: the per-value test of the exact epilogue cut the schedule into 16 pieces per iteration.
+__device__ __forceinline__ float fmax3_nan(float x, float y, float z) { return fmax_nan(fmax_nan(x, y), z); }
+__device__ __forceinline__ void epilogue_store2_fast(const RowInvArgs& a, float scale, uint32_t bb0, uint32_t bb1, uint32_t* out0,
+                                                     uint32_t* out1, float* of0, float* of1, int j, pf va, pf vb, float& bad) {
+  const pf n = pf_bcast(a.inv_n);
+  const pf x0 = vb * n, x1 = va * n;
+  float y00 = __fmul_rn(pf_lo(x0), scale), y01 = __fmul_rn(pf_hi(x0), scale), y10 = __fmul_rn(pf_lo(x1), scale), y11 = __fmul_rn(pf_hi(x1), scale);
+  if (a.out_mode == 0) {
+    y00 = __fadd_rn(bf16_bits_to_f32(bb0 & 0xffffu), y00); y10 = __fadd_rn(bits_f32(bb0 & 0xffff0000u), y10);
+    y01 = __fadd_rn(bf16_bits_to_f32(bb1 & 0xffffu), y01); y11 = __fadd_rn(bits_f32(bb1 & 0xffff0000u), y11);
+    out0[j] = pack_bf16x2_rne(y00, y10);
+    out1[j] = pack_bf16x2_rne(y01, y11);
+  } else {
+    reinterpret_cast<float2*>(of0)[j] = make_float2(y00, y10);
+    reinterpret_cast<float2*>(of1)[j] = make_float2(y01, y11);
+  }
+  bad = fmax3_nan(fmax3_nan(bad, fabsf(y00), fabsf(y01)), fabsf(y10), fabsf(y11));
+}
+__device__ __forceinline__ void epilogue_store_eo_fast(const RowInvArgs& a, float scale, uint2 bb, uint2* out64, float4* of, int m, pf va,
+                                                       pf vb, float& bad) {
+  const pf n = pf_bcast(a.inv_n);
+  const pf x0 = vb * n, x1 = va * n;
+  float y00 = __fmul_rn(pf_lo(x0), scale), y01 = __fmul_rn(pf_hi(x0), scale), y10 = __fmul_rn(pf_lo(x1), scale), y11 = __fmul_rn(pf_hi(x1), scale);
+  if (a.out_mode == 0) {
+    y00 = __fadd_rn(bf16_bits_to_f32(bb.x & 0xffffu), y00); y10 = __fadd_rn(bits_f32(bb.x & 0xffff0000u), y10);
+    y01 = __fadd_rn(bf16_bits_to_f32(bb.y & 0xffffu), y01); y11 = __fadd_rn(bits_f32(bb.y & 0xffff0000u), y11);
+    out64[m] = make_uint2(pack_bf16x2_rne(y00, y10), pack_bf16x2_rne(y01, y11));
+  } else {
+    of[m] = make_float4(y00, y10, y01, y11);
+  }
+  bad = fmax3_nan(fmax3_nan(bad, fabsf(y00), fabsf(y01)), fabsf(y10), fabsf(y11));
+}
+
 // kEO: the lanes are the even / odd halves of ONE row (decimation in frequency on the engine's input, see k_row1_inv_eo)
 __device__ __forceinline__ void epilogue_store_eo(const RowInvArgs& a, float scale, uint2 bb, uint2* out64, float4* of, int m, pf va, pf vb);
 struct RowTangleStagedEO {       // staged spectrum row (re, im), H = Ch / 2
@@ -1126,8 +1162,13 @@ __global__ void __launch_bounds__(T, 3) k_row2_inv(int R, int C, int P, const __
         for (int j = 0; j < R3; ++j) sm.load(b + j * S3, re[j], im[j]);
         if (h == 1) __syncthreads();                // the buffer has been read: the next row's stage 1 may overwrite it
         Dft<R3>::run(re, im);
+        float bad = 0.f;
 #pragma unroll
-        for (int k = 0; k < R3; ++k) epilogue_store_eo(a, scale, bb[k], out64, of, b + k * S3, re[k], im[k]);
+        for (int k = 0; k < R3; ++k) epilogue_store_eo_fast(a, scale, bb[k], out64, of, b + k * S3, re[k], im[k], bad);
+        if (not_finite(bad)) {                       // exceptional: the exact epilogue over the same outputs
+#pragma unroll
+          for (int k = 0; k < R3; ++k) epilogue_store_eo(a, scale, bb[k], out64, of, b + k * S3, re[k], im[k]);
+        }
       }
     } else {  // stage 3 (last): butterflies t and t + T, outputs straight into the epilogue
       const size_t row0 = (size_t)pair * 2;
@@ -1151,8 +1192,13 @@ __global__ void __launch_bounds__(T, 3) k_row2_inv(int R, int C, int P, const __
         for (int j = 0; j < R3; ++j) sm.load(b + j * S3, re[j], im[j]);
         if (h == 1) __syncthreads();                // the buffer has been read: the next pair's stage 1 may overwrite it
         Dft<R3>::run(re, im);
+        float bad = 0.f;
 #pragma unroll
-        for (int k = 0; k < R3; ++k) epilogue_store2(a, scale, bb0[k], bb1[k], out0, out1, of0, of1, b + k * S3, re[k], im[k]);
+        for (int k = 0; k < R3; ++k) epilogue_store2_fast(a, scale, bb0[k], bb1[k], out0, out1, of0, of1, b + k * S3, re[k], im[k], bad);
+        if (not_finite(bad)) {                       // exceptional: the exact epilogue over the same outputs
+#pragma unroll
+          for (int k = 0; k < R3; ++k) epilogue_store2(a, scale, bb0[k], bb1[k], out0, out1, of0, of1, b + k * S3, re[k], im[k]);
+        }
       }
     }
   }
@@ -1278,8 +1324,13 @@ __global__ void __launch_bounds__(T, kCtas) k_row2_inv4(int R, int C, int P, con
         for (int j = 0; j < R4; ++j) sm.load(b + j * S4, re[j], im[j]);
         if (h == 1) __syncthreads();                // the buffer has been read: the next pair's stage 1 may overwrite it
         Dft<R4>::run(re, im);
+        float bad = 0.f;
 #pragma unroll
-        for (int k = 0; k < R4; ++k) epilogue_store2(a, scale, bb0[k], bb1[k], out0, out1, of0, of1, b + k * S4, re[k], im[k]);
+        for (int k = 0; k < R4; ++k) epilogue_store2_fast(a, scale, bb0[k], bb1[k], out0, out1, of0, of1, b + k * S4, re[k], im[k], bad);
+        if (not_finite(bad)) {                       // exceptional: the exact epilogue over the same outputs
+#pragma unroll
+          for (int k = 0; k < R4; ++k) epilogue_store2(a, scale, bb0[k], bb1[k], out0, out1, of0, of1, b + k * S4, re[k], im[k]);
+        }
       }
     }
   }
@@ -1416,8 +1467,13 @@ __global__ void __launch_bounds__(T, kCtas) k_row1_inv_eo(int R, int C, int P, c
         for (int j = 0; j < R4; ++j) sm.load(b + j * S4, re[j], im[j]);
         if (h == 1) __syncthreads();                // the buffer has been read: the next row's stage 1 may overwrite it
         Dft<R4>::run(re, im);
+        float bad = 0.f;
 #pragma unroll
-        for (int k = 0; k < R4; ++k) epilogue_store_eo(a, scale, bb[k], out64, of, b + k * S4, re[k], im[k]);
+        for (int k = 0; k < R4; ++k) epilogue_store_eo_fast(a, scale, bb[k], out64, of, b + k * S4, re[k], im[k], bad);
+        if (not_finite(bad)) {                       // exceptional: the exact epilogue over the same outputs
+#pragma unroll
+          for (int k = 0; k < R4; ++k) epilogue_store_eo(a, scale, bb[k], out64, of, b + k * S4, re[k], im[k]);
+        }
       }
     }
   }
