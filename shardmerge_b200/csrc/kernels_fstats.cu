@@ -386,18 +386,11 @@ __device__ __forceinline__ float fs_blend(const BlendScal& bs, float a, float b,
 __device__ __forceinline__ float fmin_nan(float x, float y) { float r; asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(x), "f"(y)); return r; }
 
 // The fast path decides torch.sign(a) == torch.sign(b) by a * b > 0.  That is wrong only if the product is NaN or if it
-// underflowed to zero with both operands non-zero.  An operand that IS zero needs no care: sign(0) = 0 differs from the sign
-// of any non-zero value (a * b = 0 -> false, right), and if both are zero the element is in no SLERP sum (|re1| = 0 is below
-// or inside every window), counts as a key below the window either way, and blends to zero under either mask.  (Spectra of
-// later pair-tree rounds hold ~1 % exact zeros: with the stricter "no zero product" test 10 % of their items were queued.)
-__device__ __forceinline__ float fs_pq(float a, float b) { return (a == 0.f || b == 0.f) ? 1.f : fabsf(a * b); }
-// p = the four products a_i * b_i of the item (the same values decide `same` in fs_elem: computed once)
-__device__ __forceinline__ bool fs_item_plain(const float4& a, const float4& b, const float4& p) {
-  const float m = fmin_nan(fmin_nan(fabsf(p.x), fabsf(p.y)), fmin_nan(fabsf(p.z), fabsf(p.w)));
-  if (m > 0.f) return true;        // the common case: three minima and a compare
-  const float q = fmin_nan(fmin_nan(fs_pq(a.x, b.x), fs_pq(a.y, b.y)), fmin_nan(fs_pq(a.z, b.z), fs_pq(a.w, b.w)));
-  return q > 0.f;                  // false for NaN
-}
+// underflowed to zero with both operands non-zero; an item with such a product (the NaN-propagating minimum of its four
+// |products| is not > 0) is queued and the drain compares the signs exactly.  Exact zeros land there too -- spectra of later
+// pair-tree rounds hold ~1 % of them, i.e. ~10 % of their items are queued -- which costs less than a test that tells the
+// harmless zeros apart would: that test is a basic-block boundary per item, the drain handles 32 queued items in ~180
+// instructions (measured both ways, profiles/r02_fs_pass_prefetch_variants.log).
 
 struct Acc { unsigned int below, anyw; float p00, p11, p01; };
 
@@ -586,16 +579,19 @@ __global__ void __launch_bounds__(kPassThreads, kPassCtasPerSm) k_fs_pass(const 
           const size_t off = r == 0 ? off0 : off1;
           const float4 pv = make_float4(av.x * bv.x, av.y * bv.y, av.z * bv.z, av.w * bv.w);
           const bool edge = (gg == 0u) | (gg == G - 1u);
-          const bool generic = edge | !fs_item_plain(av, bv, pv);
+          // branch-free: an item with a zero / NaN product is simply queued (the drain compares signs exactly); the relaxed
+          // test for exact zeros (fs_item_plain) is not worth a basic-block boundary per item here
+          const bool generic = edge | !(fmin_nan(fmin_nan(fabsf(pv.x), fabsf(pv.y)), fmin_nan(fabsf(pv.z), fabsf(pv.w))) > 0.f);
           Acc ac{0u, 0u, 0.f, 0.f, 0.f};                 // fp32 over one float4, fp64 across
           float4 o;
           o.x = fs_elem<MODE>(x, bs, av.x, bv.x, pv.x, ac); o.y = fs_elem<MODE>(x, bs, av.y, bv.y, pv.y, ac);
           o.z = fs_elem<MODE>(x, bs, av.z, bv.z, pv.z, ac); o.w = fs_elem<MODE>(x, bs, av.w, bv.w, pv.w, ac);
           const bool fast = valid && !generic;
-          if (fast) {
-            below_in += ac.below;
-            if (MODE == 0) { d00 += (double)ac.p00; d11 += (double)ac.p11; d01 += (double)ac.p01; }
-            else *reinterpret_cast<float4*>(out + off) = o;
+          below_in += fast ? ac.below : 0u;              // selects, not a branch: the iteration stays one basic block
+          if (MODE == 0) {
+            d00 += (double)(fast ? ac.p00 : 0.f); d11 += (double)(fast ? ac.p11 : 0.f); d01 += (double)(fast ? ac.p01 : 0.f);
+          } else if (fast) {
+            *reinterpret_cast<float4*>(out + off) = o;   // a predicated store
           }
           want[r] = valid && (generic || ac.anyw != 0u);
           meta[r] = 4u * gg | (generic ? 0x80000000u : 0u);
