@@ -34,7 +34,6 @@ import asyncio
 import json
 import os
 import statistics
-import subprocess
 import sys
 import threading
 import time

@@ -18,7 +18,6 @@ TensorDiskCache round trips (shard/merge/fast_fourier.py:46-77) have no equivale
 from __future__ import annotations
 
 import ctypes
-import math
 from dataclasses import dataclass, field
 from typing import Optional
 

@@ -23,7 +23,7 @@ from typing import List, Optional
 import torch
 
 from .. import engine as E
-from ..config import MergeConfig, MergeModel
+from ..config import MergeConfig
 from ..constants import INPUT_LAYER, OUTPUT_LAYER
 from ..tensor.functions import correlated_pairs
 from .base import MergeTensorsBase

@@ -16,7 +16,7 @@ One process per GPU; torch.distributed is used only for rendezvous / barriers.
 from __future__ import annotations
 
 import heapq
-from typing import Dict, Iterable, List, Sequence, Tuple
+from typing import Dict, List, Sequence, Tuple
 
 
 def lpt(items: Sequence[Tuple[str, int]], n_ranks: int) -> List[List[str]]:

@@ -16,7 +16,7 @@ Scope notes (documented deviations, all below FFT rounding except where stated):
 from __future__ import annotations
 
 import logging
-from typing import Generator, Literal, Optional
+from typing import Generator, Literal
 
 import torch
 
