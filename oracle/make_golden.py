@@ -142,6 +142,7 @@ def layer_level_cases():
     run("add_zero_64x128", (64, 128), 10, [0.3, 0.5], mutate=lambda b, f: (b, [b.clone(), b.clone()]))
     run("onezero_64x128", (64, 128), 16, [0.3, 0.5], mutate=lambda b, f: (b, [f[0], b.clone()]))
     run("layer_range_64x128", (64, 128), 17, [0.3, 0.5, 0.4], flags={2: dict(start_layer=10)})
+    run("slerp_oddC_64x129", (64, 129), 18, [0.3, 0.5])           # odd row length (the CUDA path merges the transpose)
     return cases
 
 
